@@ -1,0 +1,36 @@
+"""Adapter giving oracle/kzg_oracle.py (pure Python restatement) the CKZG method set."""
+import os
+
+from oracle import kzg_oracle as K
+
+SETUP_TXT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "c-kzg-4844_b200", "data", "trusted_setup.txt")
+BadArgs = K.BadArgs
+
+
+class PyOracle:
+    def __init__(self, setup_path=SETUP_TXT, check=False):
+        self.s = K.load_trusted_setup_file(setup_path, check=check)
+
+    def blob_to_kzg_commitment(self, blob):
+        return K.blob_to_kzg_commitment(blob, self.s)
+
+    def compute_kzg_proof(self, blob, z):
+        return K.compute_kzg_proof(blob, z, self.s)
+
+    def compute_blob_kzg_proof(self, blob, commitment):
+        return K.compute_blob_kzg_proof(blob, commitment, self.s)
+
+    def verify_kzg_proof(self, c, z, y, p):
+        return K.verify_kzg_proof(c, z, y, p, self.s)
+
+    def verify_blob_kzg_proof(self, blob, c, p):
+        return K.verify_blob_kzg_proof(blob, c, p, self.s)
+
+    def verify_blob_kzg_proof_batch(self, blobs, cs, ps):
+        n = len(cs) // 48
+        return K.verify_blob_kzg_proof_batch(
+            [blobs[131072 * i : 131072 * (i + 1)] for i in range(n)],
+            [cs[48 * i : 48 * i + 48] for i in range(n)],
+            [ps[48 * i : 48 * i + 48] for i in range(n)],
+            self.s,
+        )

@@ -1,0 +1,59 @@
+"""Pin the oracle (both legs) on the consensus-spec vectors -- CPU only.
+
+ * oracle/_ref/libckzg_ref.so (the unmodified reference compiled by oracle/build_ref.sh) must
+   reproduce all 344 packed cases (tests/golden) -- proves the packing is faithful and gives the
+   live differential checker its credentials.
+ * oracle/kzg_oracle.py (pure-Python restatement) must reproduce the vectors of every API it
+   restates; the slow families are sampled so the CPU suite stays within minutes.
+"""
+import os
+
+import pytest
+
+import golden_vectors as gv
+import vector_runner as vr
+from oracle import ref_lib
+
+REF_APIS = [a for a in gv.apis() if "challenge" not in a]
+
+
+@pytest.fixture(scope="module")
+def ref():
+    if not os.path.exists(ref_lib.REF_SO):
+        pytest.skip("oracle/_ref not built (run oracle/build_ref.sh where /root/reference exists)")
+    k = ref_lib.CKZG()
+    yield k
+    k.close()
+
+
+@pytest.fixture(scope="module")
+def pyo():
+    from py_oracle_backend import PyOracle
+
+    return PyOracle(check=True)  # check=True also exercises the pairing on the setup
+
+
+def test_vector_count():
+    assert sum(len(gv.cases(a)) for a in gv.apis()) == 344
+
+
+@pytest.mark.parametrize("api", REF_APIS)
+def test_reference_so_reproduces_vectors(ref, api):
+    bad, n = vr.run_api(api, ref)
+    assert n > 0 and not bad, [b[0] for b in bad]
+
+
+PY_APIS = {
+    "blob_to_kzg_commitment": None,
+    "verify_kzg_proof": 40,
+    "compute_kzg_proof": 14,
+    "compute_blob_kzg_proof": 10,
+    "verify_blob_kzg_proof": 12,
+    "verify_blob_kzg_proof_batch": None,
+}
+
+
+@pytest.mark.parametrize("api", sorted(PY_APIS))
+def test_python_restatement_reproduces_vectors(pyo, api):
+    bad, n = vr.run_api(api, pyo, limit=PY_APIS[api])
+    assert n > 0 and not bad, [b[0] for b in bad]
