@@ -1,0 +1,198 @@
+"""Host-side mirror of the reference Python binding (bindings/python/ckzg_wrap.c) over ctypes.
+
+Same names, argument order and error behaviour as the `ckzg` module of the reference:
+    ts = load_trusted_setup(path, precompute)
+    blob_to_kzg_commitment(blob, ts) -> bytes48
+    compute_kzg_proof(blob, z, ts) -> (proof48, y32)
+    compute_blob_kzg_proof(blob, commitment, ts) -> bytes48
+    verify_kzg_proof(commitment, z, y, proof, ts) -> bool
+    verify_blob_kzg_proof(blob, commitment, proof, ts) -> bool
+    verify_blob_kzg_proof_batch(blobs, commitments, proofs, ts) -> bool     (concatenated bytes)
+    compute_cells_and_kzg_proofs(blob, ts) -> (cells[128], proofs[128])
+    recover_cells_and_kzg_proofs(cell_indices, cells, ts) -> (cells[128], proofs[128])
+    verify_cell_kzg_proof_batch(commitments, cell_indices, cells, proofs, ts) -> bool
+Invalid input raises ValueError (the binding's mapping of C_KZG_BADARGS, ckzg_wrap.c), anything else
+RuntimeError.  Plus the engine's batched / device-pointer entry points (include/ckzg_b200.h).
+
+No arithmetic happens here and nothing under oracle/ is imported: the library either runs on the
+GPU or raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libckzg_b200.so")
+SETUP_TXT = os.path.join(_HERE, "data", "trusted_setup.txt")
+
+BYTES_PER_BLOB = 131072
+BYTES_PER_CELL = 2048
+CELLS_PER_EXT_BLOB = 128
+HOST, DEVICE = 0, 1
+
+_lib = None
+
+
+def lib():
+    """The product shared library; raises if it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libckzg_b200.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        _lib = C.CDLL(LIB_PATH)
+        for name in (
+            "load_trusted_setup blob_to_kzg_commitment compute_kzg_proof compute_blob_kzg_proof verify_kzg_proof "
+            "verify_blob_kzg_proof verify_blob_kzg_proof_batch ckzg_b200_blob_to_kzg_commitment_batch "
+            "ckzg_b200_compute_blob_kzg_proof_batch ckzg_b200_compute_kzg_proof_batch ckzg_b200_verify_blob_kzg_proof_batch "
+            "ckzg_b200_verify_kzg_proof ckzg_b200_verify_blob_batch_stage1 ckzg_b200_verify_blob_batch_stage2 "
+            "ckzg_b200_verify_blob_batch_finish ckzg_b200_compute_challenge ckzg_b200_selftest_field ckzg_b200_selftest_g1"
+        ).split():
+            getattr(_lib, name).restype = C.c_int
+        _lib.ckzg_b200_launch_count.restype = C.c_uint64
+        _lib.ckzg_b200_launch_count.argtypes = [C.c_void_p]
+        _lib.free_trusted_setup.restype = None
+    return _lib
+
+
+def _raise(code, fn):
+    if code == 1:
+        raise ValueError("%s: invalid argument (C_KZG_BADARGS)" % fn)
+    if code == 3:
+        raise MemoryError("%s: C_KZG_MALLOC" % fn)
+    if code != 0:
+        raise RuntimeError("%s: C_KZG_ERROR (code %d) -- CUDA device/engine failure; there is no CPU path" % (fn, code))
+
+
+class TrustedSetup:
+    """Owns the caller-allocated 80-byte KZGSettings (src/setup/settings.h:27-79)."""
+
+    def __init__(self, path=SETUP_TXT, precompute=0):
+        self._s = C.create_string_buffer(80)
+        with open(path) as f:
+            tok = f.read().split()
+        n1, n2 = int(tok[0]), int(tok[1])
+        body = tok[2:]
+        lag = bytes.fromhex("".join(body[:n1]))
+        g2 = bytes.fromhex("".join(body[n1 : n1 + n2]))
+        mono = bytes.fromhex("".join(body[n1 + n2 : n1 + n2 + n1]))
+        fn = lib().load_trusted_setup
+        fn.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.c_uint64]
+        _raise(fn(self._s, mono, len(mono), lag, len(lag), g2, len(g2), precompute), "load_trusted_setup")
+        self.precompute = precompute
+
+    @property
+    def ptr(self):
+        return self._s
+
+    @property
+    def engine(self):
+        """The ckzg_b200_ctx* stored in KZGSettings.tables (8th pointer slot)."""
+        return C.c_void_p(int.from_bytes(self._s.raw[56:64], "little"))
+
+    def launch_count(self):
+        return int(lib().ckzg_b200_launch_count(self.engine))
+
+    def close(self):
+        if self._s is not None:
+            lib().free_trusted_setup(self._s)
+            self._s = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def load_trusted_setup(path=SETUP_TXT, precompute=0):
+    return TrustedSetup(path, precompute)
+
+
+def _need(b, n, what):
+    b = bytes(b)
+    if len(b) != n:
+        raise ValueError("%s must be %d bytes" % (what, n))
+    return b
+
+
+def blob_to_kzg_commitment(blob, ts):
+    out = C.create_string_buffer(48)
+    _raise(lib().blob_to_kzg_commitment(out, _need(blob, BYTES_PER_BLOB, "blob"), ts.ptr), "blob_to_kzg_commitment")
+    return out.raw
+
+
+def compute_kzg_proof(blob, z, ts):
+    proof, y = C.create_string_buffer(48), C.create_string_buffer(32)
+    _raise(lib().compute_kzg_proof(proof, y, _need(blob, BYTES_PER_BLOB, "blob"), _need(z, 32, "z"), ts.ptr), "compute_kzg_proof")
+    return proof.raw, y.raw
+
+
+def compute_blob_kzg_proof(blob, commitment, ts):
+    out = C.create_string_buffer(48)
+    _raise(
+        lib().compute_blob_kzg_proof(out, _need(blob, BYTES_PER_BLOB, "blob"), _need(commitment, 48, "commitment"), ts.ptr),
+        "compute_blob_kzg_proof",
+    )
+    return out.raw
+
+
+def verify_kzg_proof(commitment, z, y, proof, ts):
+    ok = C.c_bool(False)
+    _raise(
+        lib().verify_kzg_proof(C.byref(ok), _need(commitment, 48, "commitment"), _need(z, 32, "z"), _need(y, 32, "y"), _need(proof, 48, "proof"), ts.ptr),
+        "verify_kzg_proof",
+    )
+    return bool(ok.value)
+
+
+def verify_blob_kzg_proof(blob, commitment, proof, ts):
+    ok = C.c_bool(False)
+    _raise(
+        lib().verify_blob_kzg_proof(C.byref(ok), _need(blob, BYTES_PER_BLOB, "blob"), _need(commitment, 48, "commitment"), _need(proof, 48, "proof"), ts.ptr),
+        "verify_blob_kzg_proof",
+    )
+    return bool(ok.value)
+
+
+def verify_blob_kzg_proof_batch(blobs, commitments, proofs, ts):
+    blobs, commitments, proofs = bytes(blobs), bytes(commitments), bytes(proofs)
+    if len(blobs) % BYTES_PER_BLOB or len(commitments) % 48 or len(proofs) % 48:
+        raise ValueError("inputs must be multiples of their element size")
+    n = len(blobs) // BYTES_PER_BLOB
+    if len(commitments) // 48 != n or len(proofs) // 48 != n:
+        raise ValueError("expected same number of blobs/commitments/proofs")
+    ok = C.c_bool(False)
+    _raise(lib().verify_blob_kzg_proof_batch(C.byref(ok), blobs, commitments, proofs, C.c_uint64(n), ts.ptr), "verify_blob_kzg_proof_batch")
+    return bool(ok.value)
+
+
+# ---- engine-level batched calls (include/ckzg_b200.h) ---------------------------------------------
+
+
+def blob_to_kzg_commitment_batch(blobs, ts, status=False):
+    """n concatenated blobs (host bytes) -> n*48 bytes; one engine call."""
+    blobs = bytes(blobs)
+    n = len(blobs) // BYTES_PER_BLOB
+    out = C.create_string_buffer(48 * max(n, 1))
+    st = (C.c_int * max(n, 1))()
+    rc = lib().ckzg_b200_blob_to_kzg_commitment_batch(ts.engine, out, blobs, C.c_uint64(n), HOST, st)
+    if status:
+        return out.raw[: 48 * n], list(st)[:n]
+    _raise(rc, "ckzg_b200_blob_to_kzg_commitment_batch")
+    return out.raw[: 48 * n]
+
+
+def blob_to_kzg_commitment_device(out_ptr, blobs_ptr, n, ts):
+    """Device-resident variant: raw CUDA pointers (e.g. torch tensor .data_ptr())."""
+    _raise(
+        lib().ckzg_b200_blob_to_kzg_commitment_batch(ts.engine, C.c_void_p(out_ptr), C.c_void_p(blobs_ptr), C.c_uint64(n), DEVICE, None),
+        "ckzg_b200_blob_to_kzg_commitment_batch",
+    )
+
+
+def verify_blob_kzg_proof_batch_device(blobs_ptr, commitments_ptr, proofs_ptr, n, ts):
+    ok = C.c_int(0)
+    _raise(
+        lib().ckzg_b200_verify_blob_kzg_proof_batch(ts.engine, C.byref(ok), C.c_void_p(blobs_ptr), C.c_void_p(commitments_ptr), C.c_void_p(proofs_ptr), C.c_uint64(n), DEVICE),
+        "ckzg_b200_verify_blob_kzg_proof_batch",
+    )
+    return bool(ok.value)

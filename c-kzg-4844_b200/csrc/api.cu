@@ -1,0 +1,242 @@
+// The C ABI of the engine (include/ckzg_b200.h): context lifecycle and the batched entry points.
+// Host-side orchestration only -- every field/curve/hash operation runs in a CUDA kernel; there is
+// no CPU arithmetic path in this library (a missing/failed device surfaces as C_KZG_ERROR).
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/ckzg_b200.h"
+#include "engine.h"
+#include "verify.h"
+
+namespace kzg {
+
+void note_cuda_error(cudaError_t e, const char* file, int line) {
+    if (getenv("CKZG_B200_DEBUG")) fprintf(stderr, "[ckzg_b200] CUDA error %d (%s) at %s:%d\n", (int)e, cudaGetErrorString(e), file, line);
+}
+
+// Per-call resources: a private stream and stream-ordered allocations (re-entrant: callers share a
+// const context across threads, as the reference allows -- bindings/rust/src/bindings/mod.rs:912).
+struct Call {
+    Ctx* ctx;
+    cudaStream_t stream = nullptr;
+    std::vector<void*> allocs;
+    int prev_device = -1;
+    bool ok = false;
+
+    explicit Call(Ctx* c) : ctx(c) {
+        if (cudaGetDevice(&prev_device) != cudaSuccess) return;
+        if (cudaSetDevice(c->device) != cudaSuccess) return;
+        if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) return;
+        ok = true;
+    }
+    ~Call() {
+        if (stream) {
+            for (void* p : allocs) cudaFreeAsync(p, stream);
+            cudaStreamSynchronize(stream);
+            cudaStreamDestroy(stream);
+        }
+        if (prev_device >= 0) cudaSetDevice(prev_device);
+    }
+    template <class T>
+    int alloc(T** out, size_t count) {
+        void* p = nullptr;
+        size_t bytes = count * sizeof(T);
+        if (bytes == 0) bytes = 16;
+        cudaError_t e = cudaMallocAsync(&p, bytes, stream);
+        if (e != cudaSuccess) {
+            note_cuda_error(e, __FILE__, __LINE__);
+            return e == cudaErrorMemoryAllocation ? RET_MALLOC : RET_ERROR;
+        }
+        allocs.push_back(p);
+        *out = (T*)p;
+        return RET_OK;
+    }
+    // input in `mem` space -> device pointer (copy if host)
+    int stage_in(const uint8_t** dev, const uint8_t* src, size_t bytes, int mem) {
+        if (mem == CKZG_B200_DEVICE) {
+            *dev = src;
+            return RET_OK;
+        }
+        uint8_t* d;
+        int rc = alloc(&d, bytes);
+        if (rc) return rc;
+        KZG_CUDA_TRY(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, stream));
+        *dev = d;
+        return RET_OK;
+    }
+    Launch launch() { return Launch{ctx, stream}; }
+};
+
+#define TRY(expr)            \
+    do {                     \
+        int _rc = (expr);    \
+        if (_rc) return _rc; \
+    } while (0)
+
+static int ctx_build(Ctx* c, const uint8_t* g1_mono, const uint8_t* g1_lag, const uint8_t* g2_mono) {
+    Call call(c);
+    if (!call.ok) return RET_ERROR;
+    Launch L = call.launch();
+
+    KZG_CUDA_TRY(cudaMalloc((void**)&c->g1_monomial, N_BLOB * sizeof(G1Affine)));
+    KZG_CUDA_TRY(cudaMalloc((void**)&c->g1_lagrange_brp, N_BLOB * sizeof(G1Affine)));
+    KZG_CUDA_TRY(cudaMalloc((void**)&c->msm_table, (size_t)MSM_W * N_BLOB * sizeof(G1Affine)));
+    KZG_CUDA_TRY(cudaMalloc((void**)&c->roots, (N_EXT + 1) * sizeof(Fr)));
+    KZG_CUDA_TRY(cudaMalloc((void**)&c->roots_brp, N_EXT * sizeof(Fr)));
+
+    const uint8_t *d_mono, *d_lag;
+    int* d_bad;
+    TRY(call.stage_in(&d_mono, g1_mono, 48 * N_BLOB, CKZG_B200_HOST));
+    TRY(call.stage_in(&d_lag, g1_lag, 48 * N_BLOB, CKZG_B200_HOST));
+    TRY(call.alloc(&d_bad, 1));
+    KZG_CUDA_TRY(cudaMemsetAsync(d_bad, 0, sizeof(int), call.stream));
+
+    // setup.c:447-466: decompress without subgroup check; setup.c:488: brp of the Lagrange points
+    TRY(launch_g1_uncompress(L, c->g1_monomial, d_mono, N_BLOB, false, false, d_bad));
+    TRY(launch_g1_uncompress(L, c->g1_lagrange_brp, d_lag, N_BLOB, true, false, d_bad));
+    TRY(launch_roots(L, c->roots, c->roots_brp));
+    TRY(launch_msm_table(L, c->msm_table, c->g1_lagrange_brp));
+    TRY(setup_g2_and_lines(call.stream, L, c, g2_mono, d_bad));
+
+    int bad = 0;
+    KZG_CUDA_TRY(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, call.stream));
+    KZG_CUDA_TRY(cudaStreamSynchronize(call.stream));
+    if (bad) return RET_BADARGS;
+    // setup.c:339-358 is_trusted_setup_in_lagrange_form: e(L[1], G2[0]) == e(L[0], G2[1]) => monomial
+    int is_monomial = 0;
+    TRY(setup_is_monomial_form(call.stream, L, c, g1_lag, &is_monomial));
+    if (is_monomial) return RET_BADARGS;
+    return RET_OK;
+}
+
+static void ctx_free(Ctx* c) {
+    if (!c) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(c->device);
+    cudaFree(c->g1_monomial);
+    cudaFree(c->g1_lagrange_brp);
+    cudaFree(c->msm_table);
+    cudaFree(c->roots);
+    cudaFree(c->roots_brp);
+    cudaFree(c->g2_lines);
+    cudaFree(c->g2_points);
+    if (prev >= 0) cudaSetDevice(prev);
+    delete c;
+}
+
+}  // namespace kzg
+
+using namespace kzg;
+
+struct ckzg_b200_ctx {
+    Ctx c;
+};
+
+extern "C" {
+
+int ckzg_b200_ctx_create(ckzg_b200_ctx** out, const uint8_t* g1_monomial_bytes, const uint8_t* g1_lagrange_bytes, const uint8_t* g2_monomial_bytes, uint64_t precompute, int device) {
+    if (!out || !g1_monomial_bytes || !g1_lagrange_bytes || !g2_monomial_bytes) return RET_BADARGS;
+    *out = nullptr;
+    if (precompute > 15) return RET_BADARGS;  // setup.c:411
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        note_cuda_error(cudaErrorNoDevice, __FILE__, __LINE__);
+        return RET_ERROR;  // no CPU fallback, by design
+    }
+    if (device < 0) {
+        const char* env = getenv("CKZG_B200_DEVICE");
+        if (env)
+            device = atoi(env);
+        else if (cudaGetDevice(&device) != cudaSuccess)
+            return RET_ERROR;
+    }
+    if (device >= ndev) return RET_BADARGS;
+    Ctx* c = new (std::nothrow) Ctx();
+    if (!c) return RET_MALLOC;
+    c->device = device;
+    c->precompute = precompute;
+    int rc = ctx_build(c, g1_monomial_bytes, g1_lagrange_bytes, g2_monomial_bytes);
+    if (rc) {
+        ctx_free(c);
+        return rc;
+    }
+    *out = reinterpret_cast<ckzg_b200_ctx*>(c);
+    return RET_OK;
+}
+
+void ckzg_b200_ctx_destroy(ckzg_b200_ctx* ctx) { ctx_free(reinterpret_cast<Ctx*>(ctx)); }
+int ckzg_b200_ctx_device(const ckzg_b200_ctx* ctx) { return reinterpret_cast<const Ctx*>(ctx)->device; }
+uint64_t ckzg_b200_launch_count(const ckzg_b200_ctx* ctx) { return reinterpret_cast<const Ctx*>(ctx)->launches.load(); }
+
+// n blobs -> n commitments.  Chunked so the sort lists (384 KiB/blob) stay bounded.
+static int commit_scalars_batch(Call& call, uint8_t* out_dev48, const uint8_t* d_scalars, bool big_endian, uint64_t n, int* d_bad) {
+    Ctx* c = call.ctx;
+    Launch L = call.launch();
+    const uint64_t CHUNK = 2048;
+    uint64_t chunk = n < CHUNK ? n : CHUNK;
+    int parts = msm_pick_parts(chunk);
+    uint8_t* ws;
+    G1* d_res;
+    TRY(call.alloc(&ws, msm_workspace_bytes(chunk, parts)));
+    TRY(call.alloc(&d_res, n));
+    for (uint64_t off = 0; off < n; off += chunk) {
+        uint64_t m = (n - off < chunk) ? n - off : chunk;
+        TRY(launch_msm(L, d_res + off, d_scalars + off * BLOB_BYTES, big_endian, m, c->msm_table, d_bad ? d_bad + off : nullptr, ws, parts));
+    }
+    TRY(launch_g1_compress(L, out_dev48, d_res, n));
+    return RET_OK;
+}
+
+int ckzg_b200_blob_to_kzg_commitment_batch(ckzg_b200_ctx* ctx, uint8_t* out, const uint8_t* blobs, uint64_t n, int mem, int* status) {
+    if (!ctx || !out || !blobs) return RET_BADARGS;
+    if (n == 0) return RET_OK;
+    Call call(reinterpret_cast<Ctx*>(ctx));
+    if (!call.ok) return RET_ERROR;
+    const uint8_t* d_blobs;
+    TRY(call.stage_in(&d_blobs, blobs, n * BLOB_BYTES, mem));
+    int* d_bad;
+    TRY(call.alloc(&d_bad, n));
+    KZG_CUDA_TRY(cudaMemsetAsync(d_bad, 0, n * sizeof(int), call.stream));
+    uint8_t* d_out;
+    if (mem == CKZG_B200_DEVICE)
+        d_out = out;
+    else
+        TRY(call.alloc(&d_out, n * 48));
+    TRY(commit_scalars_batch(call, d_out, d_blobs, true, n, d_bad));
+    std::vector<int> bad(n);
+    KZG_CUDA_TRY(cudaMemcpyAsync(bad.data(), d_bad, n * sizeof(int), cudaMemcpyDeviceToHost, call.stream));
+    if (mem != CKZG_B200_DEVICE) KZG_CUDA_TRY(cudaMemcpyAsync(out, d_out, n * 48, cudaMemcpyDeviceToHost, call.stream));
+    KZG_CUDA_TRY(cudaStreamSynchronize(call.stream));
+    int rc = RET_OK;
+    for (uint64_t i = 0; i < n; i++) {
+        int s = bad[i] ? RET_BADARGS : RET_OK;
+        if (status) status[i] = s;
+        if (s && !rc) rc = s;
+    }
+    return rc;
+}
+
+int ckzg_b200_selftest_field(int op, uint32_t* out, const uint32_t* a, const uint32_t* b, uint64_t n) { return selftest_field(op, out, a, b, n); }
+int ckzg_b200_selftest_g1(int op, uint8_t* out48, int* ok_out, const uint8_t* p48, const uint32_t* k, const uint8_t* q48, uint64_t n) {
+    return selftest_g1(op, out48, ok_out, p48, k, q48, n);
+}
+
+}  // extern "C"
+
+// ---- entry points landing later this round (link-complete; fail loudly, never fall back) --------
+extern "C" {
+#ifndef KZG_HAVE_VERIFY
+int ckzg_b200_compute_blob_kzg_proof_batch(ckzg_b200_ctx*, uint8_t*, const uint8_t*, const uint8_t*, uint64_t, int, int*) { return RET_ERROR; }
+int ckzg_b200_compute_kzg_proof_batch(ckzg_b200_ctx*, uint8_t*, uint8_t*, const uint8_t*, const uint8_t*, uint64_t, int, int*) { return RET_ERROR; }
+int ckzg_b200_verify_blob_kzg_proof_batch(ckzg_b200_ctx*, int*, const uint8_t*, const uint8_t*, const uint8_t*, uint64_t, int) { return RET_ERROR; }
+int ckzg_b200_verify_kzg_proof(ckzg_b200_ctx*, int*, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*) { return RET_ERROR; }
+int ckzg_b200_verify_blob_batch_stage1(ckzg_b200_ctx*, uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, uint64_t, int) { return RET_ERROR; }
+int ckzg_b200_verify_blob_batch_stage2(ckzg_b200_ctx*, uint8_t*, const uint8_t*, uint64_t, uint64_t, uint64_t, int) { return RET_ERROR; }
+int ckzg_b200_verify_blob_batch_finish(ckzg_b200_ctx*, int*, const uint8_t*, uint64_t) { return RET_ERROR; }
+int ckzg_b200_compute_challenge(ckzg_b200_ctx*, uint8_t*, const uint8_t*, const uint8_t*) { return RET_ERROR; }
+#endif
+}

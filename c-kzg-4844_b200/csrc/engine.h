@@ -1,0 +1,88 @@
+// Internal (C++) interface of the CUDA engine: the device-resident context and the kernel launchers
+// that the C-ABI layer (api.cu) strings together.  Not installed; the public surface is include/*.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+
+#include "g1.cuh"
+
+namespace kzg {
+
+// c-kzg return codes (src/common/ret.h:24-29)
+enum { RET_OK = 0, RET_BADARGS = 1, RET_ERROR = 2, RET_MALLOC = 3 };
+
+constexpr int N_BLOB = 4096;        // FIELD_ELEMENTS_PER_BLOB (src/eip4844/blob.h:29)
+constexpr int N_EXT = 8192;         // FIELD_ELEMENTS_PER_EXT_BLOB (blob.h:42)
+constexpr int BLOB_BYTES = 131072;  // BYTES_PER_BLOB
+
+// ---- fixed-base MSM geometry (DESIGN.md "MSM") -------------------------------------------------
+// Signed c-bit digits; the table holds 2^(c*j) * G_i for every window j, so all windows of a blob
+// share one set of 2^(c-1) buckets and no doublings are needed.
+constexpr int MSM_C = 11;
+constexpr int MSM_W = 24;                    // ceil(256 / 11): covers the carry out of bit 254
+constexpr int MSM_NB = 1 << (MSM_C - 1);     // 1024 buckets per blob
+constexpr int MSM_ENTRIES = MSM_W * N_BLOB;  // 98304 (digit, point) pairs per blob
+
+struct PairingLines;  // pairing.cuh
+
+struct Ctx {
+    int device = 0;
+    std::atomic<uint64_t> launches{0};
+
+    // trusted setup, device resident (Montgomery form)
+    G1Affine* g1_monomial = nullptr;      // [4096]
+    G1Affine* g1_lagrange_brp = nullptr;  // [4096] bit-reversed Lagrange points
+    G1Affine* msm_table = nullptr;        // [MSM_W][4096]: 2^(c*j) * g1_lagrange_brp[i]
+    Fr* roots_brp = nullptr;              // [8192] brp(roots_of_unity[0..8191]) (first 4096 = blob domain)
+    Fr* roots = nullptr;                  // [8193] w^i
+    void* g2_lines = nullptr;             // precomputed Miller-loop lines for G2 gen, [tau]G2, [tau^64]G2
+    void* g2_points = nullptr;            // [65] affine G2 (Fp2 coordinates)
+    uint64_t precompute = 0;
+};
+
+struct Launch {
+    Ctx* ctx;
+    cudaStream_t stream;
+    void count(int n = 1) { ctx->launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+};
+
+#define KZG_CUDA_TRY(expr)                         \
+    do {                                           \
+        cudaError_t _e = (expr);                   \
+        if (_e != cudaSuccess) {                   \
+            kzg::note_cuda_error(_e, __FILE__, __LINE__); \
+            return (_e == cudaErrorMemoryAllocation) ? kzg::RET_MALLOC : kzg::RET_ERROR; \
+        }                                          \
+    } while (0)
+
+void note_cuda_error(cudaError_t e, const char* file, int line);
+
+// ---- setup.cu ----------------------------------------------------------------------------------
+// out[i] = uncompress(bytes[48*perm(i)]) ; ok_flag (device int) is cleared on any failure.
+int launch_g1_uncompress(Launch& L, G1Affine* out, const uint8_t* bytes, int n, bool bit_reverse, bool check_subgroup, int* d_bad);
+int launch_msm_table(Launch& L, G1Affine* table, const G1Affine* base);
+int launch_roots(Launch& L, Fr* roots, Fr* roots_brp);
+
+// ---- msm.cu ------------------------------------------------------------------------------------
+// scalars: n x 4096 x 32 bytes; `big_endian_bytes` = wire blobs (canonical check -> bad[blob] = 1),
+// else plain little-endian limbs (already reduced).  result: n XYZZ points (device).
+struct MsmWorkspace {
+    uint32_t* entries = nullptr;  // [n][MSM_ENTRIES]
+    uint32_t* starts = nullptr;   // [n][MSM_NB + 1]
+    G1* buckets = nullptr;        // [n][parts][MSM_NB]
+    int parts = 1;
+    uint64_t n = 0;
+};
+size_t msm_workspace_bytes(uint64_t n, int parts);
+int msm_pick_parts(uint64_t n);
+int launch_msm(Launch& L, G1* result, const uint8_t* scalars, bool big_endian_bytes, uint64_t n, const G1Affine* table, int* d_bad, void* workspace, int parts);
+// points -> canonical 48-byte compression (one thread per point)
+int launch_g1_compress(Launch& L, uint8_t* out48, const G1* pts, uint64_t n);
+
+// ---- selftest.cu ---------------------------------------------------------------------------------
+int selftest_field(int op, uint32_t* out, const uint32_t* a, const uint32_t* b, uint64_t n);
+int selftest_g1(int op, uint8_t* out48, int* ok_out, const uint8_t* p48, const uint32_t* k, const uint8_t* q48, uint64_t n);
+
+}  // namespace kzg

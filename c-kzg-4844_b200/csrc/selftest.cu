@@ -1,0 +1,112 @@
+// Device self-tests behind ckzg_b200_selftest_* (include/ckzg_b200.h): they run the PTX field and
+// G1 primitives on operands chosen by tests/test_gpu_units.py so the -m gpu suite can compare every
+// primitive with the Python oracle.  Not on any product path.
+#include "engine.h"
+
+namespace kzg {
+
+__global__ void selftest_field_kernel(int op, uint32_t* out, const uint32_t* a, const uint32_t* b, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (op <= 3 || op == 6) {
+        Fp x = to_mont<FpTag>(a + 12 * i);
+        Fp y = to_mont<FpTag>(b + 12 * i);
+        Fp r;
+        switch (op) {
+            case 0: r = mul(x, y); break;
+            case 1: r = add(x, y); break;
+            case 2: r = sub(x, y); break;
+            case 3: r = fp_inv(x); break;
+            default: r = sqr(x); break;
+        }
+        from_mont<FpTag>(out + 12 * i, r);
+    } else {
+        Fr x = to_mont<FrTag>(a + 8 * i);
+        Fr y = to_mont<FrTag>(b + 8 * i);
+        Fr r = (op == 4) ? mul(x, y) : fr_inv(x);
+        from_mont<FrTag>(out + 8 * i, r);
+    }
+}
+
+__global__ void selftest_g1_kernel(int op, uint8_t* out48, int* ok_out, const uint8_t* p48, const uint32_t* k, const uint8_t* q48, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t buf[48];
+    for (int j = 0; j < 48; j++) buf[j] = p48[48 * i + j];
+    G1Affine p;
+    bool ok;
+    if (op == 1)
+        ok = g1a_validate(p, buf);
+    else
+        ok = g1a_uncompress(p, buf);
+    G1Affine r = p;
+    if (ok && op == 0) {
+        uint32_t kk[8];
+        for (int j = 0; j < 8; j++) kk[j] = k[8 * i + j];
+        G1 acc = g1_mul_affine<8>(p, kk);
+        if (q48) {
+            G1Affine q;
+            for (int j = 0; j < 48; j++) buf[j] = q48[48 * i + j];
+            ok = g1a_uncompress(q, buf);
+            if (ok) g1_madd_to(acc, q, false);
+        }
+        r = g1_to_affine(acc);
+    }
+    ok_out[i] = ok ? 1 : 0;
+    if (ok) {
+        g1a_compress(buf, r);
+        for (int j = 0; j < 48; j++) out48[48 * i + j] = buf[j];
+    }
+}
+
+template <class T>
+static int dev_copy_in(T** d, const T* h, size_t count) {
+    if (!h) {
+        *d = nullptr;
+        return RET_OK;
+    }
+    KZG_CUDA_TRY(cudaMalloc((void**)d, count * sizeof(T)));
+    KZG_CUDA_TRY(cudaMemcpy(*d, h, count * sizeof(T), cudaMemcpyHostToDevice));
+    return RET_OK;
+}
+
+int selftest_field(int op, uint32_t* out, const uint32_t* a, const uint32_t* b, uint64_t n) {
+    int limbs = (op <= 3 || op == 6) ? 12 : 8;
+    uint32_t *da = nullptr, *db = nullptr, *dout = nullptr;
+    int rc;
+    if ((rc = dev_copy_in(&da, a, n * limbs))) return rc;
+    if ((rc = dev_copy_in(&db, b, n * limbs))) return rc;
+    KZG_CUDA_TRY(cudaMalloc((void**)&dout, n * limbs * sizeof(uint32_t)));
+    selftest_field_kernel<<<(unsigned)((n + 63) / 64), 64>>>(op, dout, da, db, n);
+    KZG_CUDA_TRY(cudaGetLastError());
+    KZG_CUDA_TRY(cudaMemcpy(out, dout, n * limbs * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    cudaFree(da);
+    cudaFree(db);
+    cudaFree(dout);
+    return RET_OK;
+}
+
+int selftest_g1(int op, uint8_t* out48, int* ok_out, const uint8_t* p48, const uint32_t* k, const uint8_t* q48, uint64_t n) {
+    uint8_t *dp = nullptr, *dq = nullptr, *dout = nullptr;
+    uint32_t* dk = nullptr;
+    int* dok = nullptr;
+    int rc;
+    if ((rc = dev_copy_in(&dp, p48, n * 48))) return rc;
+    if ((rc = dev_copy_in(&dq, q48, n * 48))) return rc;
+    if ((rc = dev_copy_in(&dk, k, n * 8))) return rc;
+    KZG_CUDA_TRY(cudaMalloc((void**)&dout, n * 48));
+    KZG_CUDA_TRY(cudaMemset(dout, 0, n * 48));
+    KZG_CUDA_TRY(cudaMalloc((void**)&dok, n * sizeof(int)));
+    selftest_g1_kernel<<<(unsigned)((n + 31) / 32), 32>>>(op, dout, dok, dp, dk, dq, n);
+    KZG_CUDA_TRY(cudaGetLastError());
+    KZG_CUDA_TRY(cudaMemcpy(out48, dout, n * 48, cudaMemcpyDeviceToHost));
+    KZG_CUDA_TRY(cudaMemcpy(ok_out, dok, n * sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(dp);
+    cudaFree(dq);
+    cudaFree(dk);
+    cudaFree(dout);
+    cudaFree(dok);
+    return RET_OK;
+}
+
+}  // namespace kzg

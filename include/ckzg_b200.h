@@ -1,0 +1,126 @@
+/*
+ * ckzg_b200.h -- the thin C ABI between host code and the sm_100a CUDA engine.
+ *
+ * Everything here is `extern "C"`, plain pointers and sizes.  The frozen c-kzg-4844 API
+ * (include/ckzg.h: blob_to_kzg_commitment, verify_blob_kzg_proof_batch, ...) is implemented on top of
+ * these entry points; they are also what a binding that wants *batched* or *device-resident* calls
+ * would bind directly.  Each entry cites the reference interface it replaces
+ * (paths relative to the ethereum/c-kzg-4844 tree).
+ *
+ * Return codes are the reference's C_KZG_RET values (src/common/ret.h:24-29):
+ *   0 OK, 1 BADARGS (invalid input bytes), 2 ERROR (CUDA/internal), 3 MALLOC.
+ * There is NO CPU fallback: without a usable CUDA device every call returns 2 (C_KZG_ERROR).
+ */
+#ifndef CKZG_B200_H
+#define CKZG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the engine is built with -fvisibility=hidden */
+#endif
+
+typedef struct ckzg_b200_ctx ckzg_b200_ctx; /* opaque: device-resident trusted setup + tables */
+
+/* where a caller buffer lives */
+enum { CKZG_B200_HOST = 0, CKZG_B200_DEVICE = 1 };
+
+/*
+ * Device-side load_trusted_setup (replaces src/setup/setup.c:392-505).
+ * Inputs are the three byte arrays of load_trusted_setup(): 4096x48 G1 monomial, 4096x48 G1 Lagrange,
+ * 65x96 G2 monomial.  Decompresses on the GPU (no subgroup check, as setup.c:447-477), rejects a
+ * monomial-form setup in the Lagrange slot (setup.c:339-358), builds roots of unity, the bit-reversed
+ * Lagrange points, the fixed-base window tables for the 4096-point MSM, the FK20 columns and the
+ * precomputed pairing lines.  `device` < 0 = current device.
+ */
+int ckzg_b200_ctx_create(
+    ckzg_b200_ctx **out,
+    const uint8_t *g1_monomial_bytes,
+    const uint8_t *g1_lagrange_bytes,
+    const uint8_t *g2_monomial_bytes,
+    uint64_t precompute,
+    int device
+);
+void ckzg_b200_ctx_destroy(ckzg_b200_ctx *ctx);
+int ckzg_b200_ctx_device(const ckzg_b200_ctx *ctx);
+
+/*
+ * Batched blob_to_kzg_commitment (src/eip4844/eip4844.c:264 applied to n blobs).
+ *   blobs:  n x 131072 bytes, out: n x 48 bytes, both in `mem` space.
+ *   status (optional, HOST memory, n ints): per-blob C_KZG_RET (BADARGS for a non-canonical element).
+ * Returns OK if every blob was valid, else the first non-OK status.
+ */
+int ckzg_b200_blob_to_kzg_commitment_batch(
+    ckzg_b200_ctx *ctx, uint8_t *out, const uint8_t *blobs, uint64_t n, int mem, int *status
+);
+
+/*
+ * Batched compute_blob_kzg_proof (src/eip4844/eip4844.c:506) and compute_kzg_proof (:382).
+ *   commitments: n x 48.  proofs out: n x 48.
+ *   compute_kzg_proof: zs n x 32 in, ys n x 32 out.
+ */
+int ckzg_b200_compute_blob_kzg_proof_batch(
+    ckzg_b200_ctx *ctx, uint8_t *proofs, const uint8_t *blobs, const uint8_t *commitments, uint64_t n, int mem, int *status
+);
+int ckzg_b200_compute_kzg_proof_batch(
+    ckzg_b200_ctx *ctx, uint8_t *proofs, uint8_t *ys, const uint8_t *blobs, const uint8_t *zs, uint64_t n, int mem, int *status
+);
+
+/*
+ * verify_blob_kzg_proof_batch (src/eip4844/eip4844.c:775) with the reference's exact semantics:
+ * n == 0 -> ok, n == 1 -> the single-blob equation, else one random linear combination with the
+ * Fiat-Shamir challenge of :597-680 and one pairing check.
+ */
+int ckzg_b200_verify_blob_kzg_proof_batch(
+    ckzg_b200_ctx *ctx, int *ok, const uint8_t *blobs, const uint8_t *commitments, const uint8_t *proofs, uint64_t n, int mem
+);
+
+/* verify_kzg_proof (src/eip4844/eip4844.c:302): one (commitment, z, y, proof) tuple, host pointers. */
+int ckzg_b200_verify_kzg_proof(
+    ckzg_b200_ctx *ctx, int *ok, const uint8_t *commitment, const uint8_t *z, const uint8_t *y, const uint8_t *proof
+);
+
+/*
+ * Multi-GPU split of verify_blob_kzg_proof_batch: stage 1 is per blob and shards
+ * freely; the challenge needs every (C, z, y, proof) (all-gathered by the caller, 160 B/blob); stage 2
+ * forms this rank's share of the three linear combinations; the caller all-gathers the 3 partial
+ * points (3 x 48 B per rank) and any rank finishes with one pairing.
+ *   stage1: zy out = n_local x 64 bytes (z || y, canonical big-endian), `mem` space.
+ *   stage2: tuples = N_total x 160 bytes (C48 || z32 || y32 || proof48) in `mem` space; this rank owns
+ *           [first, first + n_local).  partial out = 3 x 48 compressed points, HOST memory.
+ *   finish: partials = n_ranks x 144 bytes, HOST memory.
+ */
+int ckzg_b200_verify_blob_batch_stage1(
+    ckzg_b200_ctx *ctx, uint8_t *zy, const uint8_t *blobs, const uint8_t *commitments, const uint8_t *proofs, uint64_t n_local, int mem
+);
+int ckzg_b200_verify_blob_batch_stage2(
+    ckzg_b200_ctx *ctx, uint8_t *partial144, const uint8_t *tuples, uint64_t n_total, uint64_t first, uint64_t n_local, int mem
+);
+int ckzg_b200_verify_blob_batch_finish(ckzg_b200_ctx *ctx, int *ok, const uint8_t *partials, uint64_t n_ranks);
+
+/* Internal Fiat-Shamir challenge, exposed for the vectors in tests/compute_challenge
+ * (src/eip4844/eip4844.c:147; commitment given in its canonical 48-byte form). out = 32 bytes BE. */
+int ckzg_b200_compute_challenge(ckzg_b200_ctx *ctx, uint8_t *out32, const uint8_t *blob, const uint8_t *commitment48);
+
+/* Counters for bench.py: kernels launched by this library since the context was created. */
+uint64_t ckzg_b200_launch_count(const ckzg_b200_ctx *ctx);
+
+/* Device self-tests used by tests/test_gpu_units.py: run `op` over n operand pairs.
+ *   op 0: Fp mul, 1: Fp add, 2: Fp sub, 3: Fp inv(a), 4: Fr mul, 5: Fr inv(a), 6: Fp sqr
+ *   operands/results are plain little-endian 32-bit limbs (12 per Fp, 8 per Fr), HOST memory. */
+int ckzg_b200_selftest_field(int op, uint32_t *out, const uint32_t *a, const uint32_t *b, uint64_t n);
+/* op 0: [k]P (+Q), op 1: validate (subgroup), op 2: uncompress only; compressed points, HOST memory.
+ * ok_out[i] = 1 if the input decoded/validated.  k = 8 limbs per scalar. */
+int ckzg_b200_selftest_g1(int op, uint8_t *out48, int *ok_out, const uint8_t *p48, const uint32_t *k, const uint8_t *q48, uint64_t n);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* CKZG_B200_H */

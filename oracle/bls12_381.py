@@ -347,7 +347,7 @@ def g1_uncompress(b):
         return G1_INF
     sign = bool(b[0] & 0x20)
     x = int.from_bytes(bytes([b[0] & 0x1F]) + bytes(b[1:]), "big")
-    if x >= P:
+    if x >= P or x == 0:  # x == 0: (0,+-2) -> BLST_POINT_NOT_IN_GROUP (e1.c:289)
         return None
     y = fp_sqrt((x * x * x + 4) % P)
     if y is None:

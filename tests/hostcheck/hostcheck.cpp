@@ -1,0 +1,88 @@
+// TEST-ONLY host build of the engine's header-only arithmetic (portable uint64 path of field.cuh).
+// Compiled by tests/test_hostcheck.py with g++ into tests/hostcheck/_build/libhostcheck.so and
+// compared against the Python oracle.  Never linked into the product library: the product has no
+// CPU path.  Purpose: catch formula mistakes in the GPU-less build container before spending GPU time.
+#include <string.h>
+
+#include "g1.cuh"
+#ifdef HOSTCHECK_PAIRING
+#include "pairing.cuh"
+#endif
+
+using namespace kzg;
+
+extern "C" {
+
+// plain little-endian limbs in / out
+void hc_fp_mul(uint32_t* out, const uint32_t* a, const uint32_t* b) {
+    Fp x = to_mont<FpTag>(a), y = to_mont<FpTag>(b);
+    from_mont<FpTag>(out, mul(x, y));
+}
+void hc_fp_addsub(uint32_t* out_add, uint32_t* out_sub, uint32_t* out_neg, const uint32_t* a, const uint32_t* b) {
+    Fp x = to_mont<FpTag>(a), y = to_mont<FpTag>(b);
+    from_mont<FpTag>(out_add, add(x, y));
+    from_mont<FpTag>(out_sub, sub(x, y));
+    from_mont<FpTag>(out_neg, neg(x));
+}
+void hc_fp_inv(uint32_t* out, const uint32_t* a) {
+    from_mont<FpTag>(out, fp_inv(to_mont<FpTag>(a)));
+}
+void hc_fr_mul(uint32_t* out, const uint32_t* a, const uint32_t* b) {
+    Fr x = to_mont<FrTag>(a), y = to_mont<FrTag>(b);
+    from_mont<FrTag>(out, mul(x, y));
+}
+void hc_fr_inv(uint32_t* out, const uint32_t* a) {
+    from_mont<FrTag>(out, fr_inv(to_mont<FrTag>(a)));
+}
+int hc_fr_from_be(uint8_t* out_be, const uint8_t* in_be) {
+    Fr x;
+    int ok = fr_from_be_checked(x, in_be);
+    fr_to_be(out_be, x);
+    return ok;
+}
+void hc_fr_hash_reduce(uint8_t* out_be, const uint8_t* in_be) {
+    fr_to_be(out_be, fr_from_be_reduce(in_be));
+}
+
+// 48-byte compressed in -> validate; returns 1 ok / 0 bad; re-compressed point out
+int hc_g1_validate(uint8_t* out48, const uint8_t* in48) {
+    G1Affine a;
+    int ok = g1a_validate(a, in48);
+    if (ok) g1a_compress(out48, a);
+    return ok;
+}
+int hc_g1_uncompress(uint8_t* out48, const uint8_t* in48) {
+    G1Affine a;
+    int ok = g1a_uncompress(a, in48);
+    if (ok) g1a_compress(out48, a);
+    return ok;
+}
+// out = [k]P (+ Q if q48 != NULL), everything compressed; k = 8 plain LE limbs
+int hc_g1_mul_add(uint8_t* out48, const uint8_t* p48, const uint32_t* k, const uint8_t* q48) {
+    G1Affine p, q;
+    if (!g1a_uncompress(p, p48)) return 0;
+    G1 r = g1_mul_affine<8>(p, k);
+    if (q48) {
+        if (!g1a_uncompress(q, q48)) return 0;
+        G1 qq = g1_from_affine(q);
+        r = g1_add(r, qq);
+    }
+    g1a_compress(out48, g1_to_affine(r));
+    return 1;
+}
+// out = P + Q via madd (P lifted to XYZZ after a doubling-and-back to exercise non-trivial zz)
+int hc_g1_madd(uint8_t* out48, const uint8_t* p48, const uint8_t* q48, int negate) {
+    G1Affine p, q;
+    if (!g1a_uncompress(p, p48) || !g1a_uncompress(q, q48)) return 0;
+    G1 acc = g1_from_affine(p);
+    // make zz != 1: acc = (P + P) - P
+    if (!g1_is_inf(acc)) {
+        G1 d = g1_dbl(acc);
+        g1_madd(d, p, true);
+        acc = d;
+    }
+    g1_madd(acc, q, negate != 0);
+    g1a_compress(out48, g1_to_affine(acc));
+    return 1;
+}
+}

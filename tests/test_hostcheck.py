@@ -1,0 +1,157 @@
+"""Formula-level checks of the engine's header-only arithmetic, host-compiled (portable path of
+field.cuh) and compared with the Python oracle.  CPU only; the PTX paths are covered by the -m gpu
+tests (tests/test_gpu_units.py)."""
+import ctypes as C
+import random
+
+import pytest
+
+from oracle import bls12_381 as B
+from oracle.bls12_381 import P, R
+
+from hostcheck.build import build
+
+
+@pytest.fixture(scope="module")
+def hc():
+    return C.CDLL(build())
+
+
+def limbs(v, n):
+    return (C.c_uint32 * n)(*[(v >> (32 * i)) & 0xFFFFFFFF for i in range(n)])
+
+
+def val(arr):
+    return sum(int(x) << (32 * i) for i, x in enumerate(arr))
+
+
+EDGE_P = [0, 1, 2, P - 1, P - 2, (P - 1) // 2, (P + 1) // 2, (1 << 380), (1 << 381) - 1 - (1 << 381) % 1]
+EDGE_R = [0, 1, 2, R - 1, R - 2, (R - 1) // 2, 1 << 254, 0xFFFFFFFF, 1 << 32]
+
+
+def test_fp_ops(hc):
+    rnd = random.Random(1)
+    vals = [v % P for v in EDGE_P] + [rnd.randrange(P) for _ in range(60)]
+    out, o2, o3 = (C.c_uint32 * 12)(), (C.c_uint32 * 12)(), (C.c_uint32 * 12)()
+    for a in vals:
+        for b in vals[:12] + [rnd.randrange(P)]:
+            hc.hc_fp_mul(out, limbs(a, 12), limbs(b, 12))
+            assert val(out) == a * b % P
+            hc.hc_fp_addsub(out, o2, o3, limbs(a, 12), limbs(b, 12))
+            assert val(out) == (a + b) % P and val(o2) == (a - b) % P and val(o3) == (-a) % P
+    for a in vals[:20]:
+        hc.hc_fp_inv(out, limbs(a, 12))
+        assert val(out) == (pow(a, P - 2, P) if a else 0)
+
+
+def test_fr_ops(hc):
+    rnd = random.Random(2)
+    vals = EDGE_R + [rnd.randrange(R) for _ in range(60)]
+    out = (C.c_uint32 * 8)()
+    for a in vals:
+        for b in vals[:10] + [rnd.randrange(R)]:
+            hc.hc_fr_mul(out, limbs(a, 8), limbs(b, 8))
+            assert val(out) == a * b % R
+    for a in vals[:20]:
+        hc.hc_fr_inv(out, limbs(a, 8))
+        assert val(out) == (pow(a, R - 2, R) if a else 0)
+
+
+def test_fr_bytes(hc):
+    rnd = random.Random(3)
+    ob = C.create_string_buffer(32)
+    for v in [0, 1, R - 1, R, R + 1, (1 << 256) - 1, 2 * R, 2 * R + 5] + [rnd.randrange(1 << 256) for _ in range(50)]:
+        ok = hc.hc_fr_from_be(ob, v.to_bytes(32, "big"))
+        assert bool(ok) == (v < R)
+        if v < R:
+            assert ob.raw == v.to_bytes(32, "big")
+        hc.hc_fr_hash_reduce(ob, v.to_bytes(32, "big"))
+        assert ob.raw == (v % R).to_bytes(32, "big")
+
+
+def rand_g1(rnd):
+    return B.g1_mul(B.G1_GEN_J, rnd.randrange(1, R))
+
+
+def test_g1_mul_add_compress(hc):
+    rnd = random.Random(4)
+    out = C.create_string_buffer(48)
+    inf = B.g1_compress(B.G1_INF)
+    for it in range(12):
+        p = rand_g1(rnd)
+        q = rand_g1(rnd)
+        k = [0, 1, 2, R - 1, R, rnd.randrange(R), rnd.randrange(1 << 256)][it % 7]
+        pc, qc = B.g1_compress(p), B.g1_compress(q)
+        assert hc.hc_g1_mul_add(out, pc, limbs(k, 8), qc) == 1
+        assert out.raw == B.g1_compress(B.g1_add(B.g1_mul(p, k), q))
+        assert hc.hc_g1_mul_add(out, pc, limbs(k, 8), None) == 1
+        assert out.raw == B.g1_compress(B.g1_mul(p, k))
+    # infinity inputs
+    assert hc.hc_g1_mul_add(out, inf, limbs(5, 8), inf) == 1 and out.raw == inf
+
+
+def test_g1_madd_special_cases(hc):
+    rnd = random.Random(5)
+    out = C.create_string_buffer(48)
+    p = rand_g1(rnd)
+    q = rand_g1(rnd)
+    pc, qc, inf = B.g1_compress(p), B.g1_compress(q), B.g1_compress(B.G1_INF)
+    cases = [
+        (pc, qc, 0, B.g1_add(p, q)),
+        (pc, qc, 1, B.g1_sub(p, q)),
+        (pc, pc, 0, B.g1_dbl(p)),  # acc == a -> doubling branch
+        (pc, pc, 1, B.G1_INF),  # acc == -a -> infinity
+        (inf, qc, 0, q),
+        (inf, qc, 1, B.g1_neg(q)),
+        (pc, inf, 0, p),
+    ]
+    for a, b, negf, want in cases:
+        assert hc.hc_g1_madd(out, a, b, negf) == 1
+        assert out.raw == B.g1_compress(want)
+
+
+def test_g1_validate_edge_cases(hc):
+    """The encoding edge cases of src/test/tests.c:536-745 (validate_kzg_g1)."""
+    rnd = random.Random(6)
+    out = C.create_string_buffer(48)
+    good = B.g1_compress(rand_g1(rnd))
+
+    def check(b, want_ok):
+        got = hc.hc_g1_validate(out, bytes(b))
+        assert bool(got) == want_ok, bytes(b).hex()
+        if want_ok:
+            assert out.raw == bytes(b)
+
+    check(good, True)
+    check(B.g1_compress(B.G1_INF), True)
+    check(B.g1_compress(B.G1_GEN_J), True)
+    b = bytearray(good); b[0] &= 0x7F; check(b, False)  # compressed flag cleared
+    b = bytearray(B.g1_compress(B.G1_INF)); b[0] |= 0x20; check(b, False)  # inf with sign bit
+    b = bytearray(B.g1_compress(B.G1_INF)); b[47] = 1; check(b, False)  # inf with payload
+    b = bytearray(B.g1_compress(B.G1_INF)); b[0] = 0x40; check(b, False)  # inf without compressed bit
+    # x >= p
+    b = bytearray(P.to_bytes(48, "big")); b[0] |= 0x80; check(b, False)
+    b = bytearray((P + 1).to_bytes(48, "big")); b[0] |= 0x80; check(b, False)
+    # x = 0
+    b = bytearray(48); b[0] = 0x80; check(b, False)
+    # not on curve / on curve but not in G1
+    n_off = n_out = 0
+    x = 5
+    while n_off < 3 or n_out < 3:
+        x += 1
+        y = B.fp_sqrt((x**3 + 4) % P)
+        b = bytearray(x.to_bytes(48, "big")); b[0] |= 0x80
+        if y is None:
+            n_off += 1
+            check(b, False)
+        else:
+            in_g1 = B.g1_in_subgroup((x, y, 1))
+            n_out += not in_g1
+            check(b, in_g1)
+            # uncompress alone accepts it (no subgroup check in load_trusted_setup, setup.c:447)
+            assert hc.hc_g1_uncompress(out, bytes(b)) == 1
+    # sign bit selects the other root
+    p = B.g1_to_affine(rand_g1(rnd))
+    for y in (p[1], P - p[1]):
+        enc = B.g1_compress((p[0], y, 1))
+        assert hc.hc_g1_uncompress(out, enc) == 1 and out.raw == enc
