@@ -1,0 +1,380 @@
+#!/usr/bin/env python3
+"""bench.py -- blobs/sec of the KZG hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path, all host cores
+
+Headline workload: verify_blob_kzg_proof_batch at the north-star batch size (4096 blobs per GPU), the
+configuration BASELINE.json's metric and target are quoted on; configs[1] (n=64) and
+blob_to_kzg_commitment are measured too and reported under "extra".  One "step" = one pass of the hot
+path over one batch of synthetic blobs.
+
+  value ........ blobs/s with blobs, commitments and proofs already resident in HBM (device pointers
+                 into the engine's C ABI), CUDA-event time of the call on the stream it launches on
+  e2e .......... the same call with HOST pointers (pinned): H2D of every input and D2H of the verdict
+                 inside the timed region
+  roofline ..... dominant kernel (largest share of the step), timed live by the engine's event trace
+  cpu_baseline . the unmodified reference (oracle/_ref) on 1 host core, bounded sample (rank 0, N=1)
+
+Multi-GPU (--gpus N under torchrun): weak scaling, each rank verifies its own 4096-blob batch and the
+verdicts are combined with one NCCL all-reduce(MIN) per step inside the timed region
+(c-kzg-4844_b200/parallel.py; the single-challenge sharded mode is `--sharded`).
+Inputs are larger than L2 (512 MiB of blobs per step vs 126 MB), so no explicit flush is needed.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BLOB = 131072
+R_MOD = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+METRIC = "blobs/sec: blob_to_kzg_commitment & verify_blob_kzg_proof_batch @1/2/4/8 GPU"
+
+# algorithmic HBM bytes per blob for each kernel of the verify step (DESIGN.md "Roofline accounting")
+ALGO_BYTES_PER_BLOB = {
+    "evaluate": 131072 + 32 + 64,          # blob in, z in, z||y out (roots of unity are L2-resident constants)
+    "blob_challenge": 131072 + 48 + 64,    # blob + commitment in, z out
+    "g1_validate": 2 * (48 + 96),          # two points in, two affine points out
+    "rlc_points": 3 * 96 + 64 + 3 * 192,   # 3 bases + 2 scalars in, 3 XYZZ out
+    "rlc_scalars": 64 + 96,
+    "g1_sum": 3 * 192,
+    "pack_tuples": 320,
+    "r_challenge": 160,
+    "pairing_check": 0,
+    "msm_sort": 131072 + 393216 + 4100,
+    "msm_accumulate": 393216 + 4100 + 196608,  # digit lists + bucket offsets in, 1024 XYZZ buckets out (table gathers are L2 hits)
+    "msm_reduce": 196608 + 192,
+    "g1_compress": 192 + 48,
+}
+# algorithmic 32x32->64 multiply-accumulates per blob (SURVEY.md section 8(d) convention: Fp mul = 300, Fr mul = 136)
+ALGO_MAC_PER_BLOB = {
+    "evaluate": 112 * 256 * 136,
+    "g1_validate": 2 * 2200 * 300,
+    "rlc_points": 3 * 3600 * 300,
+    "msm_accumulate": 98304 * 10 * 300,
+}
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (profiling recipe's clocks line)."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(float(r[0])) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 7 for k in range(4) if r[3 + k].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def synth_blobs(n, seed):
+    """n random canonical blobs as one uint8 array: 32 random bytes per element, top byte drawn from
+    [0, 0x72] so every element is < r (0x73ed...) and spans the full 255-bit range."""
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 256, size=(n * 4096, 32), dtype=np.uint8)
+    a[:, 0] = rng.integers(0, 0x73, size=n * 4096, dtype=np.uint8)
+    return a.reshape(-1)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the unmodified reference CPU implementation on all host cores
+# ------------------------------------------------------------------------------------------------
+def _ref_worker(args):
+    wid, steps, warmup, n_distinct, tile = args
+    import numpy as np
+
+    from oracle import ref_lib
+
+    k = ref_lib.CKZG()
+    blobs = synth_blobs(n_distinct, 4844 + 1000 + wid).tobytes()
+    bl = [blobs[BLOB * i : BLOB * (i + 1)] for i in range(n_distinct)]
+    cms = [k.blob_to_kzg_commitment(b) for b in bl]
+    prs = [k.compute_blob_kzg_proof(b, c) for b, c in zip(bl, cms)]
+    B, Cc, P = blobs * tile, b"".join(cms) * tile, b"".join(prs) * tile
+    n = n_distinct * tile
+    for _ in range(warmup):
+        assert k.verify_blob_kzg_proof_batch(B, Cc, P)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        assert k.verify_blob_kzg_proof_batch(B, Cc, P)
+    return n * steps, time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+
+    from oracle import ref_lib
+
+    if not os.path.exists(ref_lib.REF_SO):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libckzg_ref.so missing (build with oracle/build_ref.sh)"}))
+        return
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    n_distinct, tile = 32, 16  # n = 512 per call per worker
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_ref_worker, [(w, args.steps, args.warmup, n_distinct, tile) for w in range(cores)])
+    total = sum(r[0] for r in res)
+    tmax = max(r[1] for r in res)
+    value = total / tmax
+    sample = "each of %d processes: verify_blob_kzg_proof_batch n=%d (%d distinct synthetic blobs tiled x%d), %d calls" % (cores, n_distinct * tile, n_distinct, tile, args.steps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "blobs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * tmax / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (381/255-bit Montgomery integers)",
+        "data": "synthetic", "config": {"workload": "verify_blob_kzg_proof_batch n=4096 per GPU (reference arm: bounded sample, see cpu_baseline.sample)"},
+        "cpu_baseline": {"value": value, "unit": "blobs/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "blobs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline_single_core(blobs, cms, prs, n, seconds_budget=25.0):
+    from oracle import ref_lib
+
+    if not os.path.exists(ref_lib.REF_SO):
+        return None
+    k = ref_lib.CKZG()
+    m = min(n, 4096)
+    B, Cc, P = blobs[: BLOB * m], cms[: 48 * m], prs[: 48 * m]
+    best, calls, t_start = None, 0, time.perf_counter()
+    while calls < 2 and (time.perf_counter() - t_start) < seconds_budget:
+        t0 = time.perf_counter()
+        ok = k.verify_blob_kzg_proof_batch(B, Cc, P)
+        dt = time.perf_counter() - t0
+        assert ok
+        best = dt if best is None else min(best, dt)
+        calls += 1
+    k.close()
+    return {"value": m / best, "unit": "blobs/s", "cores": 1, "kind": "reference",
+            "sample": "oracle/_ref (unmodified reference, blst ADX path) verify_blob_kzg_proof_batch n=%d, best of %d calls on one core" % (m, calls)}
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as entry
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    os.environ["CKZG_B200_DEVICE"] = str(local_rank)
+    mod = entry.load_package()
+    par = __import__("importlib").import_module("ckzg_b200.parallel")
+    ts = mod.load_trusted_setup()
+    n = args.blobs
+
+    # ---- synthetic inputs; commitments and proofs produced by the (parity-tested) engine itself ----
+    host_blobs = torch.from_numpy(synth_blobs(n, 4844 + rank)).pin_memory()
+    d_blobs = host_blobs.to(dev, non_blocking=False)
+    d_cms = torch.empty(48 * n, dtype=torch.uint8, device=dev)
+    d_prs = torch.empty(48 * n, dtype=torch.uint8, device=dev)
+    mod.blob_to_kzg_commitment_device(d_cms.data_ptr(), d_blobs.data_ptr(), n, ts)
+    mod.compute_blob_kzg_proof_device(d_prs.data_ptr(), d_blobs.data_ptr(), d_cms.data_ptr(), n, ts)
+    host_cms, host_prs = d_cms.cpu().pin_memory(), d_prs.cpu().pin_memory()
+
+    def verify_dev():
+        return mod.verify_blob_kzg_proof_batch_device(d_blobs.data_ptr(), d_cms.data_ptr(), d_prs.data_ptr(), n, ts)
+
+    def verify_host():
+        return mod.verify_blob_kzg_proof_batch_host(host_blobs.data_ptr(), host_cms.data_ptr(), host_prs.data_ptr(), n, ts)
+
+    def step(fn):
+        ok = par.verify_batch_replicas(fn, dev)
+        assert ok, "verification of valid synthetic batch failed"
+
+    # negative control: two swapped proofs must be rejected
+    bad = d_prs.clone()
+    bad[0:48], bad[48:96] = d_prs[48:96].clone(), d_prs[0:48].clone()
+    assert not mod.verify_blob_kzg_proof_batch_device(d_blobs.data_ptr(), d_cms.data_ptr(), bad.data_ptr(), n, ts), "negative control accepted"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, profile):
+        for _ in range(warmup):
+            step(fn)
+        barrier()
+        if profile:
+            mod.profile_enable(ts, True)
+        l0 = ts.launch_count()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        time.sleep(0.25)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step(fn)
+        barrier()
+        wall = time.perf_counter() - t0
+        clocks = sampler.stop()
+        prof = mod.profile_dump(ts) if profile else None
+        if profile:
+            mod.profile_enable(ts, False)
+        launches = ts.launch_count() - l0
+        dev_ms = (prof["call_ms"] / steps) if prof else None
+        # max over ranks of both clocks
+        t = torch.tensor([wall, dev_ms if dev_ms is not None else 0.0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), prof, launches, clocks
+
+    wall, dev_ms, prof, launches, clocks = timed(verify_dev, args.steps, args.warmup, True)
+    # device-resident number: CUDA events on the launching stream (engine trace), max over ranks
+    ms_per_step = dev_ms
+    value = world * n / (ms_per_step / 1000.0)
+    e_wall, _, _, _, _ = timed(verify_host, args.steps, max(1, args.warmup - 1), False)
+    e2e_value = world * n / (e_wall / args.steps)
+
+    # ---- roofline of the dominant kernel ----
+    peak, peak_src = load_peaks()
+    kern = {k: v for k, v in prof["kernels"].items() if k not in ("begin", "end")}
+    total_ms = sum(v[0] for v in kern.values()) or 1.0
+    dom = max(kern, key=lambda k: kern[k][0])
+    dom_ms_per_launch = kern[dom][0] / kern[dom][1]
+    launches_per_step = kern[dom][1] / args.steps
+    units_per_launch = n / launches_per_step
+    algo_bytes = ALGO_BYTES_PER_BLOB.get(dom, 0) * units_per_launch
+    achieved = algo_bytes / (dom_ms_per_launch * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "peak_source": peak_src, "share_of_step": kern[dom][0] / total_ms, "ms_per_launch": dom_ms_per_launch,
+        "algorithmic_bytes_per_blob": ALGO_BYTES_PER_BLOB.get(dom, 0),
+        "note": "integer-pipe bound path (SURVEY 8d): HBM fraction is reported for completeness, see int_pipe",
+    }
+    sm_mhz = clocks.get("sm_mhz") or 1965
+    peak_mac = 148 * 64 * sm_mhz * 1e6
+    int_pipe = {}
+    for k, mac in ALGO_MAC_PER_BLOB.items():
+        if k in kern and kern[k][0] > 0:
+            t_s = kern[k][0] / args.steps * 1e-3
+            int_pipe[k] = {"mac_per_s": mac * n / t_s, "frac_of_peak": mac * n / t_s / peak_mac}
+    shares = {k: round(v[0] / total_ms, 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])}
+
+    extra = {}
+    if rank == 0 and not args.no_extra:
+        # configs[1]: n = 64 in one call (latency-bound case), and commitments
+        def v64():
+            return mod.verify_blob_kzg_proof_batch_device(d_blobs.data_ptr(), d_cms.data_ptr(), d_prs.data_ptr(), 64, ts)
+        for _ in range(3):
+            assert v64()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            v64()
+        extra["verify_blob_kzg_proof_batch_n64_blobs_per_s"] = 64 * 5 / (time.perf_counter() - t0)
+        m = min(n, 1024)
+        out = torch.empty(48 * m, dtype=torch.uint8, device=dev)
+        for _ in range(2):
+            mod.blob_to_kzg_commitment_device(out.data_ptr(), d_blobs.data_ptr(), m, ts)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            mod.blob_to_kzg_commitment_device(out.data_ptr(), d_blobs.data_ptr(), m, ts)
+        extra["blob_to_kzg_commitment_batch%d_blobs_per_s" % m] = m * 3 / (time.perf_counter() - t0)
+        one = bytes(host_blobs[:BLOB].numpy().tobytes())
+        for _ in range(2):
+            mod.blob_to_kzg_commitment(one, ts)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            mod.blob_to_kzg_commitment(one, ts)
+        extra["blob_to_kzg_commitment_single_call_ms"] = 1000 * (time.perf_counter() - t0) / 5
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_single_core(bytes(host_blobs.numpy().tobytes()), bytes(host_cms.numpy().tobytes()), bytes(host_prs.numpy().tobytes()), n)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "blobs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "wall_ms_per_step": 1000.0 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32 limbs (381/255-bit Montgomery integers)", "data": "synthetic",
+            "config": {
+                "workload": "verify_blob_kzg_proof_batch n=%d per GPU (north_star batch; configs[1] n=64 under extra)" % n,
+                "blobs_per_gpu": n, "parallelism": "replicas x%d + 1 all-reduce(MIN)" % world if world > 1 else "single GPU",
+                "l2": "inputs (%.0f MiB/step) exceed the 126 MB L2; no explicit flush" % (n * BLOB / 2**20),
+            },
+            "e2e": {"value": e2e_value, "unit": "blobs/s", "h2d_bytes_per_step": n * (BLOB + 96), "d2h_bytes_per_step": 8, "ms_per_step": 1000.0 * e_wall / args.steps},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "int_pipe": int_pipe, "kernel_share": shares, "extra": extra,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--blobs", type=int, default=4096, help="blobs per GPU per step")
+    ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -189,6 +189,71 @@ def blob_to_kzg_commitment_device(out_ptr, blobs_ptr, n, ts):
     )
 
 
+def compute_blob_kzg_proof_device(out_ptr, blobs_ptr, commitments_ptr, n, ts):
+    _raise(
+        lib().ckzg_b200_compute_blob_kzg_proof_batch(ts.engine, C.c_void_p(out_ptr), C.c_void_p(blobs_ptr), C.c_void_p(commitments_ptr), C.c_uint64(n), DEVICE, None),
+        "ckzg_b200_compute_blob_kzg_proof_batch",
+    )
+
+
+def verify_blob_kzg_proof_batch_host(blobs_ptr, commitments_ptr, proofs_ptr, n, ts):
+    """Same engine call with HOST pointers given as integers (e.g. pinned torch tensors)."""
+    ok = C.c_int(0)
+    _raise(
+        lib().ckzg_b200_verify_blob_kzg_proof_batch(ts.engine, C.byref(ok), C.c_void_p(blobs_ptr), C.c_void_p(commitments_ptr), C.c_void_p(proofs_ptr), C.c_uint64(n), HOST),
+        "ckzg_b200_verify_blob_kzg_proof_batch",
+    )
+    return bool(ok.value)
+
+
+def verify_stage1(blobs_ptr, commitments_ptr, proofs_ptr, n, ts, mem=DEVICE):
+    """Per-blob stage of the sharded verifier -> n x 64 bytes (z || y), see parallel.py."""
+    out = C.create_string_buffer(64 * max(n, 1))
+    if mem == DEVICE:
+        import torch
+
+        dev_out = torch.empty(64 * max(n, 1), dtype=torch.uint8, device="cuda")
+        _raise(
+            lib().ckzg_b200_verify_blob_batch_stage1(ts.engine, C.c_void_p(dev_out.data_ptr()), C.c_void_p(blobs_ptr), C.c_void_p(commitments_ptr), C.c_void_p(proofs_ptr), C.c_uint64(n), DEVICE),
+            "ckzg_b200_verify_blob_batch_stage1",
+        )
+        return bytes(dev_out.cpu().numpy().tobytes())[: 64 * n]
+    _raise(
+        lib().ckzg_b200_verify_blob_batch_stage1(ts.engine, out, C.c_void_p(blobs_ptr), C.c_void_p(commitments_ptr), C.c_void_p(proofs_ptr), C.c_uint64(n), HOST),
+        "ckzg_b200_verify_blob_batch_stage1",
+    )
+    return out.raw[: 64 * n]
+
+
+def verify_stage2(tuples, n_total, first, n_local, ts):
+    part = C.create_string_buffer(144)
+    _raise(
+        lib().ckzg_b200_verify_blob_batch_stage2(ts.engine, part, bytes(tuples), C.c_uint64(n_total), C.c_uint64(first), C.c_uint64(n_local), HOST),
+        "ckzg_b200_verify_blob_batch_stage2",
+    )
+    return part.raw
+
+
+def verify_finish(partials, n_ranks, ts):
+    ok = C.c_int(0)
+    _raise(lib().ckzg_b200_verify_blob_batch_finish(ts.engine, C.byref(ok), bytes(partials), C.c_uint64(n_ranks)), "ckzg_b200_verify_blob_batch_finish")
+    return bool(ok.value)
+
+
+def profile_enable(ts, on=True):
+    lib().ckzg_b200_profile_enable.restype = None
+    lib().ckzg_b200_profile_enable(ts.engine, C.c_int(1 if on else 0))
+
+
+def profile_dump(ts):
+    import json
+
+    buf = C.create_string_buffer(1 << 16)
+    lib().ckzg_b200_profile_dump.restype = C.c_int
+    lib().ckzg_b200_profile_dump(ts.engine, buf, C.c_size_t(len(buf)))
+    return json.loads(buf.value.decode())
+
+
 def verify_blob_kzg_proof_batch_device(blobs_ptr, commitments_ptr, proofs_ptr, n, ts):
     ok = C.c_int(0)
     _raise(

@@ -10,71 +10,13 @@
 #include "../../include/ckzg_b200.h"
 #include "engine.h"
 #include "verify.h"
+#include "call.h"
 
 namespace kzg {
 
 void note_cuda_error(cudaError_t e, const char* file, int line) {
     if (getenv("CKZG_B200_DEBUG")) fprintf(stderr, "[ckzg_b200] CUDA error %d (%s) at %s:%d\n", (int)e, cudaGetErrorString(e), file, line);
 }
-
-// Per-call resources: a private stream and stream-ordered allocations (re-entrant: callers share a
-// const context across threads, as the reference allows -- bindings/rust/src/bindings/mod.rs:912).
-struct Call {
-    Ctx* ctx;
-    cudaStream_t stream = nullptr;
-    std::vector<void*> allocs;
-    int prev_device = -1;
-    bool ok = false;
-
-    explicit Call(Ctx* c) : ctx(c) {
-        if (cudaGetDevice(&prev_device) != cudaSuccess) return;
-        if (cudaSetDevice(c->device) != cudaSuccess) return;
-        if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) return;
-        ok = true;
-    }
-    ~Call() {
-        if (stream) {
-            for (void* p : allocs) cudaFreeAsync(p, stream);
-            cudaStreamSynchronize(stream);
-            cudaStreamDestroy(stream);
-        }
-        if (prev_device >= 0) cudaSetDevice(prev_device);
-    }
-    template <class T>
-    int alloc(T** out, size_t count) {
-        void* p = nullptr;
-        size_t bytes = count * sizeof(T);
-        if (bytes == 0) bytes = 16;
-        cudaError_t e = cudaMallocAsync(&p, bytes, stream);
-        if (e != cudaSuccess) {
-            note_cuda_error(e, __FILE__, __LINE__);
-            return e == cudaErrorMemoryAllocation ? RET_MALLOC : RET_ERROR;
-        }
-        allocs.push_back(p);
-        *out = (T*)p;
-        return RET_OK;
-    }
-    // input in `mem` space -> device pointer (copy if host)
-    int stage_in(const uint8_t** dev, const uint8_t* src, size_t bytes, int mem) {
-        if (mem == CKZG_B200_DEVICE) {
-            *dev = src;
-            return RET_OK;
-        }
-        uint8_t* d;
-        int rc = alloc(&d, bytes);
-        if (rc) return rc;
-        KZG_CUDA_TRY(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, stream));
-        *dev = d;
-        return RET_OK;
-    }
-    Launch launch() { return Launch{ctx, stream}; }
-};
-
-#define TRY(expr)            \
-    do {                     \
-        int _rc = (expr);    \
-        if (_rc) return _rc; \
-    } while (0)
 
 static int ctx_build(Ctx* c, const uint8_t* g1_mono, const uint8_t* g1_lag, const uint8_t* g2_mono) {
     Call call(c);
@@ -172,8 +114,10 @@ void ckzg_b200_ctx_destroy(ckzg_b200_ctx* ctx) { ctx_free(reinterpret_cast<Ctx*>
 int ckzg_b200_ctx_device(const ckzg_b200_ctx* ctx) { return reinterpret_cast<const Ctx*>(ctx)->device; }
 uint64_t ckzg_b200_launch_count(const ckzg_b200_ctx* ctx) { return reinterpret_cast<const Ctx*>(ctx)->launches.load(); }
 
+}  // extern "C" (reopened below)
+namespace kzg {
 // n blobs -> n commitments.  Chunked so the sort lists (384 KiB/blob) stay bounded.
-static int commit_scalars_batch(Call& call, uint8_t* out_dev48, const uint8_t* d_scalars, bool big_endian, uint64_t n, int* d_bad) {
+int commit_scalars_batch(Call& call, uint8_t* out_dev48, const uint8_t* d_scalars, bool big_endian, uint64_t n, int* d_bad) {
     Ctx* c = call.ctx;
     Launch L = call.launch();
     const uint64_t CHUNK = 2048;
@@ -190,6 +134,8 @@ static int commit_scalars_batch(Call& call, uint8_t* out_dev48, const uint8_t* d
     TRY(launch_g1_compress(L, out_dev48, d_res, n));
     return RET_OK;
 }
+}  // namespace kzg
+extern "C" {
 
 int ckzg_b200_blob_to_kzg_commitment_batch(ckzg_b200_ctx* ctx, uint8_t* out, const uint8_t* blobs, uint64_t n, int mem, int* status) {
     if (!ctx || !out || !blobs) return RET_BADARGS;
@@ -220,6 +166,24 @@ int ckzg_b200_blob_to_kzg_commitment_batch(ckzg_b200_ctx* ctx, uint8_t* out, con
     return rc;
 }
 
+void ckzg_b200_profile_enable(ckzg_b200_ctx* ctx, int on) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    std::lock_guard<std::mutex> g(c->prof.mu);
+    c->prof.enabled = on != 0;
+    c->prof.nk = 0;
+    c->prof.call_ms = 0;
+    c->prof.calls = 0;
+}
+int ckzg_b200_profile_dump(ckzg_b200_ctx* ctx, char* buf, size_t cap) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    std::lock_guard<std::mutex> g(c->prof.mu);
+    int n = snprintf(buf, cap, "{\"calls\": %llu, \"call_ms\": %.6f, \"kernels\": {", (unsigned long long)c->prof.calls, c->prof.call_ms);
+    for (int i = 0; i < c->prof.nk && n > 0 && (size_t)n < cap; i++)
+        n += snprintf(buf + n, cap - n, "%s\"%s\": [%.6f, %llu]", i ? ", " : "", c->prof.names[i], c->prof.ms[i], (unsigned long long)c->prof.cnt[i]);
+    if (n > 0 && (size_t)n < cap) n += snprintf(buf + n, cap - n, "}}");
+    return n;
+}
+
 int ckzg_b200_selftest_field(int op, uint32_t* out, const uint32_t* a, const uint32_t* b, uint64_t n) { return selftest_field(op, out, a, b, n); }
 int ckzg_b200_selftest_g1(int op, uint8_t* out48, int* ok_out, const uint8_t* p48, const uint32_t* k, const uint8_t* q48, uint64_t n) {
     return selftest_g1(op, out48, ok_out, p48, k, q48, n);
@@ -229,14 +193,9 @@ int ckzg_b200_selftest_g1(int op, uint8_t* out48, int* ok_out, const uint8_t* p4
 
 // ---- entry points landing later this round (link-complete; fail loudly, never fall back) --------
 extern "C" {
-#ifndef KZG_HAVE_VERIFY
-int ckzg_b200_compute_blob_kzg_proof_batch(ckzg_b200_ctx*, uint8_t*, const uint8_t*, const uint8_t*, uint64_t, int, int*) { return RET_ERROR; }
-int ckzg_b200_compute_kzg_proof_batch(ckzg_b200_ctx*, uint8_t*, uint8_t*, const uint8_t*, const uint8_t*, uint64_t, int, int*) { return RET_ERROR; }
-int ckzg_b200_verify_blob_kzg_proof_batch(ckzg_b200_ctx*, int*, const uint8_t*, const uint8_t*, const uint8_t*, uint64_t, int) { return RET_ERROR; }
-int ckzg_b200_verify_kzg_proof(ckzg_b200_ctx*, int*, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*) { return RET_ERROR; }
-int ckzg_b200_verify_blob_batch_stage1(ckzg_b200_ctx*, uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, uint64_t, int) { return RET_ERROR; }
-int ckzg_b200_verify_blob_batch_stage2(ckzg_b200_ctx*, uint8_t*, const uint8_t*, uint64_t, uint64_t, uint64_t, int) { return RET_ERROR; }
-int ckzg_b200_verify_blob_batch_finish(ckzg_b200_ctx*, int*, const uint8_t*, uint64_t) { return RET_ERROR; }
-int ckzg_b200_compute_challenge(ckzg_b200_ctx*, uint8_t*, const uint8_t*, const uint8_t*) { return RET_ERROR; }
+#ifndef KZG_HAVE_CELLS
+int ckzg_b200_compute_cells_and_kzg_proofs_batch(ckzg_b200_ctx*, uint8_t*, uint8_t*, const uint8_t*, uint64_t, int, int*) { return RET_ERROR; }
+int ckzg_b200_recover_cells_and_kzg_proofs_batch(ckzg_b200_ctx*, uint8_t*, uint8_t*, const uint64_t*, const uint8_t*, uint64_t, uint64_t, int, int*) { return RET_ERROR; }
+int ckzg_b200_verify_cell_kzg_proof_batch(ckzg_b200_ctx*, int*, const uint8_t*, const uint64_t*, const uint8_t*, const uint8_t*, uint64_t, int) { return RET_ERROR; }
 #endif
 }

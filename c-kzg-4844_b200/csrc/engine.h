@@ -4,7 +4,12 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <string.h>
+
 #include <atomic>
+#include <mutex>
+#include <utility>
+#include <vector>
 
 #include "g1.cuh"
 
@@ -27,9 +32,36 @@ constexpr int MSM_ENTRIES = MSM_W * N_BLOB;  // 98304 (digit, point) pairs per b
 
 struct PairingLines;  // pairing.cuh
 
+struct Prof {
+    std::mutex mu;
+    bool enabled = false;
+    static constexpr int MAXK = 64;
+    const char* names[MAXK];
+    double ms[MAXK];
+    uint64_t cnt[MAXK];
+    int nk = 0;
+    double call_ms = 0;  // begin-to-end device time of all calls
+    uint64_t calls = 0;
+    void add(const char* name, double v) {
+        for (int i = 0; i < nk; i++)
+            if (names[i] == name || strcmp(names[i], name) == 0) {
+                ms[i] += v;
+                cnt[i]++;
+                return;
+            }
+        if (nk < MAXK) {
+            names[nk] = name;
+            ms[nk] = v;
+            cnt[nk] = 1;
+            nk++;
+        }
+    }
+};
+
 struct Ctx {
     int device = 0;
     std::atomic<uint64_t> launches{0};
+    Prof prof;
 
     // trusted setup, device resident (Montgomery form)
     G1Affine* g1_monomial = nullptr;      // [4096]
@@ -42,10 +74,27 @@ struct Ctx {
     uint64_t precompute = 0;
 };
 
+// Optional per-kernel timing (ckzg_b200_profile_*): when enabled, every count() drops a CUDA event on
+// the call's stream; the time between consecutive events is attributed to the kernel(s) just
+// launched.  Events sit on the launching stream, so this is what bench.py uses for the roofline.
+struct ProfTrace {
+    std::vector<std::pair<cudaEvent_t, const char*>> ev;
+};
+
 struct Launch {
     Ctx* ctx;
     cudaStream_t stream;
-    void count(int n = 1) { ctx->launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+    ProfTrace* trace;
+    void count(int n = 1, const char* name = nullptr) {
+        ctx->launches.fetch_add((uint64_t)n, std::memory_order_relaxed);
+        if (trace) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) == cudaSuccess) {
+                cudaEventRecord(e, stream);
+                trace->ev.push_back({e, name ? name : "other"});
+            }
+        }
+    }
 };
 
 #define KZG_CUDA_TRY(expr)                         \

@@ -281,12 +281,14 @@ int launch_msm(Launch& L, G1* result, const uint8_t* scalars, bool big_endian_by
 
     msm_sort_kernel<<<(unsigned)n, SORT_THREADS, 0, L.stream>>>(entries, starts, scalars, big_endian_bytes, d_bad);
     KZG_CUDA_TRY(cudaGetLastError());
+    L.count(1, "msm_sort");
     dim3 grid(MSM_NB / ACC_THREADS, parts, (unsigned)n);
     msm_accumulate_kernel<<<grid, ACC_THREADS, 0, L.stream>>>(buckets, entries, starts, table, parts);
     KZG_CUDA_TRY(cudaGetLastError());
+    L.count(1, "msm_accumulate");
     msm_reduce_kernel<<<(unsigned)n, RED_THREADS, 0, L.stream>>>(result, buckets, parts);
     KZG_CUDA_TRY(cudaGetLastError());
-    L.count(3);
+    L.count(1, "msm_reduce");
     return RET_OK;
 }
 
@@ -294,7 +296,7 @@ int launch_g1_compress(Launch& L, uint8_t* out48, const G1* pts, uint64_t n) {
     if (n == 0) return RET_OK;
     g1_compress_kernel<<<(unsigned)((n + 63) / 64), 64, 0, L.stream>>>(out48, pts, n);
     KZG_CUDA_TRY(cudaGetLastError());
-    L.count(1);
+    L.count(1, "g1_compress");
     return RET_OK;
 }
 

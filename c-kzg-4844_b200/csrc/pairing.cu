@@ -1,6 +1,102 @@
-// (first slice) placeholder until the pairing lands: keeps the setup path linkable.
+// Pairing-side kernels: G2 setup (decompression + line tables for the three fixed G2 arguments),
+// the monomial-form sanity check of load_trusted_setup (src/setup/setup.c:339-358) and the final
+// pairing check of the verifiers (pairings_verify, src/common/utils.c:172-196).
+//
+// One pairing check per verify call is a latency problem (~19k dependent Fp products), not a
+// throughput one; this first version runs it on a single thread per check.
+#include "pairing.cuh"
 #include "verify.h"
+
 namespace kzg {
-int setup_g2_and_lines(cudaStream_t, Launch&, Ctx*, const uint8_t*, int*) { return RET_OK; }
-int setup_is_monomial_form(cudaStream_t, Launch&, Ctx*, const uint8_t*, int* is_monomial) { *is_monomial = 0; return RET_OK; }
+
+__global__ void g2_uncompress_kernel(G2Affine* out, const uint8_t* bytes, int n, int* bad) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t buf[96];
+    for (int k = 0; k < 96; k++) buf[k] = bytes[96 * i + k];
+    G2Affine q;
+    if (!g2a_uncompress(q, buf)) *bad = 1;
+    out[i] = q;
 }
+
+// lines[0] <- G2[0] (generator slot), lines[1] <- G2[1] = [tau]G2, lines[2] <- G2[64] = [tau^64]G2
+__global__ void g2_lines_kernel(G2Lines* lines, const G2Affine* g2) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3) return;
+    const int src[3] = {0, 1, 64};
+    G2Affine q = g2[src[i]];
+    g2_precompute_lines(lines[i], q);
+}
+
+// e(L[1], G2[0]) == e(L[0], G2[1])  <=>  e(-L[1], G2[0]) * e(L[0], G2[1]) == 1
+__global__ void monomial_form_kernel(int* out, const uint8_t* lag01, const G2Lines* lines) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    uint8_t buf[48];
+    G1Affine l0, l1;
+    for (int k = 0; k < 48; k++) buf[k] = lag01[k];
+    bool ok0 = g1a_uncompress(l0, buf);
+    for (int k = 0; k < 48; k++) buf[k] = lag01[48 + k];
+    bool ok1 = g1a_uncompress(l1, buf);
+    if (!ok0 || !ok1) {
+        *out = 0;  // decoding errors are reported by the main decompression pass
+        return;
+    }
+    G1Affine n1 = g1a_neg(l1);
+    if (g1a_is_inf(l1)) n1 = l1;
+    *out = pairing_product_is_one(n1, &lines[0], l0, &lines[1]) ? 1 : 0;
+}
+
+// ok = [ e(-A, Q_a) * e(B, Q_b) == 1 ],  A/B XYZZ sums; `sub_gen_scalar` (optional, plain limbs):
+// B -= [s]G1 first (the [sum r^i y_i]G term of verify_kzg_proof_batch, eip4844.c:736-746).
+__global__ void pairing_check_kernel(int* ok, const G1* A, const G1* B, const G1* B_extra, const G2Lines* lines, int line_a, int line_b) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    G1 b = *B;
+    if (B_extra) {
+        G1 e = *B_extra;
+        g1_add_to(b, e);
+    }
+    G1Affine a_aff = g1_to_affine(*A);
+    G1Affine b_aff = g1_to_affine(b);
+    if (!g1a_is_inf(a_aff)) a_aff = g1a_neg(a_aff);
+    *ok = pairing_product_is_one(a_aff, &lines[line_a], b_aff, &lines[line_b]) ? 1 : 0;
+}
+
+int setup_g2_and_lines(cudaStream_t stream, Launch& L, Ctx* c, const uint8_t* g2_host, int* d_bad) {
+    KZG_CUDA_TRY(cudaMalloc(&c->g2_points, 65 * sizeof(G2Affine)));
+    KZG_CUDA_TRY(cudaMalloc(&c->g2_lines, 3 * sizeof(G2Lines)));
+    uint8_t* d_bytes = nullptr;
+    KZG_CUDA_TRY(cudaMallocAsync((void**)&d_bytes, 65 * 96, stream));
+    KZG_CUDA_TRY(cudaMemcpyAsync(d_bytes, g2_host, 65 * 96, cudaMemcpyHostToDevice, stream));
+    g2_uncompress_kernel<<<3, 32, 0, stream>>>((G2Affine*)c->g2_points, d_bytes, 65, d_bad);
+    KZG_CUDA_TRY(cudaGetLastError());
+    g2_lines_kernel<<<1, 32, 0, stream>>>((G2Lines*)c->g2_lines, (const G2Affine*)c->g2_points);
+    KZG_CUDA_TRY(cudaGetLastError());
+    KZG_CUDA_TRY(cudaFreeAsync(d_bytes, stream));
+    L.count(2);
+    return RET_OK;
+}
+
+int setup_is_monomial_form(cudaStream_t stream, Launch& L, Ctx* c, const uint8_t* g1_lagrange_host, int* is_monomial) {
+    uint8_t* d_bytes = nullptr;
+    int* d_out = nullptr;
+    KZG_CUDA_TRY(cudaMallocAsync((void**)&d_bytes, 96, stream));
+    KZG_CUDA_TRY(cudaMallocAsync((void**)&d_out, sizeof(int), stream));
+    KZG_CUDA_TRY(cudaMemcpyAsync(d_bytes, g1_lagrange_host, 96, cudaMemcpyHostToDevice, stream));
+    monomial_form_kernel<<<1, 32, 0, stream>>>(d_out, d_bytes, (const G2Lines*)c->g2_lines);
+    KZG_CUDA_TRY(cudaGetLastError());
+    KZG_CUDA_TRY(cudaMemcpyAsync(is_monomial, d_out, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    KZG_CUDA_TRY(cudaStreamSynchronize(stream));
+    KZG_CUDA_TRY(cudaFreeAsync(d_bytes, stream));
+    KZG_CUDA_TRY(cudaFreeAsync(d_out, stream));
+    L.count(1);
+    return RET_OK;
+}
+
+int launch_pairing_check(Launch& L, int* d_ok, const G1* A, const G1* B, const G1* B_extra, int line_a, int line_b) {
+    pairing_check_kernel<<<1, 32, 0, L.stream>>>(d_ok, A, B, B_extra, (const G2Lines*)L.ctx->g2_lines, line_a, line_b);
+    KZG_CUDA_TRY(cudaGetLastError());
+    L.count(1, "pairing_check");
+    return RET_OK;
+}
+
+}  // namespace kzg

@@ -1,0 +1,593 @@
+// Per-blob stage and random-linear-combination stage of the EIP-4844 provers / verifiers.
+//
+// Replaces, for the GPU engine (all paths relative to the reference tree):
+//   compute_challenge ......................... src/eip4844/eip4844.c:147-178
+//   blob_to_polynomial / bytes_to_bls_field ... src/eip4844/blob.c:31, src/common/bytes.c:64
+//   evaluate_polynomial_in_evaluation_form .... src/eip4844/eip4844.c:192-240 (+ fr_batch_inv :80)
+//   compute_kzg_proof_impl (quotient) ......... src/eip4844/eip4844.c:417-494
+//   compute_r_powers_for_verify_kzg_proof_batch src/eip4844/eip4844.c:597-680
+//   verify_kzg_proof_batch (lincombs) ......... src/eip4844/eip4844.c:697-765
+//
+// Layout: one CTA per blob for the polynomial work (coalesced 32-byte element loads, the 4096
+// denominators inverted with ONE field inversion per blob through a block-wide product scan), one
+// thread per blob for the inherently serial 131 KB SHA-256, one thread per scalar multiplication in
+// the linear combinations.
+#include "sha256.cuh"
+#include "verify.h"
+
+namespace kzg {
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+__device__ __forceinline__ void load_fr_be(uint32_t s[8], const uint8_t* p) {  // 16-byte aligned
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 hi = __ldg(q), lo = __ldg(q + 1);
+    s[7] = bswap32(hi.x); s[6] = bswap32(hi.y); s[5] = bswap32(hi.z); s[4] = bswap32(hi.w);
+    s[3] = bswap32(lo.x); s[2] = bswap32(lo.y); s[1] = bswap32(lo.z); s[0] = bswap32(lo.w);
+}
+__device__ __forceinline__ void store_fr_be(uint8_t* p, const Fr& a) {  // 16-byte aligned
+    uint32_t t[8];
+    from_mont<FrTag>(t, a);
+    uint4 hi = make_uint4(bswap32(t[7]), bswap32(t[6]), bswap32(t[5]), bswap32(t[4]));
+    uint4 lo = make_uint4(bswap32(t[3]), bswap32(t[2]), bswap32(t[1]), bswap32(t[0]));
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = hi;
+    q[1] = lo;
+}
+__device__ __forceinline__ Fr load_fr(const Fr* p) {
+    Fr r;
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+
+// digest (8 words) -> field element: hash_to_bls_field (src/common/bytes.c:123)
+__device__ __forceinline__ Fr fr_from_digest(const uint32_t h[8]) {
+    uint32_t t[8], s[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) t[i] = h[7 - i];
+#pragma unroll 1
+    for (int k = 0; k < 2; k++) {
+        uint32_t bw = limbs_sub<8>(s, t, FR_MOD);
+        if (!bw) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) t[i] = s[i];
+        }
+    }
+    return to_mont<FrTag>(t);
+}
+
+// ------------------------------------------------------------------------------------------------
+// compute_challenge: one thread per blob, 2050 compressions
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) blob_challenge_kernel(Fr* __restrict__ z_out, uint8_t* __restrict__ zy, const uint8_t* __restrict__ blobs,
+                                                          const uint8_t* __restrict__ commitments, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4* blob = reinterpret_cast<const uint4*>(blobs + i * BLOB_BYTES);  // 8192 x 16 bytes
+    const uint8_t* cm = commitments + i * 48;
+    Sha256 st;
+    sha256_init(st);
+    uint32_t w[16];
+    // block 0: "FSBLOBVERIFY_V1_" || u64be(0) || u64be(4096) || blob[0..32)
+    w[0] = 0x4653424cu; w[1] = 0x4f425645u; w[2] = 0x52494659u; w[3] = 0x5f56315fu;  // "FSBL" "OBVE" "RIFY" "_V1_"
+    w[4] = 0; w[5] = 0; w[6] = 0; w[7] = 4096;
+    uint4 a = __ldg(blob), b = __ldg(blob + 1);
+    w[8] = bswap32(a.x); w[9] = bswap32(a.y); w[10] = bswap32(a.z); w[11] = bswap32(a.w);
+    w[12] = bswap32(b.x); w[13] = bswap32(b.y); w[14] = bswap32(b.z); w[15] = bswap32(b.w);
+    sha256_block(st, w);
+    // blocks 1..2047: blob[64k-32 .. 64k+32)
+#pragma unroll 1
+    for (int k = 1; k < 2048; k++) {
+        const uint4* p = blob + (4 * k - 2);
+        uint4 v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2), v3 = __ldg(p + 3);
+        w[0] = bswap32(v0.x); w[1] = bswap32(v0.y); w[2] = bswap32(v0.z); w[3] = bswap32(v0.w);
+        w[4] = bswap32(v1.x); w[5] = bswap32(v1.y); w[6] = bswap32(v1.z); w[7] = bswap32(v1.w);
+        w[8] = bswap32(v2.x); w[9] = bswap32(v2.y); w[10] = bswap32(v2.z); w[11] = bswap32(v2.w);
+        w[12] = bswap32(v3.x); w[13] = bswap32(v3.y); w[14] = bswap32(v3.z); w[15] = bswap32(v3.w);
+        sha256_block(st, w);
+    }
+    // block 2048: blob[131040..131072) || commitment[0..32)
+    {
+        uint4 v0 = __ldg(blob + 8190), v1 = __ldg(blob + 8191);
+        w[0] = bswap32(v0.x); w[1] = bswap32(v0.y); w[2] = bswap32(v0.z); w[3] = bswap32(v0.w);
+        w[4] = bswap32(v1.x); w[5] = bswap32(v1.y); w[6] = bswap32(v1.z); w[7] = bswap32(v1.w);
+        for (int j = 0; j < 8; j++) w[8 + j] = be32(cm + 4 * j);
+        sha256_block(st, w);
+    }
+    // final block: commitment[32..48) || 0x80 || zeros || bit length (131152 * 8)
+    for (int j = 0; j < 4; j++) w[j] = be32(cm + 32 + 4 * j);
+    w[4] = 0x80000000u;
+    for (int j = 5; j < 15; j++) w[j] = 0;
+    w[14] = 0;
+    w[15] = 131152u * 8u;
+    sha256_block(st, w);
+    Fr z = fr_from_digest(st.h);
+    z_out[i] = z;
+    store_fr_be(zy + i * 64, z);
+}
+
+__global__ void z_from_bytes_kernel(Fr* z_out, uint8_t* zy, const uint8_t* z_bytes, uint64_t n, int* bad) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t buf[32];
+    for (int k = 0; k < 32; k++) buf[k] = z_bytes[32 * i + k];
+    Fr z;
+    if (!fr_from_be_checked(z, buf)) bad[i] = 1;
+    z_out[i] = z;
+    if (zy)
+        for (int k = 0; k < 32; k++) zy[64 * i + k] = buf[k];
+}
+
+__global__ void fr_from_bytes_kernel(Fr* out, const uint8_t* bytes, uint64_t stride, uint64_t n, int* bad) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t buf[32];
+    for (int k = 0; k < 32; k++) buf[k] = bytes[stride * i + k];
+    Fr v;
+    if (!fr_from_be_checked(v, buf) && bad) bad[i] = 1;
+    out[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// barycentric evaluation: one CTA of 256 threads per blob, 16 elements per thread
+// ------------------------------------------------------------------------------------------------
+constexpr int EV_THREADS = 256;
+constexpr int EV_PER = N_BLOB / EV_THREADS;  // 16
+
+__global__ void __launch_bounds__(EV_THREADS) evaluate_kernel(Fr* __restrict__ y_out, uint8_t* __restrict__ zy, Fr* __restrict__ inv_out, int* __restrict__ m_out,
+                                                             const uint8_t* __restrict__ blobs, const Fr* __restrict__ z_in, const Fr* __restrict__ roots_brp,
+                                                             int* __restrict__ bad, int bad_stride) {
+    __shared__ Fr sh_a[EV_THREADS];  // prefix scan / reduction scratch
+    __shared__ Fr sh_b[EV_THREADS];  // suffix scan
+    __shared__ Fr sh_bcast;
+    __shared__ int s_m, s_bad;
+    const int blob = blockIdx.x, t = threadIdx.x;
+    const uint8_t* src = blobs + (size_t)blob * BLOB_BYTES;
+    const Fr z = z_in[blob];
+    if (t == 0) {
+        s_m = -1;
+        s_bad = 0;
+    }
+    __syncthreads();
+
+    // pass 1: p_k -> Montgomery (canonical check), running product of the denominators z - w_i
+    Fr pk[EV_PER], pre[EV_PER];
+    Fr prod = Fr::one();
+#pragma unroll 1
+    for (int k = 0; k < EV_PER; k++) {
+        int i = t + EV_THREADS * k;
+        uint32_t s[8];
+        load_fr_be(s, src + 32 * i);
+        if (limbs_geq<8>(s, FR_MOD)) s_bad = 1;  // bytes_to_bls_field, bytes.c:67
+        pk[k] = to_mont<FrTag>(s);
+        Fr d = sub(z, load_fr(roots_brp + i));
+        if (is_zero(d)) {  // z is the i-th evaluation point (eip4844.c:213)
+            s_m = i;
+            d = Fr::one();
+        }
+        pre[k] = prod;
+        prod = mul(prod, d);
+    }
+    // block-wide exclusive prefix and suffix products of the 256 per-thread products
+    sh_a[t] = prod;
+    sh_b[t] = prod;
+    __syncthreads();
+#pragma unroll 1
+    for (int off = 1; off < EV_THREADS; off <<= 1) {
+        Fr pa = sh_a[t], pb = sh_b[t];
+        bool ha = t >= off, hb = t + off < EV_THREADS;
+        Fr xa = ha ? sh_a[t - off] : pa;
+        Fr xb = hb ? sh_b[t + off] : pb;
+        __syncthreads();
+        if (ha) sh_a[t] = mul(pa, xa);
+        if (hb) sh_b[t] = mul(pb, xb);
+        __syncthreads();
+    }
+    // inclusive scans done: sh_a[t] = prod_0..t, sh_b[t] = prod_t..255
+    if (t == 0) sh_bcast = fr_inv(sh_a[EV_THREADS - 1]);  // the one inversion of this blob
+    __syncthreads();
+    Fr acc = sh_bcast;
+    if (t > 0) acc = mul(acc, sh_a[t - 1]);
+    if (t < EV_THREADS - 1) acc = mul(acc, sh_b[t + 1]);
+    // acc = 1 / (this thread's product)
+    __syncthreads();
+
+    // pass 2: unwind -> 1/(z - w_i); accumulate p_i * w_i / (z - w_i)
+    Fr sum = Fr::zero();
+    const int m = s_m;
+#pragma unroll 1
+    for (int k = EV_PER - 1; k >= 0; k--) {
+        int i = t + EV_THREADS * k;
+        Fr w = load_fr(roots_brp + i);
+        Fr d = sub(z, w);
+        if (i == m) d = Fr::one();
+        Fr inv = mul(acc, pre[k]);
+        acc = mul(acc, d);
+        if (inv_out) inv_out[(size_t)blob * N_BLOB + i] = inv;
+        sum = add(sum, mul(mul(pk[k], w), inv));
+    }
+    sh_a[t] = sum;
+    __syncthreads();
+#pragma unroll 1
+    for (int s = EV_THREADS / 2; s > 0; s >>= 1) {
+        if (t < s) sh_a[t] = add(sh_a[t], sh_a[t + s]);
+        __syncthreads();
+    }
+    if (t == 0) {
+        Fr y;
+        if (m >= 0) {
+            uint32_t s[8];
+            load_fr_be(s, src + 32 * m);
+            y = to_mont<FrTag>(s);
+        } else {
+            // sum * (z^4096 - 1) / 4096
+            Fr zp = z;
+#pragma unroll 1
+            for (int k = 0; k < 12; k++) zp = sqr(zp);
+            y = mul(mul(sh_a[0], Fr::from_limbs(FR_INV_4096)), sub(zp, Fr::one()));
+        }
+        y_out[blob] = y;
+        if (zy) store_fr_be(zy + (size_t)blob * 64 + 32, y);
+        if (m_out) m_out[blob] = m;
+        if (s_bad && bad) bad[(size_t)blob * bad_stride] = 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// quotient polynomial (evaluation form) -> plain little-endian scalars for the MSM
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) quotient_kernel(uint8_t* __restrict__ q_out, const uint8_t* __restrict__ blobs, const Fr* __restrict__ y_in,
+                                                       const Fr* __restrict__ inv, const int* __restrict__ m_in) {
+    const int blob = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t s[8];
+    load_fr_be(s, blobs + (size_t)blob * BLOB_BYTES + 32 * i);
+    Fr p = to_mont<FrTag>(s);
+    // (p_i - y) / (w_i - z) = (y - p_i) * 1/(z - w_i)
+    Fr q = mul(sub(y_in[blob], p), load_fr(inv + (size_t)blob * N_BLOB + i));
+    if (i == m_in[blob]) q = Fr::zero();  // fixed up by quotient_in_domain_kernel
+    uint32_t o[8];
+    from_mont<FrTag>(o, q);
+    uint4* dst = reinterpret_cast<uint4*>(q_out + (size_t)blob * BLOB_BYTES + 32 * i);
+    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+// z == w_m: q_m = (1/z) * sum_{i != m} (p_i - y) * w_i / (z - w_i)      (eip4844.c:460-481)
+__global__ void __launch_bounds__(256) quotient_in_domain_kernel(uint8_t* __restrict__ q_out, const uint8_t* __restrict__ blobs, const Fr* __restrict__ z_in,
+                                                                 const Fr* __restrict__ y_in, const Fr* __restrict__ inv, const Fr* __restrict__ roots_brp,
+                                                                 const int* __restrict__ m_in) {
+    __shared__ Fr sh[256];
+    const int blob = blockIdx.x, t = threadIdx.x;
+    const int m = m_in[blob];
+    if (m < 0) return;
+    const Fr y = y_in[blob];
+    Fr sum = Fr::zero();
+#pragma unroll 1
+    for (int k = 0; k < N_BLOB / 256; k++) {
+        int i = t + 256 * k;
+        if (i == m) continue;
+        uint32_t s[8];
+        load_fr_be(s, blobs + (size_t)blob * BLOB_BYTES + 32 * i);
+        Fr p = to_mont<FrTag>(s);
+        Fr term = mul(mul(sub(p, y), load_fr(roots_brp + i)), load_fr(inv + (size_t)blob * N_BLOB + i));
+        sum = add(sum, term);
+    }
+    sh[t] = sum;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (t < s) sh[t] = add(sh[t], sh[t + s]);
+        __syncthreads();
+    }
+    if (t == 0) {
+        Fr q = mul(sh[0], fr_inv(z_in[blob]));
+        uint32_t o[8];
+        from_mont<FrTag>(o, q);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(q_out + (size_t)blob * BLOB_BYTES + 32 * m);
+        for (int j = 0; j < 8; j++) dst[j] = o[j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// point validation
+// ------------------------------------------------------------------------------------------------
+__global__ void g1_validate_kernel(G1Affine* __restrict__ out, const uint8_t* __restrict__ bytes, uint64_t n, int* __restrict__ bad, int bad_stride) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t buf[48];
+    for (int k = 0; k < 48; k++) buf[k] = bytes[i * 48 + k];
+    G1Affine a;
+    if (!g1a_validate(a, buf)) {
+        bad[i * bad_stride] = 1;
+        a = g1a_inf();
+    }
+    out[i] = a;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batch challenge r
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_tuples_kernel(uint8_t* __restrict__ tuples, const uint8_t* __restrict__ cm, const uint8_t* __restrict__ zy, const uint8_t* __restrict__ pf, uint64_t n) {
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 4-byte word
+    uint64_t i = g / 40, wd = g % 40;
+    if (i >= n) return;
+    const uint32_t* src;
+    if (wd < 12)
+        src = reinterpret_cast<const uint32_t*>(cm + i * 48) + wd;
+    else if (wd < 28)
+        src = reinterpret_cast<const uint32_t*>(zy + i * 64) + (wd - 12);
+    else
+        src = reinterpret_cast<const uint32_t*>(pf + i * 48) + (wd - 28);
+    reinterpret_cast<uint32_t*>(tuples)[g] = *src;
+}
+
+// single thread: "RCKZGBATCH___V1_" || u64be(4096) || u64be(n) || n x 160 bytes
+__global__ void r_challenge_kernel(Fr* r_out, const uint8_t* __restrict__ tuples, uint64_t n) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    Sha256 st;
+    sha256_init(st);
+    uint32_t w[16];
+    w[0] = 0x52434b5au; w[1] = 0x47424154u; w[2] = 0x43485f5fu; w[3] = 0x5f56315fu;  // "RCKZ" "GBAT" "CH__" "_V1_"
+    w[4] = 0; w[5] = 4096; w[6] = (uint32_t)(n >> 32); w[7] = (uint32_t)n;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(tuples);
+    const uint64_t words = n * 40;  // payload words after the 8 header words
+    uint64_t pos = 0;               // payload words consumed
+    int fill = 8;
+    while (pos < words) {
+        while (fill < 16 && pos < words) w[fill++] = bswap32(__ldg(src + pos++));
+        if (fill == 16) {
+            sha256_block(st, w);
+            fill = 0;
+        }
+    }
+    // padding: total bytes = 32 + 160 n
+    uint64_t bits = (32 + 160 * n) * 8;
+    w[fill++] = 0x80000000u;
+    if (fill > 14) {
+        while (fill < 16) w[fill++] = 0;
+        sha256_block(st, w);
+        fill = 0;
+    }
+    while (fill < 14) w[fill++] = 0;
+    w[14] = (uint32_t)(bits >> 32);
+    w[15] = (uint32_t)bits;
+    sha256_block(st, w);
+    *r_out = fr_from_digest(st.h);
+}
+
+// ------------------------------------------------------------------------------------------------
+// random linear combination
+// ------------------------------------------------------------------------------------------------
+// s1[i] = r^(first+i), s2[i] = s1[i] * z_i (plain limbs), ty[i] = s1[i] * y_i (Montgomery)
+__global__ void rlc_scalars_kernel(uint32_t* __restrict__ s1, uint32_t* __restrict__ s2, Fr* __restrict__ ty, const Fr* __restrict__ z, const Fr* __restrict__ y,
+                                   const Fr* __restrict__ r, bool use_r, uint64_t first, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr p = Fr::one();
+    if (use_r) {
+        Fr base = *r;
+        uint64_t e = first + i;
+        while (e) {
+            if (e & 1) p = mul(p, base);
+            base = sqr(base);
+            e >>= 1;
+        }
+    }
+    from_mont<FrTag>(s1 + 8 * i, p);
+    from_mont<FrTag>(s2 + 8 * i, mul(p, z[i]));
+    ty[i] = mul(p, y[i]);
+}
+
+// sum of n field elements -> plain limbs of -(sum) ... kept positive here; the caller subtracts the point
+__global__ void __launch_bounds__(256) fr_sum_kernel(uint32_t* out_plain, const Fr* __restrict__ in, uint64_t n) {
+    __shared__ Fr sh[256];
+    const int t = threadIdx.x;
+    Fr s = Fr::zero();
+    for (uint64_t i = t; i < n; i += 256) s = add(s, in[i]);
+    sh[t] = s;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) {
+        if (t < k) sh[t] = add(sh[t], sh[t + k]);
+        __syncthreads();
+    }
+    if (t == 0) from_mont<FrTag>(out_plain, sh[0]);
+}
+
+// thread j < n: U[j] = [s1_j] proof_j; n <= j < 2n: T[j-n] = [s2] proof; 2n <= j < 3n: T[j-n] = [s1] C;
+// j == 3n: Y = -[ysum] G1
+__global__ void __launch_bounds__(64) rlc_points_kernel(G1* __restrict__ U, G1* __restrict__ T, G1* __restrict__ Y, const G1Affine* __restrict__ cm, const G1Affine* __restrict__ pf,
+                                                        const uint32_t* __restrict__ s1, const uint32_t* __restrict__ s2, const uint32_t* __restrict__ ysum, uint64_t n) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > 3 * n) return;
+    G1Affine base;
+    const uint32_t* k;
+    G1* dst;
+    if (j < n) {
+        base = pf[j]; k = s1 + 8 * j; dst = U + j;
+    } else if (j < 2 * n) {
+        base = pf[j - n]; k = s2 + 8 * (j - n); dst = T + (j - n);
+    } else if (j < 3 * n) {
+        base = cm[j - 2 * n]; k = s1 + 8 * (j - 2 * n); dst = T + (j - n);
+    } else {
+        base = g1a_neg(g1a_generator()); k = ysum; dst = Y;
+    }
+    uint32_t kk[8];
+    for (int q = 0; q < 8; q++) kk[q] = k[q];
+    *dst = g1_mul_affine<8>(base, kk);
+}
+
+// tree sum: each block folds up to 128 * 8 inputs into one output
+constexpr int SUM_THREADS = 128;
+constexpr int SUM_PER = 8;
+__global__ void __launch_bounds__(SUM_THREADS) g1_sum_kernel(G1* __restrict__ out, const G1* __restrict__ in, uint64_t n) {
+    __shared__ G1 sh[SUM_THREADS];
+    const int t = threadIdx.x;
+    uint64_t base = (uint64_t)blockIdx.x * SUM_THREADS * SUM_PER;
+    G1 acc = g1_inf();
+#pragma unroll 1
+    for (int k = 0; k < SUM_PER; k++) {
+        uint64_t i = base + (uint64_t)k * SUM_THREADS + t;
+        if (i < n) {
+            G1 p = in[i];
+            g1_add_to(acc, p);
+        }
+    }
+    sh[t] = acc;
+    __syncthreads();
+#pragma unroll 1
+    for (int s = SUM_THREADS / 2; s > 0; s >>= 1) {
+        if (t < s) {
+            G1 x = sh[t], y = sh[t + s];
+            g1_add_to(x, y);
+            sh[t] = x;
+        }
+        __syncthreads();
+    }
+    if (t == 0) out[blockIdx.x] = sh[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+static inline unsigned blocks_for(uint64_t n, unsigned per) { return (unsigned)((n + per - 1) / per); }
+
+int launch_blob_challenges(Launch& L, Fr* z, uint8_t* zy, const uint8_t* blobs, const uint8_t* commitments48, uint64_t n) {
+    if (!n) return RET_OK;
+    blob_challenge_kernel<<<blocks_for(n, 32), 32, 0, L.stream>>>(z, zy, blobs, commitments48, n);
+    KZG_CUDA_TRY(cudaGetLastError());
+    L.count(1, "blob_challenge");
+    return RET_OK;
+}
+int launch_z_from_bytes(Launch& L, Fr* z, uint8_t* zy, const uint8_t* z_bytes, uint64_t n, int* bad) {
+    if (!n) return RET_OK;
+    z_from_bytes_kernel<<<blocks_for(n, 64), 64, 0, L.stream>>>(z, zy, z_bytes, n, bad);
+    KZG_CUDA_TRY(cudaGetLastError());
+    L.count();
+    return RET_OK;
+}
+int launch_fr_from_bytes(Launch& L, Fr* out, const uint8_t* bytes32, uint64_t stride, uint64_t n, int* bad) {
+    if (!n) return RET_OK;
+    fr_from_bytes_kernel<<<blocks_for(n, 64), 64, 0, L.stream>>>(out, bytes32, stride, n, bad);
+    KZG_CUDA_TRY(cudaGetLastError());
+    L.count();
+    return RET_OK;
+}
+int launch_evaluate(Launch& L, Fr* y, uint8_t* zy, Fr* inv_or_null, int* m_or_null, const uint8_t* blobs, const Fr* z, uint64_t n, int* bad, int bad_stride) {
+    if (!n) return RET_OK;
+    evaluate_kernel<<<(unsigned)n, EV_THREADS, 0, L.stream>>>(y, zy, inv_or_null, m_or_null, blobs, z, L.ctx->roots_brp, bad, bad_stride);
+    KZG_CUDA_TRY(cudaGetLastError());
+    L.count(1, "evaluate");
+    return RET_OK;
+}
+int launch_quotient(Launch& L, uint8_t* q_scalars, const uint8_t* blobs, const Fr* z, const Fr* y, const Fr* inv, const int* m, uint64_t n) {
+    if (!n) return RET_OK;
+    dim3 grid(N_BLOB / 256, (unsigned)n);
+    quotient_kernel<<<grid, 256, 0, L.stream>>>(q_scalars, blobs, y, inv, m);
+    KZG_CUDA_TRY(cudaGetLastError());
+    quotient_in_domain_kernel<<<(unsigned)n, 256, 0, L.stream>>>(q_scalars, blobs, z, y, inv, L.ctx->roots_brp, m);
+    KZG_CUDA_TRY(cudaGetLastError());
+    L.count(2, "quotient");
+    return RET_OK;
+}
+int launch_g1_validate(Launch& L, G1Affine* out, const uint8_t* bytes48, uint64_t n, int* bad, int bad_stride) {
+    if (!n) return RET_OK;
+    g1_validate_kernel<<<blocks_for(n, 32), 32, 0, L.stream>>>(out, bytes48, n, bad, bad_stride);
+    KZG_CUDA_TRY(cudaGetLastError());
+    L.count(1, "g1_validate");
+    return RET_OK;
+}
+int launch_pack_tuples(Launch& L, uint8_t* tuples, const uint8_t* commitments48, const uint8_t* zy, const uint8_t* proofs48, uint64_t n) {
+    if (!n) return RET_OK;
+    pack_tuples_kernel<<<blocks_for(n * 40, 256), 256, 0, L.stream>>>(tuples, commitments48, zy, proofs48, n);
+    KZG_CUDA_TRY(cudaGetLastError());
+    L.count(1, "pack_tuples");
+    return RET_OK;
+}
+int launch_r_challenge(Launch& L, Fr* r, const uint8_t* tuples, uint64_t n) {
+    r_challenge_kernel<<<1, 32, 0, L.stream>>>(r, tuples, n);
+    KZG_CUDA_TRY(cudaGetLastError());
+    L.count(1, "r_challenge");
+    return RET_OK;
+}
+
+static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+static size_t rlc_fold(uint64_t n) { return (2 * n) / (SUM_THREADS * SUM_PER) + 2; }
+size_t rlc_scratch_bytes(uint64_t n) {
+    size_t fold = rlc_fold(n);
+    return al256(n * 32) * 2 + al256(n * sizeof(Fr)) + al256(32) + al256(sizeof(G1)) + al256((n + fold) * sizeof(G1)) +
+           al256((2 * n + fold + 2) * sizeof(G1));
+}
+
+__global__ void lift_affine_kernel(G1* out, const G1Affine* in, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = g1_from_affine(in[i]);
+}
+int launch_lift_affine(Launch& L, G1* out, const G1Affine* in, uint64_t n) {
+    if (!n) return RET_OK;
+    lift_affine_kernel<<<blocks_for(n, 64), 64, 0, L.stream>>>(out, in, n);
+    KZG_CUDA_TRY(cudaGetLastError());
+    L.count();
+    return RET_OK;
+}
+
+int launch_g1_sum(Launch& L, G1* out, G1* in, uint64_t n) {
+    // ping-pong inside `in` is not possible (block outputs overlap later inputs only after they are
+    // consumed by the same block), so fold in place level by level: block b writes slot b, which was
+    // read by block 0 of the same launch only if b < SUM_THREADS*SUM_PER -- use a second buffer.
+    // Callers pass scratch of at least ceil(n / 1024) + 1 points after `in`'s n points.
+    G1* a = in;
+    G1* b = in + n;
+    uint64_t m = n;
+    while (m > 1) {
+        unsigned blocks = blocks_for(m, SUM_THREADS * SUM_PER);
+        g1_sum_kernel<<<blocks, SUM_THREADS, 0, L.stream>>>(b, a, m);
+        KZG_CUDA_TRY(cudaGetLastError());
+        L.count(1, "g1_sum");
+        G1* t = a;
+        a = b;
+        b = t;
+        m = blocks;
+    }
+    KZG_CUDA_TRY(cudaMemcpyAsync(out, a, sizeof(G1), cudaMemcpyDeviceToDevice, L.stream));
+    return RET_OK;
+}
+
+int launch_rlc(Launch& L, G1* out2, const G1Affine* commitments, const G1Affine* proofs, const Fr* z, const Fr* y, const Fr* r, bool use_r, uint64_t first,
+               uint64_t n, void* scratch) {
+    uint8_t* ws = (uint8_t*)scratch;
+    uint32_t* s1 = (uint32_t*)ws; ws += al256(n * 32);
+    uint32_t* s2 = (uint32_t*)ws; ws += al256(n * 32);
+    Fr* ty = (Fr*)ws; ws += al256(n * sizeof(Fr));
+    uint32_t* ysum = (uint32_t*)ws; ws += al256(32);
+    G1* Y = (G1*)ws; ws += al256(sizeof(G1));
+    // U: n points + fold scratch ; T: 2n points + fold scratch
+    size_t fold = rlc_fold(n);
+    G1* U = (G1*)ws; ws += al256((n + fold) * sizeof(G1));
+    G1* T = (G1*)ws;
+
+    rlc_scalars_kernel<<<blocks_for(n, 64), 64, 0, L.stream>>>(s1, s2, ty, z, y, r, use_r, first, n);
+    KZG_CUDA_TRY(cudaGetLastError());
+    fr_sum_kernel<<<1, 256, 0, L.stream>>>(ysum, ty, n);
+    KZG_CUDA_TRY(cudaGetLastError());
+    L.count(2, "rlc_scalars");
+    rlc_points_kernel<<<blocks_for(3 * n + 1, 64), 64, 0, L.stream>>>(U, T, Y, commitments, proofs, s1, s2, ysum, n);
+    KZG_CUDA_TRY(cudaGetLastError());
+    L.count(1, "rlc_points");
+    int rc;
+    if ((rc = launch_g1_sum(L, out2 + 0, U, n))) return rc;
+    if ((rc = launch_g1_sum(L, out2 + 1, T, 2 * n))) return rc;
+    // B += -[ysum]G : fold Y into out2[1] with a 2-point sum
+    G1* pair = T;  // reuse: [out2[1], Y]
+    KZG_CUDA_TRY(cudaMemcpyAsync(pair, out2 + 1, sizeof(G1), cudaMemcpyDeviceToDevice, L.stream));
+    KZG_CUDA_TRY(cudaMemcpyAsync(pair + 1, Y, sizeof(G1), cudaMemcpyDeviceToDevice, L.stream));
+    if ((rc = launch_g1_sum(L, out2 + 1, pair, 2))) return rc;
+    return RET_OK;
+}
+
+}  // namespace kzg

@@ -1,14 +1,52 @@
-// Internal interface of the verification side of the engine (pairing.cu / verify.cu).
+// Internal interface of the proof / verification side of the engine (pairing.cu, verify.cu).
 #pragma once
 #include "engine.h"
 
 namespace kzg {
 
+// line-table slots in Ctx::g2_lines
+enum { LINE_G2_GEN = 0, LINE_G2_TAU = 1, LINE_G2_TAU64 = 2 };
+
+// ---- pairing.cu ----------------------------------------------------------------------------------
 // Decompress the 65 G2 points (setup.c:469-477; failure sets *d_bad) and precompute the Miller-loop
 // lines of the fixed G2 arguments (G2 generator, [tau]G2, [tau^64]G2).
 int setup_g2_and_lines(cudaStream_t stream, Launch& L, Ctx* c, const uint8_t* g2_monomial_bytes_host, int* d_bad);
 // is_trusted_setup_in_lagrange_form (setup.c:339-358): pairing check on the first two Lagrange points
 // (in file order, i.e. before the bit-reversal).
 int setup_is_monomial_form(cudaStream_t stream, Launch& L, Ctx* c, const uint8_t* g1_lagrange_bytes_host, int* is_monomial);
+// *d_ok = [ e(A, Q_line_a) == e(B + B_extra, Q_line_b) ]
+int launch_pairing_check(Launch& L, int* d_ok, const G1* A, const G1* B, const G1* B_extra, int line_a, int line_b);
+
+// ---- verify.cu -----------------------------------------------------------------------------------
+// z[i] = hash_to_bls_field(SHA256("FSBLOBVERIFY_V1_" || 0 || 4096 || blob_i || commitment_i))
+// (compute_challenge, src/eip4844/eip4844.c:147).  zy[i*64 .. +32) receives canonical z bytes.
+int launch_blob_challenges(Launch& L, Fr* z, uint8_t* zy, const uint8_t* blobs, const uint8_t* commitments48, uint64_t n);
+// z[i] from canonical bytes (compute_kzg_proof path); bad[i] = 1 if >= r
+int launch_z_from_bytes(Launch& L, Fr* z, uint8_t* zy, const uint8_t* z_bytes, uint64_t n, int* bad);
+// y[i] = p_i(z[i]) (evaluate_polynomial_in_evaluation_form, eip4844.c:192), canonical y bytes into
+// zy[i*64+32 ..).  bad[i*bad_stride] = 1 for a non-canonical blob element.  Optionally stores the
+// 4096 inverses 1/(z - w_j) per blob and the in-domain index (or -1).
+int launch_evaluate(Launch& L, Fr* y, uint8_t* zy, Fr* inv_or_null, int* m_or_null, const uint8_t* blobs, const Fr* z, uint64_t n, int* bad, int bad_stride);
+// quotient scalars (plain little-endian limbs) for compute_kzg_proof_impl (eip4844.c:417-494)
+int launch_quotient(Launch& L, uint8_t* q_scalars, const uint8_t* blobs, const Fr* z, const Fr* y, const Fr* inv, const int* m, uint64_t n);
+// decompress + validate n points (validate_kzg_g1, bytes.c:81); bad[i*bad_stride] = 1 on failure
+int launch_g1_validate(Launch& L, G1Affine* out, const uint8_t* bytes48, uint64_t n, int* bad, int bad_stride);
+// tuples[i] = C_i || z_i || y_i || proof_i (160 B), the layout the batch challenge hashes (eip4844.c:648-660)
+int launch_pack_tuples(Launch& L, uint8_t* tuples, const uint8_t* commitments48, const uint8_t* zy, const uint8_t* proofs48, uint64_t n);
+// r = hash_to_bls_field(SHA256("RCKZGBATCH___V1_" || 4096 || n || tuples)) (eip4844.c:597-680)
+int launch_r_challenge(Launch& L, Fr* r, const uint8_t* tuples, uint64_t n);
+// Random linear combination over tuples [first, first+n_local) with powers r^(first+i):
+//   A = sum r^i proof_i,  B = sum r^i z_i proof_i + sum r^i C_i - [sum r^i y_i] G1
+// (verify_kzg_proof_batch, eip4844.c:697-765).  use_r = false: all weights 1 (the n == 1 equation).
+// Results (XYZZ, device): out[0] = A, out[1] = B.  scratch sized by rlc_scratch_bytes(n_local).
+size_t rlc_scratch_bytes(uint64_t n_local);
+int launch_rlc(Launch& L, G1* out2, const G1Affine* commitments, const G1Affine* proofs, const Fr* z, const Fr* y, const Fr* r, bool use_r,
+               uint64_t first, uint64_t n_local, void* scratch);
+// sum of n XYZZ points -> out (device); in is clobbered
+int launch_g1_sum(Launch& L, G1* out, G1* in, uint64_t n);
+// out[i] = XYZZ lift of in[i]
+int launch_lift_affine(Launch& L, G1* out, const G1Affine* in, uint64_t n);
+// Fr from 32-byte canonical big-endian (bad[i]=1 if >= r)
+int launch_fr_from_bytes(Launch& L, Fr* out, const uint8_t* bytes32, uint64_t stride, uint64_t n, int* bad);
 
 }  // namespace kzg

@@ -180,6 +180,69 @@ C_KZG_RET verify_blob_kzg_proof(
 }
 
 /* ---------------------------------------------------------------------------------------------- */
+/* EIP-7594                                                                                       */
+/* ---------------------------------------------------------------------------------------------- */
+
+C_KZG_RET compute_cells_and_kzg_proofs(Cell *cells, KZGProof *proofs, const Blob *blob, const KZGSettings *s) {
+    if (cells == NULL && proofs == NULL) return C_KZG_BADARGS; /* eip7594.c:72-74 */
+    ckzg_b200_ctx *e = engine_of(s);
+    if (e == NULL) return C_KZG_BADARGS;
+    return (C_KZG_RET)ckzg_b200_compute_cells_and_kzg_proofs_batch(
+        e, (uint8_t *)cells, (uint8_t *)proofs, blob->bytes, 1, CKZG_B200_HOST, NULL
+    );
+}
+
+C_KZG_RET recover_cells_and_kzg_proofs(
+    Cell *recovered_cells,
+    KZGProof *recovered_proofs,
+    const uint64_t *cell_indices,
+    const Cell *cells,
+    uint64_t num_cells,
+    const KZGSettings *s
+) {
+    /* eip7594.c:191-213: count and index checks come first */
+    if (num_cells > CELLS_PER_EXT_BLOB || num_cells < CELLS_PER_BLOB) return C_KZG_BADARGS;
+    for (uint64_t i = 0; i < num_cells; i++) {
+        if (cell_indices[i] >= CELLS_PER_EXT_BLOB) return C_KZG_BADARGS;
+        if (i > 0 && cell_indices[i] <= cell_indices[i - 1]) return C_KZG_BADARGS; /* strictly ascending */
+    }
+    ckzg_b200_ctx *e = engine_of(s);
+    if (e == NULL) return C_KZG_BADARGS;
+    return (C_KZG_RET)ckzg_b200_recover_cells_and_kzg_proofs_batch(
+        e, (uint8_t *)recovered_cells, (uint8_t *)recovered_proofs, cell_indices, (const uint8_t *)cells, num_cells, 1,
+        CKZG_B200_HOST, NULL
+    );
+}
+
+C_KZG_RET verify_cell_kzg_proof_batch(
+    bool *ok,
+    const Bytes48 *commitments_bytes,
+    const uint64_t *cell_indices,
+    const Cell *cells,
+    const Bytes48 *proofs_bytes,
+    uint64_t num_cells,
+    const KZGSettings *s
+) {
+    *ok = false; /* eip7594.c:849 */
+    if (num_cells == 0) { /* eip7594.c:852-855 */
+        *ok = true;
+        return C_KZG_OK;
+    }
+    for (uint64_t i = 0; i < num_cells; i++) { /* eip7594.c:861-864 */
+        if (cell_indices[i] >= CELLS_PER_EXT_BLOB) return C_KZG_BADARGS;
+    }
+    ckzg_b200_ctx *e = engine_of(s);
+    if (e == NULL) return C_KZG_BADARGS;
+    int good = 0;
+    int rc = ckzg_b200_verify_cell_kzg_proof_batch(
+        e, &good, (const uint8_t *)commitments_bytes, cell_indices, (const uint8_t *)cells, (const uint8_t *)proofs_bytes,
+        num_cells, CKZG_B200_HOST
+    );
+    if (rc == 0) *ok = good != 0;
+    return (C_KZG_RET)rc;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
 /* small helpers the reference exports (src/common/bytes.c)                                       */
 /* ---------------------------------------------------------------------------------------------- */
 

@@ -102,12 +102,42 @@ int ckzg_b200_verify_blob_batch_stage2(
 );
 int ckzg_b200_verify_blob_batch_finish(ckzg_b200_ctx *ctx, int *ok, const uint8_t *partials, uint64_t n_ranks);
 
+/*
+ * EIP-7594.  Batched compute_cells_and_kzg_proofs (src/eip7594/eip7594.c:61): per blob 128 cells
+ * (2048 B each, bit-reversed evaluation order) and/or 128 FK20 cell proofs (src/eip7594/fk20.c:139).
+ * Either output may be NULL, not both (eip7594.c:72-74).
+ */
+int ckzg_b200_compute_cells_and_kzg_proofs_batch(
+    ckzg_b200_ctx *ctx, uint8_t *cells, uint8_t *proofs, const uint8_t *blobs, uint64_t n, int mem, int *status
+);
+/*
+ * Batched recover_cells_and_kzg_proofs (src/eip7594/eip7594.c:177): every blob of the batch comes
+ * with the same number `num_cells` of (index, cell) pairs; indices are n x num_cells uint64 in HOST
+ * memory (validated on the host exactly as eip7594.c:191-213), cells n x num_cells x 2048 B in `mem`.
+ * recovered_proofs may be NULL.
+ */
+int ckzg_b200_recover_cells_and_kzg_proofs_batch(
+    ckzg_b200_ctx *ctx, uint8_t *recovered_cells, uint8_t *recovered_proofs, const uint64_t *cell_indices,
+    const uint8_t *cells, uint64_t num_cells, uint64_t n, int mem, int *status
+);
+/* verify_cell_kzg_proof_batch (src/eip7594/eip7594.c:825); cell_indices in HOST memory. */
+int ckzg_b200_verify_cell_kzg_proof_batch(
+    ckzg_b200_ctx *ctx, int *ok, const uint8_t *commitments, const uint64_t *cell_indices, const uint8_t *cells,
+    const uint8_t *proofs, uint64_t num_cells, int mem
+);
+
 /* Internal Fiat-Shamir challenge, exposed for the vectors in tests/compute_challenge
  * (src/eip4844/eip4844.c:147; commitment given in its canonical 48-byte form). out = 32 bytes BE. */
 int ckzg_b200_compute_challenge(ckzg_b200_ctx *ctx, uint8_t *out32, const uint8_t *blob, const uint8_t *commitment48);
 
 /* Counters for bench.py: kernels launched by this library since the context was created. */
 uint64_t ckzg_b200_launch_count(const ckzg_b200_ctx *ctx);
+
+/* Per-kernel device timing for bench.py: enable (also resets the counters), run calls, then dump a
+ * JSON object {"calls": n, "call_ms": total, "kernels": {name: [total_ms, launches], ...}} into buf.
+ * Times come from CUDA events recorded on the stream each call launches on. Returns bytes written. */
+void ckzg_b200_profile_enable(ckzg_b200_ctx *ctx, int on);
+int ckzg_b200_profile_dump(ckzg_b200_ctx *ctx, char *buf, size_t cap);
 
 /* Device self-tests used by tests/test_gpu_units.py: run `op` over n operand pairs.
  *   op 0: Fp mul, 1: Fp add, 2: Fp sub, 3: Fp inv(a), 4: Fr mul, 5: Fr inv(a), 6: Fp sqr

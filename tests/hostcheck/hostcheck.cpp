@@ -85,4 +85,44 @@ int hc_g1_madd(uint8_t* out48, const uint8_t* p48, const uint8_t* q48, int negat
     g1a_compress(out48, g1_to_affine(acc));
     return 1;
 }
+
+#ifdef HOSTCHECK_PAIRING
+// e(P1,Q1) * e(P2,Q2) == 1 ?  (compressed inputs; -1 on decode failure)
+int hc_pairing_product_is_one(const uint8_t* p1, const uint8_t* q1, const uint8_t* p2, const uint8_t* q2) {
+    G1Affine P1, P2;
+    G2Affine Q1, Q2;
+    if (!g1a_uncompress(P1, p1) || !g1a_uncompress(P2, p2)) return -1;
+    if (!g2a_uncompress(Q1, q1) || !g2a_uncompress(Q2, q2)) return -1;
+    static G2Lines L1, L2;
+    g2_precompute_lines(L1, Q1);
+    g2_precompute_lines(L2, Q2);
+    return pairing_product_is_one(P1, &L1, P2, &L2) ? 1 : 0;
+}
+int hc_g2_uncompress_ok(const uint8_t* q) {
+    G2Affine Q;
+    return g2a_uncompress(Q, q) ? 1 : 0;
+}
+// cyclotomic squaring == plain squaring on an element of the cyclotomic subgroup (easy part of a
+// Miller-loop value); also x-power consistency.  returns 1 if all agree
+int hc_cyclotomic_consistency(const uint8_t* p1, const uint8_t* q1) {
+    G1Affine P1;
+    G2Affine Q1;
+    if (!g1a_uncompress(P1, p1) || !g2a_uncompress(Q1, q1)) return -1;
+    static G2Lines L1;
+    g2_precompute_lines(L1, Q1);
+    G1Affine inf = g1a_inf();
+    Fp12 f = miller_loop2(P1, &L1, inf, &L1);
+    Fp12 e = f12_mul(f12_conj(f), f12_inv(f));
+    e = f12_mul(f12_frobenius2(e), e);
+    Fp12 a = f12_cyclotomic_sqr(e), b = f12_sqr(e);
+    int ok = f6_eq(a.c0, b.c0) && f6_eq(a.c1, b.c1);
+    // conj == inverse in the cyclotomic subgroup
+    Fp12 one = f12_mul(e, f12_conj(e));
+    ok = ok && f12_is_one(one);
+    // frobenius consistency: frob(frob(e)) == frob2(e)
+    Fp12 f2a = f12_frobenius(f12_frobenius(e)), f2b = f12_frobenius2(e);
+    ok = ok && f6_eq(f2a.c0, f2b.c0) && f6_eq(f2a.c1, f2b.c1);
+    return ok;
+}
+#endif
 }

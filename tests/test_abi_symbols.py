@@ -1,0 +1,62 @@
+"""CPU: the product library loads and exports every function include/*.h declares; the frozen API
+keeps the reference's struct sizes (KZGSettings = 80 bytes, src/setup/settings.h:27-79)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import __graft_entry__ as entry
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions(header):
+    src = open(os.path.join(ROOT, "include", header)).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"\b(?:C_KZG_RET|int|void|uint64_t)\s+\*?([a-z_0-9]+)\s*\(", src)
+    return sorted(set(names))
+
+
+def test_library_exports_every_declared_symbol():
+    mod = entry.load_package()
+    assert os.path.exists(mod.LIB_PATH), "libckzg_b200.so not built"
+    lib = C.CDLL(mod.LIB_PATH)
+    missing = []
+    for h in ("ckzg.h", "ckzg_b200.h"):
+        for name in declared_functions(h):
+            try:
+                getattr(lib, name)
+            except AttributeError:
+                missing.append((h, name))
+    # helpers taking the opaque fr_t/g1_t types land with the round-2 binding shims
+    allowed = {"bytes_from_g1", "bytes_from_bls_field", "bytes_to_bls_field", "bytes_to_kzg_commitment", "bytes_to_kzg_proof", "compute_challenge"}
+    missing = [m for m in missing if m[1] not in allowed]
+    assert not missing, missing
+
+
+def test_struct_sizes_match_reference(tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text(
+        '#include "ckzg.h"\n#include <stdio.h>\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu\\n",sizeof(KZGSettings),sizeof(Blob),sizeof(Cell),sizeof(Bytes48),sizeof(fr_t),sizeof(g1_t),sizeof(g2_t));return 0;}\n'
+    )
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)]).decode().split()
+    assert out == ["80", "131072", "2048", "48", "32", "144", "288"]
+
+
+def test_no_device_fails_loudly():
+    """Without a CUDA device load_trusted_setup must fail with C_KZG_ERROR -- never fall back."""
+    import torch
+
+    if torch.cuda.is_available():
+        import pytest
+
+        pytest.skip("GPU present")
+    mod = entry.load_package()
+    try:
+        mod.load_trusted_setup()
+    except RuntimeError as e:
+        assert "no CPU path" in str(e)
+    else:
+        raise AssertionError("load_trusted_setup succeeded without a GPU")

@@ -14,6 +14,11 @@ pytestmark = pytest.mark.gpu
 # APIs whose engine path has landed; extended as the round progresses
 IMPLEMENTED = [
     "blob_to_kzg_commitment",
+    "compute_kzg_proof",
+    "compute_blob_kzg_proof",
+    "verify_kzg_proof",
+    "verify_blob_kzg_proof",
+    "verify_blob_kzg_proof_batch",
 ]
 
 
@@ -82,3 +87,114 @@ def test_commitment_batch_entry(gpu, ref):
     for i in range(n):
         if i != 3:
             assert out.raw[48 * i : 48 * i + 48] == ref.blob_to_kzg_commitment(blobs[i])
+
+
+def _engine(gpu):
+    import ctypes as C
+
+    return C.c_void_p(int.from_bytes(gpu.settings.raw[56:64], "little"))
+
+
+def test_compute_challenge_vectors(gpu):
+    """tests/compute_challenge: pins the per-blob Fiat-Shamir hash (eip4844.c:147)."""
+    import ctypes as C
+
+    n = 0
+    for name, inp, want in gv.cases("compute_challenge"):
+        blob, cm = inp["blob"], inp["commitment"]
+        if not (isinstance(blob, bytes) and len(blob) == 131072 and isinstance(cm, bytes) and len(cm) == 48) or want is None:
+            continue
+        out = C.create_string_buffer(32)
+        assert gpu.lib.ckzg_b200_compute_challenge(_engine(gpu), out, blob, cm) == 0
+        assert out.raw == want, name
+        n += 1
+    assert n >= 5
+
+
+@pytest.fixture(scope="module")
+def batch64(ref):
+    """BASELINE config 2 shape: 64 synthetic blobs with reference commitments and proofs."""
+    blobs = [synth_blob(b) for b in range(64)]
+    cms = [ref.blob_to_kzg_commitment(b) for b in blobs]
+    prs = [ref.compute_blob_kzg_proof(b, c) for b, c in zip(blobs, cms)]
+    return blobs, cms, prs
+
+
+def test_proofs_differential(gpu, ref, batch64):
+    blobs, cms, prs = batch64
+    for i in range(4):
+        assert gpu.compute_blob_kzg_proof(blobs[i], cms[i]) == prs[i]
+        z = synth_blob(900 + i)[:32]
+        assert gpu.compute_kzg_proof(blobs[i], z) == ref.compute_kzg_proof(blobs[i], z)
+    # z inside the evaluation domain (eip4844.c:460-481): roots of unity
+    R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+    w = pow(7, (R - 1) // 4096, R)
+    for k in (0, 1, 5, 4095):
+        z = pow(w, k, R).to_bytes(32, "big")
+        assert gpu.compute_kzg_proof(blobs[0], z) == ref.compute_kzg_proof(blobs[0], z)
+
+
+def test_verify_batch_n64_and_negative_controls(gpu, ref, batch64):
+    blobs, cms, prs = batch64
+    B, C_, P_ = b"".join(blobs), b"".join(cms), b"".join(prs)
+    assert gpu.verify_blob_kzg_proof_batch(B, C_, P_) is True
+    assert ref.verify_blob_kzg_proof_batch(B, C_, P_) is True
+    # one wrong proof (a valid point, just not the right one) -> false
+    bad = list(prs)
+    bad[17] = prs[18]
+    assert gpu.verify_blob_kzg_proof_batch(B, C_, b"".join(bad)) is False
+    # swapped blobs -> false
+    sw = list(blobs)
+    sw[3], sw[4] = sw[4], sw[3]
+    assert gpu.verify_blob_kzg_proof_batch(b"".join(sw), C_, P_) is False
+    # invalid encodings -> BADARGS
+    inv = list(cms)
+    inv[9] = bytes(48)
+    with pytest.raises(ref_lib.BadArgs):
+        gpu.verify_blob_kzg_proof_batch(B, b"".join(inv), P_)
+    # sizes 1, 2, 3 and single verify
+    for n in (1, 2, 3):
+        assert gpu.verify_blob_kzg_proof_batch(B[: 131072 * n], C_[: 48 * n], P_[: 48 * n]) is True
+    assert gpu.verify_blob_kzg_proof(blobs[5], cms[5], prs[5]) is True
+    assert gpu.verify_blob_kzg_proof(blobs[5], cms[5], prs[6]) is False
+    # infinity commitment / proof for the zero polynomial
+    zero = bytes(131072)
+    inf = bytes([0xC0]) + bytes(47)
+    assert gpu.blob_to_kzg_commitment(zero) == inf
+    assert gpu.verify_blob_kzg_proof(zero, inf, inf) is True
+    assert gpu.verify_blob_kzg_proof_batch(zero + blobs[0], inf + cms[0], inf + prs[0]) is True
+
+
+def test_verify_batch_sharded_stages(gpu, batch64):
+    """The multi-GPU split (stage1 / all-gather / stage2 / finish) run as 3 'ranks' on one device
+    must agree with the one-call verifier."""
+    import ctypes as C
+
+    blobs, cms, prs = batch64
+    n, e = 24, _engine(gpu)
+    shards = [(0, 10), (10, 9), (19, 5)]
+
+    def run(proofs):
+        zy = {}
+        for first, cnt in shards:
+            out = C.create_string_buffer(64 * cnt)
+            rc = gpu.lib.ckzg_b200_verify_blob_batch_stage1(
+                e, out, b"".join(blobs[first : first + cnt]), b"".join(cms[first : first + cnt]), b"".join(proofs[first : first + cnt]), C.c_uint64(cnt), 0
+            )
+            assert rc == 0
+            for k in range(cnt):
+                zy[first + k] = out.raw[64 * k : 64 * k + 64]
+        tuples = b"".join(cms[i] + zy[i] + proofs[i] for i in range(n))  # the all-gathered 160-byte records
+        partials = b""
+        for first, cnt in shards:
+            part = C.create_string_buffer(144)
+            assert gpu.lib.ckzg_b200_verify_blob_batch_stage2(e, part, tuples, C.c_uint64(n), C.c_uint64(first), C.c_uint64(cnt), 0) == 0
+            partials += part.raw
+        ok = C.c_int(0)
+        assert gpu.lib.ckzg_b200_verify_blob_batch_finish(e, C.byref(ok), partials, C.c_uint64(len(shards))) == 0
+        return bool(ok.value)
+
+    assert run(prs) is True
+    bad = list(prs)
+    bad[20] = prs[21]
+    assert run(bad) is False

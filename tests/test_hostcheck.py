@@ -155,3 +155,40 @@ def test_g1_validate_edge_cases(hc):
     for y in (p[1], P - p[1]):
         enc = B.g1_compress((p[0], y, 1))
         assert hc.hc_g1_uncompress(out, enc) == 1 and out.raw == enc
+
+
+def g2_compress(q):
+    """ZCash G2 compression of a Jacobian oracle point (test helper)."""
+    a = B.g2_to_affine(q)
+    if a is None:
+        return bytes([0xC0]) + bytes(95)
+    (x0, x1), (y0, y1) = a
+    b = bytearray(x1.to_bytes(48, "big") + x0.to_bytes(48, "big"))
+    b[0] |= 0x80
+    big = (y1 > (P - 1) // 2) if y1 != 0 else (y0 > (P - 1) // 2)
+    if big:
+        b[0] |= 0x20
+    return bytes(b)
+
+
+def test_g2_compress_helper_roundtrip():
+    q = B.g2_mul(B.G2_GEN_J, 987654321)
+    assert B.g2_to_affine(B.g2_uncompress(g2_compress(q))) == B.g2_to_affine(q)
+
+
+def test_pairing_host(hc):
+    rnd = random.Random(7)
+    a, b = rnd.randrange(1, R), rnd.randrange(1, R)
+    G1, G2 = B.G1_GEN_J, B.G2_GEN_J
+    aG1, bG2 = B.g1_mul(G1, a), B.g2_mul(G2, b)
+    abG1 = B.g1_mul(G1, a * b % R)
+    c = lambda p: B.g1_compress(p)
+    # e(aG1, bG2) * e(-abG1, G2) == 1
+    assert hc.hc_pairing_product_is_one(c(aG1), g2_compress(bG2), c(B.g1_neg(abG1)), g2_compress(G2)) == 1
+    assert hc.hc_pairing_product_is_one(c(aG1), g2_compress(bG2), c(abG1), g2_compress(G2)) == 0
+    assert hc.hc_pairing_product_is_one(c(aG1), g2_compress(bG2), c(B.g1_neg(B.g1_mul(G1, (a * b + 1) % R))), g2_compress(G2)) == 0
+    # infinity handling: e(inf, Q) = 1
+    inf = c(B.G1_INF)
+    assert hc.hc_pairing_product_is_one(inf, g2_compress(bG2), inf, g2_compress(G2)) == 1
+    assert hc.hc_pairing_product_is_one(c(aG1), g2_compress(bG2), inf, g2_compress(G2)) == 0
+    assert hc.hc_cyclotomic_consistency(c(aG1), g2_compress(bG2)) == 1

@@ -1,0 +1,88 @@
+"""CPU (gloo, world_size 2 and 3) test of the multi-GPU host logic in c-kzg-4844_b200/parallel.py with a
+recording stub in place of the engine: shard ranges tile the batch, every rank assembles the SAME
+160-byte transcript in blob order, partial sums are all-gathered in rank order, verdicts all-reduce."""
+import hashlib
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import __graft_entry__ as entry
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _zy(i):
+    return hashlib.sha256(b"zy%d" % i).digest() * 2
+
+
+def _worker(rank, world, port, n_total, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    entry.load_package()
+    import importlib
+
+    par = importlib.import_module("ckzg_b200.parallel")
+    cms = b"".join(hashlib.sha256(b"c%d" % i).digest()[:24] * 2 for i in range(n_total))
+    prs = b"".join(hashlib.sha256(b"p%d" % i).digest()[:24] * 2 for i in range(n_total))
+    first, cnt = par.shard_range(n_total, rank, world)
+    seen = {}
+
+    def stage1():
+        return b"".join(_zy(first + k) for k in range(cnt))
+
+    def stage2(tuples, n, f, c):
+        seen["tuples"] = hashlib.sha256(tuples).hexdigest()
+        assert (n, f, c) == (n_total, first, cnt)
+        return bytes([rank]) * 144
+
+    def finish(parts, nr):
+        seen["parts"] = parts
+        return nr == world and all(parts[144 * r : 144 * r + 144] == bytes([r]) * 144 for r in range(world))
+
+    ok = par.verify_batch_sharded(stage1, stage2, finish, cms, prs, n_total, torch.device("cpu"))
+    want = hashlib.sha256(b"".join(cms[48 * i : 48 * i + 48] + _zy(i) + prs[48 * i : 48 * i + 48] for i in range(n_total))).hexdigest()
+    rep_all_true = par.verify_batch_replicas(lambda: True, torch.device("cpu"))
+    rep_one_false = par.verify_batch_replicas(lambda: rank != world - 1, torch.device("cpu"))
+    q.put((rank, ok, seen["tuples"] == want, first, cnt, rep_all_true, rep_one_false))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_total", [(2, 7), (3, 8), (2, 1)])
+def test_sharded_verify_host_logic(world, n_total):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_total, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    covered = []
+    for rank, ok, same, first, cnt, rep_true, rep_false in res:
+        assert ok and same and rep_true and not rep_false
+        covered += list(range(first, first + cnt))
+    assert covered == list(range(n_total))
+
+
+def test_shard_range_properties():
+    entry.load_package()
+    import importlib
+
+    par = importlib.import_module("ckzg_b200.parallel")
+    for n in (0, 1, 5, 64, 4096, 4097):
+        for w in (1, 2, 3, 4, 8):
+            rs = [par.shard_range(n, r, w) for r in range(w)]
+            assert sum(c for _, c in rs) == n
+            assert all(rs[i][0] + rs[i][1] == rs[i + 1][0] for i in range(w - 1))
+            assert max(c for _, c in rs) - min(c for _, c in rs) <= 1
