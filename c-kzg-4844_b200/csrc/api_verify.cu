@@ -2,6 +2,7 @@
 // kernels of verify.cu / msm.cu / pairing.cu.  Host code here only sequences launches and copies.
 #include <string.h>
 
+#include "../src/host_sha256.h"
 #include "call.h"
 #include "verify.h"
 
@@ -81,6 +82,39 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* d_blobs, const uint8_t* 
     TRY(launch_g1_validate(L, s.pf, d_pf, n, s.bad, 0));
     TRY(launch_blob_challenges(L, s.z, s.zy, d_blobs, d_cm, n));
     TRY(launch_evaluate(L, s.y, s.zy, nullptr, nullptr, d_blobs, s.z, n, s.bad, 0));
+    return RET_OK;
+}
+
+// r = hash_to_bls_field(SHA256("RCKZGBATCH___V1_" || u64be(4096) || u64be(n) || n x (C || z || y || proof)))
+// (compute_r_powers_for_verify_kzg_proof_batch, eip4844.c:612-668).  The transcript is one serial hash
+// chain: hashed on the host (src/host_sha256.c explains why); the 32-byte digest goes back to the
+// device, which reduces it mod r.  Inputs are host pointers; zy is n x 64 (z || y).
+int r_from_transcript(Call& call, Fr* d_r, const uint8_t* cm, const uint8_t* zy, const uint8_t* pf, const uint8_t* tuples, uint64_t n) {
+    Launch L = call.launch();
+    ckzg_host_sha256 h;
+    ckzg_host_sha256_init(&h);
+    uint8_t head[32] = {'R', 'C', 'K', 'Z', 'G', 'B', 'A', 'T', 'C', 'H', '_', '_', '_', 'V', '1', '_'};
+    for (int i = 0; i < 8; i++) {
+        head[16 + i] = (uint8_t)((uint64_t)N_BLOB >> (56 - 8 * i));
+        head[24 + i] = (uint8_t)(n >> (56 - 8 * i));
+    }
+    ckzg_host_sha256_update(&h, head, 32);
+    if (tuples) {
+        ckzg_host_sha256_update(&h, tuples, 160 * n);
+    } else {
+        for (uint64_t i = 0; i < n; i++) {
+            ckzg_host_sha256_update(&h, cm + 48 * i, 48);
+            ckzg_host_sha256_update(&h, zy + 64 * i, 64);
+            ckzg_host_sha256_update(&h, pf + 48 * i, 48);
+        }
+    }
+    uint8_t digest[32];
+    ckzg_host_sha256_final(&h, digest);
+    uint8_t* d_digest;
+    TRY(call.alloc(&d_digest, 32));
+    KZG_CUDA_TRY(cudaMemcpyAsync(d_digest, digest, 32, cudaMemcpyHostToDevice, call.stream));
+    KZG_CUDA_TRY(cudaStreamSynchronize(call.stream));  // `digest` is a stack buffer
+    TRY(launch_r_from_digest(L, d_r, d_digest));
     return RET_OK;
 }
 
@@ -174,17 +208,26 @@ int ckzg_b200_verify_blob_kzg_proof_batch(ckzg_b200_ctx* ctx, int* ok, const uin
     TRY(verify_stage1(call, s, d_blobs, d_cm, d_pf, n));
     // the reference stops at the first invalid input (eip4844.c:813-831) before any pairing work
     int bad = 0;
+    bool use_r = n > 1;  // n == 1: the single-proof equation, no challenge (eip4844.c:798)
+    std::vector<uint8_t> h_zy, h_cp;
+    if (use_r) {
+        h_zy.resize(n * 64);
+        KZG_CUDA_TRY(cudaMemcpyAsync(h_zy.data(), s.zy, n * 64, cudaMemcpyDeviceToHost, call.stream));
+        if (mem == CKZG_B200_DEVICE) {
+            h_cp.resize(n * 96);
+            KZG_CUDA_TRY(cudaMemcpyAsync(h_cp.data(), d_cm, n * 48, cudaMemcpyDeviceToHost, call.stream));
+            KZG_CUDA_TRY(cudaMemcpyAsync(h_cp.data() + n * 48, d_pf, n * 48, cudaMemcpyDeviceToHost, call.stream));
+        }
+    }
     TRY(read_flag(call, s.bad, &bad));
     if (bad) return RET_BADARGS;
 
     Fr* d_r;
     TRY(call.alloc(&d_r, 1));
-    bool use_r = n > 1;  // n == 1: the single-proof equation, no challenge (eip4844.c:798)
     if (use_r) {
-        uint8_t* d_tuples;
-        TRY(call.alloc(&d_tuples, n * 160));
-        TRY(launch_pack_tuples(L, d_tuples, d_cm, s.zy, d_pf, n));
-        TRY(launch_r_challenge(L, d_r, d_tuples, n));
+        const uint8_t* hc = (mem == CKZG_B200_DEVICE) ? h_cp.data() : commitments;
+        const uint8_t* hp = (mem == CKZG_B200_DEVICE) ? h_cp.data() + n * 48 : proofs;
+        TRY(r_from_transcript(call, d_r, hc, h_zy.data(), hp, nullptr, n));
     }
     G1* d_AB;
     void* scratch;
@@ -272,7 +315,17 @@ int ckzg_b200_verify_blob_batch_stage2(ckzg_b200_ctx* ctx, uint8_t* partial144, 
     TRY(call.stage_in(&d_tuples, tuples, n_total * 160, mem));
     Fr* d_r;
     TRY(call.alloc(&d_r, 1));
-    TRY(launch_r_challenge(L, d_r, d_tuples, n_total));
+    {
+        std::vector<uint8_t> h_t;
+        const uint8_t* ht = tuples;
+        if (mem == CKZG_B200_DEVICE) {
+            h_t.resize(n_total * 160);
+            KZG_CUDA_TRY(cudaMemcpyAsync(h_t.data(), d_tuples, n_total * 160, cudaMemcpyDeviceToHost, call.stream));
+            KZG_CUDA_TRY(cudaStreamSynchronize(call.stream));
+            ht = h_t.data();
+        }
+        TRY(r_from_transcript(call, d_r, nullptr, nullptr, nullptr, ht, n_total));
+    }
     G1* d_AB;
     uint8_t* d_out;
     TRY(call.alloc(&d_AB, 3));

@@ -132,6 +132,7 @@ int launch_g1_compress(Launch& L, uint8_t* out48, const G1* pts, uint64_t n);
 
 // ---- selftest.cu ---------------------------------------------------------------------------------
 int selftest_field(int op, uint32_t* out, const uint32_t* a, const uint32_t* b, uint64_t n);
+int selftest_mulbench(int ilp, int iters, int blocks, int threads, float* ms_out);
 int selftest_g1(int op, uint8_t* out48, int* ok_out, const uint8_t* p48, const uint32_t* k, const uint8_t* q48, uint64_t n);
 
 }  // namespace kzg

@@ -17,6 +17,8 @@
 //     collisions; the grid is (blobs x 1024 x parts) threads so a batch fills all 148 SMs;
 //   * kernel 3 (msm_reduce): per blob, sum_k k*B_k with 8-bucket running sums per thread, a small
 //     scalar multiplication for the chunk offset and a shared-memory tree.
+#include <stdlib.h>
+
 #include "engine.h"
 
 namespace kzg {
@@ -169,7 +171,8 @@ __global__ void __launch_bounds__(SORT_THREADS) msm_sort_kernel(
 // ------------------------------------------------------------------------------------------------
 constexpr int ACC_THREADS = 128;
 
-__global__ void __launch_bounds__(ACC_THREADS) msm_accumulate_kernel(
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(ACC_THREADS, MIN_BLOCKS) msm_accumulate_kernel(
     G1* __restrict__ buckets, const uint32_t* __restrict__ entries, const uint32_t* __restrict__ starts,
     const G1Affine* __restrict__ table, int parts
 ) {
@@ -283,7 +286,13 @@ int launch_msm(Launch& L, G1* result, const uint8_t* scalars, bool big_endian_by
     KZG_CUDA_TRY(cudaGetLastError());
     L.count(1, "msm_sort");
     dim3 grid(MSM_NB / ACC_THREADS, parts, (unsigned)n);
-    msm_accumulate_kernel<<<grid, ACC_THREADS, 0, L.stream>>>(buckets, entries, starts, table, parts);
+    static const int variant = getenv("CKZG_B200_ACC_VARIANT") ? atoi(getenv("CKZG_B200_ACC_VARIANT")) : 3;
+    if (variant == 4)
+        msm_accumulate_kernel<4><<<grid, ACC_THREADS, 0, L.stream>>>(buckets, entries, starts, table, parts);
+    else if (variant == 5)
+        msm_accumulate_kernel<5><<<grid, ACC_THREADS, 0, L.stream>>>(buckets, entries, starts, table, parts);
+    else
+        msm_accumulate_kernel<3><<<grid, ACC_THREADS, 0, L.stream>>>(buckets, entries, starts, table, parts);
     KZG_CUDA_TRY(cudaGetLastError());
     L.count(1, "msm_accumulate");
     msm_reduce_kernel<<<(unsigned)n, RED_THREADS, 0, L.stream>>>(result, buckets, parts);

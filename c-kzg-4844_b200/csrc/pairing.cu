@@ -3,8 +3,10 @@
 // pairing check of the verifiers (pairings_verify, src/common/utils.c:172-196).
 //
 // One pairing check per verify call is a latency problem (~19k dependent Fp products), not a
-// throughput one; this first version runs it on a single thread per check.
+// throughput one: it runs as ONE 64-thread CTA with the products of each Fp12
+// operation spread over the lanes (pairing_coop.cuh).
 #include "pairing.cuh"
+#include "pairing_coop.cuh"
 #include "verify.h"
 
 namespace kzg {
@@ -29,36 +31,40 @@ __global__ void g2_lines_kernel(G2Lines* lines, const G2Affine* g2) {
 }
 
 // e(L[1], G2[0]) == e(L[0], G2[1])  <=>  e(-L[1], G2[0]) * e(L[0], G2[1]) == 1
-__global__ void monomial_form_kernel(int* out, const uint8_t* lag01, const G2Lines* lines) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    uint8_t buf[48];
-    G1Affine l0, l1;
-    for (int k = 0; k < 48; k++) buf[k] = lag01[k];
-    bool ok0 = g1a_uncompress(l0, buf);
-    for (int k = 0; k < 48; k++) buf[k] = lag01[48 + k];
-    bool ok1 = g1a_uncompress(l1, buf);
-    if (!ok0 || !ok1) {
-        *out = 0;  // decoding errors are reported by the main decompression pass
-        return;
+// One CTA of COOP_LANES threads (pairing_coop.cuh); every thread reaches every barrier.
+__global__ void __launch_bounds__(COOP_LANES) monomial_form_kernel(int* out, const uint8_t* lag01, const G2Lines* lines) {
+    __shared__ CoopWS ws;
+    __shared__ G1 pts[2];
+    __shared__ int dec_ok[2];
+    if (threadIdx.x < 2) {
+        uint8_t buf[48];
+        G1Affine a;
+        for (int k = 0; k < 48; k++) buf[k] = lag01[48 * threadIdx.x + k];
+        dec_ok[threadIdx.x] = g1a_uncompress(a, buf) ? 1 : 0;
+        pts[threadIdx.x] = g1_from_affine(a);
     }
-    G1Affine n1 = g1a_neg(l1);
-    if (g1a_is_inf(l1)) n1 = l1;
-    *out = pairing_product_is_one(n1, &lines[0], l0, &lines[1]) ? 1 : 0;
+    __syncthreads();
+    // pts[0] = L[0], pts[1] = L[1]: first pairing argument is -L[1] against G2[0], second L[0] against G2[1]
+    coop_pairing_product_is_one(ws, pts[1], &lines[0], pts[0], &lines[1], true);
+    if (threadIdx.x == 0) *out = (dec_ok[0] && dec_ok[1]) ? ws.result : 0;  // decoding errors are reported by the main pass
 }
 
-// ok = [ e(-A, Q_a) * e(B, Q_b) == 1 ],  A/B XYZZ sums; `sub_gen_scalar` (optional, plain limbs):
-// B -= [s]G1 first (the [sum r^i y_i]G term of verify_kzg_proof_batch, eip4844.c:736-746).
-__global__ void pairing_check_kernel(int* ok, const G1* A, const G1* B, const G1* B_extra, const G2Lines* lines, int line_a, int line_b) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    G1 b = *B;
-    if (B_extra) {
-        G1 e = *B_extra;
-        g1_add_to(b, e);
+// ok = [ e(A, Q_a) == e(B + B_extra, Q_b) ] = [ e(-A, Q_a) * e(B + B_extra, Q_b) == 1 ];  A, B XYZZ sums.
+__global__ void __launch_bounds__(COOP_LANES) pairing_check_kernel(int* ok, const G1* A, const G1* B, const G1* B_extra, const G2Lines* lines, int line_a, int line_b) {
+    __shared__ CoopWS ws;
+    __shared__ G1 pts[2];
+    if (threadIdx.x == 0) {
+        pts[0] = *A;
+        G1 b = *B;
+        if (B_extra) {
+            G1 e = *B_extra;
+            g1_add_to(b, e);
+        }
+        pts[1] = b;
     }
-    G1Affine a_aff = g1_to_affine(*A);
-    G1Affine b_aff = g1_to_affine(b);
-    if (!g1a_is_inf(a_aff)) a_aff = g1a_neg(a_aff);
-    *ok = pairing_product_is_one(a_aff, &lines[line_a], b_aff, &lines[line_b]) ? 1 : 0;
+    __syncthreads();
+    coop_pairing_product_is_one(ws, pts[0], &lines[line_a], pts[1], &lines[line_b], true);
+    if (threadIdx.x == 0) *ok = ws.result;
 }
 
 int setup_g2_and_lines(cudaStream_t stream, Launch& L, Ctx* c, const uint8_t* g2_host, int* d_bad) {
@@ -82,7 +88,7 @@ int setup_is_monomial_form(cudaStream_t stream, Launch& L, Ctx* c, const uint8_t
     KZG_CUDA_TRY(cudaMallocAsync((void**)&d_bytes, 96, stream));
     KZG_CUDA_TRY(cudaMallocAsync((void**)&d_out, sizeof(int), stream));
     KZG_CUDA_TRY(cudaMemcpyAsync(d_bytes, g1_lagrange_host, 96, cudaMemcpyHostToDevice, stream));
-    monomial_form_kernel<<<1, 32, 0, stream>>>(d_out, d_bytes, (const G2Lines*)c->g2_lines);
+    monomial_form_kernel<<<1, COOP_LANES, 0, stream>>>(d_out, d_bytes, (const G2Lines*)c->g2_lines);
     KZG_CUDA_TRY(cudaGetLastError());
     KZG_CUDA_TRY(cudaMemcpyAsync(is_monomial, d_out, sizeof(int), cudaMemcpyDeviceToHost, stream));
     KZG_CUDA_TRY(cudaStreamSynchronize(stream));
@@ -93,7 +99,7 @@ int setup_is_monomial_form(cudaStream_t stream, Launch& L, Ctx* c, const uint8_t
 }
 
 int launch_pairing_check(Launch& L, int* d_ok, const G1* A, const G1* B, const G1* B_extra, int line_a, int line_b) {
-    pairing_check_kernel<<<1, 32, 0, L.stream>>>(d_ok, A, B, B_extra, (const G2Lines*)L.ctx->g2_lines, line_a, line_b);
+    pairing_check_kernel<<<1, COOP_LANES, 0, L.stream>>>(d_ok, A, B, B_extra, (const G2Lines*)L.ctx->g2_lines, line_a, line_b);
     KZG_CUDA_TRY(cudaGetLastError());
     L.count(1, "pairing_check");
     return RET_OK;

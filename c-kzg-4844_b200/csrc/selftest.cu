@@ -59,6 +59,60 @@ __global__ void selftest_g1_kernel(int op, uint8_t* out48, int* ok_out, const ui
     }
 }
 
+// Montgomery-multiplier throughput probe: ILP independent dependent-chains per thread.
+template <int ILP>
+__global__ void mulbench_kernel(uint32_t* out, const uint32_t* in, int iters) {
+    int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    Fp x[ILP], y;
+#pragma unroll
+    for (int k = 0; k < ILP; k++)
+#pragma unroll
+        for (int i = 0; i < 12; i++) x[k].l[i] = in[(i + k) % 12] + tid + k;
+#pragma unroll
+    for (int i = 0; i < 12; i++) y.l[i] = in[12 + i];
+    y.l[11] &= 0x0fffffffu;
+#pragma unroll
+    for (int k = 0; k < ILP; k++) x[k].l[11] &= 0x0fffffffu;
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int k = 0; k < ILP; k++) x[k] = mul(x[k], y);
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int k = 0; k < ILP; k++)
+#pragma unroll
+        for (int i = 0; i < 12; i++) acc ^= x[k].l[i];
+    out[tid] = acc;
+}
+
+int selftest_mulbench(int ilp, int iters, int blocks, int threads, float* ms_out) {
+    uint32_t h_in[24];
+    for (int i = 0; i < 24; i++) h_in[i] = 0x9e3779b9u * (i + 1);
+    uint32_t *d_in = nullptr, *d_out = nullptr;
+    KZG_CUDA_TRY(cudaMalloc((void**)&d_in, sizeof(h_in)));
+    KZG_CUDA_TRY(cudaMalloc((void**)&d_out, (size_t)blocks * threads * 4));
+    KZG_CUDA_TRY(cudaMemcpy(d_in, h_in, sizeof(h_in), cudaMemcpyHostToDevice));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (int rep = 0; rep < 2; rep++) {
+        cudaEventRecord(e0);
+        if (ilp == 1) mulbench_kernel<1><<<blocks, threads>>>(d_out, d_in, iters);
+        else if (ilp == 2) mulbench_kernel<2><<<blocks, threads>>>(d_out, d_in, iters);
+        else mulbench_kernel<4><<<blocks, threads>>>(d_out, d_in, iters);
+        cudaEventRecord(e1);
+        KZG_CUDA_TRY(cudaEventSynchronize(e1));
+    }
+    KZG_CUDA_TRY(cudaGetLastError());
+    cudaEventElapsedTime(ms_out, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return RET_OK;
+}
+
 template <class T>
 static int dev_copy_in(T** d, const T* h, size_t count) {
     if (!h) {

@@ -311,54 +311,14 @@ __global__ void g1_validate_kernel(G1Affine* __restrict__ out, const uint8_t* __
 }
 
 // ------------------------------------------------------------------------------------------------
-// batch challenge r
+// batch challenge r: the transcript hash runs on the host (src/host_sha256.c); the device reduces the
+// 32-byte digest mod r (hash_to_bls_field, src/common/bytes.c:123)
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_tuples_kernel(uint8_t* __restrict__ tuples, const uint8_t* __restrict__ cm, const uint8_t* __restrict__ zy, const uint8_t* __restrict__ pf, uint64_t n) {
-    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 4-byte word
-    uint64_t i = g / 40, wd = g % 40;
-    if (i >= n) return;
-    const uint32_t* src;
-    if (wd < 12)
-        src = reinterpret_cast<const uint32_t*>(cm + i * 48) + wd;
-    else if (wd < 28)
-        src = reinterpret_cast<const uint32_t*>(zy + i * 64) + (wd - 12);
-    else
-        src = reinterpret_cast<const uint32_t*>(pf + i * 48) + (wd - 28);
-    reinterpret_cast<uint32_t*>(tuples)[g] = *src;
-}
-
-// single thread: "RCKZGBATCH___V1_" || u64be(4096) || u64be(n) || n x 160 bytes
-__global__ void r_challenge_kernel(Fr* r_out, const uint8_t* __restrict__ tuples, uint64_t n) {
+__global__ void r_from_digest_kernel(Fr* r_out, const uint8_t* __restrict__ digest) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    Sha256 st;
-    sha256_init(st);
-    uint32_t w[16];
-    w[0] = 0x52434b5au; w[1] = 0x47424154u; w[2] = 0x43485f5fu; w[3] = 0x5f56315fu;  // "RCKZ" "GBAT" "CH__" "_V1_"
-    w[4] = 0; w[5] = 4096; w[6] = (uint32_t)(n >> 32); w[7] = (uint32_t)n;
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(tuples);
-    const uint64_t words = n * 40;  // payload words after the 8 header words
-    uint64_t pos = 0;               // payload words consumed
-    int fill = 8;
-    while (pos < words) {
-        while (fill < 16 && pos < words) w[fill++] = bswap32(__ldg(src + pos++));
-        if (fill == 16) {
-            sha256_block(st, w);
-            fill = 0;
-        }
-    }
-    // padding: total bytes = 32 + 160 n
-    uint64_t bits = (32 + 160 * n) * 8;
-    w[fill++] = 0x80000000u;
-    if (fill > 14) {
-        while (fill < 16) w[fill++] = 0;
-        sha256_block(st, w);
-        fill = 0;
-    }
-    while (fill < 14) w[fill++] = 0;
-    w[14] = (uint32_t)(bits >> 32);
-    w[15] = (uint32_t)bits;
-    sha256_block(st, w);
-    *r_out = fr_from_digest(st.h);
+    uint32_t h[8];
+    for (int i = 0; i < 8; i++) h[i] = be32(digest + 4 * i);
+    *r_out = fr_from_digest(h);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -502,17 +462,10 @@ int launch_g1_validate(Launch& L, G1Affine* out, const uint8_t* bytes48, uint64_
     L.count(1, "g1_validate");
     return RET_OK;
 }
-int launch_pack_tuples(Launch& L, uint8_t* tuples, const uint8_t* commitments48, const uint8_t* zy, const uint8_t* proofs48, uint64_t n) {
-    if (!n) return RET_OK;
-    pack_tuples_kernel<<<blocks_for(n * 40, 256), 256, 0, L.stream>>>(tuples, commitments48, zy, proofs48, n);
+int launch_r_from_digest(Launch& L, Fr* r, const uint8_t* digest32) {
+    r_from_digest_kernel<<<1, 32, 0, L.stream>>>(r, digest32);
     KZG_CUDA_TRY(cudaGetLastError());
-    L.count(1, "pack_tuples");
-    return RET_OK;
-}
-int launch_r_challenge(Launch& L, Fr* r, const uint8_t* tuples, uint64_t n) {
-    r_challenge_kernel<<<1, 32, 0, L.stream>>>(r, tuples, n);
-    KZG_CUDA_TRY(cudaGetLastError());
-    L.count(1, "r_challenge");
+    L.count(1, "r_from_digest");
     return RET_OK;
 }
 

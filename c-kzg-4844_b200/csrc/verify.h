@@ -31,10 +31,8 @@ int launch_evaluate(Launch& L, Fr* y, uint8_t* zy, Fr* inv_or_null, int* m_or_nu
 int launch_quotient(Launch& L, uint8_t* q_scalars, const uint8_t* blobs, const Fr* z, const Fr* y, const Fr* inv, const int* m, uint64_t n);
 // decompress + validate n points (validate_kzg_g1, bytes.c:81); bad[i*bad_stride] = 1 on failure
 int launch_g1_validate(Launch& L, G1Affine* out, const uint8_t* bytes48, uint64_t n, int* bad, int bad_stride);
-// tuples[i] = C_i || z_i || y_i || proof_i (160 B), the layout the batch challenge hashes (eip4844.c:648-660)
-int launch_pack_tuples(Launch& L, uint8_t* tuples, const uint8_t* commitments48, const uint8_t* zy, const uint8_t* proofs48, uint64_t n);
-// r = hash_to_bls_field(SHA256("RCKZGBATCH___V1_" || 4096 || n || tuples)) (eip4844.c:597-680)
-int launch_r_challenge(Launch& L, Fr* r, const uint8_t* tuples, uint64_t n);
+// r = hash_to_bls_field(digest): the batch transcript itself (eip4844.c:597-680) is hashed on the host
+int launch_r_from_digest(Launch& L, Fr* r, const uint8_t* digest32);
 // Random linear combination over tuples [first, first+n_local) with powers r^(first+i):
 //   A = sum r^i proof_i,  B = sum r^i z_i proof_i + sum r^i C_i - [sum r^i y_i] G1
 // (verify_kzg_proof_batch, eip4844.c:697-765).  use_r = false: all weights 1 (the n == 1 equation).

@@ -143,6 +143,9 @@ int ckzg_b200_profile_dump(ckzg_b200_ctx *ctx, char *buf, size_t cap);
  *   op 0: Fp mul, 1: Fp add, 2: Fp sub, 3: Fp inv(a), 4: Fr mul, 5: Fr inv(a), 6: Fp sqr
  *   operands/results are plain little-endian 32-bit limbs (12 per Fp, 8 per Fr), HOST memory. */
 int ckzg_b200_selftest_field(int op, uint32_t *out, const uint32_t *a, const uint32_t *b, uint64_t n);
+/* Fp Montgomery-multiplier throughput probe (the measured integer-pipe roofline denominator):
+ * blocks x threads threads each run `iters` rounds of `ilp` (1, 2 or 4) independent dependent-chains. */
+int ckzg_b200_selftest_mulbench(int ilp, int iters, int blocks, int threads, float *ms_out);
 /* op 0: [k]P (+Q), op 1: validate (subgroup), op 2: uncompress only; compressed points, HOST memory.
  * ok_out[i] = 1 if the input decoded/validated.  k = 8 limbs per scalar. */
 int ckzg_b200_selftest_g1(int op, uint8_t *out48, int *ok_out, const uint8_t *p48, const uint32_t *k, const uint8_t *q48, uint64_t n);

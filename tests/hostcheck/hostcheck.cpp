@@ -7,6 +7,7 @@
 #include "g1.cuh"
 #ifdef HOSTCHECK_PAIRING
 #include "pairing.cuh"
+#include "pairing_coop.cuh"
 #endif
 
 using namespace kzg;
@@ -123,6 +124,24 @@ int hc_cyclotomic_consistency(const uint8_t* p1, const uint8_t* q1) {
     Fp12 f2a = f12_frobenius(f12_frobenius(e)), f2b = f12_frobenius2(e);
     ok = ok && f6_eq(f2a.c0, f2b.c0) && f6_eq(f2a.c1, f2b.c1);
     return ok;
+}
+// the thread-cooperative schedule (pairing_coop.cuh), lanes emulated by loops
+int hc_coop_pairing_product_is_one(const uint8_t* p1, const uint8_t* q1, const uint8_t* p2, const uint8_t* q2, int negate_first, int scale) {
+    G1Affine P1, P2;
+    G2Affine Q1, Q2;
+    if (!g1a_uncompress(P1, p1) || !g1a_uncompress(P2, p2)) return -1;
+    if (!g2a_uncompress(Q1, q1) || !g2a_uncompress(Q2, q2)) return -1;
+    static G2Lines L1, L2;
+    g2_precompute_lines(L1, Q1);
+    g2_precompute_lines(L2, Q2);
+    G1 A = g1_from_affine(P1), Bp = g1_from_affine(P2);
+    if (scale) {  // exercise non-trivial ZZ/ZZZ: (2P - P) and (P + P - P)
+        if (!g1_is_inf(A)) { G1 d = g1_dbl(A); g1_madd(d, P1, true); A = d; }
+        if (!g1_is_inf(Bp)) { G1 d = g1_dbl(Bp); g1_madd(d, P2, true); Bp = d; }
+    }
+    static CoopWS ws;
+    coop_pairing_product_is_one(ws, A, &L1, Bp, &L2, negate_first != 0);
+    return ws.result;
 }
 #endif
 }

@@ -192,3 +192,22 @@ def test_pairing_host(hc):
     assert hc.hc_pairing_product_is_one(inf, g2_compress(bG2), inf, g2_compress(G2)) == 1
     assert hc.hc_pairing_product_is_one(c(aG1), g2_compress(bG2), inf, g2_compress(G2)) == 0
     assert hc.hc_cyclotomic_consistency(c(aG1), g2_compress(bG2)) == 1
+
+
+def test_cooperative_pairing_schedule_host(hc):
+    """pairing_coop.cuh (lane schedule from tools/gen_pairing_tables.py) == the serial pairing."""
+    rnd = random.Random(8)
+    G1, G2 = B.G1_GEN_J, B.G2_GEN_J
+    c = lambda p: B.g1_compress(p)
+    inf = c(B.G1_INF)
+    for scale in (0, 1):
+        a, b = rnd.randrange(1, R), rnd.randrange(1, R)
+        aG1, bG2, abG1 = B.g1_mul(G1, a), B.g2_mul(G2, b), B.g1_mul(G1, a * b % R)
+        # negate_first: e(-abG1, G2) * e(aG1, bG2) == 1
+        assert hc.hc_coop_pairing_product_is_one(c(abG1), g2_compress(G2), c(aG1), g2_compress(bG2), 1, scale) == 1
+        assert hc.hc_coop_pairing_product_is_one(c(abG1), g2_compress(G2), c(aG1), g2_compress(bG2), 0, scale) == 0
+        assert hc.hc_coop_pairing_product_is_one(c(B.g1_neg(abG1)), g2_compress(G2), c(aG1), g2_compress(bG2), 0, scale) == 1
+        wrong = B.g1_mul(G1, (a * b + 1) % R)
+        assert hc.hc_coop_pairing_product_is_one(c(wrong), g2_compress(G2), c(aG1), g2_compress(bG2), 1, scale) == 0
+        assert hc.hc_coop_pairing_product_is_one(inf, g2_compress(G2), inf, g2_compress(bG2), 1, scale) == 1
+        assert hc.hc_coop_pairing_product_is_one(inf, g2_compress(G2), c(aG1), g2_compress(bG2), 1, scale) == 0

@@ -1,0 +1,70 @@
+#!/usr/bin/env python3
+"""GPU-side probes (run under gpurun): Montgomery-multiplier throughput (the measured integer-pipe
+roofline denominator) and MSM accumulate register-cap variants.  Prints JSON lines."""
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def mulbench():
+    import __graft_entry__ as entry
+
+    mod = entry.load_package()
+    lib = mod.lib()
+    lib.ckzg_b200_selftest_mulbench.restype = C.c_int
+    out = []
+    iters = 2000
+    for threads in (128, 256):
+        for bps in (1, 2, 4, 8):  # blocks per SM
+            for ilp in (1, 2, 4):
+                ms = C.c_float(0)
+                blocks = 148 * bps
+                rc = lib.ckzg_b200_selftest_mulbench(ilp, iters, blocks, threads, C.byref(ms))
+                muls = blocks * threads * iters * ilp
+                out.append({"threads": threads, "blocks_per_sm": bps, "ilp": ilp, "ms": ms.value, "fp_mul_per_s": muls / (ms.value * 1e-3),
+                            "mac_per_s": 300 * muls / (ms.value * 1e-3), "rc": rc})
+    best = max(out, key=lambda r: r["mac_per_s"])
+    print(json.dumps({"probe": "mulbench", "best": best, "all": out}))
+
+
+def commit_variant():
+    import numpy as np
+    import torch
+
+    import __graft_entry__ as entry
+
+    mod = entry.load_package()
+    ts = mod.load_trusted_setup()
+    sys.path.insert(0, ROOT)
+    import bench
+
+    n = 1024
+    blobs = torch.from_numpy(bench.synth_blobs(n, 99)).cuda()
+    out = torch.empty(48 * n, dtype=torch.uint8, device="cuda")
+    for _ in range(2):
+        mod.blob_to_kzg_commitment_device(out.data_ptr(), blobs.data_ptr(), n, ts)
+    mod.profile_enable(ts, True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        mod.blob_to_kzg_commitment_device(out.data_ptr(), blobs.data_ptr(), n, ts)
+    dt = (time.perf_counter() - t0) / 3
+    prof = mod.profile_dump(ts)
+    print(json.dumps({"probe": "commit_variant", "variant": os.environ.get("CKZG_B200_ACC_VARIANT", "3"), "blobs_per_s": n / dt, "ms_per_call": dt * 1e3,
+                      "kernels_ms_per_call": {k: v[0] / 3 for k, v in prof["kernels"].items()}}))
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "commit":
+        commit_variant()
+    else:
+        mulbench()
+        for v in ("3", "4", "5"):
+            env = dict(os.environ, CKZG_B200_ACC_VARIANT=v)
+            subprocess.call([sys.executable, os.path.abspath(__file__), "commit"], env=env)

@@ -18,8 +18,10 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py --steps 1 --warmup 1 --blobs 1024 --no-extra --no-cpu-baseline > $OUT/ncu_bench_$TAG.log 2>&1
 tail -2 $OUT/ncu_bench_$TAG.log
 if [ -n "$KREGEX" ]; then
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$KREGEX -s 2 -c 2 -o $OUT/prof_$TAG \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$KREGEX -s 1 -c 1 -o $OUT/prof_$TAG \
       python bench.py --steps 1 --warmup 1 --blobs 512 --no-extra --no-cpu-baseline > $OUT/ncu_full_$TAG.log 2>&1
   tail -2 $OUT/ncu_full_$TAG.log
 fi
+echo "== probes" | tee $OUT/probe_$TAG.log
+timeout 600 python tools/gpu_probe.py 2>&1 | tail -8 | cut -c1-1500 | tee -a $OUT/probe_$TAG.log
 echo done
