@@ -12,9 +12,13 @@
 //     (4096 adds + 1024-bucket reduction) + 250 doublings);
 //   * kernel 1 (msm_sort): one CTA per blob turns the blob's big-endian scalars into signed digits and
 //     counting-sorts the (window, point) pairs by bucket in shared memory -> per-bucket lists;
-//   * kernel 2 (msm_accumulate): ONE THREAD PER BUCKET walks its list and folds table points into an
-//     XYZZ accumulator held in registers (8M+2S each).  No atomics, no shared-memory buckets, no
-//     collisions; the grid is (blobs x 1024 x parts) threads so a batch fills all 148 SMs;
+//   * kernel 2 (msm_accumulate): ONE THREAD PER WORK ITEM = (bucket, slice of at most `cap` list
+//     entries) walks its slice and folds table points into an XYZZ accumulator held in registers
+//     (8M+2S each).  No atomics, no shared-memory buckets, no collisions.  Slicing matters: the top
+//     window holds only bits 253..254 of the scalar, so its 4096 digits all land in buckets 0..3 --
+//     with one thread per bucket those four threads ran 12x longer than the rest (ncu r01b: 20.5 of 32
+//     lanes active, 3.3x spread of issued instructions across SMSPs).  `cap` also shrinks for small
+//     batches so that a single blob still spreads over the whole GPU;
 //   * kernel 3 (msm_reduce): per blob, sum_k k*B_k with 8-bucket running sums per thread, a small
 //     scalar multiplication for the chunk offset and a shared-memory tree.
 #include <stdlib.h>
@@ -98,7 +102,8 @@ __device__ __forceinline__ void store_g1(G1* p, const G1& a) {
 constexpr int SORT_THREADS = 256;
 
 __global__ void __launch_bounds__(SORT_THREADS) msm_sort_kernel(
-    uint32_t* __restrict__ entries, uint32_t* __restrict__ starts, const uint8_t* __restrict__ scalars, bool big_endian, int* __restrict__ bad
+    uint32_t* __restrict__ entries, uint32_t* __restrict__ starts, uint32_t* __restrict__ item_start, uint16_t* __restrict__ item_bucket,
+    const uint8_t* __restrict__ scalars, bool big_endian, int* __restrict__ bad, uint32_t cap, uint32_t max_items
 ) {
     __shared__ uint32_t hist[MSM_NB];
     __shared__ uint32_t warp_sums[SORT_THREADS / 32];
@@ -149,6 +154,39 @@ __global__ void __launch_bounds__(SORT_THREADS) msm_sort_kernel(
     st[4 * tid + 2] = excl + c0 + c1;
     st[4 * tid + 3] = excl + c0 + c1 + c2;
     if (tid == SORT_THREADS - 1) st[MSM_NB] = excl + tsum;
+    // work items: bucket b is cut into ceil(count_b / cap) slices (at least one); second scan
+    {
+        uint32_t p0 = c0 ? (c0 + cap - 1) / cap : 1, p1 = c1 ? (c1 + cap - 1) / cap : 1;
+        uint32_t p2 = c2 ? (c2 + cap - 1) / cap : 1, p3 = c3 ? (c3 + cap - 1) / cap : 1;
+        uint32_t ps = p0 + p1 + p2 + p3, pin = ps;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(0xffffffffu, pin, o);
+            if (lane >= o) pin += v;
+        }
+        __syncthreads();  // warp_sums reuse
+        if (lane == 31) warp_sums[warp] = pin;
+        __syncthreads();
+        uint32_t pb = 0;
+        for (int w = 0; w < warp; w++) pb += warp_sums[w];
+        uint32_t pe = pb + pin - ps;
+        uint32_t* is = item_start + (size_t)blob * (MSM_NB + 1);
+        uint16_t* ib = item_bucket + (size_t)blob * max_items;
+        uint32_t q = pe;
+        is[4 * tid] = q;
+        for (uint32_t k = 0; k < p0; k++) ib[q + k] = (uint16_t)(4 * tid);
+        q += p0;
+        is[4 * tid + 1] = q;
+        for (uint32_t k = 0; k < p1; k++) ib[q + k] = (uint16_t)(4 * tid + 1);
+        q += p1;
+        is[4 * tid + 2] = q;
+        for (uint32_t k = 0; k < p2; k++) ib[q + k] = (uint16_t)(4 * tid + 2);
+        q += p2;
+        is[4 * tid + 3] = q;
+        for (uint32_t k = 0; k < p3; k++) ib[q + k] = (uint16_t)(4 * tid + 3);
+        q += p3;
+        if (tid == SORT_THREADS - 1) is[MSM_NB] = q;
+    }
     __syncthreads();
 
     // pass 2: scatter (order inside a bucket is irrelevant: group addition commutes)
@@ -171,18 +209,60 @@ __global__ void __launch_bounds__(SORT_THREADS) msm_sort_kernel(
 // ------------------------------------------------------------------------------------------------
 constexpr int ACC_THREADS = 128;
 
-template <int MIN_BLOCKS>
+// out-of-line multiplier for the hot loop: keeps the loop body small enough for the instruction
+// cache (ncu r01b: "no_instruction" stalls ~1 per issue with ten multipliers inlined)
+__device__ __noinline__ Fp fp_mul_nl(Fp a, Fp b) { return mul(a, b); }
+
+// acc += +-a with every product through fp_mul_nl (same formulas as g1_madd in g1.cuh)
+__device__ __forceinline__ void g1_madd_nl(G1& acc, const G1Affine& a_in, bool negate) {
+    if (g1a_is_inf(a_in)) return;
+    G1Affine a;
+    a.x = a_in.x;
+    a.y = cneg(a_in.y, negate);
+    if (g1_is_inf(acc)) {
+        acc.x = a.x;
+        acc.y = a.y;
+        acc.zz = Fp::one();
+        acc.zzz = Fp::one();
+        return;
+    }
+    Fp U2 = fp_mul_nl(a.x, acc.zz);
+    Fp S2 = fp_mul_nl(a.y, acc.zzz);
+    Fp Pd = sub(U2, acc.x);
+    Fp Rd = sub(S2, acc.y);
+    if (is_zero(Pd)) {
+        if (is_zero(Rd))
+            acc = g1_dbl_affine(a);
+        else
+            acc = g1_inf();
+        return;
+    }
+    Fp PP = fp_mul_nl(Pd, Pd);
+    Fp PPP = fp_mul_nl(Pd, PP);
+    Fp Q = fp_mul_nl(acc.x, PP);
+    Fp X3 = sub(sub(fp_mul_nl(Rd, Rd), PPP), dbl(Q));
+    Fp Y3 = sub(fp_mul_nl(Rd, sub(Q, X3)), fp_mul_nl(acc.y, PPP));
+    acc.x = X3;
+    acc.y = Y3;
+    acc.zz = fp_mul_nl(acc.zz, PP);
+    acc.zzz = fp_mul_nl(acc.zzz, PPP);
+}
+
+template <int MIN_BLOCKS, bool NL>
 __global__ void __launch_bounds__(ACC_THREADS, MIN_BLOCKS) msm_accumulate_kernel(
-    G1* __restrict__ buckets, const uint32_t* __restrict__ entries, const uint32_t* __restrict__ starts,
-    const G1Affine* __restrict__ table, int parts
+    G1* __restrict__ partial, const uint32_t* __restrict__ entries, const uint32_t* __restrict__ starts,
+    const uint32_t* __restrict__ item_start, const uint16_t* __restrict__ item_bucket, const G1Affine* __restrict__ table, uint32_t max_items
 ) {
-    const int bucket = blockIdx.x * ACC_THREADS + threadIdx.x;
-    const int part = blockIdx.y, blob = blockIdx.z;
+    const uint32_t item = blockIdx.x * ACC_THREADS + threadIdx.x;
+    const int blob = blockIdx.y;
+    const uint32_t* is = item_start + (size_t)blob * (MSM_NB + 1);
+    if (item >= is[MSM_NB]) return;
+    const uint32_t bucket = item_bucket[(size_t)blob * max_items + item];
+    const uint32_t first = is[bucket], np = is[bucket + 1] - first, part = item - first;
     const uint32_t* st = starts + (size_t)blob * (MSM_NB + 1);
-    uint32_t lo = st[bucket], hi = st[bucket + 1];
-    uint32_t len = hi - lo;
-    uint32_t b0 = lo + (uint32_t)(((uint64_t)len * part) / parts);
-    uint32_t b1 = lo + (uint32_t)(((uint64_t)len * (part + 1)) / parts);
+    const uint32_t lo = st[bucket], len = st[bucket + 1] - lo;
+    const uint32_t b0 = lo + (uint32_t)(((uint64_t)len * part) / np);
+    const uint32_t b1 = lo + (uint32_t)(((uint64_t)len * (part + 1)) / np);
     const uint32_t* e = entries + (size_t)blob * MSM_ENTRIES;
 
     G1 acc = g1_inf();
@@ -190,9 +270,12 @@ __global__ void __launch_bounds__(ACC_THREADS, MIN_BLOCKS) msm_accumulate_kernel
     for (uint32_t k = b0; k < b1; k++) {
         uint32_t v = __ldg(e + k);
         G1Affine a = load_affine(table + (v & 0x7fffffffu));
-        g1_madd(acc, a, (v >> 31) != 0);
+        if (NL)
+            g1_madd_nl(acc, a, (v >> 31) != 0);
+        else
+            g1_madd(acc, a, (v >> 31) != 0);
     }
-    store_g1(buckets + ((size_t)blob * parts + part) * MSM_NB + bucket, acc);
+    store_g1(partial + (size_t)blob * max_items + item, acc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -201,19 +284,22 @@ __global__ void __launch_bounds__(ACC_THREADS, MIN_BLOCKS) msm_accumulate_kernel
 constexpr int RED_THREADS = 128;
 constexpr int RED_CHUNK = MSM_NB / RED_THREADS;  // 8 buckets per thread
 
-__global__ void __launch_bounds__(RED_THREADS) msm_reduce_kernel(G1* __restrict__ result, const G1* __restrict__ buckets, int parts) {
+__global__ void __launch_bounds__(RED_THREADS) msm_reduce_kernel(G1* __restrict__ result, const G1* __restrict__ partial, const uint32_t* __restrict__ item_start,
+                                                                 uint32_t max_items) {
     __shared__ G1 sh[RED_THREADS];
     const int blob = blockIdx.x, t = threadIdx.x;
-    const G1* B = buckets + (size_t)blob * parts * MSM_NB;
+    const G1* B = partial + (size_t)blob * max_items;
+    const uint32_t* is = item_start + (size_t)blob * (MSM_NB + 1);
 
     // running sums over this thread's 8 buckets, top down:
     //   acc = sum_k (k+1) * B[8t+k],  run = sum_k B[8t+k]
     G1 run = g1_inf(), acc = g1_inf();
 #pragma unroll 1
     for (int k = RED_CHUNK - 1; k >= 0; k--) {
+        const uint32_t bk = (uint32_t)(t * RED_CHUNK + k);
 #pragma unroll 1
-        for (int p = 0; p < parts; p++) {
-            G1 b = load_g1(B + (size_t)p * MSM_NB + t * RED_CHUNK + k);
+        for (uint32_t it = is[bk]; it < is[bk + 1]; it++) {
+            G1 b = load_g1(B + it);
             g1_add_to(run, b);
         }
         g1_add_to(acc, run);
@@ -261,41 +347,56 @@ __global__ void g1_compress_kernel(uint8_t* __restrict__ out48, const G1* __rest
 // ------------------------------------------------------------------------------------------------
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-size_t msm_workspace_bytes(uint64_t n, int parts) {
-    return align256(n * MSM_ENTRIES * sizeof(uint32_t)) + align256(n * (MSM_NB + 1) * sizeof(uint32_t)) +
-           align256(n * parts * MSM_NB * sizeof(G1));
+static uint32_t msm_max_items(int cap) {
+    uint32_t m = MSM_NB + (MSM_ENTRIES + cap - 1) / cap;  // every bucket one slice + at most one extra per `cap` entries
+    return (m + ACC_THREADS - 1) / ACC_THREADS * ACC_THREADS;
+}
+
+// `cap` = most list entries one thread folds
+size_t msm_workspace_bytes(uint64_t n, int cap) {
+    uint32_t mi = msm_max_items(cap);
+    return align256(n * MSM_ENTRIES * sizeof(uint32_t)) + 2 * align256(n * (MSM_NB + 1) * sizeof(uint32_t)) + align256(n * mi * sizeof(uint16_t)) +
+           align256(n * mi * sizeof(G1));
 }
 
 int msm_pick_parts(uint64_t n) {
-    // enough threads to cover 148 SMs x 4 CTAs of 128: split bucket lists when the batch is small
-    int parts = 1;
-    while (parts < 16 && n * MSM_NB * parts < 148ull * 512ull) parts *= 2;
-    return parts;
+    // large batches: 128 entries per thread (mean bucket ~96); small ones: slice finer so that the
+    // blob still covers 148 SMs x 4 CTAs of 128 threads
+    int cap = 128;
+    while (cap > 8 && n * (MSM_NB + MSM_ENTRIES / cap) < 148ull * 512ull) cap /= 2;
+    return cap;
 }
 
-int launch_msm(Launch& L, G1* result, const uint8_t* scalars, bool big_endian_bytes, uint64_t n, const G1Affine* table, int* d_bad, void* workspace, int parts) {
+int launch_msm(Launch& L, G1* result, const uint8_t* scalars, bool big_endian_bytes, uint64_t n, const G1Affine* table, int* d_bad, void* workspace, int cap) {
     if (n == 0) return RET_OK;
+    const uint32_t mi = msm_max_items(cap);
     uint8_t* ws = (uint8_t*)workspace;
     uint32_t* entries = (uint32_t*)ws;
     ws += align256(n * MSM_ENTRIES * sizeof(uint32_t));
     uint32_t* starts = (uint32_t*)ws;
     ws += align256(n * (MSM_NB + 1) * sizeof(uint32_t));
-    G1* buckets = (G1*)ws;
+    uint32_t* item_start = (uint32_t*)ws;
+    ws += align256(n * (MSM_NB + 1) * sizeof(uint32_t));
+    uint16_t* item_bucket = (uint16_t*)ws;
+    ws += align256(n * mi * sizeof(uint16_t));
+    G1* partial = (G1*)ws;
 
-    msm_sort_kernel<<<(unsigned)n, SORT_THREADS, 0, L.stream>>>(entries, starts, scalars, big_endian_bytes, d_bad);
+    msm_sort_kernel<<<(unsigned)n, SORT_THREADS, 0, L.stream>>>(entries, starts, item_start, item_bucket, scalars, big_endian_bytes, d_bad, (uint32_t)cap, mi);
     KZG_CUDA_TRY(cudaGetLastError());
     L.count(1, "msm_sort");
-    dim3 grid(MSM_NB / ACC_THREADS, parts, (unsigned)n);
+    dim3 grid(mi / ACC_THREADS, (unsigned)n);
     static const int variant = getenv("CKZG_B200_ACC_VARIANT") ? atoi(getenv("CKZG_B200_ACC_VARIANT")) : 3;
-    if (variant == 4)
-        msm_accumulate_kernel<4><<<grid, ACC_THREADS, 0, L.stream>>>(buckets, entries, starts, table, parts);
-    else if (variant == 5)
-        msm_accumulate_kernel<5><<<grid, ACC_THREADS, 0, L.stream>>>(buckets, entries, starts, table, parts);
+    if (variant == 13)
+        msm_accumulate_kernel<3, true><<<grid, ACC_THREADS, 0, L.stream>>>(partial, entries, starts, item_start, item_bucket, table, mi);
+    else if (variant == 14)
+        msm_accumulate_kernel<4, true><<<grid, ACC_THREADS, 0, L.stream>>>(partial, entries, starts, item_start, item_bucket, table, mi);
+    else if (variant == 4)
+        msm_accumulate_kernel<4, false><<<grid, ACC_THREADS, 0, L.stream>>>(partial, entries, starts, item_start, item_bucket, table, mi);
     else
-        msm_accumulate_kernel<3><<<grid, ACC_THREADS, 0, L.stream>>>(buckets, entries, starts, table, parts);
+        msm_accumulate_kernel<3, false><<<grid, ACC_THREADS, 0, L.stream>>>(partial, entries, starts, item_start, item_bucket, table, mi);
     KZG_CUDA_TRY(cudaGetLastError());
     L.count(1, "msm_accumulate");
-    msm_reduce_kernel<<<(unsigned)n, RED_THREADS, 0, L.stream>>>(result, buckets, parts);
+    msm_reduce_kernel<<<(unsigned)n, RED_THREADS, 0, L.stream>>>(result, partial, item_start, mi);
     KZG_CUDA_TRY(cudaGetLastError());
     L.count(1, "msm_reduce");
     return RET_OK;

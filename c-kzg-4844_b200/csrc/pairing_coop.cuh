@@ -37,7 +37,15 @@ constexpr int COOP_NREG = 8;
 #define COOP_END }
 #endif
 
+// lane schedules copied into shared memory at kernel start (a few KB; constant-bank reads through
+// generic pointers were the slow part of the first version)
+struct CoopTables {
+    int16_t off[4][3][56];   // [op][x/y/o][...]
+    int8_t xt[4][160], yt[4][160], ot[4][336];
+};
+
 struct CoopWS {
+    CoopTables tb;
     Fp prod[54];
     Fp reg[COOP_NREG][12];
     Fp line[2][5];  // per pair: A.c0*s, A.c1*s, B.c0*xs, B.c1*xs, ys
@@ -63,14 +71,37 @@ struct CoopOp {
     const int16_t *xo, *yo, *oo;
     const int8_t *xt, *yt, *ot;
 };
-KZG_HD CoopOp coop_table_mul() { return CoopOp{COOP_MUL_NPROD, COOP_MUL_XOFF, COOP_MUL_YOFF, COOP_MUL_OOFF, COOP_MUL_XT, COOP_MUL_YT, COOP_MUL_OT}; }
-KZG_HD CoopOp coop_table_sqr() { return CoopOp{COOP_SQR_NPROD, COOP_SQR_XOFF, COOP_SQR_YOFF, COOP_SQR_OOFF, COOP_SQR_XT, COOP_SQR_YT, COOP_SQR_OT}; }
-KZG_HD CoopOp coop_table_line() { return CoopOp{COOP_LINE_NPROD, COOP_LINE_XOFF, COOP_LINE_YOFF, COOP_LINE_OOFF, COOP_LINE_XT, COOP_LINE_YT, COOP_LINE_OT}; }
-KZG_HD CoopOp coop_table_cyc() { return CoopOp{COOP_CYC_NPROD, COOP_CYC_XOFF, COOP_CYC_YOFF, COOP_CYC_OOFF, COOP_CYC_XT, COOP_CYC_YT, COOP_CYC_OT}; }
+enum { COOP_OP_MUL = 0, COOP_OP_SQR = 1, COOP_OP_LINE = 2, COOP_OP_CYC = 3 };
+
+KZG_HD void coop_copy_table(CoopTables& tb, int op, int lane, int nprod, const int16_t* xo, const int16_t* yo, const int16_t* oo, const int8_t* xt, const int8_t* yt,
+                            const int8_t* ot) {
+    for (int i = lane; i <= nprod; i += COOP_LANES) {
+        tb.off[op][0][i] = xo[i];
+        tb.off[op][1][i] = yo[i];
+    }
+    for (int i = lane; i <= 12; i += COOP_LANES) tb.off[op][2][i] = oo[i];
+    for (int i = lane; i < xo[nprod]; i += COOP_LANES) tb.xt[op][i] = xt[i];
+    for (int i = lane; i < yo[nprod]; i += COOP_LANES) tb.yt[op][i] = yt[i];
+    for (int i = lane; i < oo[12]; i += COOP_LANES) tb.ot[op][i] = ot[i];
+}
+// must run once before any coop_run
+KZG_HD void coop_init_tables(CoopWS& ws) {
+    COOP_BEGIN
+    coop_copy_table(ws.tb, COOP_OP_MUL, lane, COOP_MUL_NPROD, COOP_MUL_XOFF, COOP_MUL_YOFF, COOP_MUL_OOFF, COOP_MUL_XT, COOP_MUL_YT, COOP_MUL_OT);
+    coop_copy_table(ws.tb, COOP_OP_SQR, lane, COOP_SQR_NPROD, COOP_SQR_XOFF, COOP_SQR_YOFF, COOP_SQR_OOFF, COOP_SQR_XT, COOP_SQR_YT, COOP_SQR_OT);
+    coop_copy_table(ws.tb, COOP_OP_LINE, lane, COOP_LINE_NPROD, COOP_LINE_XOFF, COOP_LINE_YOFF, COOP_LINE_OOFF, COOP_LINE_XT, COOP_LINE_YT, COOP_LINE_OT);
+    coop_copy_table(ws.tb, COOP_OP_CYC, lane, COOP_CYC_NPROD, COOP_CYC_XOFF, COOP_CYC_YOFF, COOP_CYC_OOFF, COOP_CYC_XT, COOP_CYC_YT, COOP_CYC_OT);
+    COOP_END
+}
+KZG_HD CoopOp coop_table(const CoopWS& ws, int op) {
+    const int np[4] = {COOP_MUL_NPROD, COOP_SQR_NPROD, COOP_LINE_NPROD, COOP_CYC_NPROD};
+    return CoopOp{np[op], ws.tb.off[op][0], ws.tb.off[op][1], ws.tb.off[op][2], ws.tb.xt[op], ws.tb.yt[op], ws.tb.ot[op]};
+}
 
 // dst = op(a, b); dst may alias a or b (outputs only read the products, and -- cyclotomic square --
 // the SAME coefficient of a that the lane overwrites).
-KZG_HD void coop_run(CoopWS& ws, const CoopOp& T, Fp* dst, const Fp* a, const Fp* b) {
+KZG_HD_NOINLINE void coop_run(CoopWS& ws, int op, Fp* dst, const Fp* a, const Fp* b) {
+    const CoopOp T = coop_table(ws, op);
     COOP_BEGIN
     for (int L = lane; L < T.nprod; L += COOP_LANES) {
         Fp x = coop_sum_inputs(T.xt, T.xo[L], T.xo[L + 1], a, b);
@@ -92,13 +123,13 @@ KZG_HD void coop_run(CoopWS& ws, const CoopOp& T, Fp* dst, const Fp* a, const Fp
     COOP_END
 }
 
-KZG_HD void coop_mul(CoopWS& ws, int d, int a, int b) { coop_run(ws, coop_table_mul(), ws.reg[d], ws.reg[a], ws.reg[b]); }
-KZG_HD void coop_sqr(CoopWS& ws, int d, int a) { coop_run(ws, coop_table_sqr(), ws.reg[d], ws.reg[a], ws.reg[a]); }
-KZG_HD void coop_cyc(CoopWS& ws, int d, int a) { coop_run(ws, coop_table_cyc(), ws.reg[d], ws.reg[a], ws.reg[a]); }
-KZG_HD void coop_line(CoopWS& ws, int d, int a, int pair) { coop_run(ws, coop_table_line(), ws.reg[d], ws.reg[a], ws.line[pair]); }
+KZG_HD void coop_mul(CoopWS& ws, int d, int a, int b) { coop_run(ws, COOP_OP_MUL, ws.reg[d], ws.reg[a], ws.reg[b]); }
+KZG_HD void coop_sqr(CoopWS& ws, int d, int a) { coop_run(ws, COOP_OP_SQR, ws.reg[d], ws.reg[a], ws.reg[a]); }
+KZG_HD void coop_cyc(CoopWS& ws, int d, int a) { coop_run(ws, COOP_OP_CYC, ws.reg[d], ws.reg[a], ws.reg[a]); }
+KZG_HD void coop_line(CoopWS& ws, int d, int a, int pair) { coop_run(ws, COOP_OP_LINE, ws.reg[d], ws.reg[a], ws.line[pair]); }
 
 // conjugation over Fp6: negate the coefficients of the odd powers of w
-KZG_HD void coop_conj(CoopWS& ws, int d, int a) {
+KZG_HD_NOINLINE void coop_conj(CoopWS& ws, int d, int a) {
     COOP_BEGIN
     if (lane < 12) {
         int k = lane >> 1;
@@ -106,7 +137,7 @@ KZG_HD void coop_conj(CoopWS& ws, int d, int a) {
     }
     COOP_END
 }
-KZG_HD void coop_copy(CoopWS& ws, int d, int a) {
+KZG_HD_NOINLINE void coop_copy(CoopWS& ws, int d, int a) {
     COOP_BEGIN
     if (lane < 12) ws.reg[d][lane] = ws.reg[a][lane];
     COOP_END
@@ -117,7 +148,7 @@ KZG_HD void coop_set_one(CoopWS& ws, int d) {
     COOP_END
 }
 // a^(p^power), power = 1 or 2; d != a.  Lane k < 6 owns the Fp2 coefficient of w^k.
-KZG_HD void coop_frobenius(CoopWS& ws, int d, int a, int power) {
+KZG_HD_NOINLINE void coop_frobenius(CoopWS& ws, int d, int a, int power) {
     COOP_BEGIN
     if (lane < 6) {
         Fp2 c;
@@ -155,7 +186,7 @@ KZG_HD void coop_from_tower(Fp* c, const Fp12& r) {
     c[10] = r.c1.c2.c0; c[11] = r.c1.c2.c1;
 }
 // the one inversion of the final exponentiation: serial on lane 0
-KZG_HD void coop_inv(CoopWS& ws, int d, int a) {
+KZG_HD_NOINLINE void coop_inv(CoopWS& ws, int d, int a) {
     COOP_BEGIN
     if (lane == 0) {
         Fp12 v = coop_to_tower(ws.reg[a]);
@@ -185,7 +216,7 @@ KZG_HD void coop_load_points(CoopWS& ws, const G1& P1, const G2Lines* L1, const 
 }
 
 // line k of both pairs, evaluated at the (scaled) points -> ws.line
-KZG_HD void coop_prepare_lines(CoopWS& ws, const G2Lines* L1, const G2Lines* L2, int k) {
+KZG_HD_NOINLINE void coop_prepare_lines(CoopWS& ws, const G2Lines* L1, const G2Lines* L2, int k) {
     COOP_BEGIN
     if (lane < 10) {
         int pair = lane / 5, j = lane % 5;
@@ -202,7 +233,7 @@ KZG_HD void coop_prepare_lines(CoopWS& ws, const G2Lines* L1, const G2Lines* L2,
 }
 
 // reg[d] = reg[s]^z for the (negative) curve parameter; d != s; reg[s] in the cyclotomic subgroup
-KZG_HD void coop_pow_x(CoopWS& ws, int d, int s) {
+KZG_HD_NOINLINE void coop_pow_x(CoopWS& ws, int d, int s) {
     coop_copy(ws, d, s);
     const uint64_t z = BLS_X_ABS;
     for (int b = 62; b >= 0; b--) {
@@ -215,6 +246,7 @@ KZG_HD void coop_pow_x(CoopWS& ws, int d, int s) {
 // ws.result = [ e(+-P1, Q1) * e(P2, Q2) == 1 ]
 KZG_HD void coop_pairing_product_is_one(CoopWS& ws, const G1& P1, const G2Lines* L1, const G1& P2, const G2Lines* L2, bool negate_first) {
     enum { F = 0, E = 1, T0 = 2, T1 = 3, T2 = 4, T3 = 5, X = 6, Y = 7 };
+    coop_init_tables(ws);
     coop_load_points(ws, P1, L1, P2, L2, negate_first);
     const bool use0 = ws.use[0] != 0, use1 = ws.use[1] != 0;
     // ---- Miller loop ----

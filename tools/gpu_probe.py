@@ -65,6 +65,6 @@ if __name__ == "__main__":
         commit_variant()
     else:
         mulbench()
-        for v in ("3", "4", "5"):
+        for v in ("3", "13", "4", "14"):
             env = dict(os.environ, CKZG_B200_ACC_VARIANT=v)
             subprocess.call([sys.executable, os.path.abspath(__file__), "commit"], env=env)
