@@ -85,6 +85,50 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* d_blobs, const uint8_t* 
     return RET_OK;
 }
 
+// Same stage for HOST blobs: the 128 KiB-per-blob upload is cut into chunks on a second stream and the
+// per-blob kernels of chunk k run while chunk k+1 is still crossing PCIe (copy engine || SMs).
+int verify_stage1_pipelined(Call& call, Stage1& s, const uint8_t* h_blobs, const uint8_t* d_cm, const uint8_t* d_pf, uint64_t n) {
+    Launch L = call.launch();
+    uint8_t* d_blobs;
+    TRY(call.alloc(&d_blobs, n * BLOB_BYTES));
+    TRY(call.alloc(&s.cm, n));
+    TRY(call.alloc(&s.pf, n));
+    TRY(call.alloc(&s.z, n));
+    TRY(call.alloc(&s.y, n));
+    TRY(call.alloc(&s.zy, n * 64));
+    TRY(call.alloc(&s.bad, 1));
+    KZG_CUDA_TRY(cudaMemsetAsync(s.bad, 0, sizeof(int), call.stream));
+    cudaStream_t copy;
+    cudaEvent_t ready;
+    KZG_CUDA_TRY(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+    // the buffers come from call.stream's pool: the copy stream must not start before the allocation point
+    KZG_CUDA_TRY(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    KZG_CUDA_TRY(cudaEventRecord(ready, call.stream));
+    KZG_CUDA_TRY(cudaStreamWaitEvent(copy, ready, 0));
+    cudaEventDestroy(ready);
+    TRY(launch_g1_validate(L, s.cm, d_cm, n, s.bad, 0));
+    TRY(launch_g1_validate(L, s.pf, d_pf, n, s.bad, 0));
+    const uint64_t CH = 256;
+    int rc = RET_OK;
+    for (uint64_t off = 0; off < n && rc == RET_OK; off += CH) {
+        uint64_t m = (n - off < CH) ? n - off : CH;
+        cudaEvent_t ev;
+        if (cudaMemcpyAsync(d_blobs + off * BLOB_BYTES, h_blobs + off * BLOB_BYTES, m * BLOB_BYTES, cudaMemcpyHostToDevice, copy) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+            rc = RET_ERROR;
+            break;
+        }
+        cudaEventRecord(ev, copy);
+        cudaStreamWaitEvent(call.stream, ev, 0);
+        cudaEventDestroy(ev);
+        if ((rc = launch_blob_challenges(L, s.z + off, s.zy + off * 64, d_blobs + off * BLOB_BYTES, d_cm + off * 48, m))) break;
+        rc = launch_evaluate(L, s.y + off, s.zy + off * 64, nullptr, nullptr, d_blobs + off * BLOB_BYTES, s.z + off, m, s.bad, 0);
+    }
+    cudaStreamSynchronize(copy);  // before the pool frees d_blobs at the end of the call
+    cudaStreamDestroy(copy);
+    return rc;
+}
+
 // r = hash_to_bls_field(SHA256("RCKZGBATCH___V1_" || u64be(4096) || u64be(n) || n x (C || z || y || proof)))
 // (compute_r_powers_for_verify_kzg_proof_batch, eip4844.c:612-668).  The transcript is one serial hash
 // chain: hashed on the host (src/host_sha256.c explains why); the 32-byte digest goes back to the
@@ -201,11 +245,15 @@ int ckzg_b200_verify_blob_kzg_proof_batch(ckzg_b200_ctx* ctx, int* ok, const uin
     if (!call.ok) return RET_ERROR;
     Launch L = call.launch();
     const uint8_t *d_blobs, *d_cm, *d_pf;
-    TRY(call.stage_in(&d_blobs, blobs, n * BLOB_BYTES, mem));
     TRY(call.stage_in(&d_cm, commitments, n * 48, mem));
     TRY(call.stage_in(&d_pf, proofs, n * 48, mem));
     Stage1 s;
-    TRY(verify_stage1(call, s, d_blobs, d_cm, d_pf, n));
+    if (mem == CKZG_B200_HOST && n > 256) {
+        TRY(verify_stage1_pipelined(call, s, blobs, d_cm, d_pf, n));
+    } else {
+        TRY(call.stage_in(&d_blobs, blobs, n * BLOB_BYTES, mem));
+        TRY(verify_stage1(call, s, d_blobs, d_cm, d_pf, n));
+    }
     // the reference stops at the first invalid input (eip4844.c:813-831) before any pairing work
     int bad = 0;
     bool use_r = n > 1;  // n == 1: the single-proof equation, no challenge (eip4844.c:798)

@@ -385,7 +385,7 @@ int launch_msm(Launch& L, G1* result, const uint8_t* scalars, bool big_endian_by
     KZG_CUDA_TRY(cudaGetLastError());
     L.count(1, "msm_sort");
     dim3 grid(mi / ACC_THREADS, (unsigned)n);
-    static const int variant = getenv("CKZG_B200_ACC_VARIANT") ? atoi(getenv("CKZG_B200_ACC_VARIANT")) : 3;
+    static const int variant = getenv("CKZG_B200_ACC_VARIANT") ? atoi(getenv("CKZG_B200_ACC_VARIANT")) : 14;  // r01c probe: 14 (noinline multiplier, 128 regs) fastest
     if (variant == 13)
         msm_accumulate_kernel<3, true><<<grid, ACC_THREADS, 0, L.stream>>>(partial, entries, starts, item_start, item_bucket, table, mi);
     else if (variant == 14)

@@ -198,3 +198,18 @@ def test_verify_batch_sharded_stages(gpu, batch64):
     bad = list(prs)
     bad[20] = prs[21]
     assert run(bad) is False
+
+
+def test_verify_batch_pipelined_upload_path(gpu, batch64):
+    """n > 256 host blobs take the chunked-upload path (copy stream || per-blob kernels)."""
+    blobs, cms, prs = batch64
+    reps = 5  # 320 tuples (duplicates are legal input)
+    B, C_, P_ = b"".join(blobs) * reps, b"".join(cms) * reps, b"".join(prs) * reps
+    assert gpu.verify_blob_kzg_proof_batch(B, C_, P_) is True
+    bad = bytearray(P_)
+    bad[48 * 300 : 48 * 301] = prs[0]  # tuple 300 is blob 44: wrong proof
+    assert gpu.verify_blob_kzg_proof_batch(B, C_, bytes(bad)) is False
+    nb = bytearray(B)
+    nb[131072 * 299 + 64 : 131072 * 299 + 96] = (0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001).to_bytes(32, "big")
+    with pytest.raises(ref_lib.BadArgs):
+        gpu.verify_blob_kzg_proof_batch(bytes(nb), C_, P_)

@@ -60,11 +60,32 @@ def commit_variant():
                       "kernels_ms_per_call": {k: v[0] / 3 for k, v in prof["kernels"].items()}}))
 
 
+def single_commit():
+    import __graft_entry__ as entry
+    import bench
+
+    mod = entry.load_package()
+    ts = mod.load_trusted_setup()
+    blob = bench.synth_blobs(1, 5).tobytes()
+    for _ in range(3):
+        mod.blob_to_kzg_commitment(blob, ts)
+    mod.profile_enable(ts, True)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        mod.blob_to_kzg_commitment(blob, ts)
+    dt = (time.perf_counter() - t0) / 10
+    prof = mod.profile_dump(ts)
+    print(json.dumps({"probe": "single_commit", "ms_per_call_wall": dt * 1e3, "device_ms_per_call": prof["call_ms"] / 10, "kernels_ms_per_call": {k: v[0] / 10 for k, v in prof["kernels"].items()}}))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "commit":
+    if len(sys.argv) > 1 and sys.argv[1] == "single":
+        single_commit()
+    elif len(sys.argv) > 1 and sys.argv[1] == "commit":
         commit_variant()
     else:
         mulbench()
+        subprocess.call([sys.executable, os.path.abspath(__file__), "single"])
         for v in ("3", "13", "4", "14"):
             env = dict(os.environ, CKZG_B200_ACC_VARIANT=v)
             subprocess.call([sys.executable, os.path.abspath(__file__), "commit"], env=env)
