@@ -1,0 +1,36 @@
+// Internal interface of the EIP-7594 side of the engine (cells.cu, fk20.cu, recover.cu).
+#pragma once
+#include "engine.h"
+
+namespace kzg {
+
+constexpr int CELLS_EXT = 128;        // CELLS_PER_EXT_BLOB (src/eip7594/cell.h:37)
+constexpr int CELL_FR = 64;           // FIELD_ELEMENTS_PER_CELL (cell.h:28)
+constexpr int CELL_BYTES = 2048;      // BYTES_PER_CELL
+constexpr int FK_POINTS = CELLS_EXT * CELL_FR;  // 8192 fixed bases X^[j][i] (x_ext_fft_columns, setup.c:272-289)
+
+// Fixed-base tables for the 128 x MSM(64) of FK20: T[p][w][m] = (m+1) * 2^(8w) * X^_p, affine,
+// p = j*64 + i, w < 32 windows of 8 signed bits, m < 128.  3.2 GB of HBM buys a pure
+// gather-and-add MSM: 2048 mixed additions, no buckets, no doublings (the role the reference gives
+// to `precompute`, setup.c:291-323 / README.md:110-143 -- 96 MiB at precompute=8).
+constexpr int FK_C = 8;
+constexpr int FK_W = 32;
+constexpr int FK_M = 1 << (FK_C - 1);  // 128 multiples per window
+constexpr size_t FK_TABLE_POINTS = (size_t)FK_POINTS * FK_W * FK_M;
+
+// ---- cells.cu ------------------------------------------------------------------------------------
+// cells (n x 128 x 2048 B, may be null) and/or monomial coefficients (n x 4096 Fr, may be null)
+int launch_blob_to_cells(Launch& L, uint8_t* cells, Fr* mono, const uint8_t* blobs, uint64_t n, int* d_bad);
+// S[blob][j][i] = plain limbs of FFT128(c_i)[j] / 128  (fk20.c:199-209)
+int launch_fk20_scalars(Launch& L, uint32_t* S, const Fr* mono, uint64_t n);
+
+// ---- fk20.cu -------------------------------------------------------------------------------------
+// setup: X^ columns (init_fk20_multi_settings, setup.c:238-330) + the window tables
+int fk20_setup(Launch& L, Ctx* c);
+// u_brp[blob][brp7(j)] = sum_i S[blob][j][i] * X^[j][i]
+int launch_fk20_msm(Launch& L, G1* u_brp, const uint32_t* S, uint64_t n);
+// proofs[blob][128] (XYZZ, final bit-reversed order) from u_brp: unscaled inverse G1 FFT, zero the
+// upper half, forward G1 FFT (fk20.c:257-269 + eip7594.c:133)
+int launch_fk20_g1_ffts(Launch& L, G1* proofs, G1* u_brp, uint64_t n);
+
+}  // namespace kzg

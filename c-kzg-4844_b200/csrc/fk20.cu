@@ -1,0 +1,325 @@
+// FK20 cell proofs, G1 side: fixed-base tables, the 128 x MSM(64) and the two G1 FFTs.
+//
+// Replaces (paths relative to the reference tree):
+//   init_fk20_multi_settings .............. src/setup/setup.c:238-330 (x_ext_fft_columns, tables)
+//   compute_fk20_cell_proofs, phases 1b-2 .. src/eip7594/fk20.c:213-270 (MSMs, g1_ifft_unscaled, g1_fft)
+//   g1_fft_fast ........................... src/eip7594/fft.c:164-185
+//   blst_p1s_mult_wbits(_precompute) ...... blst/src/multi_scalar.c:133-262
+//
+// B200 design: the 8192 bases X^[j][i] are fixed, so setup stores every small multiple of every
+// window shift, T[p][w][m] = (m+1) 2^(8w) X^_p (3.2 GB of the 180 GB HBM).  An MSM(64) is then a
+// pure gather-and-add of 64 x 32 table points: one warp per MSM, two base points per lane, a
+// shared-memory tree at the end -- no buckets, no doublings, no sorting.  The G1 FFTs keep the
+// 128-point vector of a blob in shared memory, one butterfly per thread per stage; ordering is
+// arranged so that no permutation pass exists (MSM j stores to slot brp7(j); inverse DIT gives
+// natural order; forward DIF leaves the proofs in the bit-reversed order the API returns).
+#include "cells.h"
+
+namespace kzg {
+
+__device__ __forceinline__ G1 ld_g1(const G1* p) {
+    G1 a;
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4* d = reinterpret_cast<uint4*>(&a);
+#pragma unroll
+    for (int i = 0; i < 12; i++) d[i] = q[i];
+    return a;
+}
+__device__ __forceinline__ void st_g1(G1* p, const G1& a) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    const uint4* d = reinterpret_cast<const uint4*>(&a);
+#pragma unroll
+    for (int i = 0; i < 12; i++) q[i] = d[i];
+}
+__device__ __forceinline__ G1Affine ld_affine(const G1Affine* p) {
+    G1Affine a;
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4* d = reinterpret_cast<uint4*>(&a);
+#pragma unroll
+    for (int i = 0; i < 6; i++) d[i] = __ldg(q + i);
+    return a;
+}
+__device__ __forceinline__ Fr ld_fr2(const Fr* p) {
+    Fr r;
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ int brp7(int v) { return (int)(__brev((uint32_t)v) >> 25); }
+
+// [k]P for an XYZZ point and a plain 256-bit scalar (twiddle factors: public data)
+__device__ __noinline__ G1 g1_mul_xyzz(const G1& p, const uint32_t* k) {
+    G1 acc = g1_inf();
+    bool started = false;
+    for (int i = 7; i >= 0; i--) {
+        uint32_t w = k[i];
+#pragma unroll 1
+        for (int b = 31; b >= 0; b--) {
+            if (started) g1_dbl_to(acc);
+            if ((w >> b) & 1u) {
+                if (started)
+                    g1_add_to(acc, p);
+                else
+                    acc = p;
+                started = true;
+            }
+        }
+    }
+    return acc;
+}
+
+// twiddle w8192^idx as plain limbs
+__device__ __forceinline__ void twiddle_plain(uint32_t* k, const Fr* __restrict__ roots, int idx) { from_mont<FrTag>(k, ld_fr2(roots + idx)); }
+
+// ------------------------------------------------------------------------------------------------
+// G1 FFT over 128 points held in shared memory, 64 threads, one butterfly per thread per stage
+// ------------------------------------------------------------------------------------------------
+constexpr int GF_THREADS = 64;
+
+// inverse, decimation in time: bit-reversed input -> natural output, unscaled (g1_ifft_unscaled,
+// fft.c:227).  Only the lower 64 outputs are kept by FK20 (fk20.c:264-266), so the last stage skips
+// the discarded half.
+__device__ __forceinline__ void g1_ifft128_dit_lower(G1* sh, const Fr* __restrict__ roots, int tid) {
+#pragma unroll 1
+    for (int half = 1; half <= 64; half <<= 1) {
+        const int tw_step = (N_EXT / 2) / half;
+        int j = tid & (half - 1);
+        int i0 = ((tid - j) << 1) + j, i1 = i0 + half;
+        G1 u = sh[i0], v = sh[i1];
+        if (j != 0) {
+            uint32_t k[8];
+            twiddle_plain(k, roots, N_EXT - j * tw_step);
+            v = g1_mul_xyzz(v, k);
+        }
+        G1 s = u;
+        g1_add_to(s, v);
+        sh[i0] = s;
+        if (half != 64) {
+            G1 d = g1_neg(v);
+            g1_add_to(d, u);
+            sh[i1] = d;
+        }
+        __syncthreads();
+    }
+}
+// forward, decimation in frequency: natural input whose upper half is infinity -> bit-reversed output
+// (g1_fft, fft.c:199, on [v_0..v_63, inf x 64])
+__device__ __forceinline__ void g1_fft128_dif_upper_zero(G1* sh, const Fr* __restrict__ roots, int tid) {
+    {  // first stage: (u, inf) -> (u, [w^j] u)
+        int j = tid;  // half = 64: j = tid, i0 = tid, i1 = tid + 64
+        G1 u = sh[tid];
+        if (j != 0) {
+            uint32_t k[8];
+            twiddle_plain(k, roots, j * (N_EXT / 128));
+            u = g1_mul_xyzz(u, k);
+        }
+        sh[tid + 64] = u;
+        __syncthreads();
+    }
+#pragma unroll 1
+    for (int half = 32; half >= 1; half >>= 1) {
+        const int tw_step = (N_EXT / 2) / half;
+        int j = tid & (half - 1);
+        int i0 = ((tid - j) << 1) + j, i1 = i0 + half;
+        G1 u = sh[i0], v = sh[i1];
+        G1 s = u;
+        g1_add_to(s, v);
+        G1 d = g1_neg(v);
+        g1_add_to(d, u);
+        if (j != 0) {
+            uint32_t k[8];
+            twiddle_plain(k, roots, j * tw_step);
+            d = g1_mul_xyzz(d, k);
+        }
+        sh[i0] = s;
+        sh[i1] = d;
+        __syncthreads();
+    }
+}
+
+template <bool WITH_INVERSE>
+__global__ void __launch_bounds__(GF_THREADS) g1_fft128_kernel(G1* __restrict__ out, const G1* __restrict__ in, const Fr* __restrict__ roots) {
+    __shared__ G1 sh[128];
+    const int vec = blockIdx.x, tid = threadIdx.x;
+    sh[tid] = ld_g1(in + (size_t)vec * 128 + tid);
+    sh[tid + 64] = ld_g1(in + (size_t)vec * 128 + tid + 64);
+    __syncthreads();
+    if (WITH_INVERSE) g1_ifft128_dit_lower(sh, roots, tid);
+    g1_fft128_dif_upper_zero(sh, roots, tid);
+    st_g1(out + (size_t)vec * 128 + tid, sh[tid]);
+    st_g1(out + (size_t)vec * 128 + tid + 64, sh[tid + 64]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// setup: X^ columns and the window tables
+// ------------------------------------------------------------------------------------------------
+// xin[offset][k] = g1_monomial[4096 - 64 - 1 - offset - 64 k] for k < 63, infinity otherwise (setup.c:272-282)
+__global__ void fk_gather_x_kernel(G1* __restrict__ xin, const G1Affine* __restrict__ g1_monomial) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 64 * 128) return;
+    int offset = e >> 7, k = e & 127;
+    G1 p = g1_inf();
+    if (k < 63) p = g1_from_affine(g1_monomial[N_BLOB - 64 - 1 - offset - 64 * k]);
+    st_g1(xin + e, p);
+}
+// FFT output slot q of vector `offset` is row brp7(q):  xhat[row * 64 + offset] (affine)
+__global__ void fk_xhat_affine_kernel(G1Affine* __restrict__ xhat, const G1* __restrict__ fft_out) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 64 * 128) return;
+    int offset = e >> 7, q = e & 127;
+    G1 p = ld_g1(fft_out + e);
+    xhat[brp7(q) * 64 + offset] = g1_to_affine(p);
+}
+// bases[p][w] = 2^(8w) * xhat[p], affine
+__global__ void fk_bases_kernel(G1Affine* __restrict__ bases, const G1Affine* __restrict__ xhat) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= FK_POINTS) return;
+    G1Affine a = xhat[p];
+    bases[(size_t)p * FK_W] = a;
+    G1 acc = g1_from_affine(a);
+#pragma unroll 1
+    for (int w = 1; w < FK_W; w++) {
+#pragma unroll 1
+        for (int k = 0; k < FK_C; k++) g1_dbl_to(acc);
+        G1Affine q = g1_to_affine(acc);
+        bases[(size_t)p * FK_W + w] = q;
+        acc = g1_from_affine(q);
+    }
+}
+// table[(p*32 + w)*128 + m] = (m+1) * bases[p][w], affine; one thread per (p, w), batches of 16
+// converted with one inversion each (Montgomery's trick)
+constexpr int FK_BATCH = 16;
+__global__ void __launch_bounds__(64) fk_multiples_kernel(G1Affine* __restrict__ table, const G1Affine* __restrict__ bases) {
+    size_t pw = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pw >= (size_t)FK_POINTS * FK_W) return;
+    const G1Affine base = bases[pw];
+    G1Affine* dst = table + pw * FK_M;
+    G1 run = g1_from_affine(base);
+    G1 pts[FK_BATCH];
+    Fp pre[FK_BATCH];
+#pragma unroll 1
+    for (int m0 = 0; m0 < FK_M; m0 += FK_BATCH) {
+        Fp prod = Fp::one();
+#pragma unroll 1
+        for (int k = 0; k < FK_BATCH; k++) {
+            pts[k] = run;
+            pre[k] = prod;
+            Fp zc = mul(run.zz, run.zzz);
+            if (is_zero(zc)) zc = Fp::one();  // infinity: keep the chain invertible, emit (0,0) below
+            prod = mul(prod, zc);
+            g1_madd_to(run, base, false);
+        }
+        Fp inv = fp_inv(prod);
+#pragma unroll 1
+        for (int k = FK_BATCH - 1; k >= 0; k--) {
+            G1Affine a = g1a_inf();
+            const G1& pt = pts[k];
+            Fp zc = mul(pt.zz, pt.zzz);
+            if (!is_zero(zc)) {
+                Fp iz = mul(inv, pre[k]);  // 1 / (zz * zzz)
+                inv = mul(inv, zc);
+                a.x = mul(pt.x, mul(iz, pt.zzz));
+                a.y = mul(pt.y, mul(iz, pt.zz));
+            }
+            dst[m0 + k] = a;
+        }
+    }
+}
+
+int fk20_setup(Launch& L, Ctx* c) {
+    KZG_CUDA_TRY(cudaMalloc((void**)&c->fk_table, FK_TABLE_POINTS * sizeof(G1Affine)));
+    G1 *xin = nullptr, *xout = nullptr;
+    G1Affine *xhat = nullptr, *bases = nullptr;
+    KZG_CUDA_TRY(cudaMallocAsync((void**)&xin, 64 * 128 * sizeof(G1), L.stream));
+    KZG_CUDA_TRY(cudaMallocAsync((void**)&xout, 64 * 128 * sizeof(G1), L.stream));
+    KZG_CUDA_TRY(cudaMallocAsync((void**)&xhat, FK_POINTS * sizeof(G1Affine), L.stream));
+    KZG_CUDA_TRY(cudaMallocAsync((void**)&bases, (size_t)FK_POINTS * FK_W * sizeof(G1Affine), L.stream));
+    fk_gather_x_kernel<<<64 * 128 / 128, 128, 0, L.stream>>>(xin, c->g1_monomial);
+    KZG_CUDA_TRY(cudaGetLastError());
+    g1_fft128_kernel<false><<<64, GF_THREADS, 0, L.stream>>>(xout, xin, c->roots);
+    KZG_CUDA_TRY(cudaGetLastError());
+    fk_xhat_affine_kernel<<<64 * 128 / 64, 64, 0, L.stream>>>(xhat, xout);
+    KZG_CUDA_TRY(cudaGetLastError());
+    fk_bases_kernel<<<FK_POINTS / 64, 64, 0, L.stream>>>(bases, xhat);
+    KZG_CUDA_TRY(cudaGetLastError());
+    fk_multiples_kernel<<<(unsigned)((size_t)FK_POINTS * FK_W / 64), 64, 0, L.stream>>>((G1Affine*)c->fk_table, bases);
+    KZG_CUDA_TRY(cudaGetLastError());
+    KZG_CUDA_TRY(cudaFreeAsync(xin, L.stream));
+    KZG_CUDA_TRY(cudaFreeAsync(xout, L.stream));
+    KZG_CUDA_TRY(cudaFreeAsync(xhat, L.stream));
+    KZG_CUDA_TRY(cudaFreeAsync(bases, L.stream));
+    L.count(5, "fk20_setup");
+    return RET_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 128 x MSM(64) per blob: one warp per MSM
+// ------------------------------------------------------------------------------------------------
+constexpr int FM_WARPS = 4;
+
+__global__ void __launch_bounds__(32 * FM_WARPS) fk20_msm_kernel(G1* __restrict__ u_brp, const uint32_t* __restrict__ S, const G1Affine* __restrict__ table, uint64_t total) {
+    __shared__ G1 sh[FM_WARPS][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t msm = (uint64_t)blockIdx.x * FM_WARPS + warp;  // = blob * 128 + j
+    const bool active = msm < total;
+    G1 acc = g1_inf();
+    if (active) {
+        const int j = (int)(msm & 127);
+#pragma unroll 1
+        for (int h = 0; h < 2; h++) {
+            const int i = lane + 32 * h;
+            const uint4* sp = reinterpret_cast<const uint4*>(S + (msm * 64 + i) * 8);
+            uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
+            uint32_t s[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+            const G1Affine* tp = table + ((size_t)(j * 64 + i) * FK_W) * FK_M;
+            uint32_t carry = 0;
+#pragma unroll 1
+            for (int w = 0; w < FK_W; w++) {
+                uint32_t d = ((s[w >> 2] >> ((w & 3) * 8)) & 0xffu) + carry;
+                bool negd = d > (uint32_t)FK_M;
+                carry = negd ? 1u : 0u;
+                uint32_t mag = negd ? (256u - d) : d;
+                if (mag != 0) {
+                    G1Affine a = ld_affine(tp + (size_t)w * FK_M + (mag - 1));
+                    g1_madd_to(acc, a, negd);
+                }
+            }
+        }
+    }
+    sh[warp][lane] = acc;
+    __syncwarp();
+#pragma unroll 1
+    for (int s = 16; s > 0; s >>= 1) {
+        if (lane < s) {
+            G1 x = sh[warp][lane], y = sh[warp][lane + s];
+            g1_add_to(x, y);
+            sh[warp][lane] = x;
+        }
+        __syncwarp();
+    }
+    if (active && lane == 0) {
+        const uint64_t blob = msm >> 7;
+        st_g1(u_brp + blob * 128 + brp7((int)(msm & 127)), sh[warp][0]);
+    }
+}
+
+int launch_fk20_msm(Launch& L, G1* u_brp, const uint32_t* S, uint64_t n) {
+    if (!n) return RET_OK;
+    uint64_t total = n * 128;
+    fk20_msm_kernel<<<(unsigned)((total + FM_WARPS - 1) / FM_WARPS), 32 * FM_WARPS, 0, L.stream>>>(u_brp, S, (const G1Affine*)L.ctx->fk_table, total);
+    KZG_CUDA_TRY(cudaGetLastError());
+    L.count(1, "fk20_msm");
+    return RET_OK;
+}
+
+int launch_fk20_g1_ffts(Launch& L, G1* proofs, G1* u_brp, uint64_t n) {
+    if (!n) return RET_OK;
+    g1_fft128_kernel<true><<<(unsigned)n, GF_THREADS, 0, L.stream>>>(proofs, u_brp, L.ctx->roots);
+    KZG_CUDA_TRY(cudaGetLastError());
+    L.count(1, "fk20_g1_ffts");
+    return RET_OK;
+}
+
+}  // namespace kzg

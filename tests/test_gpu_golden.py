@@ -19,6 +19,8 @@ IMPLEMENTED = [
     "verify_kzg_proof",
     "verify_blob_kzg_proof",
     "verify_blob_kzg_proof_batch",
+    "compute_cells",
+    "compute_cells_and_kzg_proofs",
 ]
 
 
@@ -213,3 +215,20 @@ def test_verify_batch_pipelined_upload_path(gpu, batch64):
     nb[131072 * 299 + 64 : 131072 * 299 + 96] = (0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001).to_bytes(32, "big")
     with pytest.raises(ref_lib.BadArgs):
         gpu.verify_blob_kzg_proof_batch(bytes(nb), C_, P_)
+
+
+def test_cells_and_proofs_differential(gpu, ref):
+    """compute_cells_and_kzg_proofs on synthetic blobs == reference (cells AND FK20 proofs)."""
+    for b in (3, 11):
+        blob = synth_blob(b)
+        gc, gp = gpu.compute_cells_and_kzg_proofs(blob)
+        rc, rp = ref.compute_cells_and_kzg_proofs(blob)
+        assert gc == rc
+        assert gp == rp
+    # cells only / proofs only
+    blob = synth_blob(12)
+    rc, rp = ref.compute_cells_and_kzg_proofs(blob)
+    assert gpu.compute_cells_and_kzg_proofs(blob, True, False)[0] == rc
+    assert gpu.compute_cells_and_kzg_proofs(blob, False, True)[1] == rp
+    # the first 64 cells are the blob itself
+    assert rc[:131072] == blob
