@@ -44,6 +44,7 @@ static int ctx_build(Ctx* c, const uint8_t* g1_mono, const uint8_t* g1_lag, cons
     TRY(launch_msm_table(L, c->msm_table, c->g1_lagrange_brp));
     TRY(setup_g2_and_lines(call.stream, L, c, g2_mono, d_bad));
     TRY(fk20_setup(L, c));
+    TRY(recover_setup(L, c));
 
     int bad = 0;
     KZG_CUDA_TRY(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, call.stream));
@@ -69,6 +70,8 @@ static void ctx_free(Ctx* c) {
     cudaFree(c->g2_lines);
     cudaFree(c->g2_points);
     cudaFree(c->fk_table);
+    cudaFree(c->rec_shiftA);
+    cudaFree(c->rec_shiftB);
     if (prev >= 0) cudaSetDevice(prev);
     delete c;
 }
@@ -210,7 +213,5 @@ int ckzg_b200_selftest_g1(int op, uint8_t* out48, int* ok_out, const uint8_t* p4
 // ---- entry points landing later this round (link-complete; fail loudly, never fall back) --------
 extern "C" {
 #ifndef KZG_HAVE_CELLS
-int ckzg_b200_recover_cells_and_kzg_proofs_batch(ckzg_b200_ctx*, uint8_t*, uint8_t*, const uint64_t*, const uint8_t*, uint64_t, uint64_t, int, int*) { return RET_ERROR; }
-int ckzg_b200_verify_cell_kzg_proof_batch(ckzg_b200_ctx*, int*, const uint8_t*, const uint64_t*, const uint8_t*, const uint8_t*, uint64_t, int) { return RET_ERROR; }
 #endif
 }

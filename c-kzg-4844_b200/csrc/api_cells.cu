@@ -1,8 +1,13 @@
 // C ABI, EIP-7594 entry points (include/ckzg_b200.h): cells + FK20 proofs, batched over blobs.
 #include <string.h>
 
+#include <string>
+#include <unordered_map>
+
+#include "../src/host_sha256.h"
 #include "call.h"
 #include "cells.h"
+#include "verify.h"
 
 using namespace kzg;
 
@@ -82,6 +87,204 @@ int ckzg_b200_compute_cells_and_kzg_proofs_batch(ckzg_b200_ctx* ctx, uint8_t* ce
         if (s && !rc) rc = s;
     }
     return rc;
+}
+
+
+int ckzg_b200_recover_cells_and_kzg_proofs_batch(ckzg_b200_ctx* ctx, uint8_t* recovered_cells, uint8_t* recovered_proofs, const uint64_t* cell_indices, const uint8_t* cells,
+                                                 uint64_t num_cells, uint64_t n, int mem, int* status) {
+    if (!ctx || !recovered_cells || !cell_indices || !cells) return RET_BADARGS;
+    if (n == 0) return RET_OK;
+    // eip7594.c:191-213: count and index checks (host side, before anything else)
+    if (num_cells > 128 || num_cells < 64) return RET_BADARGS;
+    std::vector<int16_t> slot(n * 128, (int16_t)-1);
+    std::vector<uint8_t> present(n * 128, 0);
+    for (uint64_t b = 0; b < n; b++) {
+        const uint64_t* idx = cell_indices + b * num_cells;
+        for (uint64_t i = 0; i < num_cells; i++) {
+            if (idx[i] >= 128) return RET_BADARGS;
+            if (i > 0 && idx[i] <= idx[i - 1]) return RET_BADARGS;
+            slot[b * 128 + idx[i]] = (int16_t)i;
+            present[b * 128 + idx[i]] = 1;
+        }
+    }
+    Call call(reinterpret_cast<Ctx*>(ctx));
+    if (!call.ok) return RET_ERROR;
+    Launch L = call.launch();
+    const bool dev = mem == CKZG_B200_DEVICE;
+    const uint64_t CHUNK = 256;
+    const uint64_t chunk = n < CHUNK ? n : CHUNK;
+    const uint8_t *d_cells_in, *d_slot, *d_present;
+    TRY(call.stage_in(&d_cells_in, cells, n * num_cells * CELL_BYTES, mem));
+    TRY(call.stage_in(&d_slot, (const uint8_t*)slot.data(), slot.size() * sizeof(int16_t), CKZG_B200_HOST));
+    TRY(call.stage_in(&d_present, present.data(), present.size(), CKZG_B200_HOST));
+    int* d_bad;
+    TRY(call.alloc(&d_bad, n));
+    KZG_CUDA_TRY(cudaMemsetAsync(d_bad, 0, n * sizeof(int), call.stream));
+    uint8_t *d_cells_out, *d_proofs = nullptr, *scratch;
+    Fr* d_mono = nullptr;
+    if (dev)
+        d_cells_out = recovered_cells;
+    else
+        TRY(call.alloc(&d_cells_out, chunk * 2 * BLOB_BYTES));
+    TRY(call.alloc(&scratch, recover_scratch_bytes(chunk)));
+    if (recovered_proofs) {
+        TRY(call.alloc(&d_mono, chunk * N_BLOB));
+        if (dev)
+            d_proofs = recovered_proofs;
+        else
+            TRY(call.alloc(&d_proofs, chunk * 128 * 48));
+    }
+    for (uint64_t off = 0; off < n; off += chunk) {
+        const uint64_t m = (n - off < chunk) ? n - off : chunk;
+        uint8_t* c_out = dev ? d_cells_out + off * 2 * BLOB_BYTES : d_cells_out;
+        uint8_t* p_out = d_proofs ? (dev ? d_proofs + off * 128 * 48 : d_proofs) : nullptr;
+        TRY(launch_recover(L, c_out, d_mono, d_cells_in + off * num_cells * CELL_BYTES, (const int16_t*)d_slot + off * 128, d_present + off * 128, num_cells, m, d_bad + off,
+                           scratch));
+        if (recovered_proofs) TRY(fk20_proofs_from_mono(call, p_out, d_mono, m));
+        if (!dev) {
+            KZG_CUDA_TRY(cudaMemcpyAsync(recovered_cells + off * 2 * BLOB_BYTES, c_out, m * 2 * BLOB_BYTES, cudaMemcpyDeviceToHost, call.stream));
+            if (recovered_proofs) KZG_CUDA_TRY(cudaMemcpyAsync(recovered_proofs + off * 128 * 48, p_out, m * 128 * 48, cudaMemcpyDeviceToHost, call.stream));
+        }
+    }
+    std::vector<int> bad(n);
+    KZG_CUDA_TRY(cudaMemcpyAsync(bad.data(), d_bad, n * sizeof(int), cudaMemcpyDeviceToHost, call.stream));
+    KZG_CUDA_TRY(cudaStreamSynchronize(call.stream));
+    int rc = RET_OK;
+    for (uint64_t i = 0; i < n; i++) {
+        int s = bad[i] ? RET_BADARGS : RET_OK;
+        if (status) status[i] = s;
+        if (s && !rc) rc = s;
+    }
+    return rc;
+}
+
+
+int ckzg_b200_verify_cell_kzg_proof_batch(ckzg_b200_ctx* ctx, int* ok, const uint8_t* commitments, const uint64_t* cell_indices, const uint8_t* cells, const uint8_t* proofs,
+                                          uint64_t n, int mem) {
+    if (!ctx || !ok) return RET_BADARGS;
+    *ok = 0;
+    if (n == 0) {  // eip7594.c:852-855
+        *ok = 1;
+        return RET_OK;
+    }
+    if (!commitments || !cell_indices || !cells || !proofs) return RET_BADARGS;
+    for (uint64_t i = 0; i < n; i++)
+        if (cell_indices[i] >= 128) return RET_BADARGS;  // eip7594.c:861-864
+    Call call(reinterpret_cast<Ctx*>(ctx));
+    if (!call.ok) return RET_ERROR;
+    Launch L = call.launch();
+    const bool dev = mem == CKZG_B200_DEVICE;
+
+    // host views of the byte inputs (the transcript is hashed on the host, src/host_sha256.c)
+    std::vector<uint8_t> h_cm, h_cells, h_pf;
+    const uint8_t *hc = commitments, *hcells = cells, *hp = proofs;
+    if (dev) {
+        h_cm.resize(n * 48);
+        h_cells.resize(n * CELL_BYTES);
+        h_pf.resize(n * 48);
+        KZG_CUDA_TRY(cudaMemcpyAsync(h_cm.data(), commitments, n * 48, cudaMemcpyDeviceToHost, call.stream));
+        KZG_CUDA_TRY(cudaMemcpyAsync(h_cells.data(), cells, n * CELL_BYTES, cudaMemcpyDeviceToHost, call.stream));
+        KZG_CUDA_TRY(cudaMemcpyAsync(h_pf.data(), proofs, n * 48, cudaMemcpyDeviceToHost, call.stream));
+        KZG_CUDA_TRY(cudaStreamSynchronize(call.stream));
+        hc = h_cm.data();
+        hcells = h_cells.data();
+        hp = h_pf.data();
+    }
+    // deduplicate commitments in first-appearance order (eip7594.c:345-376)
+    std::vector<uint8_t> uniq;
+    std::vector<uint64_t> cm_index(n);
+    {
+        std::unordered_map<std::string, uint64_t> seen;
+        seen.reserve(256);
+        for (uint64_t i = 0; i < n; i++) {
+            std::string key((const char*)hc + 48 * i, 48);
+            auto it = seen.find(key);
+            if (it == seen.end()) {
+                uint64_t id = seen.size();
+                seen.emplace(std::move(key), id);
+                uniq.insert(uniq.end(), hc + 48 * i, hc + 48 * i + 48);
+                cm_index[i] = id;
+            } else {
+                cm_index[i] = it->second;
+            }
+        }
+    }
+    const uint64_t u = uniq.size() / 48;
+    // challenge transcript (eip7594.c:390-482)
+    uint8_t digest[32];
+    {
+        ckzg_host_sha256 h;
+        ckzg_host_sha256_init(&h);
+        uint8_t head[48] = {'R', 'C', 'K', 'Z', 'G', 'C', 'B', 'A', 'T', 'C', 'H', '_', '_', 'V', '1', '_'};
+        const uint64_t vals[4] = {(uint64_t)N_BLOB, (uint64_t)CELL_FR, u, n};
+        for (int v = 0; v < 4; v++)
+            for (int i = 0; i < 8; i++) head[16 + 8 * v + i] = (uint8_t)(vals[v] >> (56 - 8 * i));
+        ckzg_host_sha256_update(&h, head, 48);
+        ckzg_host_sha256_update(&h, uniq.data(), uniq.size());
+        for (uint64_t i = 0; i < n; i++) {
+            uint8_t ids[16];
+            for (int b = 0; b < 8; b++) {
+                ids[b] = (uint8_t)(cm_index[i] >> (56 - 8 * b));
+                ids[8 + b] = (uint8_t)(cell_indices[i] >> (56 - 8 * b));
+            }
+            ckzg_host_sha256_update(&h, ids, 16);
+            ckzg_host_sha256_update(&h, hcells + i * CELL_BYTES, CELL_BYTES);
+            ckzg_host_sha256_update(&h, hp + 48 * i, 48);
+        }
+        ckzg_host_sha256_final(&h, digest);
+    }
+    // CSR groupings: cells by column, cells by unique commitment
+    std::vector<uint32_t> col_start(129, 0), col_items(n), cm_start(u + 1, 0), cm_items(n);
+    for (uint64_t i = 0; i < n; i++) {
+        col_start[cell_indices[i] + 1]++;
+        cm_start[cm_index[i] + 1]++;
+    }
+    for (int c = 0; c < 128; c++) col_start[c + 1] += col_start[c];
+    for (uint64_t c = 0; c < u; c++) cm_start[c + 1] += cm_start[c];
+    {
+        std::vector<uint32_t> cc(col_start.begin(), col_start.end() - 1), mc(cm_start.begin(), cm_start.end() - 1);
+        for (uint64_t i = 0; i < n; i++) {
+            col_items[cc[cell_indices[i]]++] = (uint32_t)i;
+            cm_items[mc[cm_index[i]]++] = (uint32_t)i;
+        }
+    }
+
+    const uint8_t *d_cells, *d_pf, *d_uniq, *d_digest, *d_cs, *d_ci, *d_ms, *d_mi;
+    TRY(call.stage_in(&d_cells, cells, n * CELL_BYTES, mem));
+    TRY(call.stage_in(&d_pf, proofs, n * 48, mem));
+    TRY(call.stage_in(&d_uniq, uniq.data(), uniq.size(), CKZG_B200_HOST));
+    TRY(call.stage_in(&d_digest, digest, 32, CKZG_B200_HOST));
+    TRY(call.stage_in(&d_cs, (const uint8_t*)col_start.data(), col_start.size() * 4, CKZG_B200_HOST));
+    TRY(call.stage_in(&d_ci, (const uint8_t*)col_items.data(), col_items.size() * 4, CKZG_B200_HOST));
+    TRY(call.stage_in(&d_ms, (const uint8_t*)cm_start.data(), cm_start.size() * 4, CKZG_B200_HOST));
+    TRY(call.stage_in(&d_mi, (const uint8_t*)cm_items.data(), cm_items.size() * 4, CKZG_B200_HOST));
+    G1Affine *d_pf_pts, *d_cm_pts;
+    Fr* d_r;
+    int *d_bad, *d_ok;
+    G1* d_AB;
+    uint8_t* scratch;
+    TRY(call.alloc(&d_pf_pts, n));
+    TRY(call.alloc(&d_cm_pts, u));
+    TRY(call.alloc(&d_r, 1));
+    TRY(call.alloc(&d_bad, 1));
+    TRY(call.alloc(&d_ok, 1));
+    TRY(call.alloc(&d_AB, 2));
+    TRY(call.alloc(&scratch, verify_cells_scratch_bytes(n, u)));
+    KZG_CUDA_TRY(cudaMemsetAsync(d_bad, 0, sizeof(int), call.stream));
+    TRY(launch_r_from_digest(L, d_r, d_digest));
+    TRY(launch_g1_validate(L, d_pf_pts, d_pf, n, d_bad, 0));    // bytes_to_kzg_proof, eip7594.c:917-920
+    TRY(launch_g1_validate(L, d_cm_pts, d_uniq, u, d_bad, 0));  // bytes_to_kzg_commitment, :513
+    TRY(launch_verify_cells(L, d_AB, d_pf_pts, d_cm_pts, d_cells, d_r, (const uint32_t*)d_cs, (const uint32_t*)d_ci, (const uint32_t*)d_ms, (const uint32_t*)d_mi, n, u, d_bad,
+                            scratch));
+    int bad = 0;
+    KZG_CUDA_TRY(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, call.stream));
+    KZG_CUDA_TRY(cudaStreamSynchronize(call.stream));
+    if (bad) return RET_BADARGS;
+    // e(B, G2) == e(A, [tau^64]G2)   (eip7594.c:966)
+    TRY(launch_pairing_check(L, d_ok, d_AB + 0, d_AB + 1, nullptr, LINE_G2_TAU64, LINE_G2_GEN));
+    KZG_CUDA_TRY(cudaMemcpyAsync(ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, call.stream));
+    KZG_CUDA_TRY(cudaStreamSynchronize(call.stream));
+    return RET_OK;
 }
 
 }  // extern "C"

@@ -33,4 +33,17 @@ int launch_fk20_msm(Launch& L, G1* u_brp, const uint32_t* S, uint64_t n);
 // upper half, forward G1 FFT (fk20.c:257-269 + eip7594.c:133)
 int launch_fk20_g1_ffts(Launch& L, G1* proofs, G1* u_brp, uint64_t n);
 
+// ---- recover.cu ----------------------------------------------------------------------------------
+int recover_setup(Launch& L, Ctx* c);
+size_t recover_scratch_bytes(uint64_t n);
+// recover_cells (recovery.c:200): cells_out n x 128 x 2048 B (device), mono_out n x 4096 Fr or null
+int launch_recover(Launch& L, uint8_t* cells_out, Fr* mono_out, const uint8_t* cells_in, const int16_t* slot, const uint8_t* present, uint64_t num_cells, uint64_t n, int* d_bad,
+                   void* scratch);
+
+// ---- verify_cells.cu -----------------------------------------------------------------------------
+size_t verify_cells_scratch_bytes(uint64_t n, uint64_t u);
+// out2[0] = sum r^k pi_k, out2[1] = sum w_c C_c - [I] + sum r^k h_k^64 pi_k  (eip7594.c:825-974)
+int launch_verify_cells(Launch& L, G1* out2, const G1Affine* proofs, const G1Affine* commitments, const uint8_t* cells, const Fr* r, const uint32_t* col_start,
+                        const uint32_t* col_items, const uint32_t* cm_start, const uint32_t* cm_items, uint64_t n, uint64_t u, int* d_bad, void* scratch);
+
 }  // namespace kzg

@@ -71,6 +71,8 @@ struct Ctx {
     Fr* roots = nullptr;                  // [8193] w^i
     void* g2_lines = nullptr;             // precomputed Miller-loop lines for G2 gen, [tau]G2, [tau^64]G2
     void* g2_points = nullptr;            // [65] affine G2 (Fp2 coordinates)
+    void* rec_shiftA = nullptr;           // 7^k / 8192   (recover.cu)
+    void* rec_shiftB = nullptr;           // 7^-k / 8192
     void* fk_table = nullptr;             // FK20 fixed-base multiples, cells.h (3.2 GB)
     uint64_t precompute = 0;
 };

@@ -281,15 +281,44 @@ __global__ void __launch_bounds__(ACC_THREADS, MIN_BLOCKS) msm_accumulate_kernel
 // ------------------------------------------------------------------------------------------------
 // kernel 3: sum_b (b+1) * B_b per blob
 // ------------------------------------------------------------------------------------------------
+// Small batches use a small `cap`, so a bucket can own many partial sums (the four top-window buckets:
+// >100 each at cap 8).  One warp per bucket folds them: lane-strided serial sums + a 5-level tree.
+__global__ void __launch_bounds__(128) msm_combine_kernel(G1* __restrict__ combined, const G1* __restrict__ partial, const uint32_t* __restrict__ item_start, uint32_t max_items) {
+    __shared__ G1 sh[4][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bucket = blockIdx.x * 4 + warp, blob = blockIdx.y;
+    const uint32_t* is = item_start + (size_t)blob * (MSM_NB + 1);
+    const G1* B = partial + (size_t)blob * max_items;
+    G1 acc = g1_inf();
+#pragma unroll 1
+    for (uint32_t it = is[bucket] + lane; it < is[bucket + 1]; it += 32) {
+        G1 b = load_g1(B + it);
+        g1_add_to(acc, b);
+    }
+    sh[warp][lane] = acc;
+    __syncwarp();
+#pragma unroll 1
+    for (int s = 16; s > 0; s >>= 1) {
+        if (lane < s) {
+            G1 x = sh[warp][lane], y = sh[warp][lane + s];
+            g1_add_to(x, y);
+            sh[warp][lane] = x;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) store_g1(combined + (size_t)blob * MSM_NB + bucket, sh[warp][0]);
+}
+
 constexpr int RED_THREADS = 128;
 constexpr int RED_CHUNK = MSM_NB / RED_THREADS;  // 8 buckets per thread
 
+// item_start == nullptr: `partial` already holds one sum per bucket (msm_combine_kernel ran)
 __global__ void __launch_bounds__(RED_THREADS) msm_reduce_kernel(G1* __restrict__ result, const G1* __restrict__ partial, const uint32_t* __restrict__ item_start,
                                                                  uint32_t max_items) {
     __shared__ G1 sh[RED_THREADS];
     const int blob = blockIdx.x, t = threadIdx.x;
     const G1* B = partial + (size_t)blob * max_items;
-    const uint32_t* is = item_start + (size_t)blob * (MSM_NB + 1);
+    const uint32_t* is = item_start ? item_start + (size_t)blob * (MSM_NB + 1) : nullptr;
 
     // running sums over this thread's 8 buckets, top down:
     //   acc = sum_k (k+1) * B[8t+k],  run = sum_k B[8t+k]
@@ -297,8 +326,9 @@ __global__ void __launch_bounds__(RED_THREADS) msm_reduce_kernel(G1* __restrict_
 #pragma unroll 1
     for (int k = RED_CHUNK - 1; k >= 0; k--) {
         const uint32_t bk = (uint32_t)(t * RED_CHUNK + k);
+        const uint32_t it0 = is ? is[bk] : bk, it1 = is ? is[bk + 1] : bk + 1;
 #pragma unroll 1
-        for (uint32_t it = is[bk]; it < is[bk + 1]; it++) {
+        for (uint32_t it = it0; it < it1; it++) {
             G1 b = load_g1(B + it);
             g1_add_to(run, b);
         }
@@ -356,7 +386,7 @@ static uint32_t msm_max_items(int cap) {
 size_t msm_workspace_bytes(uint64_t n, int cap) {
     uint32_t mi = msm_max_items(cap);
     return align256(n * MSM_ENTRIES * sizeof(uint32_t)) + 2 * align256(n * (MSM_NB + 1) * sizeof(uint32_t)) + align256(n * mi * sizeof(uint16_t)) +
-           align256(n * mi * sizeof(G1));
+           align256(n * mi * sizeof(G1)) + (cap < 128 ? align256(n * MSM_NB * sizeof(G1)) : 0);
 }
 
 int msm_pick_parts(uint64_t n) {
@@ -396,9 +426,19 @@ int launch_msm(Launch& L, G1* result, const uint8_t* scalars, bool big_endian_by
         msm_accumulate_kernel<3, false><<<grid, ACC_THREADS, 0, L.stream>>>(partial, entries, starts, item_start, item_bucket, table, mi);
     KZG_CUDA_TRY(cudaGetLastError());
     L.count(1, "msm_accumulate");
-    msm_reduce_kernel<<<(unsigned)n, RED_THREADS, 0, L.stream>>>(result, partial, item_start, mi);
-    KZG_CUDA_TRY(cudaGetLastError());
-    L.count(1, "msm_reduce");
+    if (cap < 128) {
+        G1* combined = (G1*)((uint8_t*)partial + align256(n * mi * sizeof(G1)));
+        dim3 cgrid(MSM_NB / 4, (unsigned)n);
+        msm_combine_kernel<<<cgrid, 128, 0, L.stream>>>(combined, partial, item_start, mi);
+        KZG_CUDA_TRY(cudaGetLastError());
+        msm_reduce_kernel<<<(unsigned)n, RED_THREADS, 0, L.stream>>>(result, combined, nullptr, MSM_NB);
+        KZG_CUDA_TRY(cudaGetLastError());
+        L.count(2, "msm_reduce");
+    } else {
+        msm_reduce_kernel<<<(unsigned)n, RED_THREADS, 0, L.stream>>>(result, partial, item_start, mi);
+        KZG_CUDA_TRY(cudaGetLastError());
+        L.count(1, "msm_reduce");
+    }
     return RET_OK;
 }
 

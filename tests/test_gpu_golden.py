@@ -21,6 +21,8 @@ IMPLEMENTED = [
     "verify_blob_kzg_proof_batch",
     "compute_cells",
     "compute_cells_and_kzg_proofs",
+    "recover_cells_and_kzg_proofs",
+    "verify_cell_kzg_proof_batch",
 ]
 
 
@@ -232,3 +234,94 @@ def test_cells_and_proofs_differential(gpu, ref):
     assert gpu.compute_cells_and_kzg_proofs(blob, False, True)[1] == rp
     # the first 64 cells are the blob itself
     assert rc[:131072] == blob
+
+
+@pytest.fixture(scope="module")
+def cells3(ref):
+    """3 synthetic blobs with reference commitments, cells and cell proofs."""
+    out = []
+    for b in (21, 22, 23):
+        blob = synth_blob(b)
+        cm = ref.blob_to_kzg_commitment(blob)
+        cells, proofs = ref.compute_cells_and_kzg_proofs(blob)
+        out.append((blob, cm, [cells[2048 * k : 2048 * k + 2048] for k in range(128)], [proofs[48 * k : 48 * k + 48] for k in range(128)]))
+    return out
+
+
+def test_recover_differential(gpu, ref, cells3):
+    import random
+
+    rnd = random.Random(77)
+    blob, cm, cells, proofs = cells3[0]
+    all_cells, all_proofs = b"".join(cells), b"".join(proofs)
+    patterns = [
+        list(range(0, 128, 2)),  # every other cell (BASELINE config 4 shape)
+        list(range(64)),  # first half
+        list(range(64, 128)),  # second half
+        list(range(128)),  # nothing missing
+        sorted(rnd.sample(range(128), 64)),
+        sorted(rnd.sample(range(128), 100)),
+        [0] + list(range(65, 128)),
+    ]
+    for idx in patterns:
+        given = b"".join(cells[i] for i in idx)
+        gc, gp = gpu.recover_cells_and_kzg_proofs(idx, given, True)
+        assert gc == all_cells, idx[:4]
+        assert gp == all_proofs, idx[:4]
+        gc2, _ = gpu.recover_cells_and_kzg_proofs(idx, given, False)
+        assert gc2 == all_cells
+    # inconsistent input (cells from two different blobs): must still agree with the reference bit for bit
+    idx = list(range(0, 128, 2))
+    mixed = b"".join(cells3[i % 2][2][k] for i, k in enumerate(idx))
+    assert gpu.recover_cells_and_kzg_proofs(idx, mixed, True) == ref.recover_cells_and_kzg_proofs(idx, mixed, True)
+    # argument errors (eip7594.c:191-213)
+    for bad_idx in ([0] * 64, list(range(63)), list(range(1, 64)) + [200], list(range(64))[::-1]):
+        with pytest.raises(ref_lib.BadArgs):
+            gpu.recover_cells_and_kzg_proofs(bad_idx, b"".join(cells[0:len(bad_idx)]), True)
+    R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+    bad_cell = R.to_bytes(32, "big") + cells[0][32:]
+    with pytest.raises(ref_lib.BadArgs):
+        gpu.recover_cells_and_kzg_proofs(list(range(64)), bad_cell + b"".join(cells[1:64]), True)
+
+
+def test_verify_cells_differential(gpu, ref, cells3):
+    import random
+
+    rnd = random.Random(78)
+    # all cells of three blobs, row-major by blob (bindings/go/main_test.go:1016-1028 shape)
+    cms, idx, cl, pf = [], [], [], []
+    for blob, cm, cells, proofs in cells3:
+        for k in range(128):
+            cms.append(cm), idx.append(k), cl.append(cells[k]), pf.append(proofs[k])
+    def call(be, sel, mutate=None):
+        c = [cms[i] for i in sel]
+        ii = [idx[i] for i in sel]
+        ce = [cl[i] for i in sel]
+        pp = [pf[i] for i in sel]
+        if mutate:
+            mutate(c, ii, ce, pp)
+        return be.verify_cell_kzg_proof_batch(b"".join(c), ii, b"".join(ce), b"".join(pp))
+    full = list(range(384))
+    assert call(gpu, full) is True
+    for sel in ([5], [0, 1, 2], rnd.sample(full, 40), full[:128], [7, 7, 7, 135, 135], sorted(rnd.sample(full, 200), reverse=True)):
+        assert call(gpu, sel) is True
+        assert call(ref, sel) is True
+    def wrong_proof(c, ii, ce, pp):
+        pp[3] = pp[4]
+    def wrong_cell(c, ii, ce, pp):
+        ce[2] = ce[2][:32] + (int.from_bytes(ce[2][32:64], "big") ^ 1).to_bytes(32, "big") + ce[2][64:]
+    def wrong_commitment(c, ii, ce, pp):
+        c[0] = cells3[1][1] if c[0] != cells3[1][1] else cells3[0][1]
+    def wrong_index(c, ii, ce, pp):
+        ii[1] = (ii[1] + 1) % 128
+    for m in (wrong_proof, wrong_cell, wrong_commitment, wrong_index):
+        sel = full[:20]
+        assert call(gpu, sel, m) is False
+        assert call(ref, sel, m) is False
+    with pytest.raises(ref_lib.BadArgs):
+        call(gpu, full[:4], lambda c, ii, ce, pp: ii.__setitem__(0, 128))
+    with pytest.raises(ref_lib.BadArgs):
+        call(gpu, full[:4], lambda c, ii, ce, pp: pp.__setitem__(1, bytes(48)))
+    with pytest.raises(ref_lib.BadArgs):
+        call(gpu, full[:4], lambda c, ii, ce, pp: c.__setitem__(2, bytes(48)))
+    assert gpu.verify_cell_kzg_proof_batch(b"", [], b"", b"") is True
