@@ -328,6 +328,62 @@ def run_b200(args):
         for _ in range(3):
             mod.blob_to_kzg_commitment_device(out.data_ptr(), d_blobs.data_ptr(), m, ts)
         extra["blob_to_kzg_commitment_batch%d_blobs_per_s" % m] = m * 3 / (time.perf_counter() - t0)
+        # EIP-7594 (north_star target 1): BASELINE configs[2] shape = 256 blobs, cells + FK20 proofs
+        m7 = min(n, 256)
+        d_cells = torch.empty(m7 * 2 * BLOB, dtype=torch.uint8, device=dev)
+        d_cprf = torch.empty(m7 * 128 * 48, dtype=torch.uint8, device=dev)
+        mod.compute_cells_and_kzg_proofs_device(d_cells.data_ptr(), d_cprf.data_ptr(), d_blobs.data_ptr(), m7, ts)
+        torch.cuda.synchronize()
+        mod.profile_enable(ts, True)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            mod.compute_cells_and_kzg_proofs_device(d_cells.data_ptr(), d_cprf.data_ptr(), d_blobs.data_ptr(), m7, ts)
+        dt = (time.perf_counter() - t0) / 3
+        p7 = mod.profile_dump(ts)
+        mod.profile_enable(ts, False)
+        extra["compute_cells_and_kzg_proofs_batch%d_blobs_per_s" % m7] = m7 / dt
+        extra["compute_cells_and_kzg_proofs_kernels_ms"] = {k: round(v[0] / 3, 3) for k, v in p7["kernels"].items() if k not in ("begin", "end")}
+        h_cells = torch.empty(m7 * 2 * BLOB, dtype=torch.uint8).pin_memory()
+        h_cprf = torch.empty(m7 * 128 * 48, dtype=torch.uint8).pin_memory()
+        mod.compute_cells_and_kzg_proofs_host(h_cells.data_ptr(), h_cprf.data_ptr(), host_blobs.data_ptr(), m7, ts)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            mod.compute_cells_and_kzg_proofs_host(h_cells.data_ptr(), h_cprf.data_ptr(), host_blobs.data_ptr(), m7, ts)
+        extra["compute_cells_and_kzg_proofs_batch%d_e2e_blobs_per_s" % m7] = m7 * 3 / (time.perf_counter() - t0)
+        for _ in range(1):
+            mod.compute_cells_and_kzg_proofs_device(d_cells.data_ptr(), 0, d_blobs.data_ptr(), m7, ts)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            mod.compute_cells_and_kzg_proofs_device(d_cells.data_ptr(), 0, d_blobs.data_ptr(), m7, ts)
+        extra["compute_cells_only_batch%d_blobs_per_s" % m7] = m7 * 3 / (time.perf_counter() - t0)
+        # configs[3] shape: recover from the even-indexed cells (50 % missing)
+        idx = list(range(0, 128, 2)) * m7
+        cells_view = d_cells.view(m7, 128, 2048)
+        given = cells_view[:, 0::2, :].contiguous()
+        rec_c = torch.empty(m7 * 2 * BLOB, dtype=torch.uint8, device=dev)
+        rec_p = torch.empty(m7 * 128 * 48, dtype=torch.uint8, device=dev)
+        mod.recover_cells_and_kzg_proofs_device(rec_c.data_ptr(), rec_p.data_ptr(), idx, given.data_ptr(), 64, m7, ts)
+        torch.cuda.synchronize()
+        assert torch.equal(rec_c, d_cells) and torch.equal(rec_p, d_cprf), "recover != compute"
+        t0 = time.perf_counter()
+        for _ in range(3):
+            mod.recover_cells_and_kzg_proofs_device(rec_c.data_ptr(), rec_p.data_ptr(), idx, given.data_ptr(), 64, m7, ts)
+        extra["recover_cells_and_kzg_proofs_half_missing_batch%d_blobs_per_s" % m7] = m7 * 3 / (time.perf_counter() - t0)
+        # verify_cell_kzg_proof_batch: 8 blobs x 128 cells through the frozen API (host bytes)
+        nb = 8
+        hc = h_cells.numpy().tobytes()
+        hp = h_cprf.numpy().tobytes()
+        cm_host = bytes(host_cms.numpy().tobytes())
+        vc_cm = [cm_host[48 * b : 48 * b + 48] for b in range(nb) for _ in range(128)]
+        vc_idx = [k for _ in range(nb) for k in range(128)]
+        vc_cells = [hc[2048 * i : 2048 * (i + 1)] for i in range(nb * 128)]
+        vc_prf = [hp[48 * i : 48 * (i + 1)] for i in range(nb * 128)]
+        assert mod.verify_cell_kzg_proof_batch(vc_cm, vc_idx, vc_cells, vc_prf, ts)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            mod.verify_cell_kzg_proof_batch(vc_cm, vc_idx, vc_cells, vc_prf, ts)
+        extra["verify_cell_kzg_proof_batch_8x128_blobs_per_s"] = nb * 3 / (time.perf_counter() - t0)
         one = bytes(host_blobs[:BLOB].numpy().tobytes())
         for _ in range(2):
             mod.blob_to_kzg_commitment(one, ts)

@@ -240,6 +240,73 @@ def verify_finish(partials, n_ranks, ts):
     return bool(ok.value)
 
 
+def compute_cells_and_kzg_proofs(blob, ts):
+    """-> (cells[128], proofs[128]) as in bindings/python/ckzg_wrap.c"""
+    cells = C.create_string_buffer(CELLS_PER_EXT_BLOB * BYTES_PER_CELL)
+    proofs = C.create_string_buffer(CELLS_PER_EXT_BLOB * 48)
+    lib().compute_cells_and_kzg_proofs.restype = C.c_int
+    _raise(lib().compute_cells_and_kzg_proofs(cells, proofs, _need(blob, BYTES_PER_BLOB, "blob"), ts.ptr), "compute_cells_and_kzg_proofs")
+    return ([cells.raw[BYTES_PER_CELL * k : BYTES_PER_CELL * (k + 1)] for k in range(128)], [proofs.raw[48 * k : 48 * k + 48] for k in range(128)])
+
+
+def recover_cells_and_kzg_proofs(cell_indices, cells, ts):
+    n = len(cell_indices)
+    if len(cells) != n:
+        raise ValueError("expected same number of indices and cells")
+    idx = (C.c_uint64 * max(n, 1))(*cell_indices)
+    out_c = C.create_string_buffer(CELLS_PER_EXT_BLOB * BYTES_PER_CELL)
+    out_p = C.create_string_buffer(CELLS_PER_EXT_BLOB * 48)
+    lib().recover_cells_and_kzg_proofs.restype = C.c_int
+    _raise(
+        lib().recover_cells_and_kzg_proofs(out_c, out_p, idx, b"".join(_need(c, BYTES_PER_CELL, "cell") for c in cells), C.c_uint64(n), ts.ptr),
+        "recover_cells_and_kzg_proofs",
+    )
+    return ([out_c.raw[BYTES_PER_CELL * k : BYTES_PER_CELL * (k + 1)] for k in range(128)], [out_p.raw[48 * k : 48 * k + 48] for k in range(128)])
+
+
+def verify_cell_kzg_proof_batch(commitments, cell_indices, cells, proofs, ts):
+    n = len(cell_indices)
+    if not (len(commitments) == len(cells) == len(proofs) == n):
+        raise ValueError("expected same number of commitments, indices, cells and proofs")
+    idx = (C.c_uint64 * max(n, 1))(*cell_indices)
+    ok = C.c_bool(False)
+    lib().verify_cell_kzg_proof_batch.restype = C.c_int
+    _raise(
+        lib().verify_cell_kzg_proof_batch(
+            C.byref(ok), b"".join(_need(c, 48, "commitment") for c in commitments), idx, b"".join(_need(c, BYTES_PER_CELL, "cell") for c in cells),
+            b"".join(_need(p, 48, "proof") for p in proofs), C.c_uint64(n), ts.ptr,
+        ),
+        "verify_cell_kzg_proof_batch",
+    )
+    return bool(ok.value)
+
+
+def compute_cells_and_kzg_proofs_device(cells_ptr, proofs_ptr, blobs_ptr, n, ts):
+    """Batched, device pointers (0 = skip that output)."""
+    lib().ckzg_b200_compute_cells_and_kzg_proofs_batch.restype = C.c_int
+    _raise(
+        lib().ckzg_b200_compute_cells_and_kzg_proofs_batch(ts.engine, C.c_void_p(cells_ptr or None), C.c_void_p(proofs_ptr or None), C.c_void_p(blobs_ptr), C.c_uint64(n), DEVICE, None),
+        "ckzg_b200_compute_cells_and_kzg_proofs_batch",
+    )
+
+
+def compute_cells_and_kzg_proofs_host(cells_ptr, proofs_ptr, blobs_ptr, n, ts):
+    lib().ckzg_b200_compute_cells_and_kzg_proofs_batch.restype = C.c_int
+    _raise(
+        lib().ckzg_b200_compute_cells_and_kzg_proofs_batch(ts.engine, C.c_void_p(cells_ptr or None), C.c_void_p(proofs_ptr or None), C.c_void_p(blobs_ptr), C.c_uint64(n), HOST, None),
+        "ckzg_b200_compute_cells_and_kzg_proofs_batch",
+    )
+
+
+def recover_cells_and_kzg_proofs_device(cells_out_ptr, proofs_out_ptr, cell_indices, cells_ptr, num_cells, n, ts):
+    idx = (C.c_uint64 * (n * num_cells))(*cell_indices)
+    lib().ckzg_b200_recover_cells_and_kzg_proofs_batch.restype = C.c_int
+    _raise(
+        lib().ckzg_b200_recover_cells_and_kzg_proofs_batch(ts.engine, C.c_void_p(cells_out_ptr), C.c_void_p(proofs_out_ptr or None), idx, C.c_void_p(cells_ptr), C.c_uint64(num_cells), C.c_uint64(n), DEVICE, None),
+        "ckzg_b200_recover_cells_and_kzg_proofs_batch",
+    )
+
+
 def profile_enable(ts, on=True):
     lib().ckzg_b200_profile_enable.restype = None
     lib().ckzg_b200_profile_enable(ts.engine, C.c_int(1 if on else 0))

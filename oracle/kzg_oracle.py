@@ -352,3 +352,217 @@ def verify_blob_kzg_proof_batch(blobs, commitments_bytes, proofs_bytes, s):
         pr = bytes_to_kzg_proof(proofs_bytes[i])
         cs.append(c), zs.append(z), ys.append(y), prs.append(pr)
     return verify_kzg_proof_batch(cs, zs, ys, prs, s)
+
+
+# ---------------------------------------------------------------------------------------------
+# EIP-7594 (src/eip7594/*.c) -- restated with Python integers; slow (seconds per blob), used on a
+# handful of cases, the bulk differential checks use oracle/_ref.
+# ---------------------------------------------------------------------------------------------
+
+
+def fr_fft(vals, s, inverse=False):
+    """src/eip7594/fft.c:100-146: radix-2 transform over the 8192-th root domain with stride 8192/n;
+    the inverse scales by 1/n."""
+    n = len(vals)
+    assert n & (n - 1) == 0 and n <= FIELD_ELEMENTS_PER_EXT_BLOB
+    stride = FIELD_ELEMENTS_PER_EXT_BLOB // n
+    roots = s.roots_of_unity
+
+    def rec(v, st):
+        m = len(v)
+        if m == 1:
+            return v
+        ev, od = rec(v[0::2], st * 2), rec(v[1::2], st * 2)
+        out = [0] * m
+        for i in range(m // 2):
+            w = roots[(FIELD_ELEMENTS_PER_EXT_BLOB - i * st) % FIELD_ELEMENTS_PER_EXT_BLOB] if inverse else roots[i * st]
+            t = od[i] * w % R
+            out[i] = (ev[i] + t) % R
+            out[i + m // 2] = (ev[i] - t) % R
+        return out
+
+    out = rec([v % R for v in vals], stride)
+    if inverse:
+        inv = pow(n, -1, R)
+        out = [v * inv % R for v in out]
+    return out
+
+
+def g1_fft(points, s, inverse=False):
+    """src/eip7594/fft.c:164-240 (g1_fft / g1_ifft_unscaled: no 1/n)."""
+    n = len(points)
+    stride = FIELD_ELEMENTS_PER_EXT_BLOB // n
+    roots = s.roots_of_unity
+
+    def rec(v, st):
+        m = len(v)
+        if m == 1:
+            return v
+        ev, od = rec(v[0::2], st * 2), rec(v[1::2], st * 2)
+        out = [None] * m
+        for i in range(m // 2):
+            w = roots[(FIELD_ELEMENTS_PER_EXT_BLOB - i * st) % FIELD_ELEMENTS_PER_EXT_BLOB] if inverse else roots[i * st]
+            t = od[i] if w == 1 else B.g1_mul(od[i], w)
+            out[i] = B.g1_add(ev[i], t)
+            out[i + m // 2] = B.g1_sub(ev[i], t)
+        return out
+
+    return rec(list(points), stride)
+
+
+def poly_lagrange_to_monomial(lagrange, s):
+    """src/eip7594/poly.c:58: bit-reversal then inverse FFT."""
+    return fr_fft(bit_reversal_permutation(list(lagrange)), s, inverse=True)
+
+
+def compute_cells(blob, s):
+    """cells half of compute_cells_and_kzg_proofs (src/eip7594/eip7594.c:88-121) -> (cells bytes, monomial)"""
+    mono = poly_lagrange_to_monomial(blob_to_polynomial(blob), s) + [0] * FIELD_ELEMENTS_PER_BLOB
+    data = bit_reversal_permutation(fr_fft(mono, s))
+    return b"".join(bytes_from_bls_field(v) for v in data), mono
+
+
+def fk20_x_ext_fft_columns(s):
+    """init_fk20_multi_settings (src/setup/setup.c:238-330): x_ext_fft[offset] = G1-FFT of 64 setup points
+    padded with 64 identities; cached on the settings object."""
+    if getattr(s, "_fk20", None) is None:
+        cols = []
+        for offset in range(FIELD_ELEMENTS_PER_CELL):
+            start = FIELD_ELEMENTS_PER_BLOB - FIELD_ELEMENTS_PER_CELL - 1 - offset
+            x = [s.g1_monomial[start - i * FIELD_ELEMENTS_PER_CELL] for i in range(CELLS_PER_BLOB - 1)] + [B.G1_INF]
+            cols.append(g1_fft(x + [B.G1_INF] * CELLS_PER_BLOB, s))
+        s._fk20 = cols
+    return s._fk20
+
+
+def compute_fk20_cell_proofs(mono, s):
+    """src/eip7594/fk20.c:139-286 -> 128 Jacobian points in natural order (caller bit-reverses)."""
+    n2 = 2 * CELLS_PER_BLOB
+    cols = fk20_x_ext_fft_columns(s)
+    inv = pow(n2, -1, R)
+    coeffs = []
+    for i in range(FIELD_ELEMENTS_PER_CELL):
+        c = [0] * n2  # circulant_coeffs_stride, fk20.c:55-78
+        dmi = FIELD_ELEMENTS_PER_BLOB - 1 - i
+        c[0] = mono[dmi]
+        for j in range(1, CELLS_PER_BLOB - 1):
+            c[n2 - j] = mono[dmi - j * FIELD_ELEMENTS_PER_CELL]
+        coeffs.append([v * inv % R for v in fr_fft(c, s)])
+    u = [g1_lincomb_fast([cols[i][j] for i in range(FIELD_ELEMENTS_PER_CELL)], [coeffs[i][j] for i in range(FIELD_ELEMENTS_PER_CELL)], c=5) for j in range(n2)]
+    v = g1_fft(u, s, inverse=True)
+    v = v[:CELLS_PER_BLOB] + [B.G1_INF] * CELLS_PER_BLOB
+    return g1_fft(v, s)
+
+
+def compute_cells_and_kzg_proofs(blob, s, want_proofs=True):
+    """src/eip7594/eip7594.c:61 -> (cells 262144 B, proofs 6144 B or None)"""
+    cells, mono = compute_cells(blob, s)
+    if not want_proofs:
+        return cells, None
+    proofs = bit_reversal_permutation(compute_fk20_cell_proofs(mono, s))
+    return cells, b"".join(bytes_from_g1(p) for p in proofs)
+
+
+def recover_cells(cell_indices, cells_fr, s):
+    """src/eip7594/recovery.c:200-365 (cells_fr: 8192 values in cell order, zeros where missing)."""
+    n = FIELD_ELEMENTS_PER_EXT_BLOB
+    cells_brp = bit_reversal_permutation(list(cells_fr))
+    missing = [reverse_bits_limited(CELLS_PER_EXT_BLOB, i) for i in range(CELLS_PER_EXT_BLOB) if i not in cell_indices]
+    # vanishing polynomial (recovery.c:46-162)
+    short = [1]
+    for m in missing:
+        r = s.roots_of_unity[m * (n // CELLS_PER_EXT_BLOB)]
+        nxt = [0] * (len(short) + 1)
+        for j, cj in enumerate(short):
+            nxt[j] = (nxt[j] - cj * r) % R
+            nxt[j + 1] = (nxt[j + 1] + cj) % R
+        short = nxt
+    z = [0] * n
+    for i, cj in enumerate(short):
+        z[i * FIELD_ELEMENTS_PER_CELL] = cj
+    z_eval = fr_fft(z, s)
+    ez = [a * b % R for a, b in zip(cells_brp, z_eval)]
+    q = fr_fft(ez, s, inverse=True)
+    shift = lambda p, f: [c * pow(f, k, R) % R for k, c in enumerate(p)]
+    q_coset = fr_fft(shift(q, 7), s)
+    z_coset = fr_fft(shift(z, 7), s)
+    p_coset = [a * pow(b, -1, R) % R for a, b in zip(q_coset, z_coset)]
+    p = shift(fr_fft(p_coset, s, inverse=True), pow(7, -1, R))
+    return bit_reversal_permutation(fr_fft(p, s))
+
+
+def recover_cells_and_kzg_proofs(cell_indices, cells, s, want_proofs=True):
+    """src/eip7594/eip7594.c:177"""
+    nc = len(cell_indices)
+    if nc > CELLS_PER_EXT_BLOB or nc < CELLS_PER_BLOB or len(cells) != nc:
+        raise BadArgs("cell count")
+    for i, ci in enumerate(cell_indices):
+        if ci >= CELLS_PER_EXT_BLOB or (i and ci <= cell_indices[i - 1]):
+            raise BadArgs("cell index")
+    data = [0] * FIELD_ELEMENTS_PER_EXT_BLOB
+    for ci, cell in zip(cell_indices, cells):
+        for j in range(FIELD_ELEMENTS_PER_CELL):
+            data[ci * FIELD_ELEMENTS_PER_CELL + j] = bytes_to_bls_field(cell[32 * j : 32 * j + 32])
+    rec = data if nc == CELLS_PER_EXT_BLOB else recover_cells(list(cell_indices), data, s)
+    out_cells = b"".join(bytes_from_bls_field(v) for v in rec)
+    if not want_proofs:
+        return out_cells, None
+    mono = poly_lagrange_to_monomial(rec, s)
+    proofs = bit_reversal_permutation(compute_fk20_cell_proofs(mono, s))
+    return out_cells, b"".join(bytes_from_g1(p) for p in proofs)
+
+
+def compute_verify_cell_kzg_proof_batch_challenge(unique_commitments, commitment_indices, cell_indices, cells, proofs):
+    """src/eip7594/eip7594.c:390-482"""
+    h = hashlib.sha256()
+    h.update(RANDOM_CHALLENGE_DOMAIN_VERIFY_CELL_KZG_PROOF_BATCH)
+    for v in (FIELD_ELEMENTS_PER_BLOB, FIELD_ELEMENTS_PER_CELL, len(unique_commitments), len(cell_indices)):
+        h.update(v.to_bytes(8, "big"))
+    for c in unique_commitments:
+        h.update(bytes(c))
+    for ci, col, cell, pr in zip(commitment_indices, cell_indices, cells, proofs):
+        h.update(ci.to_bytes(8, "big") + col.to_bytes(8, "big") + bytes(cell) + bytes(pr))
+    return hash_to_bls_field(h.digest())
+
+
+def verify_cell_kzg_proof_batch(commitments, cell_indices, cells, proofs, s):
+    """src/eip7594/eip7594.c:825-974"""
+    n = len(cell_indices)
+    if n == 0:
+        return True
+    if any(c >= CELLS_PER_EXT_BLOB for c in cell_indices):
+        raise BadArgs("cell index")
+    uniq, cidx = [], []
+    for c in commitments:  # deduplicate_commitments, :345-376
+        c = bytes(c)
+        if c not in uniq:
+            uniq.append(c)
+        cidx.append(uniq.index(c))
+    r = compute_verify_cell_kzg_proof_batch_challenge(uniq, cidx, cell_indices, cells, proofs)
+    rp = compute_powers(r, n)
+    proofs_g1 = [bytes_to_kzg_proof(p) for p in proofs]
+    proof_lincomb = g1_lincomb_fast(proofs_g1, rp, c=5)
+    cm_g1 = [bytes_to_kzg_commitment(c) for c in uniq]
+    weights = [0] * len(uniq)
+    for k in range(n):
+        weights[cidx[k]] = (weights[cidx[k]] + rp[k]) % R
+    final = g1_lincomb_fast(cm_g1, weights, c=5)
+    # aggregated interpolation polynomial (:615-770)
+    agg = [[0] * FIELD_ELEMENTS_PER_CELL for _ in range(CELLS_PER_EXT_BLOB)]
+    used = set()
+    for k in range(n):
+        col = cell_indices[k]
+        used.add(col)
+        for j in range(FIELD_ELEMENTS_PER_CELL):
+            agg[col][j] = (agg[col][j] + bytes_to_bls_field(cells[k][32 * j : 32 * j + 32]) * rp[k]) % R
+    poly = [0] * FIELD_ELEMENTS_PER_CELL
+    for col in sorted(used):
+        coeffs = fr_fft(bit_reversal_permutation(agg[col]), s, inverse=True)
+        hinv = s.roots_of_unity[FIELD_ELEMENTS_PER_EXT_BLOB - reverse_bits_limited(CELLS_PER_EXT_BLOB, col)]
+        for k in range(FIELD_ELEMENTS_PER_CELL):
+            poly[k] = (poly[k] + coeffs[k] * pow(hinv, k, R)) % R
+    interp = g1_lincomb_fast(s.g1_monomial[:FIELD_ELEMENTS_PER_CELL], poly, c=5)
+    final = B.g1_sub(final, interp)
+    wp = [rp[k] * s.roots_of_unity[reverse_bits_limited(CELLS_PER_EXT_BLOB, cell_indices[k]) * FIELD_ELEMENTS_PER_CELL] % R for k in range(n)]
+    final = B.g1_add(final, g1_lincomb_fast(proofs_g1, wp, c=5))
+    return B.pairings_verify(final, B.G2_GEN_J, proof_lincomb, s.g2_monomial[FIELD_ELEMENTS_PER_CELL])
