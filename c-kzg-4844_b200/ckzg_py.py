@@ -307,9 +307,10 @@ def recover_cells_and_kzg_proofs_device(cells_out_ptr, proofs_out_ptr, cell_indi
     )
 
 
-def profile_enable(ts, on=True):
+def profile_enable(ts, level=2):
+    """0 off, 1 whole-call device time only, 2 per-kernel times (stages serialised)."""
     lib().ckzg_b200_profile_enable.restype = None
-    lib().ckzg_b200_profile_enable(ts.engine, C.c_int(1 if on else 0))
+    lib().ckzg_b200_profile_enable(ts.engine, C.c_int(int(level)))
 
 
 def profile_dump(ts):

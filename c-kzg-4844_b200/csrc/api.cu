@@ -187,7 +187,7 @@ int ckzg_b200_blob_to_kzg_commitment_batch(ckzg_b200_ctx* ctx, uint8_t* out, con
 void ckzg_b200_profile_enable(ckzg_b200_ctx* ctx, int on) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     std::lock_guard<std::mutex> g(c->prof.mu);
-    c->prof.enabled = on != 0;
+    c->prof.level = on < 0 ? 0 : (on > 2 ? 2 : on);
     c->prof.nk = 0;
     c->prof.call_ms = 0;
     c->prof.calls = 0;

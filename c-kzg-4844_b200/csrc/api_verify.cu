@@ -2,6 +2,8 @@
 // kernels of verify.cu / msm.cu / pairing.cu.  Host code here only sequences launches and copies.
 #include <string.h>
 
+#include <algorithm>
+
 #include "../src/host_sha256.h"
 #include "call.h"
 #include "verify.h"
@@ -69,8 +71,17 @@ struct Stage1 {
     uint8_t* zy = nullptr;
     int* bad = nullptr;  // single flag
 };
-int verify_stage1(Call& call, Stage1& s, const uint8_t* d_blobs, const uint8_t* d_cm, const uint8_t* d_pf, uint64_t n) {
+// `blobs` lives in `mem` space.  The per-blob Fiat-Shamir hash is latency bound (2050 dependent SHA-256
+// blocks per thread: ~4 ms whatever the batch size, on 1 warp per SM), so it runs on side streams
+// concurrently with the point validations; HOST blobs are uploaded in chunks on a copy stream and every
+// chunk's (hash -> evaluate) chain starts as soon as its bytes have landed (copy engine || SMs).
+// With per-kernel profiling on (level 2) everything runs on the call's stream so event attribution is exact.
+int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_cm, const uint8_t* d_pf, uint64_t n, int mem) {
     Launch L = call.launch();
+    const bool host = (mem == CKZG_B200_HOST);
+    uint8_t* d_up = nullptr;
+    if (host) TRY(call.alloc(&d_up, n * BLOB_BYTES));
+    const uint8_t* d_blobs = host ? d_up : blobs;
     TRY(call.alloc(&s.cm, n));
     TRY(call.alloc(&s.pf, n));
     TRY(call.alloc(&s.z, n));
@@ -78,54 +89,65 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* d_blobs, const uint8_t* 
     TRY(call.alloc(&s.zy, n * 64));
     TRY(call.alloc(&s.bad, 1));
     KZG_CUDA_TRY(cudaMemsetAsync(s.bad, 0, sizeof(int), call.stream));
-    TRY(launch_g1_validate(L, s.cm, d_cm, n, s.bad, 0));
-    TRY(launch_g1_validate(L, s.pf, d_pf, n, s.bad, 0));
-    TRY(launch_blob_challenges(L, s.z, s.zy, d_blobs, d_cm, n));
-    TRY(launch_evaluate(L, s.y, s.zy, nullptr, nullptr, d_blobs, s.z, n, s.bad, 0));
-    return RET_OK;
-}
-
-// Same stage for HOST blobs: the 128 KiB-per-blob upload is cut into chunks on a second stream and the
-// per-blob kernels of chunk k run while chunk k+1 is still crossing PCIe (copy engine || SMs).
-int verify_stage1_pipelined(Call& call, Stage1& s, const uint8_t* h_blobs, const uint8_t* d_cm, const uint8_t* d_pf, uint64_t n) {
-    Launch L = call.launch();
-    uint8_t* d_blobs;
-    TRY(call.alloc(&d_blobs, n * BLOB_BYTES));
-    TRY(call.alloc(&s.cm, n));
-    TRY(call.alloc(&s.pf, n));
-    TRY(call.alloc(&s.z, n));
-    TRY(call.alloc(&s.y, n));
-    TRY(call.alloc(&s.zy, n * 64));
-    TRY(call.alloc(&s.bad, 1));
-    KZG_CUDA_TRY(cudaMemsetAsync(s.bad, 0, sizeof(int), call.stream));
-    cudaStream_t copy;
-    cudaEvent_t ready;
-    KZG_CUDA_TRY(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
-    // the buffers come from call.stream's pool: the copy stream must not start before the allocation point
-    KZG_CUDA_TRY(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-    KZG_CUDA_TRY(cudaEventRecord(ready, call.stream));
-    KZG_CUDA_TRY(cudaStreamWaitEvent(copy, ready, 0));
-    cudaEventDestroy(ready);
-    TRY(launch_g1_validate(L, s.cm, d_cm, n, s.bad, 0));
-    TRY(launch_g1_validate(L, s.pf, d_pf, n, s.bad, 0));
-    const uint64_t CH = 256;
-    int rc = RET_OK;
-    for (uint64_t off = 0; off < n && rc == RET_OK; off += CH) {
-        uint64_t m = (n - off < CH) ? n - off : CH;
-        cudaEvent_t ev;
-        if (cudaMemcpyAsync(d_blobs + off * BLOB_BYTES, h_blobs + off * BLOB_BYTES, m * BLOB_BYTES, cudaMemcpyHostToDevice, copy) != cudaSuccess ||
-            cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
-            rc = RET_ERROR;
-            break;
-        }
-        cudaEventRecord(ev, copy);
-        cudaStreamWaitEvent(call.stream, ev, 0);
-        cudaEventDestroy(ev);
-        if ((rc = launch_blob_challenges(L, s.z + off, s.zy + off * 64, d_blobs + off * BLOB_BYTES, d_cm + off * 48, m))) break;
-        rc = launch_evaluate(L, s.y + off, s.zy + off * 64, nullptr, nullptr, d_blobs + off * BLOB_BYTES, s.z + off, m, s.bad, 0);
+    if (call.trace_kernels || n < 64) {  // serial form
+        if (host) KZG_CUDA_TRY(cudaMemcpyAsync(d_up, blobs, n * BLOB_BYTES, cudaMemcpyHostToDevice, call.stream));
+        TRY(launch_g1_validate(L, s.cm, d_cm, n, s.bad, 0));
+        TRY(launch_g1_validate(L, s.pf, d_pf, n, s.bad, 0));
+        TRY(launch_blob_challenges(L, s.z, s.zy, d_blobs, d_cm, n));
+        TRY(launch_evaluate(L, s.y, s.zy, nullptr, nullptr, d_blobs, s.z, n, s.bad, 0));
+        return RET_OK;
     }
-    cudaStreamSynchronize(copy);  // before the pool frees d_blobs at the end of the call
-    cudaStreamDestroy(copy);
+    // fork: side streams start after the allocations / memset enqueued so far
+    const uint64_t CH = host ? 512 : n;
+    const int nside = (int)std::min<uint64_t>(8, (n + CH - 1) / CH);
+    cudaStream_t side[8], copy = nullptr;
+    cudaEvent_t ev;
+    KZG_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    KZG_CUDA_TRY(cudaEventRecord(ev, call.stream));
+    int rc = RET_OK;
+    for (int i = 0; i < nside; i++) {
+        if (cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking) != cudaSuccess) return RET_ERROR;
+        cudaStreamWaitEvent(side[i], ev, 0);
+    }
+    if (host) {
+        if (cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking) != cudaSuccess) return RET_ERROR;
+        cudaStreamWaitEvent(copy, ev, 0);
+    }
+    cudaEventDestroy(ev);
+    // main stream: point validation (independent of the blobs)
+    if ((rc = launch_g1_validate(L, s.cm, d_cm, n, s.bad, 0)) == RET_OK) rc = launch_g1_validate(L, s.pf, d_pf, n, s.bad, 0);
+    int c = 0;
+    for (uint64_t off = 0; off < n && rc == RET_OK; off += CH, c++) {
+        const uint64_t m = (n - off < CH) ? n - off : CH;
+        cudaStream_t st = side[c % nside];
+        if (host) {
+            cudaEvent_t landed;
+            if (cudaMemcpyAsync(d_up + off * BLOB_BYTES, blobs + off * BLOB_BYTES, m * BLOB_BYTES, cudaMemcpyHostToDevice, copy) != cudaSuccess ||
+                cudaEventCreateWithFlags(&landed, cudaEventDisableTiming) != cudaSuccess) {
+                rc = RET_ERROR;
+                break;
+            }
+            cudaEventRecord(landed, copy);
+            cudaStreamWaitEvent(st, landed, 0);
+            cudaEventDestroy(landed);
+        }
+        Launch Ls = call.launch_on(st);
+        if ((rc = launch_blob_challenges(Ls, s.z + off, s.zy + off * 64, d_blobs + off * BLOB_BYTES, d_cm + off * 48, m))) break;
+        rc = launch_evaluate(Ls, s.y + off, s.zy + off * 64, nullptr, nullptr, d_blobs + off * BLOB_BYTES, s.z + off, m, s.bad, 0);
+    }
+    // join
+    for (int i = 0; i < nside; i++) {
+        cudaEvent_t done;
+        if (cudaEventCreateWithFlags(&done, cudaEventDisableTiming) == cudaSuccess) {
+            cudaEventRecord(done, side[i]);
+            cudaStreamWaitEvent(call.stream, done, 0);
+            cudaEventDestroy(done);
+        } else {
+            cudaStreamSynchronize(side[i]);
+        }
+        cudaStreamDestroy(side[i]);
+    }
+    if (copy) cudaStreamDestroy(copy);
     return rc;
 }
 
@@ -248,12 +270,8 @@ int ckzg_b200_verify_blob_kzg_proof_batch(ckzg_b200_ctx* ctx, int* ok, const uin
     TRY(call.stage_in(&d_cm, commitments, n * 48, mem));
     TRY(call.stage_in(&d_pf, proofs, n * 48, mem));
     Stage1 s;
-    if (mem == CKZG_B200_HOST && n > 256) {
-        TRY(verify_stage1_pipelined(call, s, blobs, d_cm, d_pf, n));
-    } else {
-        TRY(call.stage_in(&d_blobs, blobs, n * BLOB_BYTES, mem));
-        TRY(verify_stage1(call, s, d_blobs, d_cm, d_pf, n));
-    }
+    (void)d_blobs;
+    TRY(verify_stage1(call, s, blobs, d_cm, d_pf, n, mem));
     // the reference stops at the first invalid input (eip4844.c:813-831) before any pairing work
     int bad = 0;
     bool use_r = n > 1;  // n == 1: the single-proof equation, no challenge (eip4844.c:798)
@@ -340,11 +358,11 @@ int ckzg_b200_verify_blob_batch_stage1(ckzg_b200_ctx* ctx, uint8_t* zy, const ui
     Call call(reinterpret_cast<Ctx*>(ctx));
     if (!call.ok) return RET_ERROR;
     const uint8_t *d_blobs, *d_cm, *d_pf;
-    TRY(call.stage_in(&d_blobs, blobs, n * BLOB_BYTES, mem));
+    (void)d_blobs;
     TRY(call.stage_in(&d_cm, commitments, n * 48, mem));
     TRY(call.stage_in(&d_pf, proofs, n * 48, mem));
     Stage1 s;
-    TRY(verify_stage1(call, s, d_blobs, d_cm, d_pf, n));
+    TRY(verify_stage1(call, s, blobs, d_cm, d_pf, n, mem));
     int bad = 0;
     TRY(read_flag(call, s.bad, &bad));
     if (bad) return RET_BADARGS;

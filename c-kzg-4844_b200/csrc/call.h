@@ -15,7 +15,8 @@ struct Call {
     std::vector<void*> allocs;
     int prev_device = -1;
     bool ok = false;
-    bool profiling = false;
+    bool profiling = false;       // whole-call begin/end events
+    bool trace_kernels = false;   // per-kernel events (level 2)
     ProfTrace trace;
 
     explicit Call(Ctx* c) : ctx(c) {
@@ -23,13 +24,14 @@ struct Call {
         if (cudaSetDevice(c->device) != cudaSuccess) return;
         if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) return;
         ok = true;
-        profiling = c->prof.enabled;
-        if (profiling) launch().count(0, "begin");
+        profiling = c->prof.level >= 1;
+        trace_kernels = c->prof.level >= 2;
+        if (profiling) mark("begin");
     }
     ~Call() {
         if (stream) {
             for (void* p : allocs) cudaFreeAsync(p, stream);
-            if (profiling) launch().count(0, "end");
+            if (profiling) mark("end");
             cudaStreamSynchronize(stream);
             if (profiling && trace.ev.size() >= 2) {
                 std::lock_guard<std::mutex> g(ctx->prof.mu);
@@ -74,7 +76,15 @@ struct Call {
         *dev = d;
         return RET_OK;
     }
-    Launch launch() { return Launch{ctx, stream, profiling ? &trace : nullptr}; }
+    Launch launch() { return Launch{ctx, stream, trace_kernels ? &trace : nullptr}; }
+    Launch launch_on(cudaStream_t s) { return Launch{ctx, s, nullptr}; }
+    void mark(const char* name) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) == cudaSuccess) {
+            cudaEventRecord(e, stream);
+            trace.ev.push_back({e, name});
+        }
+    }
 };
 
 #define TRY(expr)            \

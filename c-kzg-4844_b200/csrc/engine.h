@@ -34,7 +34,7 @@ struct PairingLines;  // pairing.cuh
 
 struct Prof {
     std::mutex mu;
-    bool enabled = false;
+    int level = 0;  // 0 off, 1 whole-call events only, 2 per-kernel events (concurrent stages run serially)
     static constexpr int MAXK = 64;
     const char* names[MAXK];
     double ms[MAXK];

@@ -14,6 +14,7 @@
 // arranged so that no permutation pass exists (MSM j stores to slot brp7(j); inverse DIT gives
 // natural order; forward DIF leaves the proofs in the bit-reversed order the API returns).
 #include "cells.h"
+#include "fft_twiddles.cuh"
 
 namespace kzg {
 
@@ -49,107 +50,109 @@ __device__ __forceinline__ Fr ld_fr2(const Fr* p) {
 }
 __device__ __forceinline__ int brp7(int v) { return (int)(__brev((uint32_t)v) >> 25); }
 
-// [k]P for an XYZZ point and a plain 256-bit scalar (twiddle factors: public data)
-__device__ __noinline__ G1 g1_mul_xyzz(const G1& p, const uint32_t* k) {
-    G1 acc = g1_inf();
-    bool started = false;
-    for (int i = 7; i >= 0; i--) {
-        uint32_t w = k[i];
+// [w128^e]P through the GLV split k = k1 + k2*lambda (both < 2^128, digits precomputed in
+// fft_twiddles.cuh): one table of odd multiples of P serves both halves because the second base is
+// -phi(P) = (beta*x, -y).  129 doublings + ~52 additions instead of 255 + 128.  Every lane of a warp
+// calls this with the SAME e (lanes span blobs, see g1_fft_stage_kernel), so the digit-dependent
+// branches are warp-uniform and the NAF sparsity is real.
+__device__ __noinline__ G1 g1_mul_twiddle(const G1& p, int e) {
+    if (e == 0) return p;
+    G1 tab[8];  // (2i+1) P
+    tab[0] = p;
+    G1 p2 = p;
+    g1_dbl_to(p2);
 #pragma unroll 1
-        for (int b = 31; b >= 0; b--) {
-            if (started) g1_dbl_to(acc);
-            if ((w >> b) & 1u) {
-                if (started)
-                    g1_add_to(acc, p);
-                else
-                    acc = p;
-                started = true;
-            }
+    for (int i = 1; i < 8; i++) {
+        tab[i] = tab[i - 1];
+        g1_add_to(tab[i], p2);
+    }
+    const Fp beta = Fp::from_limbs(FP_BETA_A);
+    const int8_t* d1 = FFT_TW_NAF[e][0];
+    const int8_t* d2 = FFT_TW_NAF[e][1];
+    G1 acc = g1_inf();
+#pragma unroll 1
+    for (int i = FFT_TW_TOP[e] - 1; i >= 0; i--) {
+        g1_dbl_to(acc);
+        int a = d1[i], b = d2[i];
+        if (a != 0) {
+            G1 t = tab[((a < 0 ? -a : a) - 1) >> 1];
+            if (a < 0) t.y = neg(t.y);
+            g1_add_to(acc, t);
+        }
+        if (b != 0) {
+            G1 t = tab[((b < 0 ? -b : b) - 1) >> 1];
+            t.x = mul(t.x, beta);
+            if (b > 0) t.y = neg(t.y);  // base is -phi(P)
+            g1_add_to(acc, t);
         }
     }
     return acc;
 }
 
-// twiddle w8192^idx as plain limbs
-__device__ __forceinline__ void twiddle_plain(uint32_t* k, const Fr* __restrict__ roots, int idx) { from_mont<FrTag>(k, ld_fr2(roots + idx)); }
-
 // ------------------------------------------------------------------------------------------------
-// G1 FFT over 128 points held in shared memory, 64 threads, one butterfly per thread per stage
+// G1 FFT over 128 points per vector, one radix-2 stage per launch, data in global memory (L2).
+// Thread = (butterfly b, vector v) with the 32 lanes of a warp spanning 32 VECTORS of the same
+// butterfly: they share the twiddle, so control flow never diverges.
 // ------------------------------------------------------------------------------------------------
-constexpr int GF_THREADS = 64;
+constexpr int GS_WARPS = 4;
+enum { GS_INVERSE = 0, GS_FORWARD_FIRST = 1, GS_FORWARD = 2 };
 
-// inverse, decimation in time: bit-reversed input -> natural output, unscaled (g1_ifft_unscaled,
-// fft.c:227).  Only the lower 64 outputs are kept by FK20 (fk20.c:264-266), so the last stage skips
-// the discarded half.
-__device__ __forceinline__ void g1_ifft128_dit_lower(G1* sh, const Fr* __restrict__ roots, int tid) {
-#pragma unroll 1
-    for (int half = 1; half <= 64; half <<= 1) {
-        const int tw_step = (N_EXT / 2) / half;
-        int j = tid & (half - 1);
-        int i0 = ((tid - j) << 1) + j, i1 = i0 + half;
-        G1 u = sh[i0], v = sh[i1];
-        if (j != 0) {
-            uint32_t k[8];
-            twiddle_plain(k, roots, N_EXT - j * tw_step);
-            v = g1_mul_xyzz(v, k);
-        }
+// mode GS_INVERSE (decimation in time, g1_ifft_unscaled fft.c:227): v' = [w^-j] v; (u+v', u-v'); the
+//   last stage (half = 64) keeps only the lower output (FK20 discards the upper half, fk20.c:264-266).
+// mode GS_FORWARD_FIRST: input upper half is infinity: (u, [w^j] u).
+// mode GS_FORWARD (decimation in frequency, g1_fft fft.c:199): (u+v, [w^j](u-v)).
+__global__ void __launch_bounds__(32 * GS_WARPS) g1_fft_stage_kernel(G1* __restrict__ data, uint64_t nvec, int half, int mode) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x * GS_WARPS + warp;  // 0..63
+    const uint64_t vec = (uint64_t)blockIdx.y * 32 + lane;
+    if (vec >= nvec) return;
+    const int j = b & (half - 1);
+    const int i0 = ((b - j) << 1) + j, i1 = i0 + half;
+    const int step = 64 / half;                       // twiddle exponent of w128 per unit of j
+    G1* base = data + vec * 128;
+    if (mode == GS_FORWARD_FIRST) {
+        G1 u = ld_g1(base + i0);
+        st_g1(base + i1, g1_mul_twiddle(u, j * step));
+        return;
+    }
+    G1 u = ld_g1(base + i0), v = ld_g1(base + i1);
+    if (mode == GS_INVERSE) {
+        if (j != 0) v = g1_mul_twiddle(v, (128 - j * step) & 127);
         G1 s = u;
         g1_add_to(s, v);
-        sh[i0] = s;
+        st_g1(base + i0, s);
         if (half != 64) {
             G1 d = g1_neg(v);
             g1_add_to(d, u);
-            sh[i1] = d;
+            st_g1(base + i1, d);
         }
-        __syncthreads();
-    }
-}
-// forward, decimation in frequency: natural input whose upper half is infinity -> bit-reversed output
-// (g1_fft, fft.c:199, on [v_0..v_63, inf x 64])
-__device__ __forceinline__ void g1_fft128_dif_upper_zero(G1* sh, const Fr* __restrict__ roots, int tid) {
-    {  // first stage: (u, inf) -> (u, [w^j] u)
-        int j = tid;  // half = 64: j = tid, i0 = tid, i1 = tid + 64
-        G1 u = sh[tid];
-        if (j != 0) {
-            uint32_t k[8];
-            twiddle_plain(k, roots, j * (N_EXT / 128));
-            u = g1_mul_xyzz(u, k);
-        }
-        sh[tid + 64] = u;
-        __syncthreads();
-    }
-#pragma unroll 1
-    for (int half = 32; half >= 1; half >>= 1) {
-        const int tw_step = (N_EXT / 2) / half;
-        int j = tid & (half - 1);
-        int i0 = ((tid - j) << 1) + j, i1 = i0 + half;
-        G1 u = sh[i0], v = sh[i1];
+    } else {
         G1 s = u;
         g1_add_to(s, v);
         G1 d = g1_neg(v);
         g1_add_to(d, u);
-        if (j != 0) {
-            uint32_t k[8];
-            twiddle_plain(k, roots, j * tw_step);
-            d = g1_mul_xyzz(d, k);
-        }
-        sh[i0] = s;
-        sh[i1] = d;
-        __syncthreads();
+        if (j != 0) d = g1_mul_twiddle(d, j * step);
+        st_g1(base + i0, s);
+        st_g1(base + i1, d);
     }
 }
 
-template <bool WITH_INVERSE>
-__global__ void __launch_bounds__(GF_THREADS) g1_fft128_kernel(G1* __restrict__ out, const G1* __restrict__ in, const Fr* __restrict__ roots) {
-    __shared__ G1 sh[128];
-    const int vec = blockIdx.x, tid = threadIdx.x;
-    sh[tid] = ld_g1(in + (size_t)vec * 128 + tid);
-    sh[tid + 64] = ld_g1(in + (size_t)vec * 128 + tid + 64);
-    __syncthreads();
-    if (WITH_INVERSE) g1_ifft128_dit_lower(sh, roots, tid);
-    g1_fft128_dif_upper_zero(sh, roots, tid);
-    st_g1(out + (size_t)vec * 128 + tid, sh[tid]);
-    st_g1(out + (size_t)vec * 128 + tid + 64, sh[tid + 64]);
+// in place: [inverse DIT on bit-reversed input, lower half kept] -> forward DIF with upper half = infinity
+static int g1_fft128_run(Launch& L, G1* data, uint64_t nvec, bool with_inverse) {
+    dim3 grid(64 / GS_WARPS, (unsigned)((nvec + 31) / 32));
+    if (with_inverse) {
+        for (int half = 1; half <= 64; half <<= 1) {
+            g1_fft_stage_kernel<<<grid, 32 * GS_WARPS, 0, L.stream>>>(data, nvec, half, GS_INVERSE);
+            KZG_CUDA_TRY(cudaGetLastError());
+        }
+    }
+    g1_fft_stage_kernel<<<grid, 32 * GS_WARPS, 0, L.stream>>>(data, nvec, 64, GS_FORWARD_FIRST);
+    KZG_CUDA_TRY(cudaGetLastError());
+    for (int half = 32; half >= 1; half >>= 1) {
+        g1_fft_stage_kernel<<<grid, 32 * GS_WARPS, 0, L.stream>>>(data, nvec, half, GS_FORWARD);
+        KZG_CUDA_TRY(cudaGetLastError());
+    }
+    return RET_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -238,9 +241,12 @@ int fk20_setup(Launch& L, Ctx* c) {
     KZG_CUDA_TRY(cudaMallocAsync((void**)&bases, (size_t)FK_POINTS * FK_W * sizeof(G1Affine), L.stream));
     fk_gather_x_kernel<<<64 * 128 / 128, 128, 0, L.stream>>>(xin, c->g1_monomial);
     KZG_CUDA_TRY(cudaGetLastError());
-    g1_fft128_kernel<false><<<64, GF_THREADS, 0, L.stream>>>(xout, xin, c->roots);
-    KZG_CUDA_TRY(cudaGetLastError());
-    fk_xhat_affine_kernel<<<64 * 128 / 64, 64, 0, L.stream>>>(xhat, xout);
+    {
+        int rc = g1_fft128_run(L, xin, 64, false);
+        if (rc) return rc;
+    }
+    (void)xout;
+    fk_xhat_affine_kernel<<<64 * 128 / 64, 64, 0, L.stream>>>(xhat, xin);
     KZG_CUDA_TRY(cudaGetLastError());
     fk_bases_kernel<<<FK_POINTS / 64, 64, 0, L.stream>>>(bases, xhat);
     KZG_CUDA_TRY(cudaGetLastError());
@@ -316,9 +322,10 @@ int launch_fk20_msm(Launch& L, G1* u_brp, const uint32_t* S, uint64_t n) {
 
 int launch_fk20_g1_ffts(Launch& L, G1* proofs, G1* u_brp, uint64_t n) {
     if (!n) return RET_OK;
-    g1_fft128_kernel<true><<<(unsigned)n, GF_THREADS, 0, L.stream>>>(proofs, u_brp, L.ctx->roots);
-    KZG_CUDA_TRY(cudaGetLastError());
-    L.count(1, "fk20_g1_ffts");
+    int rc = g1_fft128_run(L, u_brp, n, true);  // in place
+    if (rc) return rc;
+    KZG_CUDA_TRY(cudaMemcpyAsync(proofs, u_brp, n * 128 * sizeof(G1), cudaMemcpyDeviceToDevice, L.stream));
+    L.count(14, "fk20_g1_ffts");
     return RET_OK;
 }
 

@@ -47,12 +47,15 @@ struct CoopTables {
 struct CoopWS {
     CoopTables tb;
     Fp prod[54];
+    Fp part[12][5];  // partial output sums (5 lanes per output coefficient)
     Fp reg[COOP_NREG][12];
     Fp line[2][5];  // per pair: A.c0*s, A.c1*s, B.c0*xs, B.c1*xs, ys
     Fp pt[2][3];    // per pair: s = ZZ*ZZZ, xs = X*ZZZ, ys = Y*ZZ
     int use[2];
     int result;
 };
+
+KZG_HD Fp sub_(const Fp& x, const Fp& y) { return sub(x, y); }
 
 // signed sum of inputs (indices 0..11 -> a, 12.. -> b)
 KZG_HD Fp coop_sum_inputs(const int8_t* terms, int beg, int end, const Fp* a, const Fp* b) {
@@ -109,16 +112,24 @@ KZG_HD_NOINLINE void coop_run(CoopWS& ws, int op, Fp* dst, const Fp* a, const Fp
         ws.prod[L] = mul(x, y);
     }
     COOP_END
+    // output sums: up to 36 signed terms per coefficient -> 5 lanes per coefficient, then a 5-term tail
     COOP_BEGIN
-    if (lane < 12) {
+    if (lane < 60) {
+        const int k = lane / 5, sub = lane % 5;
         Fp acc = Fp::zero();
-        for (int t = T.oo[lane]; t < T.oo[lane + 1]; t++) {
+        for (int t = T.oo[k] + sub; t < T.oo[k + 1]; t += 5) {
             int code = T.ot[t];
             int mag = code < 0 ? -code : code;
             const Fp& v = (mag > 64) ? a[mag - 65] : ws.prod[mag - 1];
-            acc = (code > 0) ? add(acc, v) : sub(acc, v);
+            acc = (code > 0) ? add(acc, v) : sub_(acc, v);
         }
-        dst[lane] = acc;
+        ws.part[k][sub] = acc;
+    }
+    COOP_END
+    COOP_BEGIN
+    if (lane < 12) {
+        Fp acc = add(add(ws.part[lane][0], ws.part[lane][1]), add(ws.part[lane][2], ws.part[lane][3]));
+        dst[lane] = add(acc, ws.part[lane][4]);
     }
     COOP_END
 }

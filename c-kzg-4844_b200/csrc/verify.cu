@@ -12,6 +12,7 @@
 // denominators inverted with ONE field inversion per blob through a block-wide product scan), one
 // thread per blob for the inherently serial 131 KB SHA-256, one thread per scalar multiplication in
 // the linear combinations.
+#include "g1_glv.cuh"
 #include "sha256.cuh"
 #include "verify.h"
 
@@ -379,7 +380,7 @@ __global__ void __launch_bounds__(64) rlc_points_kernel(G1* __restrict__ U, G1* 
     }
     uint32_t kk[8];
     for (int q = 0; q < 8; q++) kk[q] = k[q];
-    *dst = g1_mul_affine<8>(base, kk);
+    *dst = g1_mul_glv_affine(base, kk);  // scalars are field elements (< r)
 }
 
 // tree sum: each block folds up to 128 * 8 inputs into one output

@@ -16,6 +16,7 @@
 // eip7594.c:345-376); the transcript itself is hashed on the host like the blob batch transcript
 // (src/host_sha256.c).
 #include "cells.h"
+#include "g1_glv.cuh"
 #include "verify.h"
 
 namespace kzg {
@@ -62,7 +63,7 @@ __global__ void __launch_bounds__(64) vc_scalar_mul_kernel(G1* __restrict__ T, c
     if (k >= n) return;
     uint32_t kk[8];
     for (int q = 0; q < 8; q++) kk[q] = s_plain[8 * k + q];
-    T[k] = g1_mul_affine<8>(P[k], kk);
+    T[k] = g1_mul_glv_affine(P[k], kk);
 }
 
 // S[col] = sum_{k in col} T[k];  H[col] = [h_col^64] S[col], h_col^64 = roots[64 * brp7(col)]  (eip7594.c:581-601)
@@ -78,17 +79,7 @@ __global__ void __launch_bounds__(64) vc_column_sums_kernel(G1* __restrict__ S, 
     S[col] = acc;
     uint32_t k[8];
     from_mont<FrTag>(k, ld_frv(roots + 64 * brp7v(col)));
-    // [k] acc, MSB first
-    G1 m = g1_inf();
-    if (!g1_is_inf(acc)) {
-        for (int i = 7; i >= 0; i--) {
-#pragma unroll 1
-            for (int b = 31; b >= 0; b--) {
-                g1_dbl_to(m);
-                if ((k[i] >> b) & 1u) g1_add_to(m, acc);
-            }
-        }
-    }
+    G1 m = g1_mul_glv(acc, k);
     H[col] = m;
 }
 

@@ -133,10 +133,12 @@ int ckzg_b200_compute_challenge(ckzg_b200_ctx *ctx, uint8_t *out32, const uint8_
 /* Counters for bench.py: kernels launched by this library since the context was created. */
 uint64_t ckzg_b200_launch_count(const ckzg_b200_ctx *ctx);
 
-/* Per-kernel device timing for bench.py: enable (also resets the counters), run calls, then dump a
+/* Device timing for bench.py.  level 0 = off; 1 = whole-call begin/end events only (concurrent stages
+ * stay concurrent); 2 = per-kernel events, stages serialised on one stream so the attribution is exact.
+ * Enabling also resets the counters.  Run calls, then dump a
  * JSON object {"calls": n, "call_ms": total, "kernels": {name: [total_ms, launches], ...}} into buf.
  * Times come from CUDA events recorded on the stream each call launches on. Returns bytes written. */
-void ckzg_b200_profile_enable(ckzg_b200_ctx *ctx, int on);
+void ckzg_b200_profile_enable(ckzg_b200_ctx *ctx, int level);
 int ckzg_b200_profile_dump(ckzg_b200_ctx *ctx, char *buf, size_t cap);
 
 /* Device self-tests used by tests/test_gpu_units.py: run `op` over n operand pairs.

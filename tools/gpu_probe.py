@@ -49,7 +49,7 @@ def commit_variant():
     out = torch.empty(48 * n, dtype=torch.uint8, device="cuda")
     for _ in range(2):
         mod.blob_to_kzg_commitment_device(out.data_ptr(), blobs.data_ptr(), n, ts)
-    mod.profile_enable(ts, True)
+    mod.profile_enable(ts, 2)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(3):
@@ -69,7 +69,7 @@ def single_commit():
     blob = bench.synth_blobs(1, 5).tobytes()
     for _ in range(3):
         mod.blob_to_kzg_commitment(blob, ts)
-    mod.profile_enable(ts, True)
+    mod.profile_enable(ts, 2)
     t0 = time.perf_counter()
     for _ in range(10):
         mod.blob_to_kzg_commitment(blob, ts)
