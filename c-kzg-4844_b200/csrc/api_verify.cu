@@ -2,6 +2,8 @@
 // kernels of verify.cu / msm.cu / pairing.cu.  Host code here only sequences launches and copies.
 #include <string.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "../src/host_sha256.h"
@@ -237,9 +239,62 @@ int ckzg_b200_compute_blob_kzg_proof_batch(ckzg_b200_ctx* ctx, uint8_t* proofs, 
     return collect_status(call, d_bad, n, status);
 }
 
+// context-free calls (hash / encoding helpers of the reference that take no KZGSettings) run on a bare
+// context bound to the current device
+static Ctx* bare_ctx() {
+    static Ctx bare;
+    int dev = 0;
+    const char* env = getenv("CKZG_B200_DEVICE");
+    if (env)
+        dev = atoi(env);
+    else
+        cudaGetDevice(&dev);
+    bare.device = dev;
+    return &bare;
+}
+
+int ckzg_b200_hash_to_bls_field(uint8_t* out32, const uint8_t* digest32) {
+    if (!out32 || !digest32) return RET_BADARGS;
+    Call call(bare_ctx());
+    if (!call.ok) return RET_ERROR;
+    Launch L = call.launch();
+    const uint8_t* d_digest;
+    TRY(call.stage_in(&d_digest, digest32, 32, CKZG_B200_HOST));
+    Fr* d_r;
+    uint8_t* d_out;
+    TRY(call.alloc(&d_r, 1));
+    TRY(call.alloc(&d_out, 64));
+    TRY(launch_r_from_digest(L, d_r, d_digest));
+    TRY(launch_fr_to_bytes(L, d_out, d_r, 1));
+    KZG_CUDA_TRY(cudaMemcpyAsync(out32, d_out, 32, cudaMemcpyDeviceToHost, call.stream));
+    KZG_CUDA_TRY(cudaStreamSynchronize(call.stream));
+    return RET_OK;
+}
+
+int ckzg_b200_validate_g1(int* ok, const uint8_t* p48) {
+    if (!ok || !p48) return RET_BADARGS;
+    *ok = 0;
+    Call call(bare_ctx());
+    if (!call.ok) return RET_ERROR;
+    Launch L = call.launch();
+    const uint8_t* d_in;
+    TRY(call.stage_in(&d_in, p48, 48, CKZG_B200_HOST));
+    G1Affine* d_pt;
+    int* d_bad;
+    TRY(call.alloc(&d_pt, 1));
+    TRY(call.alloc(&d_bad, 1));
+    KZG_CUDA_TRY(cudaMemsetAsync(d_bad, 0, sizeof(int), call.stream));
+    TRY(launch_g1_validate(L, d_pt, d_in, 1, d_bad, 0));
+    int bad = 0;
+    KZG_CUDA_TRY(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, call.stream));
+    KZG_CUDA_TRY(cudaStreamSynchronize(call.stream));
+    *ok = bad ? 0 : 1;
+    return RET_OK;
+}
+
 int ckzg_b200_compute_challenge(ckzg_b200_ctx* ctx, uint8_t* out32, const uint8_t* blob, const uint8_t* commitment48) {
-    if (!ctx || !out32 || !blob || !commitment48) return RET_BADARGS;
-    Call call(reinterpret_cast<Ctx*>(ctx));
+    if (!out32 || !blob || !commitment48) return RET_BADARGS;
+    Call call(ctx ? reinterpret_cast<Ctx*>(ctx) : bare_ctx());
     if (!call.ok) return RET_ERROR;
     Launch L = call.launch();
     const uint8_t *d_blob, *d_cm;

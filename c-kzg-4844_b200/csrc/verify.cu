@@ -141,9 +141,36 @@ __global__ void fr_from_bytes_kernel(Fr* out, const uint8_t* bytes, uint64_t str
 constexpr int EV_THREADS = 256;
 constexpr int EV_PER = N_BLOB / EV_THREADS;  // 16
 
+// total[blob] = prod_i (z - w_i) over the 4096 evaluation points (a factor that is zero -- z in the
+// domain -- is replaced by 1, exactly as evaluate_kernel does)
+__global__ void __launch_bounds__(EV_THREADS) evaluate_products_kernel(Fr* __restrict__ total, const Fr* __restrict__ z_in, const Fr* __restrict__ roots_brp) {
+    __shared__ Fr sh[EV_THREADS];
+    const int blob = blockIdx.x, t = threadIdx.x;
+    const Fr z = z_in[blob];
+    Fr prod = Fr::one();
+#pragma unroll 1
+    for (int k = 0; k < EV_PER; k++) {
+        Fr d = sub(z, load_fr(roots_brp + t + EV_THREADS * k));
+        if (is_zero(d)) d = Fr::one();
+        prod = mul(prod, d);
+    }
+    sh[t] = prod;
+    __syncthreads();
+#pragma unroll 1
+    for (int s = EV_THREADS / 2; s > 0; s >>= 1) {
+        if (t < s) sh[t] = mul(sh[t], sh[t + s]);
+        __syncthreads();
+    }
+    if (t == 0) total[blob] = sh[0];
+}
+__global__ void evaluate_invert_kernel(Fr* __restrict__ total, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) total[i] = fr_inv(total[i]);
+}
+
 __global__ void __launch_bounds__(EV_THREADS) evaluate_kernel(Fr* __restrict__ y_out, uint8_t* __restrict__ zy, Fr* __restrict__ inv_out, int* __restrict__ m_out,
                                                              const uint8_t* __restrict__ blobs, const Fr* __restrict__ z_in, const Fr* __restrict__ roots_brp,
-                                                             int* __restrict__ bad, int bad_stride) {
+                                                             const Fr* __restrict__ total_inv, int* __restrict__ bad, int bad_stride) {
     __shared__ Fr sh_a[EV_THREADS];  // prefix scan / reduction scratch
     __shared__ Fr sh_b[EV_THREADS];  // suffix scan
     __shared__ Fr sh_bcast;
@@ -191,7 +218,9 @@ __global__ void __launch_bounds__(EV_THREADS) evaluate_kernel(Fr* __restrict__ y
         __syncthreads();
     }
     // inclusive scans done: sh_a[t] = prod_0..t, sh_b[t] = prod_t..255
-    if (t == 0) sh_bcast = fr_inv(sh_a[EV_THREADS - 1]);  // the one inversion of this blob
+    // the one inversion of this blob was done by evaluate_invert_kernel (one thread per blob: a
+    // 380-product dependent chain must not hold 255 other threads at a barrier -- ncu r01g)
+    if (t == 0) sh_bcast = total_inv[blob];
     __syncthreads();
     Fr acc = sh_bcast;
     if (t > 0) acc = mul(acc, sh_a[t - 1]);
@@ -441,9 +470,16 @@ int launch_fr_from_bytes(Launch& L, Fr* out, const uint8_t* bytes32, uint64_t st
 }
 int launch_evaluate(Launch& L, Fr* y, uint8_t* zy, Fr* inv_or_null, int* m_or_null, const uint8_t* blobs, const Fr* z, uint64_t n, int* bad, int bad_stride) {
     if (!n) return RET_OK;
-    evaluate_kernel<<<(unsigned)n, EV_THREADS, 0, L.stream>>>(y, zy, inv_or_null, m_or_null, blobs, z, L.ctx->roots_brp, bad, bad_stride);
+    Fr* total = nullptr;
+    KZG_CUDA_TRY(cudaMallocAsync((void**)&total, n * sizeof(Fr), L.stream));
+    evaluate_products_kernel<<<(unsigned)n, EV_THREADS, 0, L.stream>>>(total, z, L.ctx->roots_brp);
     KZG_CUDA_TRY(cudaGetLastError());
-    L.count(1, "evaluate");
+    evaluate_invert_kernel<<<blocks_for(n, 32), 32, 0, L.stream>>>(total, n);
+    KZG_CUDA_TRY(cudaGetLastError());
+    evaluate_kernel<<<(unsigned)n, EV_THREADS, 0, L.stream>>>(y, zy, inv_or_null, m_or_null, blobs, z, L.ctx->roots_brp, total, bad, bad_stride);
+    KZG_CUDA_TRY(cudaGetLastError());
+    KZG_CUDA_TRY(cudaFreeAsync(total, L.stream));
+    L.count(3, "evaluate");
     return RET_OK;
 }
 int launch_quotient(Launch& L, uint8_t* q_scalars, const uint8_t* blobs, const Fr* z, const Fr* y, const Fr* inv, const int* m, uint64_t n) {
@@ -463,6 +499,18 @@ int launch_g1_validate(Launch& L, G1Affine* out, const uint8_t* bytes48, uint64_
     L.count(1, "g1_validate");
     return RET_OK;
 }
+__global__ void fr_to_bytes_kernel(uint8_t* __restrict__ out, const Fr* __restrict__ in, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) store_fr_be(out + 32 * i, in[i]);
+}
+int launch_fr_to_bytes(Launch& L, uint8_t* out32, const Fr* in, uint64_t n) {
+    if (!n) return RET_OK;
+    fr_to_bytes_kernel<<<blocks_for(n, 64), 64, 0, L.stream>>>(out32, in, n);
+    KZG_CUDA_TRY(cudaGetLastError());
+    L.count(1, "fr_to_bytes");
+    return RET_OK;
+}
+
 int launch_r_from_digest(Launch& L, Fr* r, const uint8_t* digest32) {
     r_from_digest_kernel<<<1, 32, 0, L.stream>>>(r, digest32);
     KZG_CUDA_TRY(cudaGetLastError());

@@ -42,6 +42,8 @@ int launch_rlc(Launch& L, G1* out2, const G1Affine* commitments, const G1Affine*
                uint64_t first, uint64_t n_local, void* scratch);
 // sum of n XYZZ points -> out (device); in is clobbered
 int launch_g1_sum(Launch& L, G1* out, G1* in, uint64_t n);
+// canonical 32-byte big-endian encodings of n field elements
+int launch_fr_to_bytes(Launch& L, uint8_t* out32, const Fr* in, uint64_t n);
 // out[i] = XYZZ lift of in[i]
 int launch_lift_affine(Launch& L, G1* out, const G1Affine* in, uint64_t n);
 // Fr from 32-byte canonical big-endian (bad[i]=1 if >= r)

@@ -15,6 +15,8 @@
 #include "../../include/ckzg.h"
 #include "../../include/ckzg_b200.h"
 
+#include "host_sha256.h"
+
 #include <inttypes.h>
 #include <stdlib.h>
 #include <string.h>
@@ -251,4 +253,79 @@ void bytes_from_uint64(uint8_t out[8], uint64_t n) { /* bytes.c:29: big-endian *
         out[i] = (uint8_t)(n & 0xFF);
         n >>= 8;
     }
+}
+
+/*
+ * The remaining exports are "internal, exposed for testing" in the reference (bytes.h:66-74,
+ * eip4844.h:84, eip7594.h:58-68); its Go and Rust test-suites call them.  fr_t / g1_t are private to the
+ * library: here an fr_t carries the canonical big-endian scalar and a g1_t the
+ * validated 48-byte compression, so the conversions are copies; validation and the mod-r reduction
+ * still run on the GPU.
+ */
+static const uint8_t BLS_MODULUS_BE[32] = {0x73, 0xed, 0xa7, 0x53, 0x29, 0x9d, 0x7d, 0x48, 0x33, 0x39, 0xd8, 0x08, 0x09, 0xa1, 0xd8, 0x05,
+                                           0x53, 0xbd, 0xa4, 0x02, 0xff, 0xfe, 0x5b, 0xfe, 0xff, 0xff, 0xff, 0xff, 0x00, 0x00, 0x00, 0x01};
+
+C_KZG_RET bytes_to_bls_field(fr_t *out, const Bytes32 *b) { /* bytes.c:64: canonical (< r) or BADARGS */
+    if (memcmp(b->bytes, BLS_MODULUS_BE, 32) >= 0) return C_KZG_BADARGS;
+    memcpy(out, b->bytes, 32);
+    return C_KZG_OK;
+}
+
+void bytes_from_bls_field(Bytes32 *out, const fr_t *in) { memcpy(out->bytes, in, 32); } /* bytes.c:52 */
+
+static C_KZG_RET bytes_to_g1(g1_t *out, const Bytes48 *b) { /* validate_kzg_g1, bytes.c:81 */
+    int ok = 0;
+    int rc = ckzg_b200_validate_g1(&ok, b->bytes);
+    if (rc != 0) return (C_KZG_RET)rc;
+    if (!ok) return C_KZG_BADARGS;
+    memset(out, 0, sizeof(*out));
+    memcpy(out, b->bytes, 48);
+    return C_KZG_OK;
+}
+C_KZG_RET bytes_to_kzg_commitment(g1_t *out, const Bytes48 *b) { return bytes_to_g1(out, b); } /* bytes.c:101 */
+C_KZG_RET bytes_to_kzg_proof(g1_t *out, const Bytes48 *b) { return bytes_to_g1(out, b); }      /* bytes.c:112 */
+void bytes_from_g1(Bytes48 *out, const g1_t *in) { memcpy(out->bytes, in, 48); }               /* bytes.c:42 */
+
+void compute_challenge(fr_t *eval_challenge_out, const Blob *blob, const g1_t *commitment) { /* eip4844.c:147 */
+    uint8_t z[32];
+    memset(eval_challenge_out, 0, sizeof(*eval_challenge_out));
+    if (ckzg_b200_compute_challenge(NULL, z, blob->bytes, (const uint8_t *)commitment) == 0) memcpy(eval_challenge_out, z, 32);
+}
+
+C_KZG_RET compute_verify_cell_kzg_proof_batch_challenge( /* eip7594.c:390-482 */
+    fr_t *challenge_out,
+    const Bytes48 *commitments_bytes,
+    uint64_t num_commitments,
+    const uint64_t *commitment_indices,
+    const uint64_t *cell_indices,
+    const Cell *cells,
+    const Bytes48 *proofs_bytes,
+    uint64_t num_cells
+) {
+    ckzg_host_sha256 h;
+    uint8_t u64[8], digest[32], out[32];
+    ckzg_host_sha256_init(&h);
+    ckzg_host_sha256_update(&h, "RCKZGCBATCH__V1_", 16);
+    bytes_from_uint64(u64, FIELD_ELEMENTS_PER_BLOB);
+    ckzg_host_sha256_update(&h, u64, 8);
+    bytes_from_uint64(u64, FIELD_ELEMENTS_PER_CELL);
+    ckzg_host_sha256_update(&h, u64, 8);
+    bytes_from_uint64(u64, num_commitments);
+    ckzg_host_sha256_update(&h, u64, 8);
+    bytes_from_uint64(u64, num_cells);
+    ckzg_host_sha256_update(&h, u64, 8);
+    ckzg_host_sha256_update(&h, commitments_bytes, (size_t)num_commitments * BYTES_PER_COMMITMENT);
+    for (uint64_t i = 0; i < num_cells; i++) {
+        bytes_from_uint64(u64, commitment_indices[i]);
+        ckzg_host_sha256_update(&h, u64, 8);
+        bytes_from_uint64(u64, cell_indices[i]);
+        ckzg_host_sha256_update(&h, u64, 8);
+        ckzg_host_sha256_update(&h, cells[i].bytes, BYTES_PER_CELL);
+        ckzg_host_sha256_update(&h, proofs_bytes[i].bytes, BYTES_PER_PROOF);
+    }
+    ckzg_host_sha256_final(&h, digest);
+    int rc = ckzg_b200_hash_to_bls_field(out, digest);
+    if (rc != 0) return (C_KZG_RET)rc;
+    memcpy(challenge_out, out, 32);
+    return C_KZG_OK;
 }

@@ -153,6 +153,16 @@ C_KZG_RET bytes_to_bls_field(fr_t *out, const Bytes32 *b);
 C_KZG_RET bytes_to_kzg_commitment(g1_t *out, const Bytes48 *b);
 C_KZG_RET bytes_to_kzg_proof(g1_t *out, const Bytes48 *b);
 void compute_challenge(fr_t *eval_challenge_out, const Blob *blob, const g1_t *commitment);
+C_KZG_RET compute_verify_cell_kzg_proof_batch_challenge(
+    fr_t *challenge_out,
+    const Bytes48 *commitments_bytes,
+    uint64_t num_commitments,
+    const uint64_t *commitment_indices,
+    const uint64_t *cell_indices,
+    const Cell *cells,
+    const Bytes48 *proofs_bytes,
+    uint64_t num_cells
+);
 
 #ifdef __cplusplus
 }

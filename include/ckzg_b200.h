@@ -127,8 +127,14 @@ int ckzg_b200_verify_cell_kzg_proof_batch(
 );
 
 /* Internal Fiat-Shamir challenge, exposed for the vectors in tests/compute_challenge
- * (src/eip4844/eip4844.c:147; commitment given in its canonical 48-byte form). out = 32 bytes BE. */
+ * (src/eip4844/eip4844.c:147; commitment given in its canonical 48-byte form). out = 32 bytes BE.
+ * ctx may be NULL (the hash needs no setup; the current CUDA device is used). */
 int ckzg_b200_compute_challenge(ckzg_b200_ctx *ctx, uint8_t *out32, const uint8_t *blob, const uint8_t *commitment48);
+
+/* hash_to_bls_field (src/common/bytes.c:123): 32-byte digest -> canonical field element bytes (mod r on the device) */
+int ckzg_b200_hash_to_bls_field(uint8_t *out32, const uint8_t *digest32);
+/* validate_kzg_g1 (src/common/bytes.c:81) for one 48-byte point, no context needed: *ok = 1 if valid */
+int ckzg_b200_validate_g1(int *ok, const uint8_t *p48);
 
 /* Counters for bench.py: kernels launched by this library since the context was created. */
 uint64_t ckzg_b200_launch_count(const ckzg_b200_ctx *ctx);

@@ -1,0 +1,3 @@
+/* Forwarding header: the reference keeps this declaration set in src/common/ec.h; here everything lives in
+ * include/ckzg.h (one umbrella header, no blst dependency). */
+#include "../ckzg.h"

@@ -34,3 +34,18 @@ class PyOracle:
             [ps[48 * i : 48 * i + 48] for i in range(n)],
             self.s,
         )
+
+    def compute_cells_and_kzg_proofs(self, blob, want_cells=True, want_proofs=True):
+        cells, proofs = K.compute_cells_and_kzg_proofs(blob, self.s, want_proofs=want_proofs)
+        return cells, proofs
+
+    def recover_cells_and_kzg_proofs(self, cell_indices, cells, want_proofs=True):
+        n = len(cell_indices)
+        return K.recover_cells_and_kzg_proofs(list(cell_indices), [cells[2048 * i : 2048 * (i + 1)] for i in range(n)], self.s, want_proofs=want_proofs)
+
+    def verify_cell_kzg_proof_batch(self, commitments, cell_indices, cells, proofs):
+        n = len(cell_indices)
+        return K.verify_cell_kzg_proof_batch(
+            [commitments[48 * i : 48 * i + 48] for i in range(n)], list(cell_indices), [cells[2048 * i : 2048 * (i + 1)] for i in range(n)],
+            [proofs[48 * i : 48 * i + 48] for i in range(n)], self.s,
+        )

@@ -325,3 +325,92 @@ def test_verify_cells_differential(gpu, ref, cells3):
     with pytest.raises(ref_lib.BadArgs):
         call(gpu, full[:4], lambda c, ii, ce, pp: c.__setitem__(2, bytes(48)))
     assert gpu.verify_cell_kzg_proof_batch(b"", [], b"", b"") is True
+
+
+def test_helper_exports_and_challenge_vectors(gpu):
+    """The reference's test-only exports (bytes.h:66-74, eip4844.h:84, eip7594.h:58-68) through the frozen
+    API, pinned on tests/compute_challenge and tests/compute_verify_cell_kzg_proof_batch_challenge."""
+    import ctypes as C
+
+    lib = gpu.lib
+    fr, g1 = C.create_string_buffer(32), C.create_string_buffer(144)
+    out32, out48 = C.create_string_buffer(32), C.create_string_buffer(48)
+    R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+    lib.bytes_to_bls_field.restype = C.c_int
+    assert lib.bytes_to_bls_field(fr, (R - 1).to_bytes(32, "big")) == 0
+    lib.bytes_from_bls_field(out32, fr)
+    assert out32.raw == (R - 1).to_bytes(32, "big")
+    assert lib.bytes_to_bls_field(fr, R.to_bytes(32, "big")) == 1
+    lib.bytes_to_kzg_commitment.restype = C.c_int
+    n = 0
+    for name, inp, want in gv.cases("compute_challenge"):
+        blob, cm = inp["blob"], inp["commitment"]
+        if want is None or not (isinstance(blob, bytes) and len(blob) == 131072 and isinstance(cm, bytes) and len(cm) == 48):
+            continue
+        assert lib.bytes_to_kzg_commitment(g1, cm) == 0
+        lib.bytes_from_g1(out48, g1)
+        assert out48.raw == cm
+        lib.compute_challenge(fr, blob, g1)
+        lib.bytes_from_bls_field(out32, fr)
+        assert out32.raw == want, name
+        n += 1
+    assert n >= 5
+    assert lib.bytes_to_kzg_proof(g1, bytes(48)) == 1  # not a valid encoding
+    lib.compute_verify_cell_kzg_proof_batch_challenge.restype = C.c_int
+    m = 0
+    for name, inp, want in gv.cases("compute_verify_cell_kzg_proof_batch_challenge"):
+        if want is None:
+            continue
+        cms, cells, prs = inp["commitments"], inp["cosets_evals"], inp["proofs"]
+        ci = [int(x) for x in inp["commitment_indices"]]
+        ki = [int(x) for x in inp["cell_indices"]]
+        cells = [b"".join(c) if isinstance(c, list) else c for c in cells]
+        nc = len(ki)
+        rc = lib.compute_verify_cell_kzg_proof_batch_challenge(
+            fr, b"".join(cms), C.c_uint64(len(cms)), (C.c_uint64 * nc)(*ci), (C.c_uint64 * nc)(*ki), b"".join(cells), b"".join(prs), C.c_uint64(nc)
+        )
+        assert rc == 0
+        lib.bytes_from_bls_field(out32, fr)
+        assert out32.raw == want, name
+        m += 1
+    assert m >= 5
+
+
+def test_reference_python_binding_runs_on_the_engine():
+    """The reference's own CPython extension (unmodified source, tests/refbinding) linked against
+    libckzg_b200.so reproduces consensus vectors: the binding cannot tell the libraries apart."""
+    import importlib.util
+
+    from refbinding.build import OUT
+
+    if not os.path.exists(OUT):
+        pytest.skip("tests/refbinding/_build not built")
+    spec = importlib.util.spec_from_file_location("ckzg", OUT)
+    ckzg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ckzg)
+    ts = ckzg.load_trusted_setup(ref_lib.SETUP_TXT, 0)
+    n = 0
+    for name, inp, want in gv.cases("blob_to_kzg_commitment"):
+        blob = inp["blob"]
+        if not (isinstance(blob, bytes) and len(blob) == 131072):
+            continue
+        try:
+            got = ckzg.blob_to_kzg_commitment(blob, ts)
+        except Exception:
+            got = None
+        assert got == want, name
+        n += 1
+    for name, inp, want in gv.cases("verify_blob_kzg_proof_batch")[:8]:
+        blobs, cs, ps = inp["blobs"], inp["commitments"], inp["proofs"]
+        if not (all(isinstance(b, bytes) and len(b) == 131072 for b in blobs) and all(len(c) == 48 for c in cs) and all(len(p) == 48 for p in ps)) or not (len(blobs) == len(cs) == len(ps)):
+            continue
+        try:
+            got = ckzg.verify_blob_kzg_proof_batch(b"".join(blobs), b"".join(cs), b"".join(ps), ts)
+        except Exception:
+            got = None
+        assert got == want, name
+        n += 1
+    name, inp, want = [c for c in gv.cases("compute_cells_and_kzg_proofs") if c[2] is not None][0]
+    cells, proofs = ckzg.compute_cells_and_kzg_proofs(inp["blob"], ts)
+    assert [bytes(c) for c in cells] == want[0] and [bytes(p) for p in proofs] == want[1]
+    assert n >= 10

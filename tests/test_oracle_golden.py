@@ -50,6 +50,8 @@ PY_APIS = {
     "compute_blob_kzg_proof": 10,
     "verify_blob_kzg_proof": 12,
     "verify_blob_kzg_proof_batch": None,
+    "compute_cells": None,
+    "verify_cell_kzg_proof_batch": None,
 }
 
 
@@ -57,3 +59,27 @@ PY_APIS = {
 def test_python_restatement_reproduces_vectors(pyo, api):
     bad, n = vr.run_api(api, pyo, limit=PY_APIS[api])
     assert n > 0 and not bad, [b[0] for b in bad]
+
+
+def test_python_restatement_recover_cells(pyo):
+    """recover (cells only: the FK20 restatement takes ~1 min per blob, see the env-gated test below)."""
+    n = 0
+    for name, inp, want in gv.cases("recover_cells_and_kzg_proofs"):
+        cells = inp["cells"]
+        if want is None:
+            if not all(isinstance(c, bytes) and len(c) == 2048 for c in cells) or len(cells) != len(inp["cell_indices"]):
+                continue  # binding-level length errors (bindings/go/main.go:474-480)
+            with pytest.raises(Exception):
+                pyo.recover_cells_and_kzg_proofs([int(x) for x in inp["cell_indices"]], b"".join(cells), False)
+        else:
+            got, _ = pyo.recover_cells_and_kzg_proofs([int(x) for x in inp["cell_indices"]], b"".join(cells), False)
+            assert got == b"".join(want[0]), name
+        n += 1
+    assert n >= 10
+
+
+@pytest.mark.skipif(not os.environ.get("KZG_SLOW_ORACLE"), reason="FK20 in pure Python: ~1 min per blob (set KZG_SLOW_ORACLE=1)")
+def test_python_restatement_fk20_proofs(pyo):
+    name, inp, want = [c for c in gv.cases("compute_cells_and_kzg_proofs") if c[2] is not None][0]
+    cells, proofs = pyo.compute_cells_and_kzg_proofs(inp["blob"])
+    assert cells == b"".join(want[0]) and proofs == b"".join(want[1])
