@@ -1,0 +1,91 @@
+"""-m gpu: BASELINE.json sizes through size-independent properties and sampled differential checks
+(the consensus vectors stop at 7 blobs / 128 cells)."""
+import os
+import random
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+
+    import __graft_entry__ as entry
+    import bench
+
+    mod = entry.load_package()
+    ts = mod.load_trusted_setup()
+    n = 1024
+    host = torch.from_numpy(bench.synth_blobs(n, 31337))
+    dev = host.cuda()
+    cms = torch.empty(48 * n, dtype=torch.uint8, device="cuda")
+    prs = torch.empty(48 * n, dtype=torch.uint8, device="cuda")
+    mod.blob_to_kzg_commitment_device(cms.data_ptr(), dev.data_ptr(), n, ts)
+    mod.compute_blob_kzg_proof_device(prs.data_ptr(), dev.data_ptr(), cms.data_ptr(), n, ts)
+    return mod, ts, n, host, dev, cms, prs
+
+
+def test_batch1024_commitments_and_proofs_sampled_vs_reference(env):
+    from oracle import ref_lib
+
+    mod, ts, n, host, dev, cms, prs = env
+    if not os.path.exists(ref_lib.REF_SO):
+        pytest.skip("oracle/_ref not built")
+    ref = ref_lib.CKZG()
+    hb, hc, hp = host.numpy().tobytes(), cms.cpu().numpy().tobytes(), prs.cpu().numpy().tobytes()
+    for i in random.Random(5).sample(range(n), 12) + [0, n - 1]:
+        blob = hb[131072 * i : 131072 * (i + 1)]
+        c = ref.blob_to_kzg_commitment(blob)
+        assert hc[48 * i : 48 * i + 48] == c, i
+        assert hp[48 * i : 48 * i + 48] == ref.compute_blob_kzg_proof(blob, c), i
+
+
+def test_batch1024_verify_true_and_single_corruption_false(env):
+    mod, ts, n, host, dev, cms, prs = env
+    assert mod.verify_blob_kzg_proof_batch_device(dev.data_ptr(), cms.data_ptr(), prs.data_ptr(), n, ts) is True
+    # host-pointer call (chunked upload path) must agree
+    assert mod.verify_blob_kzg_proof_batch(host.numpy().tobytes(), cms.cpu().numpy().tobytes(), prs.cpu().numpy().tobytes(), ts) is True
+    bad = prs.clone()
+    i = 777
+    bad[48 * i : 48 * i + 48] = prs[48 * (i + 1) : 48 * (i + 2)].clone()
+    assert mod.verify_blob_kzg_proof_batch_device(dev.data_ptr(), cms.data_ptr(), bad.data_ptr(), n, ts) is False
+    # one flipped blob byte (still canonical): the evaluation changes -> false
+    blobs2 = dev.clone()
+    blobs2[131072 * 500 + 31] ^= 1
+    assert mod.verify_blob_kzg_proof_batch_device(blobs2.data_ptr(), cms.data_ptr(), prs.data_ptr(), n, ts) is False
+
+
+def test_cells_recover_roundtrip_batch(env):
+    """encode -> erase half -> decode at batch 128 (BASELINE configs[2]/[3] shapes), plus cell-proof verification."""
+    import torch
+
+    mod, ts, n, host, dev, cms, prs = env
+    m = 128
+    cells = torch.empty(m * 262144, dtype=torch.uint8, device="cuda")
+    cprf = torch.empty(m * 128 * 48, dtype=torch.uint8, device="cuda")
+    mod.compute_cells_and_kzg_proofs_device(cells.data_ptr(), cprf.data_ptr(), dev.data_ptr(), m, ts)
+    # first half of the extension is the blob itself
+    assert torch.equal(cells.view(m, 2, 131072)[:, 0, :].reshape(-1), dev[: m * 131072])
+    for pattern in (list(range(0, 128, 2)), list(range(64, 128)), sorted(random.Random(9).sample(range(128), 70))):
+        idx = pattern * m
+        given = cells.view(m, 128, 2048)[:, pattern, :].contiguous()
+        rc = torch.empty_like(cells)
+        rp = torch.empty_like(cprf)
+        mod.recover_cells_and_kzg_proofs_device(rc.data_ptr(), rp.data_ptr(), idx, given.data_ptr(), len(pattern), m, ts)
+        assert torch.equal(rc, cells) and torch.equal(rp, cprf), pattern[:3]
+    # cell proofs of 4 blobs verify against the blob commitments; a swapped cell does not
+    hc, hp, hcm = cells.cpu().numpy().tobytes(), cprf.cpu().numpy().tobytes(), cms.cpu().numpy().tobytes()
+    sel = [(b, k) for b in range(4) for k in range(0, 128, 3)]
+    cm_l = [hcm[48 * b : 48 * b + 48] for b, k in sel]
+    idx_l = [k for b, k in sel]
+    cell_l = [hc[(b * 128 + k) * 2048 : (b * 128 + k + 1) * 2048] for b, k in sel]
+    prf_l = [hp[(b * 128 + k) * 48 : (b * 128 + k + 1) * 48] for b, k in sel]
+    assert mod.verify_cell_kzg_proof_batch(cm_l, idx_l, cell_l, prf_l, ts) is True
+    cell_l[5], cell_l[6] = cell_l[6], cell_l[5]
+    assert mod.verify_cell_kzg_proof_batch(cm_l, idx_l, cell_l, prf_l, ts) is False
