@@ -93,15 +93,19 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
     KZG_CUDA_TRY(cudaMemsetAsync(s.bad, 0, sizeof(int), call.stream));
     if (call.trace_kernels || n < 64) {  // serial form
         if (host) KZG_CUDA_TRY(cudaMemcpyAsync(d_up, blobs, n * BLOB_BYTES, cudaMemcpyHostToDevice, call.stream));
-        TRY(launch_g1_validate(L, s.cm, d_cm, n, s.bad, 0));
-        TRY(launch_g1_validate(L, s.pf, d_pf, n, s.bad, 0));
+        TRY(launch_g1_validate2(L, s.cm, d_cm, s.pf, d_pf, n, s.bad));
         TRY(launch_blob_challenges(L, s.z, s.zy, d_blobs, d_cm, n));
         TRY(launch_evaluate(L, s.y, s.zy, nullptr, nullptr, d_blobs, s.z, n, s.bad, 0));
         return RET_OK;
     }
-    // fork: side streams start after the allocations / memset enqueued so far
+    // fork: side streams start after the allocations / memset enqueued so far.
+    // Measured on B200 (tools/gpu_probe.py modes, n = 4096 device-resident): everything on one stream
+    // 16.4 ms; hash -> evaluate chains on a side stream next to the validations 17.6 ms (the two
+    // throughput kernels get in each other's way); ONLY the latency-bound hashes on side streams, the
+    // validations and then the evaluations on the main stream: 14.3 ms.  That is the arrangement here.
     const uint64_t CH = host ? 512 : n;
-    const int nside = (int)std::min<uint64_t>(8, (n + CH - 1) / CH);
+    const int nchunks = (int)((n + CH - 1) / CH);
+    const int nside = std::min(8, nchunks);
     cudaStream_t side[8], copy = nullptr;
     cudaEvent_t ev;
     KZG_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -116,8 +120,7 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
         cudaStreamWaitEvent(copy, ev, 0);
     }
     cudaEventDestroy(ev);
-    // main stream: point validation (independent of the blobs)
-    if ((rc = launch_g1_validate(L, s.cm, d_cm, n, s.bad, 0)) == RET_OK) rc = launch_g1_validate(L, s.pf, d_pf, n, s.bad, 0);
+    std::vector<cudaEvent_t> hashed(nchunks, nullptr);
     int c = 0;
     for (uint64_t off = 0; off < n && rc == RET_OK; off += CH, c++) {
         const uint64_t m = (n - off < CH) ? n - off : CH;
@@ -135,20 +138,24 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
         }
         Launch Ls = call.launch_on(st);
         if ((rc = launch_blob_challenges(Ls, s.z + off, s.zy + off * 64, d_blobs + off * BLOB_BYTES, d_cm + off * 48, m))) break;
-        rc = launch_evaluate(Ls, s.y + off, s.zy + off * 64, nullptr, nullptr, d_blobs + off * BLOB_BYTES, s.z + off, m, s.bad, 0);
-    }
-    // join
-    for (int i = 0; i < nside; i++) {
-        cudaEvent_t done;
-        if (cudaEventCreateWithFlags(&done, cudaEventDisableTiming) == cudaSuccess) {
-            cudaEventRecord(done, side[i]);
-            cudaStreamWaitEvent(call.stream, done, 0);
-            cudaEventDestroy(done);
-        } else {
-            cudaStreamSynchronize(side[i]);
+        if (cudaEventCreateWithFlags(&hashed[c], cudaEventDisableTiming) != cudaSuccess) {
+            rc = RET_ERROR;
+            break;
         }
-        cudaStreamDestroy(side[i]);
+        cudaEventRecord(hashed[c], st);
     }
+    // main stream: point validation (independent of the blobs), then each chunk's evaluation as soon as
+    // its challenges exist
+    if (rc == RET_OK) rc = launch_g1_validate2(L, s.cm, d_cm, s.pf, d_pf, n, s.bad);
+    c = 0;
+    for (uint64_t off = 0; off < n; off += CH, c++) {
+        const uint64_t m = (n - off < CH) ? n - off : CH;
+        if (!hashed[c]) continue;
+        cudaStreamWaitEvent(call.stream, hashed[c], 0);
+        cudaEventDestroy(hashed[c]);
+        if (rc == RET_OK) rc = launch_evaluate(L, s.y + off, s.zy + off * 64, nullptr, nullptr, d_blobs + off * BLOB_BYTES, s.z + off, m, s.bad, 0);
+    }
+    for (int i = 0; i < nside; i++) cudaStreamDestroy(side[i]);
     if (copy) cudaStreamDestroy(copy);
     return rc;
 }

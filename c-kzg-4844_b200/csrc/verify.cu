@@ -537,6 +537,32 @@ int launch_quotient(Launch& L, uint8_t* q_scalars, const uint8_t* blobs, const F
     L.count(2, "quotient");
     return RET_OK;
 }
+// two arrays in ONE launch: the kernel is latency bound (one 1.9k-product chain per thread, 1 warp
+// per CTA), so validating commitments and proofs together costs the time of one
+__global__ void g1_validate2_kernel(G1Affine* __restrict__ out_a, const uint8_t* __restrict__ in_a, G1Affine* __restrict__ out_b, const uint8_t* __restrict__ in_b, uint64_t n,
+                                    int* __restrict__ bad) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * n) return;
+    const bool second = i >= n;
+    const uint64_t k = second ? i - n : i;
+    const uint8_t* src = (second ? in_b : in_a) + k * 48;
+    uint8_t buf[48];
+    for (int q = 0; q < 48; q++) buf[q] = src[q];
+    G1Affine a;
+    if (!g1a_validate(a, buf)) {
+        *bad = 1;
+        a = g1a_inf();
+    }
+    (second ? out_b : out_a)[k] = a;
+}
+int launch_g1_validate2(Launch& L, G1Affine* out_a, const uint8_t* in_a, G1Affine* out_b, const uint8_t* in_b, uint64_t n, int* bad) {
+    if (!n) return RET_OK;
+    g1_validate2_kernel<<<blocks_for(2 * n, 32), 32, 0, L.stream>>>(out_a, in_a, out_b, in_b, n, bad);
+    KZG_CUDA_TRY(cudaGetLastError());
+    L.count(1, "g1_validate");
+    return RET_OK;
+}
+
 int launch_g1_validate(Launch& L, G1Affine* out, const uint8_t* bytes48, uint64_t n, int* bad, int bad_stride) {
     if (!n) return RET_OK;
     g1_validate_kernel<<<blocks_for(n, 32), 32, 0, L.stream>>>(out, bytes48, n, bad, bad_stride);

@@ -60,6 +60,49 @@ def commit_variant():
                       "kernels_ms_per_call": {k: v[0] / 3 for k, v in prof["kernels"].items()}}))
 
 
+def verify_modes():
+    """verify n=4096 device-resident: wall time per call with stages concurrent (profile level 0/1) and
+    serialised with per-kernel events (level 2); same with pinned host pointers."""
+    import torch
+
+    import __graft_entry__ as entry
+    import bench
+
+    mod = entry.load_package()
+    ts = mod.load_trusted_setup()
+    n = 4096
+    host = torch.from_numpy(bench.synth_blobs(n, 7)).pin_memory()
+    dev = host.cuda()
+    cms = torch.empty(48 * n, dtype=torch.uint8, device="cuda")
+    prs = torch.empty(48 * n, dtype=torch.uint8, device="cuda")
+    mod.blob_to_kzg_commitment_device(cms.data_ptr(), dev.data_ptr(), n, ts)
+    mod.compute_blob_kzg_proof_device(prs.data_ptr(), dev.data_ptr(), cms.data_ptr(), n, ts)
+    hc, hp = cms.cpu().pin_memory(), prs.cpu().pin_memory()
+    out = {"probe": "verify_modes", "stage1_mode": os.environ.get("CKZG_B200_STAGE1_MODE", "1")}
+    for name, level, fn in (
+        ("device_concurrent", 0, lambda: mod.verify_blob_kzg_proof_batch_device(dev.data_ptr(), cms.data_ptr(), prs.data_ptr(), n, ts)),
+        ("device_level1", 1, lambda: mod.verify_blob_kzg_proof_batch_device(dev.data_ptr(), cms.data_ptr(), prs.data_ptr(), n, ts)),
+        ("device_serial_level2", 2, lambda: mod.verify_blob_kzg_proof_batch_device(dev.data_ptr(), cms.data_ptr(), prs.data_ptr(), n, ts)),
+        ("host_concurrent", 0, lambda: mod.verify_blob_kzg_proof_batch_host(host.data_ptr(), hc.data_ptr(), hp.data_ptr(), n, ts)),
+        ("host_serial_level2", 2, lambda: mod.verify_blob_kzg_proof_batch_host(host.data_ptr(), hc.data_ptr(), hp.data_ptr(), n, ts)),
+    ):
+        mod.profile_enable(ts, level)
+        for _ in range(3):
+            assert fn()
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(6):
+            t0 = time.perf_counter()
+            fn()
+            best = min(best, time.perf_counter() - t0)
+        out[name + "_ms"] = round(best * 1e3, 3)
+        if level == 2:
+            pr = mod.profile_dump(ts)
+            out[name + "_kernels_ms"] = {k: round(v[0] / max(1, pr["calls"]), 3) for k, v in pr["kernels"].items() if k != "begin"}
+    mod.profile_enable(ts, 0)
+    print(json.dumps(out))
+
+
 def single_commit():
     import __graft_entry__ as entry
     import bench
@@ -79,12 +122,15 @@ def single_commit():
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "single":
+    if len(sys.argv) > 1 and sys.argv[1] == "modes":
+        verify_modes()
+    elif len(sys.argv) > 1 and sys.argv[1] == "single":
         single_commit()
     elif len(sys.argv) > 1 and sys.argv[1] == "commit":
         commit_variant()
     else:
         mulbench()
+        subprocess.call([sys.executable, os.path.abspath(__file__), "modes"])
         subprocess.call([sys.executable, os.path.abspath(__file__), "single"])
         for v in ("3", "13", "4", "14"):
             env = dict(os.environ, CKZG_B200_ACC_VARIANT=v)
