@@ -89,3 +89,33 @@ def test_cells_recover_roundtrip_batch(env):
     assert mod.verify_cell_kzg_proof_batch(cm_l, idx_l, cell_l, prf_l, ts) is True
     cell_l[5], cell_l[6] = cell_l[6], cell_l[5]
     assert mod.verify_cell_kzg_proof_batch(cm_l, idx_l, cell_l, prf_l, ts) is False
+
+
+def test_concurrent_callers_share_one_settings(env):
+    """The reference allows many threads on one const KZGSettings (bindings/rust/src/bindings/mod.rs:912,
+    bindings/go/main_test.go:957-970): every call here owns its stream and pool allocations."""
+    import threading
+
+    mod, ts, n, host, dev, cms, prs = env
+    hb, hc = host.numpy().tobytes(), cms.cpu().numpy().tobytes()
+    hp = prs.cpu().numpy().tobytes()
+    errors = []
+
+    def worker(w):
+        try:
+            for k in range(6):
+                i = (w * 6 + k) % 64
+                blob = hb[131072 * i : 131072 * (i + 1)]
+                assert mod.blob_to_kzg_commitment(blob, ts) == hc[48 * i : 48 * i + 48]
+                assert mod.verify_blob_kzg_proof(blob, hc[48 * i : 48 * i + 48], hp[48 * i : 48 * i + 48], ts) is True
+                if k % 3 == 0:
+                    assert mod.verify_blob_kzg_proof_batch(hb[: 131072 * 8], hc[: 48 * 8], hp[: 48 * 8], ts) is True
+        except Exception as e:  # noqa: BLE001
+            errors.append((w, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(w,)) for w in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
