@@ -234,8 +234,38 @@ def run_b200(args):
     def verify_host():
         return mod.verify_blob_kzg_proof_batch_host(host_blobs.data_ptr(), host_cms.data_ptr(), host_prs.data_ptr(), n, ts)
 
+    # --sharded: ONE global batch of world*n blobs with a single Fiat-Shamir challenge (exact reference
+    # semantics for the concatenation): per-blob stage on each rank, all-gather of z||y (64 B/blob),
+    # partial linear combinations, all-gather of 2 compressed points per rank, one pairing.
+    all_cms = all_prs = None
+    if args.sharded:
+        if world > 1:
+            gc = [torch.empty_like(d_cms) for _ in range(world)]
+            gp = [torch.empty_like(d_prs) for _ in range(world)]
+            dist.all_gather(gc, d_cms)
+            dist.all_gather(gp, d_prs)
+            all_cms = b"".join(bytes(t.cpu().numpy().tobytes()) for t in gc)
+            all_prs = b"".join(bytes(t.cpu().numpy().tobytes()) for t in gp)
+        else:
+            all_cms, all_prs = bytes(host_cms.numpy().tobytes()), bytes(host_prs.numpy().tobytes())
+
+    def verify_sharded():
+        if world == 1:
+            zy = mod.verify_stage1(d_blobs.data_ptr(), d_cms.data_ptr(), d_prs.data_ptr(), n, ts)
+            tuples = b"".join(all_cms[48 * i : 48 * i + 48] + zy[64 * i : 64 * i + 64] + all_prs[48 * i : 48 * i + 48] for i in range(n))
+            return mod.verify_finish(mod.verify_stage2(tuples, n, 0, n, ts), 1, ts)
+        return par.verify_batch_sharded(
+            lambda: mod.verify_stage1(d_blobs.data_ptr(), d_cms.data_ptr(), d_prs.data_ptr(), n, ts),
+            lambda tuples, nt, first, nl: mod.verify_stage2(tuples, nt, first, nl, ts),
+            lambda parts, nr: mod.verify_finish(parts, nr, ts),
+            all_cms, all_prs, world * n, dev,
+        )
+
     def step(fn):
-        ok = par.verify_batch_replicas(fn, dev)
+        if args.sharded and fn is verify_dev:
+            ok = verify_sharded()
+        else:
+            ok = par.verify_batch_replicas(fn, dev)
         assert ok, "verification of valid synthetic batch failed"
 
     # negative control: two swapped proofs must be rejected
@@ -412,7 +442,7 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "u32 limbs (381/255-bit Montgomery integers)", "data": "synthetic",
             "config": {
                 "workload": "verify_blob_kzg_proof_batch n=%d per GPU (north_star batch; configs[1] n=64 under extra)" % n,
-                "blobs_per_gpu": n, "parallelism": "replicas x%d + 1 all-reduce(MIN)" % world if world > 1 else "single GPU",
+                "blobs_per_gpu": n, "parallelism": ("sharded global batch x%d: all-gather(z||y) + all-gather(partials)" % world) if args.sharded else ("replicas x%d + 1 all-reduce(MIN)" % world if world > 1 else "single GPU"),
                 "l2": "inputs (%.0f MiB/step) exceed the 126 MB L2; no explicit flush" % (n * BLOB / 2**20),
             },
             "e2e": {"value": e2e_value, "unit": "blobs/s", "h2d_bytes_per_step": n * (BLOB + 96), "d2h_bytes_per_step": 8, "ms_per_step": 1000.0 * e_wall / args.steps},
@@ -433,6 +463,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--blobs", type=int, default=4096, help="blobs per GPU per step")
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--sharded", action="store_true", help="one global batch, single challenge, all-gather exchange (parallel.verify_batch_sharded)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
