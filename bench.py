@@ -52,6 +52,10 @@ ALGO_BYTES_PER_BLOB = {
     "msm_reduce": 196608 + 192,
     "g1_compress": 192 + 48,
 }
+# measured DRAM traffic per blob (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full`
+# capture, profiles/r01_summary.md "r01k"), for the kernels that were captured
+MEASURED_TRAFFIC_PER_BLOB = {"msm_accumulate": 596_000, "evaluate": 568_000, "rlc_points": 900}
+
 # algorithmic 32x32->64 multiply-accumulates per blob (SURVEY.md section 8(d) convention: Fp mul = 300, Fr mul = 136)
 ALGO_MAC_PER_BLOB = {
     "evaluate": 112 * 256 * 136,
@@ -327,7 +331,8 @@ def run_b200(args):
     algo_bytes = ALGO_BYTES_PER_BLOB.get(dom, 0) * units_per_launch
     achieved = algo_bytes / (dom_ms_per_launch * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": (MEASURED_TRAFFIC_PER_BLOB[dom] * units_per_launch) if dom in MEASURED_TRAFFIC_PER_BLOB else None,
         "peak_source": peak_src, "share_of_step": kern[dom][0] / total_ms, "ms_per_launch": dom_ms_per_launch,
         "algorithmic_bytes_per_blob": ALGO_BYTES_PER_BLOB.get(dom, 0),
         "note": "integer-pipe bound path (SURVEY 8d): HBM fraction is reported for completeness, see int_pipe",
@@ -340,6 +345,10 @@ def run_b200(args):
             t_s = kern[k][0] / prof_steps * 1e-3
             int_pipe[k] = {"mac_per_s": mac * n / t_s, "frac_of_peak": mac * n / t_s / peak_mac}
     shares = {k: round(v[0] / total_ms, 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])}
+    roofline["per_kernel"] = {
+        k: {"ms_per_step": round(v[0] / prof_steps, 4), "algorithmic_GBps": round(ALGO_BYTES_PER_BLOB.get(k, 0) * n / (v[0] / prof_steps * 1e-3) / 1e9, 3) if v[0] > 0 else None}
+        for k, v in kern.items()
+    }
 
     extra = {}
     if rank == 0 and not args.no_extra:

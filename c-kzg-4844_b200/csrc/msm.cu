@@ -103,8 +103,9 @@ constexpr int SORT_THREADS = 256;
 
 __global__ void __launch_bounds__(SORT_THREADS) msm_sort_kernel(
     uint32_t* __restrict__ entries, uint32_t* __restrict__ starts, uint32_t* __restrict__ item_start, uint16_t* __restrict__ item_bucket,
-    const uint8_t* __restrict__ scalars, bool big_endian, int* __restrict__ bad, uint32_t cap, uint32_t max_items
+    uint16_t* __restrict__ item_order, const uint8_t* __restrict__ scalars, bool big_endian, int* __restrict__ bad, uint32_t cap, uint32_t max_items
 ) {
+    __shared__ uint32_t lhist[132];  // work items by slice length (<= cap <= 128)
     __shared__ uint32_t hist[MSM_NB];
     __shared__ uint32_t warp_sums[SORT_THREADS / 32];
     __shared__ int s_bad;
@@ -187,6 +188,34 @@ __global__ void __launch_bounds__(SORT_THREADS) msm_sort_kernel(
         q += p3;
         if (tid == SORT_THREADS - 1) is[MSM_NB] = q;
     }
+    for (int i = tid; i < 132; i += SORT_THREADS) lhist[i] = 0;
+    __syncthreads();
+    // Order the work items by slice length (longest first) so that the 32 lanes of a warp of
+    // msm_accumulate walk lists of (nearly) equal length: ncu r01k showed 26.2 of 32 lanes active with
+    // items in bucket order (Poisson spread of the bucket sizes).
+    {
+        const uint32_t* is = item_start + (size_t)blob * (MSM_NB + 1);
+        const uint16_t* ib = item_bucket + (size_t)blob * max_items;
+        uint16_t* ord = item_order + (size_t)blob * max_items;
+        const uint32_t total = is[MSM_NB];
+        auto slice_len = [&](uint32_t it) {
+            const uint32_t b = ib[it], first = is[b], np = is[b + 1] - first, part = it - first;
+            const uint32_t len = st[b + 1] - st[b];
+            return (uint32_t)(((uint64_t)len * (part + 1)) / np) - (uint32_t)(((uint64_t)len * part) / np);
+        };
+        for (uint32_t it = tid; it < total; it += SORT_THREADS) atomicAdd(&lhist[slice_len(it)], 1u);
+        __syncthreads();
+        if (tid == 0) {  // descending exclusive scan over <= 129 bins
+            uint32_t run = 0;
+            for (int l = 131; l >= 0; l--) {
+                uint32_t c = lhist[l];
+                lhist[l] = run;
+                run += c;
+            }
+        }
+        __syncthreads();
+        for (uint32_t it = tid; it < total; it += SORT_THREADS) ord[atomicAdd(&lhist[slice_len(it)], 1u)] = (uint16_t)it;
+    }
     __syncthreads();
 
     // pass 2: scatter (order inside a bucket is irrelevant: group addition commutes)
@@ -251,12 +280,14 @@ __device__ __forceinline__ void g1_madd_nl(G1& acc, const G1Affine& a_in, bool n
 template <int MIN_BLOCKS, bool NL>
 __global__ void __launch_bounds__(ACC_THREADS, MIN_BLOCKS) msm_accumulate_kernel(
     G1* __restrict__ partial, const uint32_t* __restrict__ entries, const uint32_t* __restrict__ starts,
-    const uint32_t* __restrict__ item_start, const uint16_t* __restrict__ item_bucket, const G1Affine* __restrict__ table, uint32_t max_items
+    const uint32_t* __restrict__ item_start, const uint16_t* __restrict__ item_bucket, const uint16_t* __restrict__ item_order, const G1Affine* __restrict__ table,
+    uint32_t max_items
 ) {
-    const uint32_t item = blockIdx.x * ACC_THREADS + threadIdx.x;
+    const uint32_t slot = blockIdx.x * ACC_THREADS + threadIdx.x;
     const int blob = blockIdx.y;
     const uint32_t* is = item_start + (size_t)blob * (MSM_NB + 1);
-    if (item >= is[MSM_NB]) return;
+    if (slot >= is[MSM_NB]) return;
+    const uint32_t item = item_order[(size_t)blob * max_items + slot];  // length-sorted schedule
     const uint32_t bucket = item_bucket[(size_t)blob * max_items + item];
     const uint32_t first = is[bucket], np = is[bucket + 1] - first, part = item - first;
     const uint32_t* st = starts + (size_t)blob * (MSM_NB + 1);
@@ -385,7 +416,7 @@ static uint32_t msm_max_items(int cap) {
 // `cap` = most list entries one thread folds
 size_t msm_workspace_bytes(uint64_t n, int cap) {
     uint32_t mi = msm_max_items(cap);
-    return align256(n * MSM_ENTRIES * sizeof(uint32_t)) + 2 * align256(n * (MSM_NB + 1) * sizeof(uint32_t)) + align256(n * mi * sizeof(uint16_t)) +
+    return align256(n * MSM_ENTRIES * sizeof(uint32_t)) + 2 * align256(n * (MSM_NB + 1) * sizeof(uint32_t)) + 2 * align256(n * mi * sizeof(uint16_t)) +
            align256(n * mi * sizeof(G1)) + (cap < 128 ? align256(n * MSM_NB * sizeof(G1)) : 0);
 }
 
@@ -409,21 +440,23 @@ int launch_msm(Launch& L, G1* result, const uint8_t* scalars, bool big_endian_by
     ws += align256(n * (MSM_NB + 1) * sizeof(uint32_t));
     uint16_t* item_bucket = (uint16_t*)ws;
     ws += align256(n * mi * sizeof(uint16_t));
+    uint16_t* item_order = (uint16_t*)ws;
+    ws += align256(n * mi * sizeof(uint16_t));
     G1* partial = (G1*)ws;
 
-    msm_sort_kernel<<<(unsigned)n, SORT_THREADS, 0, L.stream>>>(entries, starts, item_start, item_bucket, scalars, big_endian_bytes, d_bad, (uint32_t)cap, mi);
+    msm_sort_kernel<<<(unsigned)n, SORT_THREADS, 0, L.stream>>>(entries, starts, item_start, item_bucket, item_order, scalars, big_endian_bytes, d_bad, (uint32_t)cap, mi);
     KZG_CUDA_TRY(cudaGetLastError());
     L.count(1, "msm_sort");
     dim3 grid(mi / ACC_THREADS, (unsigned)n);
     static const int variant = getenv("CKZG_B200_ACC_VARIANT") ? atoi(getenv("CKZG_B200_ACC_VARIANT")) : 14;  // r01c probe: 14 (noinline multiplier, 128 regs) fastest
     if (variant == 13)
-        msm_accumulate_kernel<3, true><<<grid, ACC_THREADS, 0, L.stream>>>(partial, entries, starts, item_start, item_bucket, table, mi);
+        msm_accumulate_kernel<3, true><<<grid, ACC_THREADS, 0, L.stream>>>(partial, entries, starts, item_start, item_bucket, item_order, table, mi);
     else if (variant == 14)
-        msm_accumulate_kernel<4, true><<<grid, ACC_THREADS, 0, L.stream>>>(partial, entries, starts, item_start, item_bucket, table, mi);
+        msm_accumulate_kernel<4, true><<<grid, ACC_THREADS, 0, L.stream>>>(partial, entries, starts, item_start, item_bucket, item_order, table, mi);
     else if (variant == 4)
-        msm_accumulate_kernel<4, false><<<grid, ACC_THREADS, 0, L.stream>>>(partial, entries, starts, item_start, item_bucket, table, mi);
+        msm_accumulate_kernel<4, false><<<grid, ACC_THREADS, 0, L.stream>>>(partial, entries, starts, item_start, item_bucket, item_order, table, mi);
     else
-        msm_accumulate_kernel<3, false><<<grid, ACC_THREADS, 0, L.stream>>>(partial, entries, starts, item_start, item_bucket, table, mi);
+        msm_accumulate_kernel<3, false><<<grid, ACC_THREADS, 0, L.stream>>>(partial, entries, starts, item_start, item_bucket, item_order, table, mi);
     KZG_CUDA_TRY(cudaGetLastError());
     L.count(1, "msm_accumulate");
     if (cap < 128) {
