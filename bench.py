@@ -84,7 +84,7 @@ class ClockSampler:
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
             )
             self.t = threading.Thread(target=self._read, daemon=True)
@@ -94,9 +94,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.perf_counter()] + [c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -104,11 +104,17 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = sorted(int(float(r[0])) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
-        mx = [int(float(r[1])) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        # samples taken inside the timed region [t0, t1]; if the region was shorter than the sampling
+        # period fall back to the samples of the surrounding warm-up (same load)
+        rows = [r[1:] for r in self.rows if len(r) >= 8 and (t0 is None or (t0 - 0.02 <= r[0] <= t1 + 0.02))]
+        window = "timed region"
+        if not rows:
+            rows, window = [r[1:] for r in self.rows if len(r) >= 8], "warm-up + timed region"
+        sm = sorted(int(float(r[0])) for r in rows if r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in rows if r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[k] for r in self.rows if len(r) >= 7 for k in range(4) if r[3 + k].lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        reasons = sorted({names[k] for r in rows for k in range(4) if r[3 + k].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm), "window": window}
 
 
 def synth_blobs(n, seed):
@@ -283,21 +289,21 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     def timed(fn, steps, warmup, profile):
+        sampler = ClockSampler(local_rank)
+        sampler.start()
         for _ in range(warmup):
             step(fn)
         barrier()
         if profile:
             mod.profile_enable(ts, profile)
         l0 = ts.launch_count()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
-        time.sleep(0.25)
         t0 = time.perf_counter()
         for _ in range(steps):
             step(fn)
         barrier()
-        wall = time.perf_counter() - t0
-        clocks = sampler.stop()
+        t1 = time.perf_counter()
+        wall = t1 - t0
+        clocks = sampler.stop(t0, t1)
         prof = mod.profile_dump(ts) if profile else None
         if profile:
             mod.profile_enable(ts, 0)
@@ -467,7 +473,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--blobs", type=int, default=4096, help="blobs per GPU per step")

@@ -310,8 +310,8 @@ int ckzg_b200_verify_cell_kzg_proof_batch(ckzg_b200_ctx* ctx, int* ok, const uin
     TRY(call.alloc(&scratch, verify_cells_scratch_bytes(n, u)));
     KZG_CUDA_TRY(cudaMemsetAsync(d_bad, 0, sizeof(int), call.stream));
     TRY(launch_r_from_digest(L, d_r, d_digest));
-    TRY(launch_g1_validate(L, d_pf_pts, d_pf, n, d_bad, 0));    // bytes_to_kzg_proof, eip7594.c:917-920
-    TRY(launch_g1_validate(L, d_cm_pts, d_uniq, u, d_bad, 0));  // bytes_to_kzg_commitment, :513
+    // bytes_to_kzg_proof (eip7594.c:917-920) and bytes_to_kzg_commitment (:513) in one launch
+    TRY(launch_g1_validate_ab(L, d_pf_pts, d_pf, n, d_cm_pts, d_uniq, u, d_bad));
     TRY(launch_verify_cells(L, d_AB, d_pf_pts, d_cm_pts, d_cells, d_r, (const uint32_t*)d_cs, (const uint32_t*)d_ci, (const uint32_t*)d_ms, (const uint32_t*)d_mi, n, u, d_bad,
                             scratch));
     int bad = 0;

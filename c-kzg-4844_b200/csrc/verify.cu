@@ -540,9 +540,9 @@ int launch_quotient(Launch& L, uint8_t* q_scalars, const uint8_t* blobs, const F
 // two arrays in ONE launch: the kernel is latency bound (one 1.9k-product chain per thread, 1 warp
 // per CTA), so validating commitments and proofs together costs the time of one
 __global__ void g1_validate2_kernel(G1Affine* __restrict__ out_a, const uint8_t* __restrict__ in_a, G1Affine* __restrict__ out_b, const uint8_t* __restrict__ in_b, uint64_t n,
-                                    int* __restrict__ bad) {
+                                    uint64_t nb, int* __restrict__ bad) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 2 * n) return;
+    if (i >= n + nb) return;
     const bool second = i >= n;
     const uint64_t k = second ? i - n : i;
     const uint8_t* src = (second ? in_b : in_a) + k * 48;
@@ -556,8 +556,11 @@ __global__ void g1_validate2_kernel(G1Affine* __restrict__ out_a, const uint8_t*
     (second ? out_b : out_a)[k] = a;
 }
 int launch_g1_validate2(Launch& L, G1Affine* out_a, const uint8_t* in_a, G1Affine* out_b, const uint8_t* in_b, uint64_t n, int* bad) {
-    if (!n) return RET_OK;
-    g1_validate2_kernel<<<blocks_for(2 * n, 32), 32, 0, L.stream>>>(out_a, in_a, out_b, in_b, n, bad);
+    return launch_g1_validate_ab(L, out_a, in_a, n, out_b, in_b, n, bad);
+}
+int launch_g1_validate_ab(Launch& L, G1Affine* out_a, const uint8_t* in_a, uint64_t n, G1Affine* out_b, const uint8_t* in_b, uint64_t nb, int* bad) {
+    if (!(n + nb)) return RET_OK;
+    g1_validate2_kernel<<<blocks_for(n + nb, 32), 32, 0, L.stream>>>(out_a, in_a, out_b, in_b, n, nb, bad);
     KZG_CUDA_TRY(cudaGetLastError());
     L.count(1, "g1_validate");
     return RET_OK;

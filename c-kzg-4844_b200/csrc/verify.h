@@ -33,6 +33,7 @@ int launch_quotient(Launch& L, uint8_t* q_scalars, const uint8_t* blobs, const F
 int launch_g1_validate(Launch& L, G1Affine* out, const uint8_t* bytes48, uint64_t n, int* bad, int bad_stride);
 // same for two arrays of n points in one launch (single shared flag)
 int launch_g1_validate2(Launch& L, G1Affine* out_a, const uint8_t* in_a, G1Affine* out_b, const uint8_t* in_b, uint64_t n, int* bad);
+int launch_g1_validate_ab(Launch& L, G1Affine* out_a, const uint8_t* in_a, uint64_t n, G1Affine* out_b, const uint8_t* in_b, uint64_t nb, int* bad);
 // r = hash_to_bls_field(digest): the batch transcript itself (eip4844.c:597-680) is hashed on the host
 int launch_r_from_digest(Launch& L, Fr* r, const uint8_t* digest32);
 // Random linear combination over tuples [first, first+n_local) with powers r^(first+i):

@@ -57,10 +57,18 @@ __global__ void vc_group_weights_kernel(uint32_t* __restrict__ w_plain, const Fr
     from_mont<FrTag>(w_plain + 8 * c, s);
 }
 
-// T[k] = [s_k] P_k for affine points and plain scalars
-__global__ void __launch_bounds__(64) vc_scalar_mul_kernel(G1* __restrict__ T, const G1Affine* __restrict__ P, const uint32_t* __restrict__ s_plain, uint64_t n) {
+// T[k] = [s_k] P_k for affine points and plain scalars; a second (points, scalars, out) triple may ride
+// in the same launch (the kernel is one latency-bound multiplication per thread)
+__global__ void __launch_bounds__(64) vc_scalar_mul_kernel(G1* __restrict__ T, const G1Affine* __restrict__ P, const uint32_t* __restrict__ s_plain, uint64_t n,
+                                                           G1* __restrict__ T2, const G1Affine* __restrict__ P2, const uint32_t* __restrict__ s2_plain, uint64_t n2) {
     uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
+    if (k >= n + n2) return;
+    if (k >= n) {
+        k -= n;
+        T = T2;
+        P = P2;
+        s_plain = s2_plain;
+    }
     uint32_t kk[8];
     for (int q = 0; q < 8; q++) kk[q] = s_plain[8 * k + q];
     T[k] = g1_mul_glv_affine(P[k], kk);
@@ -175,24 +183,42 @@ int launch_verify_cells(Launch& L, G1* out2, const G1Affine* proofs, const G1Aff
     KZG_CUDA_TRY(cudaGetLastError());
     L.count(2, "vc_scalars");
     // one scalar multiplication per cell proof and per unique commitment
-    vc_scalar_mul_kernel<<<nb64, 64, 0, L.stream>>>(T, proofs, rp_plain, n);
+    vc_scalar_mul_kernel<<<(unsigned)((n + u + 63) / 64), 64, 0, L.stream>>>(T, proofs, rp_plain, n, TC, commitments, w_plain, u);
     KZG_CUDA_TRY(cudaGetLastError());
-    vc_scalar_mul_kernel<<<ub64, 64, 0, L.stream>>>(TC, commitments, w_plain, u);
+    L.count(1, "vc_scalar_mul");
+    // The interpolation chain (aggregate -> 64-point inverse transforms -> 64 multiplications on the
+    // monomial setup) does not depend on the proofs: it runs on a side stream unless per-kernel profiling
+    // wants everything on one stream.
+    cudaStream_t side = L.stream;
+    const bool forked = (L.trace == nullptr);
+    if (forked) {
+        cudaEvent_t ev;
+        if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess) return RET_ERROR;
+        KZG_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        KZG_CUDA_TRY(cudaEventRecord(ev, L.stream));  // rp[] is ready at this point
+        cudaStreamWaitEvent(side, ev, 0);
+        cudaEventDestroy(ev);
+    }
+    vc_aggregate_columns_kernel<<<CELLS_EXT, 64, 0, side>>>(agg, cells, rp, col_start, col_items, d_bad);
     KZG_CUDA_TRY(cudaGetLastError());
-    L.count(2, "vc_scalar_mul");
+    vc_interpolate_kernel<<<CELLS_EXT, 64, 0, side>>>(F, agg, c->roots);
+    KZG_CUDA_TRY(cudaGetLastError());
+    vc_sum_columns_kernel<<<1, 64, 0, side>>>(coeff, F);
+    KZG_CUDA_TRY(cudaGetLastError());
+    vc_scalar_mul_kernel<<<1, 64, 0, side>>>(TI, c->g1_monomial, coeff, 64, nullptr, nullptr, nullptr, 0);
+    KZG_CUDA_TRY(cudaGetLastError());
+    L.count(4, "vc_interpolation");
     vc_column_sums_kernel<<<CELLS_EXT / 64, 64, 0, L.stream>>>(S, H, T, col_start, col_items, c->roots);
     KZG_CUDA_TRY(cudaGetLastError());
     L.count(1, "vc_column_sums");
-    // interpolation polynomial of the aggregated columns, committed on the monomial setup
-    vc_aggregate_columns_kernel<<<CELLS_EXT, 64, 0, L.stream>>>(agg, cells, rp, col_start, col_items, d_bad);
-    KZG_CUDA_TRY(cudaGetLastError());
-    vc_interpolate_kernel<<<CELLS_EXT, 64, 0, L.stream>>>(F, agg, c->roots);
-    KZG_CUDA_TRY(cudaGetLastError());
-    vc_sum_columns_kernel<<<1, 64, 0, L.stream>>>(coeff, F);
-    KZG_CUDA_TRY(cudaGetLastError());
-    vc_scalar_mul_kernel<<<1, 64, 0, L.stream>>>(TI, c->g1_monomial, coeff, 64);
-    KZG_CUDA_TRY(cudaGetLastError());
-    L.count(4, "vc_interpolation");
+    if (forked) {
+        cudaEvent_t done;
+        KZG_CUDA_TRY(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+        KZG_CUDA_TRY(cudaEventRecord(done, side));
+        cudaStreamWaitEvent(L.stream, done, 0);
+        cudaEventDestroy(done);
+        cudaStreamDestroy(side);
+    }
     int rc;
     if ((rc = launch_g1_sum(L, out2 + 0, S, CELLS_EXT))) return rc;  // A (S is clobbered: H was computed first)
     if ((rc = launch_g1_sum(L, parts + 0, TC, u))) return rc;

@@ -12,7 +12,7 @@ timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | tail -30 | tee -a $OUT/p
 echo "== smoke" | tee $OUT/smoke_$TAG.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee -a $OUT/smoke_$TAG.log
 echo "== bench" | tee $OUT/bench_$TAG.log
-timeout 900 python bench.py --steps 5 --warmup 3 2>&1 | tail -4 | tee -a $OUT/bench_$TAG.log
+timeout 900 python bench.py 2>&1 | tail -4 | tee -a $OUT/bench_$TAG.log
 echo "== ncu launch list (short bench under ncu; numbers printed there are NOT bench values)"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --steps 1 --warmup 1 --blobs 1024 --no-extra --no-cpu-baseline > $OUT/ncu_bench_$TAG.log 2>&1
