@@ -15,6 +15,7 @@
 // natural order; forward DIF leaves the proofs in the bit-reversed order the API returns).
 #include "cells.h"
 #include "fft_twiddles.cuh"
+#include "g1_hot.cuh"
 
 namespace kzg {
 
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(32 * FM_WARPS) fk20_msm_kernel(G1* __restrict_
                 uint32_t mag = negd ? (256u - d) : d;
                 if (mag != 0) {
                     G1Affine a = ld_affine(tp + (size_t)w * FK_M + (mag - 1));
-                    g1_madd_to(acc, a, negd);
+                    g1_madd_nl(acc, a, negd);
                 }
             }
         }
