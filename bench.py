@@ -330,7 +330,13 @@ def run_b200(args):
     peak, peak_src = load_peaks()
     kern = {k: v for k, v in prof["kernels"].items() if k not in ("begin", "end")}
     total_ms = sum(v[0] for v in kern.values()) or 1.0
-    dom = max(kern, key=lambda k: kern[k][0])
+    # The roofline kernel is the largest of the kernels that stream the per-blob bytes.  At n=4096 the
+    # per-call tail (one pairing check, the transcript hash, the tree sums) is comparable in time but
+    # moves no per-blob data, so an HBM figure for it would be meaningless; it is named separately.
+    per_call = ("pairing_check", "r_from_digest", "g1_sum")
+    streaming = [k for k in kern if k not in per_call and ALGO_BYTES_PER_BLOB.get(k, 0) > 0] or list(kern)
+    dom = max(streaming, key=lambda k: kern[k][0])
+    time_dom = max(kern, key=lambda k: kern[k][0])
     dom_ms_per_launch = kern[dom][0] / kern[dom][1]
     launches_per_step = kern[dom][1] / prof_steps
     units_per_launch = n / launches_per_step
@@ -341,6 +347,8 @@ def run_b200(args):
         "traffic": (MEASURED_TRAFFIC_PER_BLOB[dom] * units_per_launch) if dom in MEASURED_TRAFFIC_PER_BLOB else None,
         "peak_source": peak_src, "share_of_step": kern[dom][0] / total_ms, "ms_per_launch": dom_ms_per_launch,
         "algorithmic_bytes_per_blob": ALGO_BYTES_PER_BLOB.get(dom, 0),
+        "largest_kernel_by_time": {"kernel": time_dom, "share_of_step": kern[time_dom][0] / total_ms,
+                                   "per_call_fixed_work": time_dom in per_call},
         "note": "integer-pipe bound path (SURVEY 8d): HBM fraction is reported for completeness, see int_pipe",
     }
     sm_mhz = clocks.get("sm_mhz") or 1965
@@ -349,7 +357,10 @@ def run_b200(args):
     for k, mac in ALGO_MAC_PER_BLOB.items():
         if k in kern and kern[k][0] > 0:
             t_s = kern[k][0] / prof_steps * 1e-3
-            int_pipe[k] = {"mac_per_s": mac * n / t_s, "frac_of_peak": mac * n / t_s / peak_mac}
+            int_pipe[k] = {"mac_per_s": mac * n / t_s, "frac_of_peak": mac * n / t_s / peak_mac,
+                           # the multiplier microbenchmark (tools/gpu_probe.py mulbench, profiles/) tops out at
+                           # 9.34e12 MAC/s at 1965 MHz = 32 wide MAC/clk/SM: the attainable ceiling for this code
+                           "frac_of_measured_mul_peak": mac * n / t_s / (9.34e12 * sm_mhz / 1965.0)}
     shares = {k: round(v[0] / total_ms, 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])}
     roofline["per_kernel"] = {
         k: {"ms_per_step": round(v[0] / prof_steps, 4), "algorithmic_GBps": round(ALGO_BYTES_PER_BLOB.get(k, 0) * n / (v[0] / prof_steps * 1e-3) / 1e9, 3) if v[0] > 0 else None}

@@ -377,8 +377,92 @@ KZG_HD_NOINLINE Fe<F> pow_limbs(const Fe<F>& a, const uint32_t* e) {
 using Fp = Fe<FpTag>;
 using Fr = Fe<FrTag>;
 
-KZG_HD Fp fp_inv(const Fp& a) { return pow_limbs<FpTag, 12>(a, FP_P_MINUS_2); }  // 0 -> 0
-KZG_HD Fr fr_inv(const Fr& a) { return pow_limbs<FrTag, 8>(a, FR_R_MINUS_2); }   // 0 -> 0
+// Inversion by the binary extended Euclid in Kaliski's "almost Montgomery inverse" form (IEEE Trans.
+// Computers 44(8), 1995): phase 1 uses only shifts, additions and subtractions and returns
+// a^-1 * 2^k (mod p) with n <= k <= 2n; the power of two is then folded away with four Montgomery
+// multiplications.  ~55 simple instructions per step and ~1.4 n steps -- roughly 7x fewer
+// instructions and a much shorter dependent chain than the Fermat power (570 dependent Montgomery
+// products for Fp), which is what the latency-bound single-thread callers care about (affine
+// conversion before compression / the pairing, the Fp2 inverse of the final exponentiation, the
+// per-blob barycentric denominator).  Variable time: every input here is public.
+// Replaces what the reference gets from blst's ct_inverse_mod_383/256 (blst/src/recip.c:18-75).
+// 0 -> 0, like the Fermat form it replaces.
+template <int N>
+KZG_HD void limbs_shr1(uint32_t* a) {
+#pragma unroll
+    for (int i = 0; i < N - 1; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 31);
+    a[N - 1] >>= 1;
+}
+template <int N>
+KZG_HD void limbs_shl1(uint32_t* a) {
+#pragma unroll
+    for (int i = N - 1; i > 0; i--) a[i] = (a[i] << 1) | (a[i - 1] >> 31);
+    a[0] <<= 1;
+}
+
+template <class F>
+KZG_HD_NOINLINE Fe<F> inv_binary(const Fe<F>& a) {
+    constexpr int N = F::N;
+    if (limbs_is_zero<N>(a.l)) return a;
+    uint32_t u[N], v[N], r[N], s[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        u[i] = F::mod()[i];
+        v[i] = a.l[i];
+        r[i] = 0;
+        s[i] = (i == 0);
+    }
+    int k = 0;
+    // invariants: u, v > 0 until the end; gcd(u, v) = 1; r, s < 2p (fits: 2p < 2^(32N))
+    while (!limbs_is_zero<N>(v)) {
+        if (!(v[0] & 1u)) {
+            limbs_shr1<N>(v);
+            limbs_shl1<N>(r);
+        } else if (!(u[0] & 1u)) {
+            limbs_shr1<N>(u);
+            limbs_shl1<N>(s);
+        } else {
+            uint32_t t[N];
+            if (limbs_sub<N>(t, v, u) == 0) {  // v >= u
+#pragma unroll
+                for (int i = 0; i < N; i++) v[i] = t[i];
+                limbs_shr1<N>(v);
+                limbs_add<N>(s, s, r);
+                limbs_shl1<N>(r);
+            } else {
+                limbs_sub<N>(u, u, v);
+                limbs_shr1<N>(u);
+                limbs_add<N>(r, r, s);
+                limbs_shl1<N>(s);
+            }
+        }
+        k++;
+    }
+    if (limbs_geq<N>(r, F::mod())) limbs_sub<N>(r, r, F::mod());
+    Fe<F> x;  // x = p - r = (integer a)^-1 * 2^k  (mod p), as a plain integer
+    limbs_sub<N>(x.l, F::mod(), r);
+    // The input integer is a_true * R, so the Montgomery form of the inverse is x * 2^(2*32N - k).
+    // Multiply by that power of two in two pieces that are each < p (2^(32N-4) < p for both fields).
+    int m = 2 * 32 * N - k;
+    int m1 = m < 32 * N - 4 ? m : 32 * N - 4;
+    int m2 = m - m1;
+    Fe<F> t1, t2, r2;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        t1.l[i] = (i == (m1 >> 5)) ? (1u << (m1 & 31)) : 0u;
+        t2.l[i] = (i == (m2 >> 5)) ? (1u << (m2 & 31)) : 0u;
+        r2.l[i] = F::r2()[i];
+    }
+    x = mul(mul(x, t1), r2);  // x * 2^m1
+    x = mul(mul(x, t2), r2);  // x * 2^m
+    return x;
+}
+
+KZG_HD Fp fp_inv(const Fp& a) { return inv_binary<FpTag>(a); }  // 0 -> 0
+KZG_HD Fr fr_inv(const Fr& a) { return inv_binary<FrTag>(a); }  // 0 -> 0
+// the Fermat forms stay for the self-test, which cross-checks the two on the device
+KZG_HD Fp fp_inv_fermat(const Fp& a) { return pow_limbs<FpTag, 12>(a, FP_P_MINUS_2); }
+KZG_HD Fr fr_inv_fermat(const Fr& a) { return pow_limbs<FrTag, 8>(a, FR_R_MINUS_2); }
 
 // ------------------------------------------------------------------------------------------------
 // big-endian byte <-> limb conversion (wire format: src/common/bytes.c:52-70)

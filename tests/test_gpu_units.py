@@ -46,9 +46,12 @@ def test_fp_field_ops(lib):
         got = unpack(out, 12, n)
         want = [f(x, y) for x, y in zip(a, b)]
         assert got == want, "Fp op %d" % op
-    m = 64
-    assert lib.ckzg_b200_selftest_field(3, out, pack(a[:m], 12), pack(b[:m], 12), C.c_uint64(m)) == 0
-    assert unpack(out, 12, m) == [pow(x, P - 2, P) if x else 0 for x in a[:m]]
+    # binary-Euclid inversion on every operand, plus powers of two (longest shift-only runs)
+    a = a + [1 << i for i in range(381)]
+    m = len(a)
+    out = (C.c_uint32 * (12 * m))()
+    assert lib.ckzg_b200_selftest_field(3, out, pack(a, 12), pack(a, 12), C.c_uint64(m)) == 0
+    assert unpack(out, 12, m) == [pow(x, P - 2, P) if x else 0 for x in a]
 
 
 def test_fr_field_ops(lib):
@@ -63,9 +66,11 @@ def test_fr_field_ops(lib):
     out = (C.c_uint32 * (8 * n))()
     assert lib.ckzg_b200_selftest_field(4, out, pack(a, 8), pack(b, 8), C.c_uint64(n)) == 0
     assert unpack(out, 8, n) == [x * y % R for x, y in zip(a, b)]
-    m = 64
-    assert lib.ckzg_b200_selftest_field(5, out, pack(a[:m], 8), pack(b[:m], 8), C.c_uint64(m)) == 0
-    assert unpack(out, 8, m) == [pow(x, R - 2, R) if x else 0 for x in a[:m]]
+    a = a + [1 << i for i in range(255)]
+    m = len(a)
+    out = (C.c_uint32 * (8 * m))()
+    assert lib.ckzg_b200_selftest_field(5, out, pack(a, 8), pack(a, 8), C.c_uint64(m)) == 0
+    assert unpack(out, 8, m) == [pow(x, R - 2, R) if x else 0 for x in a]
 
 
 def test_g1_scalar_mul_and_add(lib):

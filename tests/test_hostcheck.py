@@ -39,7 +39,9 @@ def test_fp_ops(hc):
             assert val(out) == a * b % P
             hc.hc_fp_addsub(out, o2, o3, limbs(a, 12), limbs(b, 12))
             assert val(out) == (a + b) % P and val(o2) == (a - b) % P and val(o3) == (-a) % P
-    for a in vals[:20]:
+    # binary-Euclid inversion: all edge values, small values, powers of two, and a long random run
+    for a in vals + list(range(1, 40)) + [1 << i for i in range(381)] + [rnd.randrange(P) for _ in range(1500)]:
+        a %= P
         hc.hc_fp_inv(out, limbs(a, 12))
         assert val(out) == (pow(a, P - 2, P) if a else 0)
 
@@ -52,7 +54,8 @@ def test_fr_ops(hc):
         for b in vals[:10] + [rnd.randrange(R)]:
             hc.hc_fr_mul(out, limbs(a, 8), limbs(b, 8))
             assert val(out) == a * b % R
-    for a in vals[:20]:
+    for a in vals + list(range(1, 40)) + [1 << i for i in range(255)] + [rnd.randrange(R) for _ in range(1500)]:
+        a %= R
         hc.hc_fr_inv(out, limbs(a, 8))
         assert val(out) == (pow(a, R - 2, R) if a else 0)
 
