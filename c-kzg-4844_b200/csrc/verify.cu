@@ -115,12 +115,25 @@ __global__ void __launch_bounds__(64) blob_challenge_kernel(Fr* __restrict__ z_o
     const uint8_t* cm = commitments + ii * 48;
     Sha256 st;
     sha256_init(st);
+    uint4 nx0, nx1, nx2, nx3;  // schedule warp: the NEXT block's 64 message bytes, in flight during this block's expansion
+    nx0 = nx1 = nx2 = nx3 = make_uint4(0, 0, 0, 0);
 #pragma unroll 1
     for (int k = 0; k <= CH_BLOCKS; k++) {
         if (warp == 1) {
             if (k < CH_BLOCKS) {
                 uint32_t w[16];
-                challenge_message_block(w, k, blob, cm);
+                if (k >= 1 && k < 2048) {
+                    w[0] = bswap32(nx0.x); w[1] = bswap32(nx0.y); w[2] = bswap32(nx0.z); w[3] = bswap32(nx0.w);
+                    w[4] = bswap32(nx1.x); w[5] = bswap32(nx1.y); w[6] = bswap32(nx1.z); w[7] = bswap32(nx1.w);
+                    w[8] = bswap32(nx2.x); w[9] = bswap32(nx2.y); w[10] = bswap32(nx2.z); w[11] = bswap32(nx2.w);
+                    w[12] = bswap32(nx3.x); w[13] = bswap32(nx3.y); w[14] = bswap32(nx3.z); w[15] = bswap32(nx3.w);
+                } else {
+                    challenge_message_block(w, k, blob, cm);
+                }
+                if (k + 1 < 2048) {  // a global load costs about as much as half an expansion: issue it a block ahead
+                    const uint4* p = blob + (4 * (k + 1) - 2);
+                    nx0 = __ldg(p); nx1 = __ldg(p + 1); nx2 = __ldg(p + 2); nx3 = __ldg(p + 3);
+                }
                 uint32_t(*dst)[32] = kw[k & 1];
 #pragma unroll
                 for (int t = 0; t < 64; t++) {
@@ -138,13 +151,20 @@ __global__ void __launch_bounds__(64) blob_challenge_kernel(Fr* __restrict__ z_o
             uint32_t a = st.h[0], b = st.h[1], c = st.h[2], d = st.h[3], e = st.h[4], f = st.h[5], g = st.h[6], h = st.h[7];
 #pragma unroll
             for (int t = 0; t < 64; t++) {
+                // the recurrence through e is the critical path: everything that does not depend on the
+                // current e or a (h, d, K+W) is summed first, so e' is ONE three-input add behind
+                // Sigma1/Ch -- rotate, xor, add: three dependent instructions per round instead of five
+                uint32_t pa = h + src[t][lane];
+                uint32_t pe = pa + d;
                 uint32_t S1 = sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25);
                 uint32_t ch = (e & f) ^ (~e & g);
-                uint32_t t1 = h + S1 + ch + src[t][lane];
                 uint32_t S0 = sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22);
                 uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
-                h = g; g = f; f = e; e = d + t1;
-                d = c; c = b; b = a; a = t1 + S0 + mj;
+                uint32_t qa = pa + S0 + mj;
+                uint32_t en = pe + S1 + ch;
+                uint32_t an = qa + S1 + ch;
+                h = g; g = f; f = e; e = en;
+                d = c; c = b; b = a; a = an;
             }
             st.h[0] += a; st.h[1] += b; st.h[2] += c; st.h[3] += d;
             st.h[4] += e; st.h[5] += f; st.h[6] += g; st.h[7] += h;
@@ -229,16 +249,12 @@ __global__ void __launch_bounds__(EV_THREADS) evaluate_kernel(Fr* __restrict__ y
     }
     __syncthreads();
 
-    // pass 1: p_k -> Montgomery (canonical check), running product of the denominators z - w_i
-    Fr pk[EV_PER], pre[EV_PER];
+    // pass 1: running product of this thread's denominators z - w_i (the blob is not touched yet)
+    Fr pre[EV_PER];
     Fr prod = Fr::one();
 #pragma unroll 1
     for (int k = 0; k < EV_PER; k++) {
         int i = t + EV_THREADS * k;
-        uint32_t s[8];
-        load_fr_be(s, src + 32 * i);
-        if (limbs_geq<8>(s, FR_MOD)) s_bad = 1;  // bytes_to_bls_field, bytes.c:67
-        pk[k] = to_mont<FrTag>(s);
         Fr d = sub(z, load_fr(roots_brp + i));
         if (is_zero(d)) {  // z is the i-th evaluation point (eip4844.c:213)
             s_m = i;
@@ -285,7 +301,14 @@ __global__ void __launch_bounds__(EV_THREADS) evaluate_kernel(Fr* __restrict__ y
         Fr inv = mul(acc, pre[k]);
         acc = mul(acc, d);
         if (inv_out) inv_out[(size_t)blob * N_BLOB + i] = inv;
-        sum = add(sum, mul(mul(pk[k], w), inv));
+        // The blob is read exactly once, here.  The big-endian integer p_i is used as it stands, i.e. as
+        // the Montgomery form of p_i / R: the sum comes out scaled by 1/R and one product with R^2 at the
+        // end puts it right -- 4096 to-Montgomery products per blob saved, and no per-thread array of
+        // converted elements to keep in local memory between the passes (ncu r01k: 437 KB/blob of it).
+        Fr praw;
+        load_fr_be(praw.l, src + 32 * i);
+        if (limbs_geq<8>(praw.l, FR_MOD)) s_bad = 1;  // bytes_to_bls_field, bytes.c:67
+        sum = add(sum, mul(mul(praw, w), inv));
     }
     sh_a[t] = sum;
     __syncthreads();
@@ -306,6 +329,7 @@ __global__ void __launch_bounds__(EV_THREADS) evaluate_kernel(Fr* __restrict__ y
 #pragma unroll 1
             for (int k = 0; k < 12; k++) zp = sqr(zp);
             y = mul(mul(sh_a[0], Fr::from_limbs(FR_INV_4096)), sub(zp, Fr::one()));
+            y = mul(y, Fr::from_limbs(FR_R2));  // undo the 1/R carried by the raw blob elements
         }
         y_out[blob] = y;
         if (zy) store_fr_be(zy + (size_t)blob * 64 + 32, y);
