@@ -37,6 +37,57 @@ constexpr int COOP_NREG = 8;
 #define COOP_END }
 #endif
 
+// ------------------------------------------------------------------------------------------------
+// The "wide" domain.  Inside the cooperative arithmetic an Fp value is any 14-limb integer congruent
+// to v * 2^448 (Montgomery radix R_w = 2^448 on 14 limbs), NOT reduced below p.  A tower operation
+// spends most of its instructions on the small signed sums around its products (up to 8 + 8 input
+// terms per lane, 36 output terms per coefficient); with 67 spare bits those sums are plain
+// multi-limb additions -- a negative part is taken off a fixed multiple of p -- and the ONLY modular
+// reduction is the one the Montgomery multiplier performs anyway (its result is < p whatever the
+// size of the operands, as long as x*y < p * 2^448).  Bounds, in multiples of p (checked against the
+// term counts by tools/gen_pairing_tables.py):
+//   products < 1;  partial output sums < 8 + 16;  stored coefficients < 5 * 24 = 120 (256 after a
+//   conjugation);  input sums < 8 * 256 + 2048 = 4096 < 2^12, so x*y / 2^448 < 2^(2*393-448) << p.
+// The previous version reduced after every addition: ~2600 instructions per tower operation, two
+// thirds of them in the sums; this one needs ~1200 (14-limb product included).
+// Values cross to the 12-limb canonical form (pairing.cuh tower code: Frobenius, the one inversion,
+// the final comparison) through one wide product with a constant.
+// ------------------------------------------------------------------------------------------------
+struct FpWTag {
+    static constexpr int N = 14;
+    static constexpr uint32_t INV = FP_INV32;
+    KZG_HDS const uint32_t* mod() { return FPW_MOD; }
+    KZG_HDS const uint32_t* one() { return FPW_ONE; }
+    KZG_HDS const uint32_t* r2() { return FPW_R2; }
+};
+using FpW = Fe<FpWTag>;
+
+KZG_HD FpW w_ext(const Fp& a) {  // the same integer on 14 limbs
+    FpW r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = a.l[i];
+    r.l[12] = r.l[13] = 0;
+    return r;
+}
+// 12-limb Montgomery form (v * 2^384) -> wide form (v * 2^448): times 2^512 / 2^448
+KZG_HD FpW w_from_fp(const Fp& a) { return mul(w_ext(a), FpW::from_limbs(FPW_C512)); }
+// wide (any size within the bounds above) -> canonical 12-limb Montgomery form: times 2^384 / 2^448
+KZG_HD Fp w_to_fp(const FpW& v) {
+    FpW t = mul(v, w_ext(Fp::one()));
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = t.l[i];
+    return r;
+}
+KZG_HD void w_acc(FpW& acc, const FpW& v) { limbs_add<14>(acc.l, acc.l, v.l); }
+// pos + off - neg   (off >= neg by the bounds above, so the result is a non-negative integer)
+KZG_HD FpW w_combine(const FpW& pos, const uint32_t* off, const FpW& neg) {
+    FpW r;
+    limbs_add<14>(r.l, pos.l, off);
+    limbs_sub<14>(r.l, r.l, neg.l);
+    return r;
+}
+
 // lane schedules copied into shared memory at kernel start (a few KB; constant-bank reads through
 // generic pointers were the slow part of the first version)
 struct CoopTables {
@@ -46,27 +97,28 @@ struct CoopTables {
 
 struct CoopWS {
     CoopTables tb;
-    Fp prod[54];
-    Fp part[12][5];  // partial output sums (5 lanes per output coefficient)
-    Fp reg[COOP_NREG][12];
-    Fp line[2][5];  // per pair: A.c0*s, A.c1*s, B.c0*xs, B.c1*xs, ys
-    Fp pt[2][3];    // per pair: s = ZZ*ZZZ, xs = X*ZZZ, ys = Y*ZZ
+    FpW prod[54];
+    FpW part[12][5];  // partial output sums (5 lanes per output coefficient)
+    FpW reg[COOP_NREG][12];
+    FpW line[2][5];  // per pair: A.c0*s, A.c1*s, B.c0*xs, B.c1*xs, ys
+    FpW pt[2][3];    // per pair: s = ZZ*ZZZ and xs = X*ZZZ (times 2^512: see coop_prepare_lines), ys = Y*ZZ (wide)
+    FpW onew;        // the constant one, second operand of the cyclotomic square's pass-through products
+    Fp canon[12];    // scratch for the excursions into the 12-limb tower code
     int use[2];
     int result;
 };
 
-KZG_HD Fp sub_(const Fp& x, const Fp& y) { return sub(x, y); }
-
-// signed sum of inputs (indices 0..11 -> a, 12.. -> b)
-KZG_HD Fp coop_sum_inputs(const int8_t* terms, int beg, int end, const Fp* a, const Fp* b) {
-    Fp acc = Fp::zero();
+// signed sum of inputs (indices 0..11 -> a, 12.. -> b), unreduced
+KZG_HD FpW coop_sum_inputs(const int8_t* terms, int beg, int end, const FpW* a, const FpW* b) {
+    FpW pos = FpW::zero(), neg = FpW::zero();
     for (int t = beg; t < end; t++) {
         int code = terms[t];
         int idx = (code < 0 ? -code : code) - 1;
-        const Fp& v = (idx < 12) ? a[idx] : b[idx - 12];
-        acc = (code > 0) ? add(acc, v) : sub(acc, v);
+        const FpW& v = (idx < 12) ? a[idx] : b[idx - 12];
+        if (code > 0) w_acc(pos, v);
+        else w_acc(neg, v);
     }
-    return acc;
+    return w_combine(pos, FPW_OFF2048, neg);
 }
 
 struct CoopOp {
@@ -94,6 +146,7 @@ KZG_HD void coop_init_tables(CoopWS& ws) {
     coop_copy_table(ws.tb, COOP_OP_SQR, lane, COOP_SQR_NPROD, COOP_SQR_XOFF, COOP_SQR_YOFF, COOP_SQR_OOFF, COOP_SQR_XT, COOP_SQR_YT, COOP_SQR_OT);
     coop_copy_table(ws.tb, COOP_OP_LINE, lane, COOP_LINE_NPROD, COOP_LINE_XOFF, COOP_LINE_YOFF, COOP_LINE_OOFF, COOP_LINE_XT, COOP_LINE_YT, COOP_LINE_OT);
     coop_copy_table(ws.tb, COOP_OP_CYC, lane, COOP_CYC_NPROD, COOP_CYC_XOFF, COOP_CYC_YOFF, COOP_CYC_OOFF, COOP_CYC_XT, COOP_CYC_YT, COOP_CYC_OT);
+    if (lane == 0) ws.onew = FpW::one();
     COOP_END
 }
 KZG_HD CoopOp coop_table(const CoopWS& ws, int op) {
@@ -101,50 +154,59 @@ KZG_HD CoopOp coop_table(const CoopWS& ws, int op) {
     return CoopOp{np[op], ws.tb.off[op][0], ws.tb.off[op][1], ws.tb.off[op][2], ws.tb.xt[op], ws.tb.yt[op], ws.tb.ot[op]};
 }
 
-// dst = op(a, b); dst may alias a or b (outputs only read the products, and -- cyclotomic square --
-// the SAME coefficient of a that the lane overwrites).
-KZG_HD_NOINLINE void coop_run(CoopWS& ws, int op, Fp* dst, const Fp* a, const Fp* b) {
+// dst = op(a, b); dst may alias a or b (the outputs read only the products).
+KZG_HD_NOINLINE void coop_run(CoopWS& ws, int op, FpW* dst, const FpW* a, const FpW* b) {
     const CoopOp T = coop_table(ws, op);
     COOP_BEGIN
     for (int L = lane; L < T.nprod; L += COOP_LANES) {
-        Fp x = coop_sum_inputs(T.xt, T.xo[L], T.xo[L + 1], a, b);
-        Fp y = coop_sum_inputs(T.yt, T.yo[L], T.yo[L + 1], a, b);
-        ws.prod[L] = mul(x, y);
+        FpW x = coop_sum_inputs(T.xt, T.xo[L], T.xo[L + 1], a, b);
+        FpW y = coop_sum_inputs(T.yt, T.yo[L], T.yo[L + 1], a, b);
+        ws.prod[L] = mul(x, y);  // < p
     }
     COOP_END
-    // output sums: up to 36 signed terms per coefficient -> 5 lanes per coefficient, then a 5-term tail
+    // output sums: up to 36 signed products per coefficient -> 5 lanes per coefficient (<= 8 terms each)
     COOP_BEGIN
     if (lane < 60) {
         const int k = lane / 5, sub = lane % 5;
-        Fp acc = Fp::zero();
+        FpW pos = FpW::zero(), neg = FpW::zero();
         for (int t = T.oo[k] + sub; t < T.oo[k + 1]; t += 5) {
             int code = T.ot[t];
-            int mag = code < 0 ? -code : code;
-            const Fp& v = (mag > 64) ? a[mag - 65] : ws.prod[mag - 1];
-            acc = (code > 0) ? add(acc, v) : sub_(acc, v);
+            const FpW& v = ws.prod[(code < 0 ? -code : code) - 1];
+            if (code > 0) w_acc(pos, v);
+            else w_acc(neg, v);
         }
-        ws.part[k][sub] = acc;
+        ws.part[k][sub] = w_combine(pos, FPW_OFF16, neg);  // < 24 p
     }
     COOP_END
     COOP_BEGIN
     if (lane < 12) {
-        Fp acc = add(add(ws.part[lane][0], ws.part[lane][1]), add(ws.part[lane][2], ws.part[lane][3]));
-        dst[lane] = add(acc, ws.part[lane][4]);
+        FpW acc = ws.part[lane][0];
+        w_acc(acc, ws.part[lane][1]);
+        w_acc(acc, ws.part[lane][2]);
+        w_acc(acc, ws.part[lane][3]);
+        w_acc(acc, ws.part[lane][4]);
+        dst[lane] = acc;  // < 120 p
     }
     COOP_END
 }
 
 KZG_HD void coop_mul(CoopWS& ws, int d, int a, int b) { coop_run(ws, COOP_OP_MUL, ws.reg[d], ws.reg[a], ws.reg[b]); }
 KZG_HD void coop_sqr(CoopWS& ws, int d, int a) { coop_run(ws, COOP_OP_SQR, ws.reg[d], ws.reg[a], ws.reg[a]); }
-KZG_HD void coop_cyc(CoopWS& ws, int d, int a) { coop_run(ws, COOP_OP_CYC, ws.reg[d], ws.reg[a], ws.reg[a]); }
+KZG_HD void coop_cyc(CoopWS& ws, int d, int a) { coop_run(ws, COOP_OP_CYC, ws.reg[d], ws.reg[a], &ws.onew); }
 KZG_HD void coop_line(CoopWS& ws, int d, int a, int pair) { coop_run(ws, COOP_OP_LINE, ws.reg[d], ws.reg[a], ws.line[pair]); }
 
-// conjugation over Fp6: negate the coefficients of the odd powers of w
+// conjugation over Fp6: negate the coefficients of the odd powers of w (256 p - v; v < 256 p)
 KZG_HD_NOINLINE void coop_conj(CoopWS& ws, int d, int a) {
     COOP_BEGIN
     if (lane < 12) {
         int k = lane >> 1;
-        ws.reg[d][lane] = (k & 1) ? neg(ws.reg[a][lane]) : ws.reg[a][lane];
+        FpW v = ws.reg[a][lane];
+        if (k & 1) {
+            FpW t;
+            limbs_sub<14>(t.l, FPW_OFF256, v.l);
+            v = t;
+        }
+        ws.reg[d][lane] = v;
     }
     COOP_END
 }
@@ -155,24 +217,24 @@ KZG_HD_NOINLINE void coop_copy(CoopWS& ws, int d, int a) {
 }
 KZG_HD void coop_set_one(CoopWS& ws, int d) {
     COOP_BEGIN
-    if (lane < 12) ws.reg[d][lane] = (lane == 0) ? Fp::one() : Fp::zero();
+    if (lane < 12) ws.reg[d][lane] = (lane == 0) ? FpW::one() : FpW::zero();
     COOP_END
 }
-// a^(p^power), power = 1 or 2; d != a.  Lane k < 6 owns the Fp2 coefficient of w^k.
+// a^(p^power), power = 1 or 2; d != a.  Lane k < 6 owns the Fp2 coefficient of w^k (12-limb tower code).
 KZG_HD_NOINLINE void coop_frobenius(CoopWS& ws, int d, int a, int power) {
     COOP_BEGIN
     if (lane < 6) {
         Fp2 c;
-        c.c0 = ws.reg[a][2 * lane];
-        c.c1 = ws.reg[a][2 * lane + 1];
+        c.c0 = w_to_fp(ws.reg[a][2 * lane]);
+        c.c1 = w_to_fp(ws.reg[a][2 * lane + 1]);
         if (power == 1) {
             c = f2_conj(c);
             if (lane != 0) c = f2_mul(c, frob_gamma1(lane));
         } else if (lane != 0) {
             c = f2_mul_fp(c, Fp::from_limbs(FROB_GAMMA2[lane]));
         }
-        ws.reg[d][2 * lane] = c.c0;
-        ws.reg[d][2 * lane + 1] = c.c1;
+        ws.reg[d][2 * lane] = w_from_fp(c.c0);
+        ws.reg[d][2 * lane + 1] = w_from_fp(c.c1);
     }
     COOP_END
 }
@@ -196,13 +258,19 @@ KZG_HD void coop_from_tower(Fp* c, const Fp12& r) {
     c[8] = r.c0.c2.c0; c[9] = r.c0.c2.c1;
     c[10] = r.c1.c2.c0; c[11] = r.c1.c2.c1;
 }
-// the one inversion of the final exponentiation: serial on lane 0
+// the one inversion of the final exponentiation: serial on lane 0, in the 12-limb tower code
 KZG_HD_NOINLINE void coop_inv(CoopWS& ws, int d, int a) {
     COOP_BEGIN
+    if (lane < 12) ws.canon[lane] = w_to_fp(ws.reg[a][lane]);
+    COOP_END
+    COOP_BEGIN
     if (lane == 0) {
-        Fp12 v = coop_to_tower(ws.reg[a]);
-        coop_from_tower(ws.reg[d], f12_inv(v));
+        Fp12 v = coop_to_tower(ws.canon);
+        coop_from_tower(ws.canon, f12_inv(v));
     }
+    COOP_END
+    COOP_BEGIN
+    if (lane < 12) ws.reg[d][lane] = w_from_fp(ws.canon[lane]);
     COOP_END
 }
 
@@ -219,7 +287,9 @@ KZG_HD void coop_load_points(CoopWS& ws, const G1& P1, const G2Lines* L1, const 
             v = mul(Pt.y, Pt.zz);
             if (pair == 0 && negate_first) v = neg(v);
         }
-        ws.pt[pair][j] = v;
+        // s and xs meet a 12-limb line coefficient (c * 2^384) in one WIDE product that must come out as
+        // c*s * 2^448: carry them as s * 2^512, i.e. times 2^576 / 2^448.  ys enters the line as it is.
+        ws.pt[pair][j] = (j == 2) ? w_from_fp(v) : mul(w_ext(v), FpW::from_limbs(FPW_C576));
     }
     if (lane == 6) ws.use[0] = (!g1_is_inf(P1) && !L1->is_inf) ? 1 : 0;
     if (lane == 7) ws.use[1] = (!g1_is_inf(P2) && !L2->is_inf) ? 1 : 0;
@@ -232,11 +302,11 @@ KZG_HD_NOINLINE void coop_prepare_lines(CoopWS& ws, const G2Lines* L1, const G2L
     if (lane < 10) {
         int pair = lane / 5, j = lane % 5;
         const LineCoeff& l = (pair ? L2 : L1)->line[k];
-        Fp v;
-        if (j == 0) v = mul(l.A.c0, ws.pt[pair][0]);
-        else if (j == 1) v = mul(l.A.c1, ws.pt[pair][0]);
-        else if (j == 2) v = mul(l.B.c0, ws.pt[pair][1]);
-        else if (j == 3) v = mul(l.B.c1, ws.pt[pair][1]);
+        FpW v;
+        if (j == 0) v = mul(w_ext(l.A.c0), ws.pt[pair][0]);
+        else if (j == 1) v = mul(w_ext(l.A.c1), ws.pt[pair][0]);
+        else if (j == 2) v = mul(w_ext(l.B.c0), ws.pt[pair][1]);
+        else if (j == 3) v = mul(w_ext(l.B.c1), ws.pt[pair][1]);
         else v = ws.pt[pair][2];
         ws.line[pair][j] = v;
     }
@@ -304,9 +374,12 @@ KZG_HD void coop_pairing_product_is_one(CoopWS& ws, const G1& P1, const G2Lines*
     coop_mul(ws, X, X, E);            // E^3
     coop_mul(ws, T3, T3, X);
     COOP_BEGIN
+    if (lane < 12) ws.canon[lane] = w_to_fp(ws.reg[T3][lane]);
+    COOP_END
+    COOP_BEGIN
     if (lane == 0) {
-        bool one = eq(ws.reg[T3][0], Fp::one());
-        for (int i = 1; i < 12; i++) one = one && is_zero(ws.reg[T3][i]);
+        bool one = eq(ws.canon[0], Fp::one());
+        for (int i = 1; i < 12; i++) one = one && is_zero(ws.canon[i]);
         ws.result = one ? 1 : 0;
     }
     COOP_END

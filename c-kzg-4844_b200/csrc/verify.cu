@@ -511,6 +511,64 @@ __global__ void __launch_bounds__(SUM_THREADS) g1_sum_kernel(G1* __restrict__ ou
     if (t == 0) out[blockIdx.x] = sh[0];
 }
 
+// The two sums of the linear combination, folded together: level 1 (grid.y = 0: U, 1: T) turns 256
+// inputs into one partial per block, level 2 is one block whose warp 0 finishes A = sum U and whose
+// warp 1 finishes B = sum T + Y.  Two launches on the critical path of every verify call instead of the
+// five launches and five 192-byte copies of three generic tree sums (0.61 -> ~0.25 ms at n = 4096).
+constexpr int FOLD_THREADS = 128;
+constexpr int FOLD_IN = 2 * FOLD_THREADS;
+__global__ void __launch_bounds__(FOLD_THREADS) rlc_fold_kernel(G1* __restrict__ PU, G1* __restrict__ PT, const G1* __restrict__ U, const G1* __restrict__ T, uint64_t n) {
+    __shared__ G1 sh[FOLD_THREADS];
+    const int t = threadIdx.x;
+    const G1* in = blockIdx.y ? T : U;
+    const uint64_t m = blockIdx.y ? 2 * n : n;
+    const uint64_t base = (uint64_t)blockIdx.x * FOLD_IN;
+    if (base >= m) return;  // whole block: the grid is sized for T
+    G1 acc = g1_inf();
+    if (base + t < m) acc = in[base + t];
+    if (base + FOLD_THREADS + t < m) {
+        G1 p = in[base + FOLD_THREADS + t];
+        g1_add_to(acc, p);
+    }
+    sh[t] = acc;
+    __syncthreads();
+#pragma unroll 1
+    for (int s = FOLD_THREADS / 2; s > 0; s >>= 1) {
+        if (t < s) {
+            G1 x = sh[t], y = sh[t + s];
+            g1_add_to(x, y);
+            sh[t] = x;
+        }
+        __syncthreads();
+    }
+    if (t == 0) (blockIdx.y ? PT : PU)[blockIdx.x] = sh[0];
+}
+__global__ void __launch_bounds__(64) rlc_final_kernel(G1* __restrict__ out2, const G1* __restrict__ PU, uint64_t nu, const G1* __restrict__ PT, uint64_t nt, const G1* __restrict__ Y) {
+    __shared__ G1 sh[64];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const G1* in = w ? PT : PU;
+    const uint64_t cnt = w ? nt : nu;
+    G1 acc = g1_inf();
+    if (w == 1 && lane == 31) acc = *Y;
+#pragma unroll 1
+    for (uint64_t i = lane; i < cnt; i += 32) {
+        G1 p = in[i];
+        g1_add_to(acc, p);
+    }
+    sh[t] = acc;
+    __syncthreads();
+#pragma unroll 1
+    for (int s = 16; s > 0; s >>= 1) {
+        if (lane < s) {
+            G1 x = sh[t], y = sh[t + s];
+            g1_add_to(x, y);
+            sh[t] = x;
+        }
+        __syncthreads();
+    }
+    if (lane == 0) out2[w] = sh[t];
+}
+
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
@@ -617,7 +675,7 @@ int launch_r_from_digest(Launch& L, Fr* r, const uint8_t* digest32) {
 }
 
 static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
-static size_t rlc_fold(uint64_t n) { return (2 * n) / (SUM_THREADS * SUM_PER) + 2; }
+static size_t rlc_fold(uint64_t n) { return (2 * n) / FOLD_IN + 2; }
 size_t rlc_scratch_bytes(uint64_t n) {
     size_t fold = rlc_fold(n);
     return al256(n * 32) * 2 + al256(n * sizeof(Fr)) + al256(32) + al256(sizeof(G1)) + al256((n + fold) * sizeof(G1)) +
@@ -679,14 +737,14 @@ int launch_rlc(Launch& L, G1* out2, const G1Affine* commitments, const G1Affine*
     rlc_points_kernel<<<blocks_for(3 * n + 1, 64), 64, 0, L.stream>>>(U, T, Y, commitments, proofs, s1, s2, ysum, n);
     KZG_CUDA_TRY(cudaGetLastError());
     L.count(1, "rlc_points");
-    int rc;
-    if ((rc = launch_g1_sum(L, out2 + 0, U, n))) return rc;
-    if ((rc = launch_g1_sum(L, out2 + 1, T, 2 * n))) return rc;
-    // B += -[ysum]G : fold Y into out2[1] with a 2-point sum
-    G1* pair = T;  // reuse: [out2[1], Y]
-    KZG_CUDA_TRY(cudaMemcpyAsync(pair, out2 + 1, sizeof(G1), cudaMemcpyDeviceToDevice, L.stream));
-    KZG_CUDA_TRY(cudaMemcpyAsync(pair + 1, Y, sizeof(G1), cudaMemcpyDeviceToDevice, L.stream));
-    if ((rc = launch_g1_sum(L, out2 + 1, pair, 2))) return rc;
+    G1* PU = U + n;
+    G1* PT = T + 2 * n;
+    const unsigned fb = blocks_for(2 * n, FOLD_IN);
+    rlc_fold_kernel<<<dim3(fb, 2), FOLD_THREADS, 0, L.stream>>>(PU, PT, U, T, n);
+    KZG_CUDA_TRY(cudaGetLastError());
+    rlc_final_kernel<<<1, 64, 0, L.stream>>>(out2, PU, blocks_for(n, FOLD_IN), PT, fb, Y);
+    KZG_CUDA_TRY(cudaGetLastError());
+    L.count(2, "g1_sum");
     return RET_OK;
 }
 

@@ -198,7 +198,26 @@ def build(op):
     elif op == "sqr":
         out = f12_sqr(tower_from_flat(a))
     elif op == "cyc":
-        out = f12_cyc_sqr(tower_from_flat(a))
+        # The Granger-Scott outputs are 3 t +- 2 z with z an INPUT coefficient.  The wide-domain
+        # arithmetic never reduces sums, so a value that is copied from input to output would grow
+        # geometrically over the 63 consecutive squarings of an exponentiation; route every such
+        # term through a product with the constant one (input index 12) instead: products come out
+        # of the Montgomery multiplier reduced.
+        one = Form({("in", 12): 1})
+        out = flat_from_tower(f12_cyc_sqr(tower_from_flat(a)))
+        via = {}
+        fixed = []
+        for o in out:
+            f = Form()
+            for (k, idx), c in o.t.items():
+                if k == "in":
+                    if idx not in via:
+                        via[idx] = fmul(a[idx], one)
+                    f = f + Form({key: v * c for key, v in via[idx].t.items()})
+                else:
+                    f = f + Form({(k, idx): c})
+            fixed.append(f)
+        return REC.products, fixed
     elif op == "line":
         # b inputs: 12..13 = A, 14..15 = Bc (already multiplied by the x scaling), 16 = C real part
         b = atoms("b", 5, 12)
@@ -274,7 +293,7 @@ def check():
             # cyclotomic subgroup element: easy part of the final exponentiation of a random element
             f = B.f12_mul(B.f12_conj(a), B.f12_inv(a))
             f = B.f12_mul(B.f12_frobenius(B.f12_frobenius(f)), f)
-            got = eval_tables(products, outputs, to_int_list(f))
+            got = eval_tables(products, outputs, to_int_list(f) + [1])
             want = to_int_list(B.f12_mul(f, f))
         assert got == want, op
         print("%-5s %2d products  ok" % (op, len(products)), file=sys.stderr)
@@ -285,7 +304,7 @@ def emit():
     out.append("// GENERATED by tools/gen_pairing_tables.py -- do not edit.\n")
     out.append("// Lane schedules for the cooperative Fp12 arithmetic (see the generator's docstring).\n")
     out.append("// Term code t: |t|-1 = operand index, sign = add/subtract.  X/Y forms index the inputs\n")
-    out.append("// (0..11 = a, 12.. = b); output forms index the products, codes > 64 mean input (|t|-65).\n")
+    out.append("// (0..11 = a, 12.. = b; for the cyclotomic square b[0] is the constant one); output forms index the products.\n")
     out.append("#pragma once\n#include <stdint.h>\n\n")
     out.append("struct CoopOpTable {\n    int nprod;\n    const int16_t* x_off;  // nprod + 1\n    const int16_t* y_off;\n    const int16_t* o_off;  // 13\n    const int8_t* x_terms;\n    const int8_t* y_terms;\n    const int8_t* o_terms;\n};\n\n")
     for op in ("mul", "sqr", "line", "cyc"):
@@ -300,7 +319,10 @@ def emit():
         for o in outputs:
             os_ += expand(o, "p")
             oo.append(len(os_))
-        assert max(abs(t) for t in xs + ys) < 64 and max(abs(t) for t in os_) < 128
+        assert max(abs(t) for t in xs + ys) < 64 and max(abs(t) for t in os_) <= 64  # outputs: products only
+        # bounds the unreduced sums of pairing_coop.cuh rely on
+        assert max(b - a for a, b in zip(xo, xo[1:])) <= 8 and max(b - a for a, b in zip(yo, yo[1:])) <= 8
+        assert max(b - a for a, b in zip(oo, oo[1:])) <= 40 and len(products) <= 64
         U = op.upper()
         def arr(ctype, name, vals):
             return "KZG_CONST %s %s[%d] = {%s};\n" % (ctype, name, len(vals), ", ".join(str(v) for v in vals))
@@ -314,6 +336,14 @@ def emit():
         out.append(arr("int8_t", "COOP_%s_OT" % U, os_))
         out.append("\n")
         print("%-5s terms: X %d  Y %d  O %d  (max out form %d)" % (op, len(xs), len(ys), len(os_), max(b - a for a, b in zip(oo, oo[1:]))), file=sys.stderr)
+    # ---- constants of the 14-limb "wide" Montgomery domain (R_w = 2^448) ----
+    def limbs14(v):
+        assert 0 <= v < 1 << 448
+        return ", ".join("0x%08xu" % ((v >> (32 * i)) & 0xFFFFFFFF) for i in range(14))
+    out.append("// ---- wide domain: 14 limbs, R_w = 2^448; sums are never reduced, only the multiplier reduces ----\n")
+    for name, v in (("FPW_MOD", P), ("FPW_ONE", (1 << 448) % P), ("FPW_R2", (1 << 896) % P), ("FPW_C512", (1 << 512) % P),
+                    ("FPW_C576", (1 << 576) % P), ("FPW_OFF16", 16 * P), ("FPW_OFF256", 256 * P), ("FPW_OFF2048", 2048 * P)):
+        out.append("KZG_CONST uint32_t %s[14] = {%s};\n" % (name, limbs14(v)))
     path = os.path.join(ROOT, "c-kzg-4844_b200", "csrc", "pairing_tables.cuh")
     with open(path, "w") as f:
         f.write("".join(out))
