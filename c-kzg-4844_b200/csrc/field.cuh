@@ -101,6 +101,26 @@ KZG_HD uint32_t limbs_sub(uint32_t* r, const uint32_t* a, const uint32_t* b) {
 #endif
 }
 
+// acc = acc + v (m == 0) or acc - v (m == 0xffffffff), modulo 2^(32N): one carry chain over v ^ m with
+// the carry-in taken from m, so lanes that add and lanes that subtract run the same instructions
+template <int N>
+KZG_HD void limbs_addsub(uint32_t* acc, const uint32_t* v, uint32_t m) {
+#if KZG_DEVICE_PATH
+    uint32_t t;
+    asm volatile("add.cc.u32 %0, %1, %1;" : "=r"(t) : "r"(m));  // CF = (m != 0)
+#pragma unroll
+    for (int i = 0; i < N - 1; i++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(acc[i]) : "r"(v[i] ^ m));
+    asm volatile("addc.u32 %0, %0, %1;" : "+r"(acc[N - 1]) : "r"(v[N - 1] ^ m));
+#else
+    uint64_t c = m & 1u;
+    for (int i = 0; i < N; i++) {
+        c += (uint64_t)acc[i] + (v[i] ^ m);
+        acc[i] = (uint32_t)c;
+        c >>= 32;
+    }
+#endif
+}
+
 // a >= b ?
 template <int N>
 KZG_HD bool limbs_geq(const uint32_t* a, const uint32_t* b) {

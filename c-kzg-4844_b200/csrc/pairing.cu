@@ -32,10 +32,19 @@ __global__ void g2_lines_kernel(G2Lines* lines, const G2Affine* g2) {
 
 // e(L[1], G2[0]) == e(L[0], G2[1])  <=>  e(-L[1], G2[0]) * e(L[0], G2[1]) == 1
 // One CTA of COOP_LANES threads (pairing_coop.cuh); every thread reaches every barrier.
+// The workspace (lane schedules, registers, all 2 x 68 evaluated lines: ~55 KB) is dynamic shared memory.
+struct PairingSmem {
+    CoopWS ws;
+    G1 pts[2];
+    int dec_ok[2];
+};
+extern __shared__ __align__(16) unsigned char pairing_smem_raw[];
+
 __global__ void __launch_bounds__(COOP_LANES) monomial_form_kernel(int* out, const uint8_t* lag01, const G2Lines* lines) {
-    __shared__ CoopWS ws;
-    __shared__ G1 pts[2];
-    __shared__ int dec_ok[2];
+    PairingSmem& sm = *reinterpret_cast<PairingSmem*>(pairing_smem_raw);
+    CoopWS& ws = sm.ws;
+    G1* pts = sm.pts;
+    int* dec_ok = sm.dec_ok;
     if (threadIdx.x < 2) {
         uint8_t buf[48];
         G1Affine a;
@@ -51,8 +60,9 @@ __global__ void __launch_bounds__(COOP_LANES) monomial_form_kernel(int* out, con
 
 // ok = [ e(A, Q_a) == e(B + B_extra, Q_b) ] = [ e(-A, Q_a) * e(B + B_extra, Q_b) == 1 ];  A, B XYZZ sums.
 __global__ void __launch_bounds__(COOP_LANES) pairing_check_kernel(int* ok, const G1* A, const G1* B, const G1* B_extra, const G2Lines* lines, int line_a, int line_b) {
-    __shared__ CoopWS ws;
-    __shared__ G1 pts[2];
+    PairingSmem& sm = *reinterpret_cast<PairingSmem*>(pairing_smem_raw);
+    CoopWS& ws = sm.ws;
+    G1* pts = sm.pts;
     if (threadIdx.x == 0) {
         pts[0] = *A;
         G1 b = *B;
@@ -67,7 +77,16 @@ __global__ void __launch_bounds__(COOP_LANES) pairing_check_kernel(int* ok, cons
     if (threadIdx.x == 0) *ok = ws.result;
 }
 
+// > 48 KB of dynamic shared memory needs the per-function opt-in, once per device context
+static int pairing_smem_opt_in() {
+    KZG_CUDA_TRY(cudaFuncSetAttribute(monomial_form_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairingSmem)));
+    KZG_CUDA_TRY(cudaFuncSetAttribute(pairing_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairingSmem)));
+    return RET_OK;
+}
+
 int setup_g2_and_lines(cudaStream_t stream, Launch& L, Ctx* c, const uint8_t* g2_host, int* d_bad) {
+    int rc0 = pairing_smem_opt_in();
+    if (rc0) return rc0;
     KZG_CUDA_TRY(cudaMalloc(&c->g2_points, 65 * sizeof(G2Affine)));
     KZG_CUDA_TRY(cudaMalloc(&c->g2_lines, 3 * sizeof(G2Lines)));
     uint8_t* d_bytes = nullptr;
@@ -88,7 +107,7 @@ int setup_is_monomial_form(cudaStream_t stream, Launch& L, Ctx* c, const uint8_t
     KZG_CUDA_TRY(cudaMallocAsync((void**)&d_bytes, 96, stream));
     KZG_CUDA_TRY(cudaMallocAsync((void**)&d_out, sizeof(int), stream));
     KZG_CUDA_TRY(cudaMemcpyAsync(d_bytes, g1_lagrange_host, 96, cudaMemcpyHostToDevice, stream));
-    monomial_form_kernel<<<1, COOP_LANES, 0, stream>>>(d_out, d_bytes, (const G2Lines*)c->g2_lines);
+    monomial_form_kernel<<<1, COOP_LANES, sizeof(PairingSmem), stream>>>(d_out, d_bytes, (const G2Lines*)c->g2_lines);
     KZG_CUDA_TRY(cudaGetLastError());
     KZG_CUDA_TRY(cudaMemcpyAsync(is_monomial, d_out, sizeof(int), cudaMemcpyDeviceToHost, stream));
     KZG_CUDA_TRY(cudaStreamSynchronize(stream));
@@ -99,7 +118,7 @@ int setup_is_monomial_form(cudaStream_t stream, Launch& L, Ctx* c, const uint8_t
 }
 
 int launch_pairing_check(Launch& L, int* d_ok, const G1* A, const G1* B, const G1* B_extra, int line_a, int line_b) {
-    pairing_check_kernel<<<1, COOP_LANES, 0, L.stream>>>(d_ok, A, B, B_extra, (const G2Lines*)L.ctx->g2_lines, line_a, line_b);
+    pairing_check_kernel<<<1, COOP_LANES, sizeof(PairingSmem), L.stream>>>(d_ok, A, B, B_extra, (const G2Lines*)L.ctx->g2_lines, line_a, line_b);
     KZG_CUDA_TRY(cudaGetLastError());
     L.count(1, "pairing_check");
     return RET_OK;

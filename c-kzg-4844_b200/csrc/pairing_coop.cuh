@@ -80,13 +80,6 @@ KZG_HD Fp w_to_fp(const FpW& v) {
     return r;
 }
 KZG_HD void w_acc(FpW& acc, const FpW& v) { limbs_add<14>(acc.l, acc.l, v.l); }
-// pos + off - neg   (off >= neg by the bounds above, so the result is a non-negative integer)
-KZG_HD FpW w_combine(const FpW& pos, const uint32_t* off, const FpW& neg) {
-    FpW r;
-    limbs_add<14>(r.l, pos.l, off);
-    limbs_sub<14>(r.l, r.l, neg.l);
-    return r;
-}
 
 // lane schedules copied into shared memory at kernel start (a few KB; constant-bank reads through
 // generic pointers were the slow part of the first version)
@@ -100,25 +93,21 @@ struct CoopWS {
     FpW prod[54];
     FpW part[12][5];  // partial output sums (5 lanes per output coefficient)
     FpW reg[COOP_NREG][12];
-    FpW line[2][5];  // per pair: A.c0*s, A.c1*s, B.c0*xs, B.c1*xs, ys
-    FpW pt[2][3];    // per pair: s = ZZ*ZZZ and xs = X*ZZZ (times 2^512: see coop_prepare_lines), ys = Y*ZZ (wide)
+    FpW lv[2][MILLER_LINES][5];  // every line of both pairs evaluated at the (scaled) point: A.c0*s, A.c1*s, B.c0*xs, B.c1*xs, ys
+    FpW pt[2][3];    // per pair: s = ZZ*ZZZ and xs = X*ZZZ (times 2^512: see coop_load_points), ys = Y*ZZ (wide)
     FpW onew;        // the constant one, second operand of the cyclotomic square's pass-through products
+    FpW zerow;       // padding operand of the sum loops
     Fp canon[12];    // scratch for the excursions into the 12-limb tower code
     int use[2];
     int result;
 };
 
-// signed sum of inputs (indices 0..11 -> a, 12.. -> b), unreduced
-KZG_HD FpW coop_sum_inputs(const int8_t* terms, int beg, int end, const FpW* a, const FpW* b) {
-    FpW pos = FpW::zero(), neg = FpW::zero();
-    for (int t = beg; t < end; t++) {
-        int code = terms[t];
-        int idx = (code < 0 ? -code : code) - 1;
-        const FpW& v = (idx < 12) ? a[idx] : b[idx - 12];
-        if (code > 0) w_acc(pos, v);
-        else w_acc(neg, v);
-    }
-    return w_combine(pos, FPW_OFF2048, neg);
+// One step of a signed sum: code 0 = padding (adds the zero operand), else +-(index + 1) into `a`
+// (index < 12) or `b`.  No branch: every lane of the warp runs the same carry chain.
+KZG_HD void coop_acc_term(FpW& acc, int code, const FpW* a, const FpW* b, const FpW* zero) {
+    const int idx = (code < 0 ? -code : code) - 1;
+    const FpW* src = (code == 0) ? zero : (idx < 12 ? a + idx : b + (idx - 12));
+    limbs_addsub<14>(acc.l, src->l, code < 0 ? 0xffffffffu : 0u);
 }
 
 struct CoopOp {
@@ -147,6 +136,7 @@ KZG_HD void coop_init_tables(CoopWS& ws) {
     coop_copy_table(ws.tb, COOP_OP_LINE, lane, COOP_LINE_NPROD, COOP_LINE_XOFF, COOP_LINE_YOFF, COOP_LINE_OOFF, COOP_LINE_XT, COOP_LINE_YT, COOP_LINE_OT);
     coop_copy_table(ws.tb, COOP_OP_CYC, lane, COOP_CYC_NPROD, COOP_CYC_XOFF, COOP_CYC_YOFF, COOP_CYC_OOFF, COOP_CYC_XT, COOP_CYC_YT, COOP_CYC_OT);
     if (lane == 0) ws.onew = FpW::one();
+    if (lane == 1) ws.zerow = FpW::zero();
     COOP_END
 }
 KZG_HD CoopOp coop_table(const CoopWS& ws, int op) {
@@ -155,12 +145,19 @@ KZG_HD CoopOp coop_table(const CoopWS& ws, int op) {
 }
 
 // dst = op(a, b); dst may alias a or b (the outputs read only the products).
+// Sums start from a multiple of p that exceeds their negative part (2048 p for the inputs, 16 p for the
+// outputs) and run modulo 2^448, so one accumulator serves additions and subtractions alike.
 KZG_HD_NOINLINE void coop_run(CoopWS& ws, int op, FpW* dst, const FpW* a, const FpW* b) {
     const CoopOp T = coop_table(ws, op);
     COOP_BEGIN
     for (int L = lane; L < T.nprod; L += COOP_LANES) {
-        FpW x = coop_sum_inputs(T.xt, T.xo[L], T.xo[L + 1], a, b);
-        FpW y = coop_sum_inputs(T.yt, T.yo[L], T.yo[L + 1], a, b);
+        const int bx = T.xo[L], nx = T.xo[L + 1] - bx, by = T.yo[L], ny = T.yo[L + 1] - by;
+        const int n = nx > ny ? nx : ny;
+        FpW x = FpW::from_limbs(FPW_OFF2048), y = FpW::from_limbs(FPW_OFF2048);
+        for (int t = 0; t < n; t++) {  // the two chains are independent: they overlap in the pipeline
+            coop_acc_term(x, t < nx ? T.xt[bx + t] : 0, a, b, &ws.zerow);
+            coop_acc_term(y, t < ny ? T.yt[by + t] : 0, a, b, &ws.zerow);
+        }
         ws.prod[L] = mul(x, y);  // < p
     }
     COOP_END
@@ -168,14 +165,9 @@ KZG_HD_NOINLINE void coop_run(CoopWS& ws, int op, FpW* dst, const FpW* a, const 
     COOP_BEGIN
     if (lane < 60) {
         const int k = lane / 5, sub = lane % 5;
-        FpW pos = FpW::zero(), neg = FpW::zero();
-        for (int t = T.oo[k] + sub; t < T.oo[k + 1]; t += 5) {
-            int code = T.ot[t];
-            const FpW& v = ws.prod[(code < 0 ? -code : code) - 1];
-            if (code > 0) w_acc(pos, v);
-            else w_acc(neg, v);
-        }
-        ws.part[k][sub] = w_combine(pos, FPW_OFF16, neg);  // < 24 p
+        FpW acc = FpW::from_limbs(FPW_OFF16);
+        for (int t = T.oo[k] + sub; t < T.oo[k + 1]; t += 5) coop_acc_term(acc, T.ot[t], ws.prod, ws.prod + 12, &ws.zerow);
+        ws.part[k][sub] = acc;  // < 24 p
     }
     COOP_END
     COOP_BEGIN
@@ -193,7 +185,7 @@ KZG_HD_NOINLINE void coop_run(CoopWS& ws, int op, FpW* dst, const FpW* a, const 
 KZG_HD void coop_mul(CoopWS& ws, int d, int a, int b) { coop_run(ws, COOP_OP_MUL, ws.reg[d], ws.reg[a], ws.reg[b]); }
 KZG_HD void coop_sqr(CoopWS& ws, int d, int a) { coop_run(ws, COOP_OP_SQR, ws.reg[d], ws.reg[a], ws.reg[a]); }
 KZG_HD void coop_cyc(CoopWS& ws, int d, int a) { coop_run(ws, COOP_OP_CYC, ws.reg[d], ws.reg[a], &ws.onew); }
-KZG_HD void coop_line(CoopWS& ws, int d, int a, int pair) { coop_run(ws, COOP_OP_LINE, ws.reg[d], ws.reg[a], ws.line[pair]); }
+KZG_HD void coop_line(CoopWS& ws, int d, int a, int pair, int k) { coop_run(ws, COOP_OP_LINE, ws.reg[d], ws.reg[a], ws.lv[pair][k]); }
 
 // conjugation over Fp6: negate the coefficients of the odd powers of w (256 p - v; v < 256 p)
 KZG_HD_NOINLINE void coop_conj(CoopWS& ws, int d, int a) {
@@ -296,11 +288,14 @@ KZG_HD void coop_load_points(CoopWS& ws, const G1& P1, const G2Lines* L1, const 
     COOP_END
 }
 
-// line k of both pairs, evaluated at the (scaled) points -> ws.line
-KZG_HD_NOINLINE void coop_prepare_lines(CoopWS& ws, const G2Lines* L1, const G2Lines* L2, int k) {
+// Every line of both pairs evaluated at the (scaled) points -> ws.lv, in one parallel pass before the
+// Miller loop (544 independent products over the 64 lanes).  The first version did this step by step
+// inside the loop: 68 extra barriers and 68 exposed global-memory round trips, 15 % of the kernel.
+KZG_HD_NOINLINE void coop_prepare_all_lines(CoopWS& ws, const G2Lines* L1, const G2Lines* L2) {
     COOP_BEGIN
-    if (lane < 10) {
-        int pair = lane / 5, j = lane % 5;
+    for (int i = lane; i < 2 * MILLER_LINES * 5; i += COOP_LANES) {
+        const int pair = i / (MILLER_LINES * 5), r = i % (MILLER_LINES * 5), k = r / 5, j = r % 5;
+        if (!ws.use[pair]) continue;
         const LineCoeff& l = (pair ? L2 : L1)->line[k];
         FpW v;
         if (j == 0) v = mul(w_ext(l.A.c0), ws.pt[pair][0]);
@@ -308,7 +303,7 @@ KZG_HD_NOINLINE void coop_prepare_lines(CoopWS& ws, const G2Lines* L1, const G2L
         else if (j == 2) v = mul(w_ext(l.B.c0), ws.pt[pair][1]);
         else if (j == 3) v = mul(w_ext(l.B.c1), ws.pt[pair][1]);
         else v = ws.pt[pair][2];
-        ws.line[pair][j] = v;
+        ws.lv[pair][k][j] = v;
     }
     COOP_END
 }
@@ -334,16 +329,15 @@ KZG_HD void coop_pairing_product_is_one(CoopWS& ws, const G1& P1, const G2Lines*
     coop_set_one(ws, F);
     const uint64_t z = BLS_X_ABS;
     int k = 0;
+    coop_prepare_all_lines(ws, L1, L2);
     for (int b = 62; b >= 0; b--) {
         if (b != 62) coop_sqr(ws, F, F);
-        coop_prepare_lines(ws, L1, L2, k);
-        if (use0) coop_line(ws, F, F, 0);
-        if (use1) coop_line(ws, F, F, 1);
+        if (use0) coop_line(ws, F, F, 0, k);
+        if (use1) coop_line(ws, F, F, 1, k);
         k++;
         if ((z >> b) & 1ull) {
-            coop_prepare_lines(ws, L1, L2, k);
-            if (use0) coop_line(ws, F, F, 0);
-            if (use1) coop_line(ws, F, F, 1);
+            if (use0) coop_line(ws, F, F, 0, k);
+            if (use1) coop_line(ws, F, F, 1, k);
             k++;
         }
     }
