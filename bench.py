@@ -316,7 +316,7 @@ def run_b200(args):
         return float(t[0]), float(t[1]), prof, launches, clocks
 
     # timed run: whole-call CUDA events only (level 1), stages free to overlap
-    wall, dev_ms, _, launches, clocks = timed(verify_dev, args.steps, args.warmup, 1)
+    wall, dev_ms, prof1, launches, clocks = timed(verify_dev, args.steps, args.warmup, 1)
     # kernel breakdown: separate short run with per-kernel events (level 2, stages serialised)
     _, _, prof, _, _ = timed(verify_dev, 2, 1, 2)
     prof_steps = 2
@@ -495,7 +495,10 @@ def run_b200(args):
                 "l2": "inputs (%.0f MiB/step) exceed the 126 MB L2; no explicit flush" % (n * BLOB / 2**20),
             },
             "e2e": {"value": e2e_value, "unit": "blobs/s", "h2d_bytes_per_step": n * (BLOB + 96), "d2h_bytes_per_step": 8, "ms_per_step": 1000.0 * e_wall / args.steps},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "int_pipe": int_pipe, "kernel_share": shares, "extra": extra,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "int_pipe": int_pipe, "kernel_share": shares,
+            # stage boundaries inside the TIMED calls (events on the call's stream, stages overlapping as in production)
+            "stages_ms": {k: round(v[0] / args.steps, 4) for k, v in (prof1 or {}).get("kernels", {}).items() if k.startswith("stage:") or k == "end"},
+            "extra": extra,
         }
         if cpu:
             line["cpu_baseline"] = cpu

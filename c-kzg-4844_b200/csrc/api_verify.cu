@@ -334,6 +334,8 @@ int ckzg_b200_verify_blob_kzg_proof_batch(ckzg_b200_ctx* ctx, int* ok, const uin
     Stage1 s;
     (void)d_blobs;
     TRY(verify_stage1(call, s, blobs, d_cm, d_pf, n, mem));
+    const bool stage_marks = call.profiling && !call.trace_kernels;  // level 1: stage boundaries of the concurrent form
+    if (stage_marks) call.mark("stage:per_blob(validate|hash,evaluate)");
     // the reference stops at the first invalid input (eip4844.c:813-831) before any pairing work
     int bad = 0;
     bool use_r = n > 1;  // n == 1: the single-proof equation, no challenge (eip4844.c:798)
@@ -357,6 +359,7 @@ int ckzg_b200_verify_blob_kzg_proof_batch(ckzg_b200_ctx* ctx, int* ok, const uin
         const uint8_t* hp = (mem == CKZG_B200_DEVICE) ? h_cp.data() + n * 48 : proofs;
         TRY(r_from_transcript(call, d_r, hc, h_zy.data(), hp, nullptr, n));
     }
+    if (stage_marks) call.mark("stage:transcript(d2h,host_sha,r)");
     G1* d_AB;
     void* scratch;
     int* d_ok;
@@ -364,8 +367,10 @@ int ckzg_b200_verify_blob_kzg_proof_batch(ckzg_b200_ctx* ctx, int* ok, const uin
     TRY(call.alloc((uint8_t**)&scratch, rlc_scratch_bytes(n)));
     TRY(call.alloc(&d_ok, 1));
     TRY(launch_rlc(L, d_AB, s.cm, s.pf, s.z, s.y, d_r, use_r, 0, n, scratch));
+    if (stage_marks) call.mark("stage:linear_combination");
     // e(A, [tau]G2) == e(B, G2)   (eip4844.c:751)
     TRY(launch_pairing_check(L, d_ok, d_AB + 0, d_AB + 1, nullptr, LINE_G2_TAU, LINE_G2_GEN));
+    if (stage_marks) call.mark("stage:pairing");
     TRY(read_flag(call, d_ok, ok));
     return RET_OK;
 }

@@ -165,19 +165,25 @@ KZG_HD_NOINLINE void coop_run(CoopWS& ws, int op, FpW* dst, const FpW* a, const 
     COOP_BEGIN
     if (lane < 60) {
         const int k = lane / 5, sub = lane % 5;
-        FpW acc = FpW::from_limbs(FPW_OFF16);
-        for (int t = T.oo[k] + sub; t < T.oo[k + 1]; t += 5) coop_acc_term(acc, T.ot[t], ws.prod, ws.prod + 12, &ws.zerow);
+        // two accumulators (alternate terms): two independent carry chains in flight instead of one
+        FpW acc = FpW::from_limbs(FPW_OFF16), acc2 = FpW::zero();
+        const int end = T.oo[k + 1];
+        for (int t = T.oo[k] + sub; t < end; t += 10) {
+            coop_acc_term(acc, T.ot[t], ws.prod, ws.prod + 12, &ws.zerow);
+            coop_acc_term(acc2, t + 5 < end ? T.ot[t + 5] : 0, ws.prod, ws.prod + 12, &ws.zerow);
+        }
+        w_acc(acc, acc2);       // modulo 2^448: acc2 alone may be "negative"
         ws.part[k][sub] = acc;  // < 24 p
     }
     COOP_END
     COOP_BEGIN
     if (lane < 12) {
-        FpW acc = ws.part[lane][0];
-        w_acc(acc, ws.part[lane][1]);
-        w_acc(acc, ws.part[lane][2]);
-        w_acc(acc, ws.part[lane][3]);
-        w_acc(acc, ws.part[lane][4]);
-        dst[lane] = acc;  // < 120 p
+        FpW u = ws.part[lane][0], v = ws.part[lane][2];
+        w_acc(u, ws.part[lane][1]);
+        w_acc(v, ws.part[lane][3]);
+        w_acc(u, ws.part[lane][4]);
+        w_acc(u, v);
+        dst[lane] = u;  // < 120 p
     }
     COOP_END
 }

@@ -84,6 +84,7 @@ def verify_modes():
         ("device_level1", 1, lambda: mod.verify_blob_kzg_proof_batch_device(dev.data_ptr(), cms.data_ptr(), prs.data_ptr(), n, ts)),
         ("device_serial_level2", 2, lambda: mod.verify_blob_kzg_proof_batch_device(dev.data_ptr(), cms.data_ptr(), prs.data_ptr(), n, ts)),
         ("host_concurrent", 0, lambda: mod.verify_blob_kzg_proof_batch_host(host.data_ptr(), hc.data_ptr(), hp.data_ptr(), n, ts)),
+        ("host_level1", 1, lambda: mod.verify_blob_kzg_proof_batch_host(host.data_ptr(), hc.data_ptr(), hp.data_ptr(), n, ts)),
         ("host_serial_level2", 2, lambda: mod.verify_blob_kzg_proof_batch_host(host.data_ptr(), hc.data_ptr(), hp.data_ptr(), n, ts)),
     ):
         mod.profile_enable(ts, level)
@@ -96,6 +97,9 @@ def verify_modes():
             fn()
             best = min(best, time.perf_counter() - t0)
         out[name + "_ms"] = round(best * 1e3, 3)
+        if level == 1:  # stage boundaries of the concurrent arrangement (events on the call's stream)
+            pr = mod.profile_dump(ts)
+            out[name + "_stages_ms"] = {k: round(v[0] / max(1, pr["calls"]), 3) for k, v in pr["kernels"].items() if k != "begin"}
         if level == 2:
             pr = mod.profile_dump(ts)
             out[name + "_kernels_ms"] = {k: round(v[0] / max(1, pr["calls"]), 3) for k, v in pr["kernels"].items() if k != "begin"}
@@ -132,6 +136,7 @@ if __name__ == "__main__":
         mulbench()
         subprocess.call([sys.executable, os.path.abspath(__file__), "modes"])
         subprocess.call([sys.executable, os.path.abspath(__file__), "single"])
-        for v in ("3", "13", "4", "14"):
-            env = dict(os.environ, CKZG_B200_ACC_VARIANT=v)
-            subprocess.call([sys.executable, os.path.abspath(__file__), "commit"], env=env)
+        if os.environ.get("PROBE_COMMIT_VARIANTS"):  # settled in r01l; kept for re-measurement
+            for v in ("3", "13", "4", "14"):
+                env = dict(os.environ, CKZG_B200_ACC_VARIANT=v)
+                subprocess.call([sys.executable, os.path.abspath(__file__), "commit"], env=env)
