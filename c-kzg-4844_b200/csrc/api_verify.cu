@@ -68,11 +68,21 @@ int prove_batch(Call& call, uint8_t* proofs_out, uint8_t* ys_out, const uint8_t*
 
 // Per-blob stage of the verifier: validate points, challenges z, evaluations y.
 struct Stage1 {
-    G1Affine *cm = nullptr, *pf = nullptr;
+    G1Affine *cm = nullptr, *pf = nullptr;  // pf = pts, cm = pts + n (one array: vmsm.cu point layout)
     Fr *z = nullptr, *y = nullptr;
     uint8_t* zy = nullptr;
     int* bad = nullptr;  // single flag
+    // pre-shifted copies of the points for the bucket form of the linear combination (vmsm.cu); built on
+    // a side stream while the hashes / evaluations run.  `shifted` must be waited for before use.
+    bool want_shift = false;
+    G1* table = nullptr;
+    cudaEvent_t shifted = nullptr;
 };
+// CKZG_B200_RLC=points forces the one-multiplication-per-point linear combination (A/B comparison)
+bool rlc_use_vmsm() {
+    static const bool on = !(getenv("CKZG_B200_RLC") && strcmp(getenv("CKZG_B200_RLC"), "points") == 0);
+    return on;
+}
 // `blobs` lives in `mem` space.  The per-blob Fiat-Shamir hash is latency bound (2050 dependent SHA-256
 // blocks per thread: ~4 ms whatever the batch size, on 1 warp per SM), so it runs on side streams
 // concurrently with the point validations; HOST blobs are uploaded in chunks on a copy stream and every
@@ -84,8 +94,9 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
     uint8_t* d_up = nullptr;
     if (host) TRY(call.alloc(&d_up, n * BLOB_BYTES));
     const uint8_t* d_blobs = host ? d_up : blobs;
-    TRY(call.alloc(&s.cm, n));
-    TRY(call.alloc(&s.pf, n));
+    TRY(call.alloc(&s.pf, 2 * n + 1));
+    s.cm = s.pf + n;
+    if (s.want_shift) TRY(call.alloc(&s.table, vmsm_table_points(n)));
     TRY(call.alloc(&s.z, n));
     TRY(call.alloc(&s.y, n));
     TRY(call.alloc(&s.zy, n * 64));
@@ -94,9 +105,38 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
     if (call.trace_kernels || n < 64) {  // serial form
         if (host) KZG_CUDA_TRY(cudaMemcpyAsync(d_up, blobs, n * BLOB_BYTES, cudaMemcpyHostToDevice, call.stream));
         TRY(launch_g1_validate2(L, s.cm, d_cm, s.pf, d_pf, n, s.bad));
+        if (s.want_shift) TRY(launch_vmsm_shift(L, s.table, s.pf, n));
         TRY(launch_blob_challenges(L, s.z, s.zy, d_blobs, d_cm, n));
         TRY(launch_evaluate(L, s.y, s.zy, nullptr, nullptr, d_blobs, s.z, n, s.bad, 0));
         return RET_OK;
+    }
+    static const int stage1_mode = getenv("CKZG_B200_STAGE1") ? atoi(getenv("CKZG_B200_STAGE1")) : 1;
+    if (!host && stage1_mode == 1) {
+        // Device-resident blobs: hash and validation share one kernel (one warp per sub-partition), the
+        // evaluations follow on the same stream, the doubling chains of vmsm.cu go beside them.
+        TRY(launch_stage1_fused(L, s.z, s.zy, d_blobs, s.cm, d_cm, s.pf, d_pf, n, s.bad));
+        call.mark_on(call.stream, "stage:t_hash_done");
+        int rc = RET_OK;
+        if (s.want_shift) {
+            cudaStream_t sh = nullptr;
+            cudaEvent_t valid;
+            if (cudaStreamCreateWithFlags(&sh, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&valid, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&s.shifted, cudaEventDisableTiming) != cudaSuccess) {
+                rc = RET_ERROR;
+            } else {
+                cudaEventRecord(valid, call.stream);
+                cudaStreamWaitEvent(sh, valid, 0);
+                cudaEventDestroy(valid);
+                Launch Lh = call.launch_on(sh);
+                rc = launch_vmsm_shift(Lh, s.table, s.pf, n);
+                cudaEventRecord(s.shifted, sh);
+                call.mark_on(sh, "stage:t_shift_done");
+            }
+            if (sh) cudaStreamDestroy(sh);
+        }
+        if (rc == RET_OK) rc = launch_evaluate(L, s.y, s.zy, nullptr, nullptr, d_blobs, s.z, n, s.bad, 0);
+        call.mark_on(call.stream, "stage:t_evaluate_done");
+        return rc;
     }
     // fork: side streams start after the allocations / memset enqueued so far.
     // Measured on B200 (tools/gpu_probe.py modes, n = 4096 device-resident): everything on one stream
@@ -143,10 +183,30 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
             break;
         }
         cudaEventRecord(hashed[c], st);
+        if (off + CH >= n) call.mark_on(st, "stage:t_hash_done");
     }
     // main stream: point validation (independent of the blobs), then each chunk's evaluation as soon as
     // its challenges exist
     if (rc == RET_OK) rc = launch_g1_validate2(L, s.cm, d_cm, s.pf, d_pf, n, s.bad);
+    call.mark_on(call.stream, "stage:t_validate_done");
+    if (rc == RET_OK && s.want_shift) {
+        // the doubling chains (latency bound, one lane per point) go beside the evaluations
+        cudaStream_t sh = nullptr;
+        cudaEvent_t valid;
+        if (cudaStreamCreateWithFlags(&sh, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&valid, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.shifted, cudaEventDisableTiming) != cudaSuccess) {
+            rc = RET_ERROR;
+        } else {
+            cudaEventRecord(valid, call.stream);
+            cudaStreamWaitEvent(sh, valid, 0);
+            cudaEventDestroy(valid);
+            Launch Lh = call.launch_on(sh);
+            rc = launch_vmsm_shift(Lh, s.table, s.pf, n);
+            cudaEventRecord(s.shifted, sh);
+            call.mark_on(sh, "stage:t_shift_done");
+        }
+        if (sh) cudaStreamDestroy(sh);
+    }
     c = 0;
     for (uint64_t off = 0; off < n; off += CH, c++) {
         const uint64_t m = (n - off < CH) ? n - off : CH;
@@ -333,12 +393,18 @@ int ckzg_b200_verify_blob_kzg_proof_batch(ckzg_b200_ctx* ctx, int* ok, const uin
     TRY(call.stage_in(&d_pf, proofs, n * 48, mem));
     Stage1 s;
     (void)d_blobs;
-    TRY(verify_stage1(call, s, blobs, d_cm, d_pf, n, mem));
+    bool use_r = n > 1;  // n == 1: the single-proof equation, no challenge (eip4844.c:798)
+    s.want_shift = use_r && rlc_use_vmsm();
+    int rc1 = verify_stage1(call, s, blobs, d_cm, d_pf, n, mem);
+    if (s.shifted) {  // join the side stream whatever happens next
+        cudaStreamWaitEvent(call.stream, s.shifted, 0);
+        cudaEventDestroy(s.shifted);
+    }
+    TRY(rc1);
     const bool stage_marks = call.profiling && !call.trace_kernels;  // level 1: stage boundaries of the concurrent form
     if (stage_marks) call.mark("stage:per_blob(validate|hash,evaluate)");
     // the reference stops at the first invalid input (eip4844.c:813-831) before any pairing work
     int bad = 0;
-    bool use_r = n > 1;  // n == 1: the single-proof equation, no challenge (eip4844.c:798)
     std::vector<uint8_t> h_zy, h_cp;
     if (use_r) {
         h_zy.resize(n * 64);
@@ -364,9 +430,12 @@ int ckzg_b200_verify_blob_kzg_proof_batch(ckzg_b200_ctx* ctx, int* ok, const uin
     void* scratch;
     int* d_ok;
     TRY(call.alloc(&d_AB, 2));
-    TRY(call.alloc((uint8_t**)&scratch, rlc_scratch_bytes(n)));
+    TRY(call.alloc((uint8_t**)&scratch, s.want_shift ? rlc_vmsm_scratch_bytes(n) : rlc_scratch_bytes(n)));
     TRY(call.alloc(&d_ok, 1));
-    TRY(launch_rlc(L, d_AB, s.cm, s.pf, s.z, s.y, d_r, use_r, 0, n, scratch));
+    if (s.want_shift)
+        TRY(launch_rlc_vmsm(L, d_AB, s.table, s.z, s.y, d_r, n, scratch));
+    else
+        TRY(launch_rlc(L, d_AB, s.cm, s.pf, s.z, s.y, d_r, use_r, 0, n, scratch));
     if (stage_marks) call.mark("stage:linear_combination");
     // e(A, [tau]G2) == e(B, G2)   (eip4844.c:751)
     TRY(launch_pairing_check(L, d_ok, d_AB + 0, d_AB + 1, nullptr, LINE_G2_TAU, LINE_G2_GEN));

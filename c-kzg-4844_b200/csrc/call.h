@@ -18,6 +18,7 @@ struct Call {
     bool profiling = false;       // whole-call begin/end events
     bool trace_kernels = false;   // per-kernel events (level 2)
     ProfTrace trace;
+    ProfTrace timeline;           // level 1: completion times of side-stream work, relative to "begin"
 
     explicit Call(Ctx* c) : ctx(c) {
         if (cudaGetDevice(&prev_device) != cudaSuccess) return;
@@ -43,8 +44,11 @@ struct Call {
                     ctx->prof.call_ms += ms;
                     ctx->prof.calls++;
                 }
+                for (auto& t : timeline.ev)
+                    if (cudaEventSynchronize(t.first) == cudaSuccess && cudaEventElapsedTime(&ms, trace.ev.front().first, t.first) == cudaSuccess) ctx->prof.add(t.second, ms);
             }
             for (auto& e : trace.ev) cudaEventDestroy(e.first);
+            for (auto& e : timeline.ev) cudaEventDestroy(e.first);
             cudaStreamDestroy(stream);
         }
         if (prev_device >= 0) cudaSetDevice(prev_device);
@@ -78,6 +82,15 @@ struct Call {
     }
     Launch launch() { return Launch{ctx, stream, trace_kernels ? &trace : nullptr}; }
     Launch launch_on(cudaStream_t s) { return Launch{ctx, s, nullptr}; }
+    // level-1 profiling only: when did the work enqueued so far on stream `s` finish, relative to "begin"
+    void mark_on(cudaStream_t s, const char* name) {
+        if (!profiling || trace_kernels) return;
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) == cudaSuccess) {
+            cudaEventRecord(e, s);
+            timeline.ev.push_back({e, name});
+        }
+    }
     void mark(const char* name) {
         cudaEvent_t e;
         if (cudaEventCreate(&e) == cudaSuccess) {

@@ -60,9 +60,11 @@ __global__ void selftest_g1_kernel(int op, uint8_t* out48, int* ok_out, const ui
 }
 
 // Montgomery-multiplier throughput probe: ILP independent dependent-chains per thread.
+// `active` < 32: only the first `active` lanes of every warp work (does a partial warp issue faster?)
 template <int ILP>
-__global__ void mulbench_kernel(uint32_t* out, const uint32_t* in, int iters) {
+__global__ void mulbench_kernel(uint32_t* out, const uint32_t* in, int iters, int active) {
     int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((int)(threadIdx.x & 31) >= active) return;
     Fp x[ILP], y;
 #pragma unroll
     for (int k = 0; k < ILP; k++)
@@ -86,21 +88,44 @@ __global__ void mulbench_kernel(uint32_t* out, const uint32_t* in, int iters) {
     out[tid] = acc;
 }
 
-int selftest_mulbench(int ilp, int iters, int blocks, int threads, float* ms_out) {
+// FP64 FMA issue rate (8 independent chains per thread): is the DFMA pipe an alternative multiplier?
+__global__ void dfmabench_kernel(double* out, int iters) {
+    int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    double a[8], b = 1.0000001, c = 1e-9 * tid;
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = 1.0 + k + tid;
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[k] = fma(a[k], b, c);
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += a[k];
+    out[tid] = s;
+}
+
+// ilp: bits 0..7 = independent chains per thread, bits 8..15 = active lanes per warp (0 = all 32),
+// bit 16 = run the DFMA probe instead (8 FMAs per thread per iteration)
+int selftest_mulbench(int ilp_arg, int iters, int blocks, int threads, float* ms_out) {
+    const int ilp = ilp_arg & 0xff;
+    const int active = ((ilp_arg >> 8) & 0xff) ? ((ilp_arg >> 8) & 0xff) : 32;
+    const bool dfma = (ilp_arg >> 16) & 1;
     uint32_t h_in[24];
     for (int i = 0; i < 24; i++) h_in[i] = 0x9e3779b9u * (i + 1);
     uint32_t *d_in = nullptr, *d_out = nullptr;
     KZG_CUDA_TRY(cudaMalloc((void**)&d_in, sizeof(h_in)));
-    KZG_CUDA_TRY(cudaMalloc((void**)&d_out, (size_t)blocks * threads * 4));
+    KZG_CUDA_TRY(cudaMalloc((void**)&d_out, (size_t)blocks * threads * 8));
     KZG_CUDA_TRY(cudaMemcpy(d_in, h_in, sizeof(h_in), cudaMemcpyHostToDevice));
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     for (int rep = 0; rep < 2; rep++) {
         cudaEventRecord(e0);
-        if (ilp == 1) mulbench_kernel<1><<<blocks, threads>>>(d_out, d_in, iters);
-        else if (ilp == 2) mulbench_kernel<2><<<blocks, threads>>>(d_out, d_in, iters);
-        else mulbench_kernel<4><<<blocks, threads>>>(d_out, d_in, iters);
+        if (dfma) dfmabench_kernel<<<blocks, threads>>>((double*)d_out, iters);
+        else if (ilp == 1) mulbench_kernel<1><<<blocks, threads>>>(d_out, d_in, iters, active);
+        else if (ilp == 2) mulbench_kernel<2><<<blocks, threads>>>(d_out, d_in, iters, active);
+        else mulbench_kernel<4><<<blocks, threads>>>(d_out, d_in, iters, active);
         cudaEventRecord(e1);
         KZG_CUDA_TRY(cudaEventSynchronize(e1));
     }

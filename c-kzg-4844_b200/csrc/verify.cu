@@ -73,6 +73,21 @@ __device__ __forceinline__ Fr fr_from_digest(const uint32_t h[8]) {
 // ------------------------------------------------------------------------------------------------
 constexpr int CH_BLOCKS = 2050;  // (16 + 16 + 131072 + 48 + 1 + 8 bytes) padded to 64-byte blocks
 
+// Placement probe (tools/gpu_probe.py "placement"): when armed, lane 0 of every warp of the stage-1
+// kernels records which SM and which hardware warp slot it runs on -- the measurement behind the
+// arrangement of those kernels (latency-bound warps that share a sub-partition slow each other down).
+__device__ uint32_t* g_place_buf = nullptr;  // [0] = count, [1] = capacity, then records
+__device__ __forceinline__ void place_record(uint32_t kernel_id) {
+    uint32_t* buf = g_place_buf;
+    if (buf == nullptr || (threadIdx.x & 31) != 0) return;
+    uint32_t smid, warpid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(warpid));
+    const uint32_t k = atomicAdd(buf, 1u);
+    if (k < buf[1]) buf[2 + k] = (kernel_id << 28) | ((threadIdx.x >> 5) << 24) | (smid << 8) | (warpid & 0xffu);
+}
+__device__ __forceinline__ void pair_barrier() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+
 // message block `k` of the transcript "FSBLOBVERIFY_V1_" || u64be(0) || u64be(4096) || blob || commitment
 __device__ __forceinline__ void challenge_message_block(uint32_t w[16], int k, const uint4* __restrict__ blob, const uint8_t* __restrict__ cm) {
     if (k == 0) {
@@ -104,9 +119,10 @@ __device__ __forceinline__ void challenge_message_block(uint32_t w[16], int k, c
     }
 }
 
-__global__ void __launch_bounds__(64) blob_challenge_kernel(Fr* __restrict__ z_out, uint8_t* __restrict__ zy, const uint8_t* __restrict__ blobs,
-                                                          const uint8_t* __restrict__ commitments, uint64_t n) {
-    __shared__ uint32_t kw[2][64][32];  // [buffer][round][lane] = K[t] + W[t]
+// Runs on warps 0 and 1 of the CTA (they meet at named barrier 1, so other warps of the CTA are free
+// to do something else).
+__device__ __forceinline__ void challenge_warp_pair(uint32_t (*kw)[64][32], Fr* __restrict__ z_out, uint8_t* __restrict__ zy, const uint8_t* __restrict__ blobs,
+                                                    const uint8_t* __restrict__ commitments, uint64_t n) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t i = (uint64_t)blockIdx.x * 32 + lane;
     const bool live = i < n;
@@ -169,13 +185,20 @@ __global__ void __launch_bounds__(64) blob_challenge_kernel(Fr* __restrict__ z_o
             st.h[0] += a; st.h[1] += b; st.h[2] += c; st.h[3] += d;
             st.h[4] += e; st.h[5] += f; st.h[6] += g; st.h[7] += h;
         }
-        __syncthreads();
+        pair_barrier();
     }
     if (warp == 0 && live) {
         Fr z = fr_from_digest(st.h);
         z_out[i] = z;
         store_fr_be(zy + i * 64, z);
     }
+}
+
+__global__ void __launch_bounds__(64) blob_challenge_kernel(Fr* __restrict__ z_out, uint8_t* __restrict__ zy, const uint8_t* __restrict__ blobs,
+                                                          const uint8_t* __restrict__ commitments, uint64_t n) {
+    __shared__ uint32_t kw[2][64][32];  // [buffer][round][lane] = K[t] + W[t]
+    place_record(1);
+    challenge_warp_pair(kw, z_out, zy, blobs, commitments, n);
 }
 
 __global__ void z_from_bytes_kernel(Fr* z_out, uint8_t* zy, const uint8_t* z_bytes, uint64_t n, int* bad) {
@@ -623,6 +646,7 @@ int launch_quotient(Launch& L, uint8_t* q_scalars, const uint8_t* blobs, const F
 // per CTA), so validating commitments and proofs together costs the time of one
 __global__ void g1_validate2_kernel(G1Affine* __restrict__ out_a, const uint8_t* __restrict__ in_a, G1Affine* __restrict__ out_b, const uint8_t* __restrict__ in_b, uint64_t n,
                                     uint64_t nb, int* __restrict__ bad) {
+    place_record(2);
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n + nb) return;
     const bool second = i >= n;
@@ -637,6 +661,46 @@ __global__ void g1_validate2_kernel(G1Affine* __restrict__ out_a, const uint8_t*
     }
     (second ? out_b : out_a)[k] = a;
 }
+// Per-blob stage, part one, as ONE kernel: the four warps of a CTA sit on the four sub-partitions of an
+// SM; warps 0/1 hash 32 blobs (challenge_warp_pair), warp 2 validates their 32 commitments and warp 3
+// their 32 proofs.  All three are single-lane dependency chains of ~2 ms that saturate the issue port of
+// the sub-partition they run on: as separate concurrent kernels the block scheduler stacked them on the
+// same sub-partitions and each took as long as running them back to back (tools/gpu_probe.py
+// "placement", profiles/r01_summary.md r01q-r01s).
+__global__ void __launch_bounds__(128) stage1_fused_kernel(Fr* __restrict__ z_out, uint8_t* __restrict__ zy, const uint8_t* __restrict__ blobs, G1Affine* __restrict__ out_cm,
+                                                           const uint8_t* __restrict__ in_cm, G1Affine* __restrict__ out_pf, const uint8_t* __restrict__ in_pf, uint64_t n,
+                                                           int* __restrict__ bad) {
+    __shared__ uint32_t kw[2][64][32];
+    place_record(3);
+    const int warp = threadIdx.x >> 5;
+    if (warp < 2) {
+        challenge_warp_pair(kw, z_out, zy, blobs, in_cm, n);
+        return;
+    }
+    const uint64_t i = (uint64_t)blockIdx.x * 32 + (threadIdx.x & 31);
+    if (i >= n) return;
+    const uint8_t* src = (warp == 2 ? in_cm : in_pf) + i * 48;
+    uint8_t buf[48];
+    for (int q = 0; q < 48; q++) buf[q] = src[q];
+    G1Affine a;
+    if (!g1a_validate(a, buf)) {
+        *bad = 1;
+        a = g1a_inf();
+    }
+    (warp == 2 ? out_cm : out_pf)[i] = a;
+}
+int launch_stage1_fused(Launch& L, Fr* z, uint8_t* zy, const uint8_t* blobs, G1Affine* out_cm, const uint8_t* in_cm, G1Affine* out_pf, const uint8_t* in_pf, uint64_t n, int* bad) {
+    if (!n) return RET_OK;
+    stage1_fused_kernel<<<blocks_for(n, 32), 128, 0, L.stream>>>(z, zy, blobs, out_cm, in_cm, out_pf, in_pf, n, bad);
+    KZG_CUDA_TRY(cudaGetLastError());
+    L.count(1, "hash+validate");
+    return RET_OK;
+}
+int debug_set_placement_buffer(uint32_t* dev_buf) {
+    KZG_CUDA_TRY(cudaMemcpyToSymbol(g_place_buf, &dev_buf, sizeof(dev_buf)));
+    return RET_OK;
+}
+
 int launch_g1_validate2(Launch& L, G1Affine* out_a, const uint8_t* in_a, G1Affine* out_b, const uint8_t* in_b, uint64_t n, int* bad) {
     return launch_g1_validate_ab(L, out_a, in_a, n, out_b, in_b, n, bad);
 }

@@ -33,6 +33,9 @@ int launch_quotient(Launch& L, uint8_t* q_scalars, const uint8_t* blobs, const F
 int launch_g1_validate(Launch& L, G1Affine* out, const uint8_t* bytes48, uint64_t n, int* bad, int bad_stride);
 // same for two arrays of n points in one launch (single shared flag)
 int launch_g1_validate2(Launch& L, G1Affine* out_a, const uint8_t* in_a, G1Affine* out_b, const uint8_t* in_b, uint64_t n, int* bad);
+// hash (z) of n blobs and validation of their n commitments + n proofs in one launch (4 warps per 32 blobs)
+int launch_stage1_fused(Launch& L, Fr* z, uint8_t* zy, const uint8_t* blobs, G1Affine* out_cm, const uint8_t* in_cm, G1Affine* out_pf, const uint8_t* in_pf, uint64_t n, int* bad);
+int debug_set_placement_buffer(uint32_t* dev_buf);
 int launch_g1_validate_ab(Launch& L, G1Affine* out_a, const uint8_t* in_a, uint64_t n, G1Affine* out_b, const uint8_t* in_b, uint64_t nb, int* bad);
 // r = hash_to_bls_field(digest): the batch transcript itself (eip4844.c:597-680) is hashed on the host
 int launch_r_from_digest(Launch& L, Fr* r, const uint8_t* digest32);
@@ -43,6 +46,16 @@ int launch_r_from_digest(Launch& L, Fr* r, const uint8_t* digest32);
 size_t rlc_scratch_bytes(uint64_t n_local);
 int launch_rlc(Launch& L, G1* out2, const G1Affine* commitments, const G1Affine* proofs, const Fr* z, const Fr* y, const Fr* r, bool use_r,
                uint64_t first, uint64_t n_local, void* scratch);
+// ---- vmsm.cu: the same linear combination as ONE pair of bucket MSMs over pre-shifted bases --------
+// Point array layout: pts[0..n) = proofs, pts[n..2n) = commitments, slot 2n = -G1 generator (filled by
+// the shift kernel).  table[j][i] = 2^(8j) * pts[i] (XYZZ), j < VMSM_LEVELS, is independent of the
+// challenge r, so it is built while the per-blob hashes / evaluations are still running.
+constexpr int VMSM_LEVELS = 17;
+size_t vmsm_table_points(uint64_t n);   // VMSM_LEVELS * (2n + 1)
+int launch_vmsm_shift(Launch& L, G1* table, const G1Affine* pts, uint64_t n);
+size_t rlc_vmsm_scratch_bytes(uint64_t n);
+// out2[0] = A, out2[1] = B as launch_rlc (first = 0, use_r = true)
+int launch_rlc_vmsm(Launch& L, G1* out2, const G1* table, const Fr* z, const Fr* y, const Fr* r, uint64_t n, void* scratch);
 // sum of n XYZZ points -> out (device); in is clobbered
 int launch_g1_sum(Launch& L, G1* out, G1* in, uint64_t n);
 // canonical 32-byte big-endian encodings of n field elements

@@ -1,0 +1,361 @@
+// Variable-base bucket MSM for the random linear combination of verify_blob_kzg_proof_batch.
+//
+// Replaces the three g1_lincomb_naive calls + g1_mul of verify_kzg_proof_batch
+// (src/eip4844/eip4844.c:724-747; g1_lincomb_naive src/common/lincomb.c:34-50) for batches:
+//     A = sum r^i proof_i,   B = sum (r^i z_i) proof_i + sum r^i C_i - [sum r^i y_i] G1.
+// Same group elements, hence the same pairing verdict.
+//
+// Why not one scalar multiplication per point (rlc_points_kernel): a 255-bit multiplication is a chain
+// of ~2000 dependent Fp products on one lane (2.5 ms) and it can only start once the challenge r is
+// known, i.e. it sits in the serial tail of every call.  Here the part of that chain that does not
+// depend on r -- the doublings -- is moved in front of r:
+//   * vmsm_shift_kernel (runs beside the per-blob hash/evaluate stage, as soon as the points are
+//     validated): table[j][i] = 2^(8j) P_i for the 17 byte-levels of a 128-bit GLV half-scalar;
+//   * once r is known: scalars r^i, r^i z_i (rlc_vmsm_scalars_kernel) are split with the GLV
+//     endomorphism (k = k1 + q z^2, [z^2]P = -phi(P)) into 128-bit halves and recoded into signed
+//     bytes; every non-zero digit d of (point i, level j, half h) is one table entry that belongs in
+//     bucket |d| -- all levels share ONE set of 128 buckets because the shifts are already applied;
+//   * vmsm_sort_kernel: one CTA per MSM, counting sort by bucket (per-warp histograms in shared memory);
+//   * vmsm_accumulate_kernel: one thread per <= 8-entry slice of a bucket list (XYZZ + XYZZ adds);
+//   * vmsm_combine_kernel: one CTA per bucket folds its slices; vmsm_reduce_kernel: sum_b (b+1) B_b by
+//     a suffix scan and a tree over the 128 buckets.
+// The serial depth after r is ~35 group additions instead of ~190 doublings/additions, and no
+// doubling at all.
+#include "g1_glv.cuh"
+#include "verify.h"
+
+namespace kzg {
+
+constexpr int VC = 8;                    // digit width (one byte of the half-scalar)
+constexpr int VW = VMSM_LEVELS;          // 16 bytes + the carry out of the top byte
+constexpr int VNB = 1 << (VC - 1);       // 128 buckets (signed digits, magnitude 1..128)
+constexpr int VSORT_THREADS = 1024;
+constexpr int VSORT_WARPS = VSORT_THREADS / 32;
+constexpr uint32_t VCAP = 8;             // list entries folded by one accumulate thread
+constexpr int VACC_THREADS = 128;
+constexpr int VCOMB_THREADS = 128;
+
+struct VmsmJob {
+    const uint32_t* halves;  // [nh][4] 128-bit half-scalars, index h = 2 * point + phi
+    uint32_t nh;
+    uint32_t max_items;
+    uint32_t* entries;       // [nh * VW]
+    uint32_t* starts;        // [VNB + 1]
+    uint32_t* item_start;    // [VNB + 1]
+    uint32_t* item_bucket;   // [max_items]
+    G1* partial;             // [max_items]
+    G1* combined;            // [VNB]
+};
+struct VmsmJobs {
+    VmsmJob j[2];
+};
+
+__device__ __forceinline__ G1 vload_g1(const G1* p) {
+    G1 a;
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4* d = reinterpret_cast<uint4*>(&a);
+#pragma unroll
+    for (int i = 0; i < 12; i++) d[i] = q[i];
+    return a;
+}
+__device__ __forceinline__ void vstore_g1(G1* p, const G1& a) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    const uint4* d = reinterpret_cast<const uint4*>(&a);
+#pragma unroll
+    for (int i = 0; i < 12; i++) q[i] = d[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// before r: shifted copies of every point
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) vmsm_shift_kernel(G1* __restrict__ table, const G1Affine* __restrict__ pts, uint32_t npts) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npts) return;
+    G1 q = (i == npts - 1) ? g1_from_affine(g1a_neg(g1a_generator())) : g1_from_affine(pts[i]);
+#pragma unroll 1
+    for (int j = 0; j < VW; j++) {
+        vstore_g1(table + (size_t)j * npts + i, q);
+        if (j + 1 < VW) {
+#pragma unroll 1
+            for (int s = 0; s < VC; s++) g1_dbl_to(q);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// after r: scalars -> GLV halves
+// ------------------------------------------------------------------------------------------------
+// hB layout (half index = 2 * point + phi): points 0..n-1 proofs with r^i z_i, points n..2n-1
+// commitments with r^i, point 2n = -G with sum r^i y_i.  MSM A reads the r^i segment with point base 0.
+__device__ __forceinline__ void store_halves(uint32_t* hB, size_t point, const uint32_t k[8]) {
+    uint32_t k1[4], q[4];
+    glv_split(k1, q, k);
+    uint4* dst = reinterpret_cast<uint4*>(hB) + 2 * point;
+    dst[0] = make_uint4(k1[0], k1[1], k1[2], k1[3]);
+    dst[1] = make_uint4(q[0], q[1], q[2], q[3]);
+}
+__global__ void rlc_vmsm_scalars_kernel(uint32_t* __restrict__ hB, Fr* __restrict__ ty, const Fr* __restrict__ z, const Fr* __restrict__ y, const Fr* __restrict__ r,
+                                        uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr p = Fr::one();
+    {
+        Fr base = *r;
+        uint32_t e = i;
+        while (e) {
+            if (e & 1) p = mul(p, base);
+            base = sqr(base);
+            e >>= 1;
+        }
+    }
+    uint32_t s[8];
+    from_mont<FrTag>(s, p);
+    store_halves(hB, (size_t)(n + i), s);
+    from_mont<FrTag>(s, mul(p, z[i]));
+    store_halves(hB, (size_t)i, s);
+    ty[i] = mul(p, y[i]);
+}
+
+__global__ void __launch_bounds__(256) rlc_vmsm_ysum_kernel(uint32_t* __restrict__ hB, const Fr* __restrict__ ty, uint32_t n) {
+    __shared__ Fr sh[256];
+    const int t = threadIdx.x;
+    Fr s = Fr::zero();
+    for (uint32_t i = t; i < n; i += 256) s = add(s, ty[i]);
+    sh[t] = s;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) {
+        if (t < k) sh[t] = add(sh[t], sh[t + k]);
+        __syncthreads();
+    }
+    if (t == 0) {
+        uint32_t v[8];
+        from_mont<FrTag>(v, sh[0]);
+        store_halves(hB, (size_t)(2 * n), v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// counting sort of the digits by bucket: one CTA per MSM
+// ------------------------------------------------------------------------------------------------
+// calls f(level j, bucket b, negative) for every non-zero signed byte of the 128-bit value v
+template <class Fn>
+__device__ __forceinline__ void for_each_byte_digit(const uint4 v, Fn f) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t carry = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        uint32_t d = ((w[j >> 2] >> ((j & 3) * 8)) & 0xffu) + carry;
+        const bool negd = d > (uint32_t)VNB;
+        carry = negd ? 1u : 0u;
+        const uint32_t mag = negd ? (256u - d) : d;  // 1..128 (or 0)
+        if (mag != 0) f(j, mag - 1u, negd);
+    }
+    if (carry) f(16, 0u, false);
+}
+
+__global__ void __launch_bounds__(VSORT_THREADS) vmsm_sort_kernel(const __grid_constant__ VmsmJobs jobs, uint32_t npts) {
+    __shared__ uint32_t cnt[VSORT_WARPS][VNB];
+    __shared__ uint32_t bstart[VNB + 1];
+    __shared__ uint32_t istart[VNB + 1];
+    const VmsmJob& J = jobs.j[blockIdx.x];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < VSORT_WARPS * VNB; i += VSORT_THREADS) (&cnt[0][0])[i] = 0;
+    __syncthreads();
+    const uint4* hv = reinterpret_cast<const uint4*>(J.halves);
+    for (uint32_t h = tid; h < J.nh; h += VSORT_THREADS) {
+        for_each_byte_digit(hv[h], [&](int, uint32_t b, bool) { atomicAdd(&cnt[warp][b], 1u); });
+    }
+    __syncthreads();
+    if (tid < VNB) {  // exclusive prefix over the warps, per bucket
+        uint32_t run = 0;
+        for (int w = 0; w < VSORT_WARPS; w++) {
+            uint32_t c = cnt[w][tid];
+            cnt[w][tid] = run;
+            run += c;
+        }
+        bstart[tid] = run;  // bucket total for now
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t run = 0, irun = 0;
+        for (int b = 0; b < VNB; b++) {
+            const uint32_t c = bstart[b];
+            bstart[b] = run;
+            istart[b] = irun;
+            run += c;
+            irun += c ? (c + VCAP - 1) / VCAP : 1u;
+        }
+        bstart[VNB] = run;
+        istart[VNB] = irun;
+    }
+    __syncthreads();
+    if (tid <= VNB) {
+        J.starts[tid] = bstart[tid];
+        J.item_start[tid] = istart[tid];
+    }
+    if (tid < VNB) {
+        for (uint32_t k = istart[tid]; k < istart[tid + 1]; k++) J.item_bucket[k] = (uint32_t)tid;
+    }
+    for (uint32_t h = tid; h < J.nh; h += VSORT_THREADS) {
+        const uint32_t pt = h >> 1, phi = h & 1u;
+        for_each_byte_digit(hv[h], [&](int j, uint32_t b, bool negd) {
+            const uint32_t pos = bstart[b] + atomicAdd(&cnt[warp][b], 1u);
+            // second base is -phi(P): (beta X, -Y)
+            J.entries[pos] = ((uint32_t)j * npts + pt) | (phi ? 0x40000000u : 0u) | ((negd != (phi != 0)) ? 0x80000000u : 0u);
+        });
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bucket sums
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(VACC_THREADS) vmsm_accumulate_kernel(const __grid_constant__ VmsmJobs jobs, const G1* __restrict__ table) {
+    const VmsmJob& J = jobs.j[blockIdx.y];
+    const uint32_t slot = blockIdx.x * VACC_THREADS + threadIdx.x;
+    if (slot >= J.item_start[VNB]) return;
+    const uint32_t bucket = J.item_bucket[slot];
+    const uint32_t first = J.item_start[bucket], np = J.item_start[bucket + 1] - first, part = slot - first;
+    const uint32_t lo = J.starts[bucket], len = J.starts[bucket + 1] - lo;
+    const uint32_t b0 = lo + (uint32_t)(((uint64_t)len * part) / np);
+    const uint32_t b1 = lo + (uint32_t)(((uint64_t)len * (part + 1)) / np);
+    const Fp beta = Fp::from_limbs(FP_BETA_A);
+    G1 acc = g1_inf();
+#pragma unroll 1
+    for (uint32_t k = b0; k < b1; k++) {
+        const uint32_t v = J.entries[k];
+        G1 t = vload_g1(table + (v & 0x3fffffffu));
+        if (v & 0x40000000u) t.x = mul(t.x, beta);
+        if (v >> 31) t.y = neg(t.y);
+        g1_add_to(acc, t);
+    }
+    vstore_g1(J.partial + slot, acc);
+}
+
+__global__ void __launch_bounds__(VCOMB_THREADS) vmsm_combine_kernel(const __grid_constant__ VmsmJobs jobs) {
+    __shared__ G1 sh[VCOMB_THREADS];
+    const VmsmJob& J = jobs.j[blockIdx.y];
+    const int t = threadIdx.x, bucket = blockIdx.x;
+    const uint32_t it1 = J.item_start[bucket + 1];
+    G1 acc = g1_inf();
+#pragma unroll 1
+    for (uint32_t it = J.item_start[bucket] + t; it < it1; it += VCOMB_THREADS) {
+        G1 b = vload_g1(J.partial + it);
+        g1_add_to(acc, b);
+    }
+    sh[t] = acc;
+    __syncthreads();
+#pragma unroll 1
+    for (int s = VCOMB_THREADS / 2; s > 0; s >>= 1) {
+        if (t < s) {
+            G1 x = sh[t], yv = sh[t + s];
+            g1_add_to(x, yv);
+            sh[t] = x;
+        }
+        __syncthreads();
+    }
+    if (t == 0) vstore_g1(J.combined + bucket, sh[0]);
+}
+
+// sum_b (b+1) B_b = sum_b S_b with S_b = sum_{b' >= b} B_b'
+__global__ void __launch_bounds__(VNB) vmsm_reduce_kernel(G1* __restrict__ out2, const __grid_constant__ VmsmJobs jobs) {
+    __shared__ G1 sh[VNB];
+    const VmsmJob& J = jobs.j[blockIdx.x];
+    const int t = threadIdx.x;
+    G1 acc = vload_g1(J.combined + t);
+    sh[t] = acc;
+    __syncthreads();
+#pragma unroll 1
+    for (int off = 1; off < VNB; off <<= 1) {
+        const bool has = t + off < VNB;
+        G1 o;
+        if (has) o = sh[t + off];
+        __syncthreads();
+        if (has) {
+            g1_add_to(acc, o);
+            sh[t] = acc;
+        }
+        __syncthreads();
+    }
+#pragma unroll 1
+    for (int s = VNB / 2; s > 0; s >>= 1) {
+        if (t < s) {
+            G1 x = sh[t], yv = sh[t + s];
+            g1_add_to(x, yv);
+            sh[t] = x;
+        }
+        __syncthreads();
+    }
+    if (t == 0) vstore_g1(out2 + blockIdx.x, sh[0]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+static size_t val256(size_t x) { return (x + 255) & ~(size_t)255; }
+static uint32_t vmsm_max_items(uint64_t nh) { return (uint32_t)(VNB + (nh * VW + VCAP - 1) / VCAP); }
+
+size_t vmsm_table_points(uint64_t n) { return (size_t)VW * (2 * n + 1); }
+
+int launch_vmsm_shift(Launch& L, G1* table, const G1Affine* pts, uint64_t n) {
+    const uint32_t npts = (uint32_t)(2 * n + 1);
+    vmsm_shift_kernel<<<(npts + 31) / 32, 32, 0, L.stream>>>(table, pts, npts);
+    KZG_CUDA_TRY(cudaGetLastError());
+    L.count(1, "vmsm_shift");
+    return RET_OK;
+}
+
+static size_t vmsm_job_bytes(uint64_t nh) {
+    const uint32_t mi = vmsm_max_items(nh);
+    return val256(nh * VW * sizeof(uint32_t)) + 2 * val256((VNB + 1) * sizeof(uint32_t)) + val256(mi * sizeof(uint32_t)) + val256((size_t)mi * sizeof(G1)) +
+           val256(VNB * sizeof(G1));
+}
+static uint8_t* vmsm_job_carve(VmsmJob& J, uint8_t* ws, const uint32_t* halves, uint64_t nh) {
+    J.halves = halves;
+    J.nh = (uint32_t)nh;
+    J.max_items = vmsm_max_items(nh);
+    J.entries = (uint32_t*)ws; ws += val256(nh * VW * sizeof(uint32_t));
+    J.starts = (uint32_t*)ws; ws += val256((VNB + 1) * sizeof(uint32_t));
+    J.item_start = (uint32_t*)ws; ws += val256((VNB + 1) * sizeof(uint32_t));
+    J.item_bucket = (uint32_t*)ws; ws += val256(J.max_items * sizeof(uint32_t));
+    J.partial = (G1*)ws; ws += val256((size_t)J.max_items * sizeof(G1));
+    J.combined = (G1*)ws; ws += val256(VNB * sizeof(G1));
+    return ws;
+}
+
+size_t rlc_vmsm_scratch_bytes(uint64_t n) {
+    const uint64_t nhB = 2 * (2 * n + 1), nhA = 2 * n;
+    return val256(nhB * 16) + val256(n * sizeof(Fr)) + vmsm_job_bytes(nhA) + vmsm_job_bytes(nhB);
+}
+
+int launch_rlc_vmsm(Launch& L, G1* out2, const G1* table, const Fr* z, const Fr* y, const Fr* r, uint64_t n, void* scratch) {
+    if (n == 0 || 2 * n + 1 >= (1ull << 30) / VW) return RET_ERROR;
+    const uint64_t nhB = 2 * (2 * n + 1), nhA = 2 * n;
+    uint8_t* ws = (uint8_t*)scratch;
+    uint32_t* hB = (uint32_t*)ws; ws += val256(nhB * 16);
+    Fr* ty = (Fr*)ws; ws += val256(n * sizeof(Fr));
+    VmsmJobs jobs;
+    ws = vmsm_job_carve(jobs.j[0], ws, hB + 4 * (2 * n), nhA);  // A: the r^i segment, points 0..n-1 (proofs)
+    ws = vmsm_job_carve(jobs.j[1], ws, hB, nhB);
+    const uint32_t npts = (uint32_t)(2 * n + 1);
+
+    rlc_vmsm_scalars_kernel<<<(unsigned)((n + 63) / 64), 64, 0, L.stream>>>(hB, ty, z, y, r, (uint32_t)n);
+    KZG_CUDA_TRY(cudaGetLastError());
+    rlc_vmsm_ysum_kernel<<<1, 256, 0, L.stream>>>(hB, ty, (uint32_t)n);
+    KZG_CUDA_TRY(cudaGetLastError());
+    L.count(2, "rlc_scalars");
+    vmsm_sort_kernel<<<2, VSORT_THREADS, 0, L.stream>>>(jobs, npts);
+    KZG_CUDA_TRY(cudaGetLastError());
+    L.count(1, "vmsm_sort");
+    dim3 agrid((jobs.j[1].max_items + VACC_THREADS - 1) / VACC_THREADS, 2);
+    vmsm_accumulate_kernel<<<agrid, VACC_THREADS, 0, L.stream>>>(jobs, table);
+    KZG_CUDA_TRY(cudaGetLastError());
+    L.count(1, "vmsm_accumulate");
+    vmsm_combine_kernel<<<dim3(VNB, 2), VCOMB_THREADS, 0, L.stream>>>(jobs);
+    KZG_CUDA_TRY(cudaGetLastError());
+    vmsm_reduce_kernel<<<2, VNB, 0, L.stream>>>(out2, jobs);
+    KZG_CUDA_TRY(cudaGetLastError());
+    L.count(2, "vmsm_reduce");
+    return RET_OK;
+}
+
+}  // namespace kzg

@@ -152,8 +152,13 @@ int ckzg_b200_profile_dump(ckzg_b200_ctx *ctx, char *buf, size_t cap);
  *   operands/results are plain little-endian 32-bit limbs (12 per Fp, 8 per Fr), HOST memory. */
 int ckzg_b200_selftest_field(int op, uint32_t *out, const uint32_t *a, const uint32_t *b, uint64_t n);
 /* Fp Montgomery-multiplier throughput probe (the measured integer-pipe roofline denominator):
- * blocks x threads threads each run `iters` rounds of `ilp` (1, 2 or 4) independent dependent-chains. */
+ * blocks x threads threads each run `iters` rounds of `ilp` (1, 2 or 4) independent dependent-chains.
+ * ilp bits 8..15: active lanes per warp (0 = 32); bit 16: FP64 FMA probe (8 FMAs per thread per round). */
 int ckzg_b200_selftest_mulbench(int ilp, int iters, int blocks, int threads, float *ms_out);
+/* Arms (dev_buf != NULL) or disarms the placement probe of the stage-1 kernels: dev_buf is a DEVICE array
+ * of uint32, [0] = record count (set to 0), [1] = capacity, records follow:
+ * kernel id << 28 | warp in block << 24 | %smid << 8 | %warpid.  Test/measurement hook. */
+int ckzg_b200_debug_placement(uint32_t *dev_buf);
 /* op 0: [k]P (+Q), op 1: validate (subgroup), op 2: uncompress only; compressed points, HOST memory.
  * ok_out[i] = 1 if the input decoded/validated.  k = 8 limbs per scalar. */
 int ckzg_b200_selftest_g1(int op, uint8_t *out48, int *ok_out, const uint8_t *p48, const uint32_t *k, const uint8_t *q48, uint64_t n);
