@@ -12,6 +12,7 @@
 // denominators inverted with ONE field inversion per blob through a block-wide product scan), one
 // thread per blob for the inherently serial 131 KB SHA-256, one thread per scalar multiplication in
 // the linear combinations.
+#define KZG_FP_MUL_OUTLINE 1
 #include "g1_glv.cuh"
 #include "sha256.cuh"
 #include "verify.h"

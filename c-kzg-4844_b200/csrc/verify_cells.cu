@@ -15,6 +15,7 @@
 // commitment is prepared on the host as CSR index lists (dedup order is part of the transcript,
 // eip7594.c:345-376); the transcript itself is hashed on the host like the blob batch transcript
 // (src/host_sha256.c).
+#define KZG_FP_MUL_OUTLINE 1
 #include "cells.h"
 #include "g1_glv.cuh"
 #include "verify.h"

@@ -21,6 +21,7 @@
 //     a suffix scan and a tree over the 128 buckets.
 // The serial depth after r is ~35 group additions instead of ~190 doublings/additions, and no
 // doubling at all.
+#define KZG_FP_MUL_OUTLINE 1
 #include "g1_glv.cuh"
 #include "verify.h"
 
