@@ -72,6 +72,8 @@ static void ctx_free(Ctx* c) {
     cudaFree(c->fk_table);
     cudaFree(c->rec_shiftA);
     cudaFree(c->rec_shiftB);
+    for (auto& b : c->pin_free) cudaFreeHost(b.first);
+    c->pin_free.clear();
     if (prev >= 0) cudaSetDevice(prev);
     delete c;
 }

@@ -224,8 +224,7 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
 // (compute_r_powers_for_verify_kzg_proof_batch, eip4844.c:612-668).  The transcript is one serial hash
 // chain: hashed on the host (src/host_sha256.c explains why); the 32-byte digest goes back to the
 // device, which reduces it mod r.  Inputs are host pointers; zy is n x 64 (z || y).
-int r_from_transcript(Call& call, Fr* d_r, const uint8_t* cm, const uint8_t* zy, const uint8_t* pf, const uint8_t* tuples, uint64_t n) {
-    Launch L = call.launch();
+void transcript_digest(uint8_t digest[32], const uint8_t* cm, const uint8_t* zy, const uint8_t* pf, const uint8_t* tuples, uint64_t n) {
     ckzg_host_sha256 h;
     ckzg_host_sha256_init(&h);
     uint8_t head[32] = {'R', 'C', 'K', 'Z', 'G', 'B', 'A', 'T', 'C', 'H', '_', '_', '_', 'V', '1', '_'};
@@ -243,8 +242,12 @@ int r_from_transcript(Call& call, Fr* d_r, const uint8_t* cm, const uint8_t* zy,
             ckzg_host_sha256_update(&h, pf + 48 * i, 48);
         }
     }
-    uint8_t digest[32];
     ckzg_host_sha256_final(&h, digest);
+}
+int r_from_transcript(Call& call, Fr* d_r, const uint8_t* cm, const uint8_t* zy, const uint8_t* pf, const uint8_t* tuples, uint64_t n) {
+    Launch L = call.launch();
+    uint8_t digest[32];
+    transcript_digest(digest, cm, zy, pf, tuples, n);
     uint8_t* d_digest;
     TRY(call.alloc(&d_digest, 32));
     KZG_CUDA_TRY(cudaMemcpyAsync(d_digest, digest, 32, cudaMemcpyHostToDevice, call.stream));
@@ -395,35 +398,60 @@ int ckzg_b200_verify_blob_kzg_proof_batch(ckzg_b200_ctx* ctx, int* ok, const uin
     (void)d_blobs;
     bool use_r = n > 1;  // n == 1: the single-proof equation, no challenge (eip4844.c:798)
     s.want_shift = use_r && rlc_use_vmsm();
+    // Host copies for the batch transcript (pinned): z||y and the flag after stage 1; for device-resident
+    // inputs also the commitments and proofs, fetched on a side stream while stage 1 runs.
+    uint8_t* pin = nullptr;
+    cudaEvent_t fetched = nullptr;
+    TRY(call.pin(&pin, n * 160 + 64));
+    uint8_t *h_zy = pin, *h_c = pin + n * 64, *h_p = pin + n * 112;
+    int* h_bad = (int*)(pin + n * 160);
+    if (use_r && mem == CKZG_B200_DEVICE) {
+        cudaStream_t cp = nullptr;
+        if (cudaStreamCreateWithFlags(&cp, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&fetched, cudaEventDisableTiming) != cudaSuccess) return RET_ERROR;
+        cudaMemcpyAsync(h_c, d_cm, n * 48, cudaMemcpyDeviceToHost, cp);
+        cudaMemcpyAsync(h_p, d_pf, n * 48, cudaMemcpyDeviceToHost, cp);
+        cudaEventRecord(fetched, cp);
+        cudaStreamDestroy(cp);
+    }
     int rc1 = verify_stage1(call, s, blobs, d_cm, d_pf, n, mem);
     if (s.shifted) {  // join the side stream whatever happens next
         cudaStreamWaitEvent(call.stream, s.shifted, 0);
         cudaEventDestroy(s.shifted);
     }
-    TRY(rc1);
+    if (rc1) {
+        if (fetched) {
+            cudaEventSynchronize(fetched);
+            cudaEventDestroy(fetched);
+        }
+        return rc1;
+    }
     const bool stage_marks = call.profiling && !call.trace_kernels;  // level 1: stage boundaries of the concurrent form
     if (stage_marks) call.mark("stage:per_blob(validate|hash,evaluate)");
     // the reference stops at the first invalid input (eip4844.c:813-831) before any pairing work
-    int bad = 0;
-    std::vector<uint8_t> h_zy, h_cp;
-    if (use_r) {
-        h_zy.resize(n * 64);
-        KZG_CUDA_TRY(cudaMemcpyAsync(h_zy.data(), s.zy, n * 64, cudaMemcpyDeviceToHost, call.stream));
-        if (mem == CKZG_B200_DEVICE) {
-            h_cp.resize(n * 96);
-            KZG_CUDA_TRY(cudaMemcpyAsync(h_cp.data(), d_cm, n * 48, cudaMemcpyDeviceToHost, call.stream));
-            KZG_CUDA_TRY(cudaMemcpyAsync(h_cp.data() + n * 48, d_pf, n * 48, cudaMemcpyDeviceToHost, call.stream));
-        }
+    if (use_r) cudaMemcpyAsync(h_zy, s.zy, n * 64, cudaMemcpyDeviceToHost, call.stream);
+    cudaMemcpyAsync(h_bad, s.bad, sizeof(int), cudaMemcpyDeviceToHost, call.stream);
+    cudaError_t se = cudaStreamSynchronize(call.stream);
+    if (fetched) {
+        if (se == cudaSuccess) se = cudaEventSynchronize(fetched);
+        cudaEventDestroy(fetched);
     }
-    TRY(read_flag(call, s.bad, &bad));
-    if (bad) return RET_BADARGS;
+    KZG_CUDA_TRY(se);
+    if (*h_bad) return RET_BADARGS;
 
     Fr* d_r;
     TRY(call.alloc(&d_r, 1));
+    uint8_t digest[32] = {0};
     if (use_r) {
-        const uint8_t* hc = (mem == CKZG_B200_DEVICE) ? h_cp.data() : commitments;
-        const uint8_t* hp = (mem == CKZG_B200_DEVICE) ? h_cp.data() + n * 48 : proofs;
-        TRY(r_from_transcript(call, d_r, hc, h_zy.data(), hp, nullptr, n));
+        const uint8_t* hc = (mem == CKZG_B200_DEVICE) ? h_c : commitments;
+        const uint8_t* hp = (mem == CKZG_B200_DEVICE) ? h_p : proofs;
+        transcript_digest(digest, hc, h_zy, hp, nullptr, n);
+        if (!s.want_shift) {
+            uint8_t* d_digest;
+            TRY(call.alloc(&d_digest, 32));
+            memcpy(pin + n * 160 + 16, digest, 32);  // pinned: no synchronisation needed before the launch
+            KZG_CUDA_TRY(cudaMemcpyAsync(d_digest, pin + n * 160 + 16, 32, cudaMemcpyHostToDevice, call.stream));
+            TRY(launch_r_from_digest(L, d_r, d_digest));
+        }
     }
     if (stage_marks) call.mark("stage:transcript(d2h,host_sha,r)");
     G1* d_AB;
@@ -433,7 +461,7 @@ int ckzg_b200_verify_blob_kzg_proof_batch(ckzg_b200_ctx* ctx, int* ok, const uin
     TRY(call.alloc((uint8_t**)&scratch, s.want_shift ? rlc_vmsm_scratch_bytes(n) : rlc_scratch_bytes(n)));
     TRY(call.alloc(&d_ok, 1));
     if (s.want_shift)
-        TRY(launch_rlc_vmsm(L, d_AB, s.table, s.z, s.y, d_r, n, scratch));
+        TRY(launch_rlc_vmsm(L, d_AB, s.table, s.z, s.y, digest, n, scratch));  // the digest travels as a kernel argument
     else
         TRY(launch_rlc(L, d_AB, s.cm, s.pf, s.z, s.y, d_r, use_r, 0, n, scratch));
     if (stage_marks) call.mark("stage:linear_combination");

@@ -13,6 +13,7 @@ struct Call {
     Ctx* ctx;
     cudaStream_t stream = nullptr;
     std::vector<void*> allocs;
+    std::vector<std::pair<void*, size_t>> pinned;  // returned to the context's pool after the final sync
     int prev_device = -1;
     bool ok = false;
     bool profiling = false;       // whole-call begin/end events
@@ -47,6 +48,7 @@ struct Call {
                 for (auto& t : timeline.ev)
                     if (cudaEventSynchronize(t.first) == cudaSuccess && cudaEventElapsedTime(&ms, trace.ev.front().first, t.first) == cudaSuccess) ctx->prof.add(t.second, ms);
             }
+            for (auto& b : pinned) ctx->pin_release(b.first, b.second);
             for (auto& e : trace.ev) cudaEventDestroy(e.first);
             for (auto& e : timeline.ev) cudaEventDestroy(e.first);
             cudaStreamDestroy(stream);
@@ -65,6 +67,15 @@ struct Call {
         }
         allocs.push_back(p);
         *out = (T*)p;
+        return RET_OK;
+    }
+    // pinned host scratch, valid until the call object dies
+    int pin(uint8_t** out, size_t bytes) {
+        size_t cap = 0;
+        void* p = ctx->pin_acquire(bytes, &cap);
+        if (!p) return RET_MALLOC;
+        pinned.push_back({p, cap});
+        *out = (uint8_t*)p;
         return RET_OK;
     }
     // input in `mem` space -> device pointer (copy if host)

@@ -75,6 +75,46 @@ struct Ctx {
     void* rec_shiftB = nullptr;           // 7^-k / 8192
     void* fk_table = nullptr;             // FK20 fixed-base multiples, cells.h (3.2 GB)
     uint64_t precompute = 0;
+
+    // Small pool of pinned host buffers for the device->host hops inside a call (a pageable destination
+    // makes cudaMemcpyAsync stage through the driver and block).  Buffers are reused across calls and
+    // released with the context.
+    std::mutex pin_mu;
+    std::vector<std::pair<void*, size_t>> pin_free;
+    void* pin_acquire(size_t bytes, size_t* got) {
+        {
+            std::lock_guard<std::mutex> g(pin_mu);
+            for (size_t i = 0; i < pin_free.size(); i++)
+                if (pin_free[i].second >= bytes) {
+                    void* p = pin_free[i].first;
+                    *got = pin_free[i].second;
+                    pin_free.erase(pin_free.begin() + i);
+                    return p;
+                }
+        }
+        void* p = nullptr;
+        size_t cap = bytes < 4096 ? 4096 : bytes;
+        if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+        *got = cap;
+        return p;
+    }
+    void pin_release(void* p, size_t cap) {
+        std::lock_guard<std::mutex> g(pin_mu);
+        if (pin_free.size() < 8) {
+            pin_free.push_back({p, cap});
+            return;
+        }
+        // keep the pool small: drop the smallest
+        size_t k = 0;
+        for (size_t i = 1; i < pin_free.size(); i++)
+            if (pin_free[i].second < pin_free[k].second) k = i;
+        if (pin_free[k].second < cap) {
+            cudaFreeHost(pin_free[k].first);
+            pin_free[k] = {p, cap};
+        } else {
+            cudaFreeHost(p);
+        }
+    }
 };
 
 // Optional per-kernel timing (ckzg_b200_profile_*): when enabled, every count() drops a CUDA event on

@@ -95,13 +95,31 @@ __device__ __forceinline__ void store_halves(uint32_t* hB, size_t point, const u
     dst[0] = make_uint4(k1[0], k1[1], k1[2], k1[3]);
     dst[1] = make_uint4(q[0], q[1], q[2], q[3]);
 }
-__global__ void rlc_vmsm_scalars_kernel(uint32_t* __restrict__ hB, Fr* __restrict__ ty, const Fr* __restrict__ z, const Fr* __restrict__ y, const Fr* __restrict__ r,
+struct Digest8 {
+    uint32_t h[8];  // big-endian words of the SHA-256 digest
+};
+// r = hash_to_bls_field(digest) (src/common/bytes.c:123): the digest is below 2^256 < 3r
+__device__ __forceinline__ Fr fr_from_digest_words(const uint32_t h[8]) {
+    uint32_t t[8], s[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) t[i] = h[7 - i];
+#pragma unroll 1
+    for (int k = 0; k < 2; k++) {
+        uint32_t bw = limbs_sub<8>(s, t, FR_MOD);
+        if (!bw) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) t[i] = s[i];
+        }
+    }
+    return to_mont<FrTag>(t);
+}
+__global__ void rlc_vmsm_scalars_kernel(uint32_t* __restrict__ hB, Fr* __restrict__ ty, const Fr* __restrict__ z, const Fr* __restrict__ y, const Digest8 digest,
                                         uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Fr p = Fr::one();
     {
-        Fr base = *r;
+        Fr base = fr_from_digest_words(digest.h);
         uint32_t e = i;
         while (e) {
             if (e & 1) p = mul(p, base);
@@ -328,7 +346,10 @@ size_t rlc_vmsm_scratch_bytes(uint64_t n) {
     return val256(nhB * 16) + val256(n * sizeof(Fr)) + vmsm_job_bytes(nhA) + vmsm_job_bytes(nhB);
 }
 
-int launch_rlc_vmsm(Launch& L, G1* out2, const G1* table, const Fr* z, const Fr* y, const Fr* r, uint64_t n, void* scratch) {
+int launch_rlc_vmsm(Launch& L, G1* out2, const G1* table, const Fr* z, const Fr* y, const uint8_t* digest32, uint64_t n, void* scratch) {
+    Digest8 dg;
+    for (int i = 0; i < 8; i++)
+        dg.h[i] = ((uint32_t)digest32[4 * i] << 24) | ((uint32_t)digest32[4 * i + 1] << 16) | ((uint32_t)digest32[4 * i + 2] << 8) | (uint32_t)digest32[4 * i + 3];
     if (n == 0 || 2 * n + 1 >= (1ull << 30) / VW) return RET_ERROR;
     const uint64_t nhB = 2 * (2 * n + 1), nhA = 2 * n;
     uint8_t* ws = (uint8_t*)scratch;
@@ -339,7 +360,7 @@ int launch_rlc_vmsm(Launch& L, G1* out2, const G1* table, const Fr* z, const Fr*
     ws = vmsm_job_carve(jobs.j[1], ws, hB, nhB);
     const uint32_t npts = (uint32_t)(2 * n + 1);
 
-    rlc_vmsm_scalars_kernel<<<(unsigned)((n + 63) / 64), 64, 0, L.stream>>>(hB, ty, z, y, r, (uint32_t)n);
+    rlc_vmsm_scalars_kernel<<<(unsigned)((n + 63) / 64), 64, 0, L.stream>>>(hB, ty, z, y, dg, (uint32_t)n);
     KZG_CUDA_TRY(cudaGetLastError());
     rlc_vmsm_ysum_kernel<<<1, 256, 0, L.stream>>>(hB, ty, (uint32_t)n);
     KZG_CUDA_TRY(cudaGetLastError());
