@@ -12,6 +12,9 @@
 // denominators inverted with ONE field inversion per blob through a block-wide product scan), one
 // thread per blob for the inherently serial 131 KB SHA-256, one thread per scalar multiplication in
 // the linear combinations.
+#include <stdlib.h>
+#include <string.h>
+
 #define KZG_FP_MUL_OUTLINE 1
 #include "g1_glv.cuh"
 #include "sha256.cuh"
@@ -372,6 +375,84 @@ __global__ void __launch_bounds__(EV_THREADS) evaluate_kernel(Fr* __restrict__ y
 }
 
 // ------------------------------------------------------------------------------------------------
+// Inversion-free evaluation for the verifiers (no per-element inverses are needed there).
+//
+//   p(z) = (z^N - 1)/N * sum_i f_i w_i / (z - w_i)  =  (1/N) * sum_i f_i w_i * prod_{j != i} (z - w_j)
+//
+// The blob is in bit-reversed order, so leaves 2j, 2j+1 are the points +-w and every node of the
+// binary tree over the blob owns the points of one binomial  z^(2m) - c^2 = (z^m - c)(z^m + c).
+// With N_node = sum_{i in node} f_i w_i prod_{j in node, j != i} (z - w_j):
+//       N_node = N_left (z^m + c) + N_right (z^m - c) = (N_left + N_right) z^m + (N_left - N_right) c,
+// c = roots_brp[2 * node index] at every level, and N_root / N = p(z): two products per node, one per
+// leaf, ~12.3k products per blob instead of 28.7k (prefix products, one inversion, back-substitution),
+// no inversion kernel in the middle, and no special case for z inside the domain -- the identity is
+// a polynomial one (evaluate_polynomial_in_evaluation_form's shortcut, eip4844.c:213, returns the
+// same value).  Raw big-endian elements are used as Montgomery forms of f/R; the factor comes back
+// with the final constant.
+// ------------------------------------------------------------------------------------------------
+KZG_CONST uint32_t FR_INV4096_R2[8] = {0x5fdf3f2au, 0xc90c999eu, 0x48481b52u, 0x4997a3e2u, 0x950dfcb5u, 0x8201d923u, 0x8175d40cu, 0x19e61b5eu};  // R^2 / 4096 mod r
+
+__global__ void evaluate_zpow_kernel(Fr* __restrict__ zpow, const Fr* __restrict__ z, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr p = z[i];
+    zpow[i * 12] = p;
+#pragma unroll 1
+    for (int k = 1; k < 12; k++) {
+        p = sqr(p);
+        zpow[i * 12 + k] = p;
+    }
+}
+
+template <int LOG>
+__device__ __forceinline__ Fr evt_subtree(const uint8_t* __restrict__ src, int leaf0, const Fr* Z, const Fr* __restrict__ roots_brp, bool& bad) {
+    if constexpr (LOG == 0) {
+        Fr praw;
+        load_fr_be(praw.l, src + 32 * leaf0);
+        if (limbs_geq<8>(praw.l, FR_MOD)) bad = true;  // bytes_to_bls_field, bytes.c:67
+        return mul(praw, load_fr(roots_brp + leaf0));
+    } else {
+        Fr l = evt_subtree<LOG - 1>(src, leaf0, Z, roots_brp, bad);
+        Fr r = evt_subtree<LOG - 1>(src, leaf0 + (1 << (LOG - 1)), Z, roots_brp, bad);
+        Fr c = load_fr(roots_brp + 2 * (leaf0 >> LOG));
+        return add(mul(add(l, r), Z[LOG - 1]), mul(sub(l, r), c));
+    }
+}
+
+__global__ void __launch_bounds__(EV_THREADS) evaluate_tree_kernel(Fr* __restrict__ y_out, uint8_t* __restrict__ zy, const uint8_t* __restrict__ blobs, const Fr* __restrict__ zpow,
+                                                                  const Fr* __restrict__ roots_brp, int* __restrict__ bad, int bad_stride) {
+    __shared__ Fr sh[EV_THREADS];
+    const int blob = blockIdx.x, t = threadIdx.x;
+    const uint8_t* src = blobs + (size_t)blob * BLOB_BYTES;
+    const Fr* zp = zpow + (size_t)blob * 12;
+    Fr Z[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) Z[k] = load_fr(zp + k);
+    bool isbad = false;
+    Fr v = evt_subtree<4>(src, EV_PER * t, Z, roots_brp, isbad);
+    if (isbad && bad) bad[(size_t)blob * bad_stride] = 1;
+    sh[t] = v;
+    __syncthreads();
+#pragma unroll 1
+    for (int k = 4; k < 12; k++) {
+        const int active = EV_THREADS >> (k - 3);
+        Fr nv;
+        if (t < active) {
+            Fr l = sh[2 * t], r = sh[2 * t + 1];
+            nv = add(mul(add(l, r), load_fr(zp + k)), mul(sub(l, r), load_fr(roots_brp + 2 * t)));
+        }
+        __syncthreads();
+        if (t < active) sh[t] = nv;
+        __syncthreads();
+    }
+    if (t == 0) {
+        Fr y = mul(sh[0], Fr::from_limbs(FR_INV4096_R2));
+        if (y_out) y_out[blob] = y;
+        if (zy) store_fr_be(zy + (size_t)blob * 64 + 32, y);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // quotient polynomial (evaluation form) -> plain little-endian scalars for the MSM
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) quotient_kernel(uint8_t* __restrict__ q_out, const uint8_t* __restrict__ blobs, const Fr* __restrict__ y_in,
@@ -630,6 +711,18 @@ int launch_fr_from_bytes(Launch& L, Fr* out, const uint8_t* bytes32, uint64_t st
 }
 int launch_evaluate(Launch& L, Fr* y, uint8_t* zy, Fr* inv_or_null, int* m_or_null, const uint8_t* blobs, const Fr* z, uint64_t n, int* bad, int bad_stride) {
     if (!n) return RET_OK;
+    static const bool use_tree = !(getenv("CKZG_B200_EVAL") && strcmp(getenv("CKZG_B200_EVAL"), "barycentric") == 0);
+    if (!inv_or_null && !m_or_null && use_tree) {  // verifiers: only y is needed
+        Fr* zpow = nullptr;
+        KZG_CUDA_TRY(cudaMallocAsync((void**)&zpow, n * 12 * sizeof(Fr), L.stream));
+        evaluate_zpow_kernel<<<blocks_for(n, 32), 32, 0, L.stream>>>(zpow, z, n);
+        KZG_CUDA_TRY(cudaGetLastError());
+        evaluate_tree_kernel<<<(unsigned)n, EV_THREADS, 0, L.stream>>>(y, zy, blobs, zpow, L.ctx->roots_brp, bad, bad_stride);
+        KZG_CUDA_TRY(cudaGetLastError());
+        KZG_CUDA_TRY(cudaFreeAsync(zpow, L.stream));
+        L.count(2, "evaluate");
+        return RET_OK;
+    }
     Fr* total = nullptr;
     KZG_CUDA_TRY(cudaMallocAsync((void**)&total, n * sizeof(Fr), L.stream));
     evaluate_products_kernel<<<(unsigned)n, EV_THREADS, 0, L.stream>>>(total, z, L.ctx->roots_brp);

@@ -15,7 +15,7 @@
 //     endomorphism (k = k1 + q z^2, [z^2]P = -phi(P)) into 128-bit halves and recoded into signed
 //     bytes; every non-zero digit d of (point i, level j, half h) is one table entry that belongs in
 //     bucket |d| -- all levels share ONE set of 128 buckets because the shifts are already applied;
-//   * vmsm_sort_kernel: one CTA per MSM, counting sort by bucket (per-warp histograms in shared memory);
+//   * vmsm_hist_kernel / vmsm_scatter_kernel: counting sort by bucket over 64 CTAs per MSM;
 //   * vmsm_accumulate_kernel: one thread per <= 8-entry slice of a bucket list (XYZZ + XYZZ adds);
 //   * vmsm_combine_kernel: one CTA per bucket folds its slices; vmsm_reduce_kernel: sum_b (b+1) B_b by
 //     a suffix scan and a tree over the 128 buckets.
@@ -30,8 +30,9 @@ namespace kzg {
 constexpr int VC = 8;                    // digit width (one byte of the half-scalar)
 constexpr int VW = VMSM_LEVELS;          // 16 bytes + the carry out of the top byte
 constexpr int VNB = 1 << (VC - 1);       // 128 buckets (signed digits, magnitude 1..128)
-constexpr int VSORT_THREADS = 1024;
+constexpr int VSORT_THREADS = 256;
 constexpr int VSORT_WARPS = VSORT_THREADS / 32;
+constexpr int VSORT_CTAS = 64;           // CTAs per MSM in the counting sort
 constexpr uint32_t VCAP = 8;             // list entries folded by one accumulate thread
 constexpr int VACC_THREADS = 128;
 constexpr int VCOMB_THREADS = 128;
@@ -46,6 +47,7 @@ struct VmsmJob {
     uint32_t* item_bucket;   // [max_items]
     G1* partial;             // [max_items]
     G1* combined;            // [VNB]
+    uint32_t* ctahist;       // [VSORT_CTAS][VNB]
 };
 struct VmsmJobs {
     VmsmJob j[2];
@@ -172,27 +174,54 @@ __device__ __forceinline__ void for_each_byte_digit(const uint4 v, Fn f) {
     if (carry) f(16, 0u, false);
 }
 
-__global__ void __launch_bounds__(VSORT_THREADS) vmsm_sort_kernel(const __grid_constant__ VmsmJobs jobs, uint32_t npts) {
-    __shared__ uint32_t cnt[VSORT_WARPS][VNB];
-    __shared__ uint32_t bstart[VNB + 1];
-    __shared__ uint32_t istart[VNB + 1];
-    const VmsmJob& J = jobs.j[blockIdx.x];
-    const int tid = threadIdx.x, warp = tid >> 5;
-    for (int i = tid; i < VSORT_WARPS * VNB; i += VSORT_THREADS) (&cnt[0][0])[i] = 0;
+// Two launches over VSORT_CTAS CTAs per MSM, each CTA owning a contiguous slice of the half-scalars:
+//   vmsm_hist_kernel   -- per-CTA bucket histogram -> ctahist[cta][bucket]
+//   vmsm_scatter_kernel -- every CTA derives the bucket starts (sum over CTAs, scan over buckets), its own
+//                          offset inside each bucket (CTAs before it) and the offsets of its warps (a second
+//                          count in shared memory), then writes its entries; the work-item tables are filled
+//                          cooperatively (CTA c takes the buckets b = c mod VSORT_CTAS).
+// (The first version sorted each MSM in ONE 1024-thread CTA: 179 us at n = 4096, almost all of it
+// shared-memory atomic latency -- ncu r01t: short_scoreboard 11.5 stalls per issue.)
+__device__ __forceinline__ void vsort_slice(uint32_t& h0, uint32_t& h1, uint32_t nh) {
+    const uint32_t per = (nh + VSORT_CTAS - 1) / VSORT_CTAS;
+    h0 = blockIdx.x * per;
+    h1 = h0 + per < nh ? h0 + per : nh;
+    if (h0 > nh) h0 = nh;
+}
+
+__global__ void __launch_bounds__(VSORT_THREADS) vmsm_hist_kernel(const __grid_constant__ VmsmJobs jobs) {
+    __shared__ uint32_t cnt[VNB];
+    const VmsmJob& J = jobs.j[blockIdx.y];
+    const int tid = threadIdx.x;
+    if (tid < VNB) cnt[tid] = 0;
     __syncthreads();
+    uint32_t h0, h1;
+    vsort_slice(h0, h1, J.nh);
     const uint4* hv = reinterpret_cast<const uint4*>(J.halves);
-    for (uint32_t h = tid; h < J.nh; h += VSORT_THREADS) {
-        for_each_byte_digit(hv[h], [&](int, uint32_t b, bool) { atomicAdd(&cnt[warp][b], 1u); });
+    for (uint32_t h = h0 + tid; h < h1; h += VSORT_THREADS) {
+        for_each_byte_digit(hv[h], [&](int, uint32_t b, bool) { atomicAdd(&cnt[b], 1u); });
     }
     __syncthreads();
-    if (tid < VNB) {  // exclusive prefix over the warps, per bucket
-        uint32_t run = 0;
-        for (int w = 0; w < VSORT_WARPS; w++) {
-            uint32_t c = cnt[w][tid];
-            cnt[w][tid] = run;
-            run += c;
+    if (tid < VNB) J.ctahist[blockIdx.x * VNB + tid] = cnt[tid];
+}
+
+__global__ void __launch_bounds__(VSORT_THREADS) vmsm_scatter_kernel(const __grid_constant__ VmsmJobs jobs, uint32_t npts) {
+    __shared__ uint32_t cnt[VSORT_WARPS][VNB];
+    __shared__ uint32_t bstart[VNB + 1];  // global start of every bucket
+    __shared__ uint32_t mine[VNB];        // where this CTA's entries start inside the bucket
+    __shared__ uint32_t istart[VNB + 1];
+    const VmsmJob& J = jobs.j[blockIdx.y];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < VSORT_WARPS * VNB; i += VSORT_THREADS) (&cnt[0][0])[i] = 0;
+    if (tid < VNB) {
+        uint32_t total = 0, before = 0;
+        for (int c = 0; c < VSORT_CTAS; c++) {
+            const uint32_t v = J.ctahist[c * VNB + tid];
+            if (c < (int)blockIdx.x) before += v;
+            total += v;
         }
-        bstart[tid] = run;  // bucket total for now
+        bstart[tid] = total;
+        mine[tid] = before;
     }
     __syncthreads();
     if (tid == 0) {
@@ -207,18 +236,32 @@ __global__ void __launch_bounds__(VSORT_THREADS) vmsm_sort_kernel(const __grid_c
         bstart[VNB] = run;
         istart[VNB] = irun;
     }
+    uint32_t h0, h1;
+    vsort_slice(h0, h1, J.nh);
+    const uint4* hv = reinterpret_cast<const uint4*>(J.halves);
+    for (uint32_t h = h0 + tid; h < h1; h += VSORT_THREADS) {
+        for_each_byte_digit(hv[h], [&](int, uint32_t b, bool) { atomicAdd(&cnt[warp][b], 1u); });
+    }
     __syncthreads();
-    if (tid <= VNB) {
+    if (tid < VNB) {  // exclusive prefix over the warps of this CTA, on top of the CTA's own offset
+        uint32_t run = bstart[tid] + mine[tid];
+        for (int w = 0; w < VSORT_WARPS; w++) {
+            const uint32_t c = cnt[w][tid];
+            cnt[w][tid] = run;
+            run += c;
+        }
+    }
+    if (blockIdx.x == 0 && tid <= VNB) {
         J.starts[tid] = bstart[tid];
         J.item_start[tid] = istart[tid];
     }
-    if (tid < VNB) {
-        for (uint32_t k = istart[tid]; k < istart[tid + 1]; k++) J.item_bucket[k] = (uint32_t)tid;
-    }
-    for (uint32_t h = tid; h < J.nh; h += VSORT_THREADS) {
+    for (int b = blockIdx.x; b < VNB; b += VSORT_CTAS)
+        for (uint32_t k = istart[b] + tid; k < istart[b + 1]; k += VSORT_THREADS) J.item_bucket[k] = (uint32_t)b;
+    __syncthreads();
+    for (uint32_t h = h0 + tid; h < h1; h += VSORT_THREADS) {
         const uint32_t pt = h >> 1, phi = h & 1u;
         for_each_byte_digit(hv[h], [&](int j, uint32_t b, bool negd) {
-            const uint32_t pos = bstart[b] + atomicAdd(&cnt[warp][b], 1u);
+            const uint32_t pos = atomicAdd(&cnt[warp][b], 1u);
             // second base is -phi(P): (beta X, -Y)
             J.entries[pos] = ((uint32_t)j * npts + pt) | (phi ? 0x40000000u : 0u) | ((negd != (phi != 0)) ? 0x80000000u : 0u);
         });
@@ -326,7 +369,7 @@ int launch_vmsm_shift(Launch& L, G1* table, const G1Affine* pts, uint64_t n) {
 static size_t vmsm_job_bytes(uint64_t nh) {
     const uint32_t mi = vmsm_max_items(nh);
     return val256(nh * VW * sizeof(uint32_t)) + 2 * val256((VNB + 1) * sizeof(uint32_t)) + val256(mi * sizeof(uint32_t)) + val256((size_t)mi * sizeof(G1)) +
-           val256(VNB * sizeof(G1));
+           val256(VNB * sizeof(G1)) + val256(VSORT_CTAS * VNB * sizeof(uint32_t));
 }
 static uint8_t* vmsm_job_carve(VmsmJob& J, uint8_t* ws, const uint32_t* halves, uint64_t nh) {
     J.halves = halves;
@@ -338,6 +381,7 @@ static uint8_t* vmsm_job_carve(VmsmJob& J, uint8_t* ws, const uint32_t* halves, 
     J.item_bucket = (uint32_t*)ws; ws += val256(J.max_items * sizeof(uint32_t));
     J.partial = (G1*)ws; ws += val256((size_t)J.max_items * sizeof(G1));
     J.combined = (G1*)ws; ws += val256(VNB * sizeof(G1));
+    J.ctahist = (uint32_t*)ws; ws += val256(VSORT_CTAS * VNB * sizeof(uint32_t));
     return ws;
 }
 
@@ -365,9 +409,11 @@ int launch_rlc_vmsm(Launch& L, G1* out2, const G1* table, const Fr* z, const Fr*
     rlc_vmsm_ysum_kernel<<<1, 256, 0, L.stream>>>(hB, ty, (uint32_t)n);
     KZG_CUDA_TRY(cudaGetLastError());
     L.count(2, "rlc_scalars");
-    vmsm_sort_kernel<<<2, VSORT_THREADS, 0, L.stream>>>(jobs, npts);
+    vmsm_hist_kernel<<<dim3(VSORT_CTAS, 2), VSORT_THREADS, 0, L.stream>>>(jobs);
     KZG_CUDA_TRY(cudaGetLastError());
-    L.count(1, "vmsm_sort");
+    vmsm_scatter_kernel<<<dim3(VSORT_CTAS, 2), VSORT_THREADS, 0, L.stream>>>(jobs, npts);
+    KZG_CUDA_TRY(cudaGetLastError());
+    L.count(2, "vmsm_sort");
     dim3 agrid((jobs.j[1].max_items + VACC_THREADS - 1) / VACC_THREADS, 2);
     vmsm_accumulate_kernel<<<agrid, VACC_THREADS, 0, L.stream>>>(jobs, table);
     KZG_CUDA_TRY(cudaGetLastError());
