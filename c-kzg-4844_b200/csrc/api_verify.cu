@@ -72,11 +72,10 @@ struct Stage1 {
     Fr *z = nullptr, *y = nullptr;
     uint8_t* zy = nullptr;
     int* bad = nullptr;  // single flag
-    // pre-shifted copies of the points for the bucket form of the linear combination (vmsm.cu); built on
-    // a side stream while the hashes / evaluations run.  `shifted` must be waited for before use.
+    // table of shifted points for the bucket form of the linear combination (vmsm.cu), written by the
+    // validation kernels as a by-product of the subgroup test
     bool want_shift = false;
     G1* table = nullptr;
-    cudaEvent_t shifted = nullptr;
 };
 // CKZG_B200_RLC=points forces the one-multiplication-per-point linear combination (A/B comparison)
 bool rlc_use_vmsm() {
@@ -96,16 +95,21 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
     const uint8_t* d_blobs = host ? d_up : blobs;
     TRY(call.alloc(&s.pf, 2 * n + 1));
     s.cm = s.pf + n;
-    if (s.want_shift) TRY(call.alloc(&s.table, vmsm_table_points(n)));
+    if (s.want_shift) {
+        TRY(call.alloc(&s.table, vmsm_table_points(n)));
+        TRY(vmsm_place_generator(L, s.table, n));
+    }
     TRY(call.alloc(&s.z, n));
     TRY(call.alloc(&s.y, n));
     TRY(call.alloc(&s.zy, n * 64));
     TRY(call.alloc(&s.bad, 1));
     KZG_CUDA_TRY(cudaMemsetAsync(s.bad, 0, sizeof(int), call.stream));
-    if (call.trace_kernels || n < 64) {  // serial form
+    if (call.trace_kernels || (host && n < 64)) {  // serial form
         if (host) KZG_CUDA_TRY(cudaMemcpyAsync(d_up, blobs, n * BLOB_BYTES, cudaMemcpyHostToDevice, call.stream));
-        TRY(launch_g1_validate2(L, s.cm, d_cm, s.pf, d_pf, n, s.bad));
-        if (s.want_shift) TRY(launch_vmsm_shift(L, s.table, s.pf, n));
+        if (s.want_shift)
+            TRY(launch_g1_validate2_levels(L, s.cm, d_cm, s.pf, d_pf, n, s.bad, s.table));
+        else
+            TRY(launch_g1_validate2(L, s.cm, d_cm, s.pf, d_pf, n, s.bad));
         TRY(launch_blob_challenges(L, s.z, s.zy, d_blobs, d_cm, n));
         TRY(launch_evaluate(L, s.y, s.zy, nullptr, nullptr, d_blobs, s.z, n, s.bad, 0));
         return RET_OK;
@@ -113,28 +117,10 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
     static const int stage1_mode = getenv("CKZG_B200_STAGE1") ? atoi(getenv("CKZG_B200_STAGE1")) : 1;
     if (!host && stage1_mode == 1) {
         // Device-resident blobs: hash and validation share one kernel (one warp per sub-partition), the
-        // evaluations follow on the same stream, the doubling chains of vmsm.cu go beside them.
-        TRY(launch_stage1_fused(L, s.z, s.zy, d_blobs, s.cm, d_cm, s.pf, d_pf, n, s.bad));
+        // evaluations follow on the same stream.
+        TRY(launch_stage1_fused(L, s.z, s.zy, d_blobs, s.cm, d_cm, s.pf, d_pf, n, s.bad, s.table));
         call.mark_on(call.stream, "stage:t_hash_done");
-        int rc = RET_OK;
-        if (s.want_shift) {
-            cudaStream_t sh = nullptr;
-            cudaEvent_t valid;
-            if (cudaStreamCreateWithFlags(&sh, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&valid, cudaEventDisableTiming) != cudaSuccess ||
-                cudaEventCreateWithFlags(&s.shifted, cudaEventDisableTiming) != cudaSuccess) {
-                rc = RET_ERROR;
-            } else {
-                cudaEventRecord(valid, call.stream);
-                cudaStreamWaitEvent(sh, valid, 0);
-                cudaEventDestroy(valid);
-                Launch Lh = call.launch_on(sh);
-                rc = launch_vmsm_shift(Lh, s.table, s.pf, n);
-                cudaEventRecord(s.shifted, sh);
-                call.mark_on(sh, "stage:t_shift_done");
-            }
-            if (sh) cudaStreamDestroy(sh);
-        }
-        if (rc == RET_OK) rc = launch_evaluate(L, s.y, s.zy, nullptr, nullptr, d_blobs, s.z, n, s.bad, 0);
+        int rc = launch_evaluate(L, s.y, s.zy, nullptr, nullptr, d_blobs, s.z, n, s.bad, 0);
         call.mark_on(call.stream, "stage:t_evaluate_done");
         return rc;
     }
@@ -187,26 +173,9 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
     }
     // main stream: point validation (independent of the blobs), then each chunk's evaluation as soon as
     // its challenges exist
-    if (rc == RET_OK) rc = launch_g1_validate2(L, s.cm, d_cm, s.pf, d_pf, n, s.bad);
+    if (rc == RET_OK)
+        rc = s.want_shift ? launch_g1_validate2_levels(L, s.cm, d_cm, s.pf, d_pf, n, s.bad, s.table) : launch_g1_validate2(L, s.cm, d_cm, s.pf, d_pf, n, s.bad);
     call.mark_on(call.stream, "stage:t_validate_done");
-    if (rc == RET_OK && s.want_shift) {
-        // the doubling chains (latency bound, one lane per point) go beside the evaluations
-        cudaStream_t sh = nullptr;
-        cudaEvent_t valid;
-        if (cudaStreamCreateWithFlags(&sh, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&valid, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&s.shifted, cudaEventDisableTiming) != cudaSuccess) {
-            rc = RET_ERROR;
-        } else {
-            cudaEventRecord(valid, call.stream);
-            cudaStreamWaitEvent(sh, valid, 0);
-            cudaEventDestroy(valid);
-            Launch Lh = call.launch_on(sh);
-            rc = launch_vmsm_shift(Lh, s.table, s.pf, n);
-            cudaEventRecord(s.shifted, sh);
-            call.mark_on(sh, "stage:t_shift_done");
-        }
-        if (sh) cudaStreamDestroy(sh);
-    }
     c = 0;
     for (uint64_t off = 0; off < n; off += CH, c++) {
         const uint64_t m = (n - off < CH) ? n - off : CH;
@@ -414,10 +383,6 @@ int ckzg_b200_verify_blob_kzg_proof_batch(ckzg_b200_ctx* ctx, int* ok, const uin
         cudaStreamDestroy(cp);
     }
     int rc1 = verify_stage1(call, s, blobs, d_cm, d_pf, n, mem);
-    if (s.shifted) {  // join the side stream whatever happens next
-        cudaStreamWaitEvent(call.stream, s.shifted, 0);
-        cudaEventDestroy(s.shifted);
-    }
     if (rc1) {
         if (fetched) {
             cudaEventSynchronize(fetched);

@@ -286,4 +286,85 @@ KZG_HD bool g1a_validate(G1Affine& out, const uint8_t* in) {
     return g1a_in_subgroup(out);
 }
 
+// ---- validation that leaves the doubling chains behind (vmsm.cu) --------------------------------
+// The subgroup test multiplies by |z| twice.  Done LSB-first, each multiplication walks the pure
+// doubling chain D_i = 2^i P and adds D_i for the six set bits of |z| -- the same 63 doublings + 5
+// additions as the MSB-first form, but every 2^(8j) multiple of P (first chain) and of Q = [|z|]P
+// (second chain) passes by, which is exactly the table the bucket form of the verifiers' linear
+// combination needs for the base-|z| expansion of a scalar (k = a0 + a1|z| + a2|z|^2 + a3|z|^3,
+// a_i < 2^64; [|z|^2]P = -phi(P), [|z|^3]P = -phi(Q)).  levels[j * stride], j < 9: 2^(8j) P;
+// j = 9..17: 2^(8(j-9)) Q.
+constexpr int G1_LEVELS = 18;
+
+KZG_HD void g1_store(G1* dst, const G1& a) {
+#if KZG_DEVICE_PATH
+    uint4* q = reinterpret_cast<uint4*>(dst);
+    const uint4* d = reinterpret_cast<const uint4*>(&a);
+#pragma unroll
+    for (int i = 0; i < 12; i++) q[i] = d[i];
+#else
+    *dst = a;
+#endif
+}
+
+KZG_HD_NOINLINE G1 g1_mul_bls_x_levels(const G1& p, G1* levels, size_t stride) {
+    G1 d = p, acc = g1_inf();
+    const uint64_t x = BLS_X_ABS;
+#pragma unroll 1
+    for (int i = 0; i < 64; i++) {
+        if ((i & 7) == 0) g1_store(levels + (size_t)(i >> 3) * stride, d);
+        if ((x >> i) & 1ull) g1_add_to(acc, d);
+        g1_dbl_to(d);
+    }
+    g1_store(levels + (size_t)8 * stride, d);
+    return acc;
+}
+
+// g1a_validate + the 18 table levels (all infinity for an invalid or infinite point)
+KZG_HD_NOINLINE bool g1a_validate_levels(G1Affine& out, const uint8_t* in, G1* levels, size_t stride) {
+    const bool ok = g1a_uncompress(out, in);
+    if (!ok || g1a_is_inf(out)) {
+        const G1 inf = g1_inf();
+#pragma unroll 1
+        for (int j = 0; j < G1_LEVELS; j++) g1_store(levels + (size_t)j * stride, inf);
+        return ok;
+    }
+    G1 p = g1_from_affine(out);
+    G1 q = g1_mul_bls_x_levels(p, levels, stride);
+    G1 t = g1_mul_bls_x_levels(q, levels + (size_t)9 * stride, stride);
+    G1Affine e;
+    e.x = mul(out.x, Fp::from_limbs(FP_BETA_A));
+    e.y = out.y;
+    g1_madd_to(t, e, false);  // phi(P) + [z^2]P
+    return g1_is_inf(t);
+}
+
+// base-|z| digits of a scalar k < r (8 plain limbs): k = a[0] + a[1]|z| + a[2]|z|^2 + a[3]|z|^3, a[i] < |z| < 2^64
+KZG_HD void basez_split(uint64_t a[4], const uint32_t k[8]) {
+    const uint64_t Z = BLS_X_ABS;
+    uint32_t cur[8], nxt[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) cur[i] = k[i];
+#pragma unroll 1
+    for (int step = 0; step < 3; step++) {
+        const int nl = 8 - 2 * step;  // the quotient loses 63.7 bits per step
+        uint64_t r = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) nxt[i] = 0;
+#pragma unroll 1
+        for (int bit = 32 * nl - 1; bit >= 0; bit--) {
+            const uint64_t top = r >> 63;
+            r = (r << 1) | ((cur[bit >> 5] >> (bit & 31)) & 1u);
+            if (top || r >= Z) {
+                r -= Z;
+                nxt[bit >> 5] |= 1u << (bit & 31);
+            }
+        }
+        a[step] = r;
+#pragma unroll
+        for (int i = 0; i < 8; i++) cur[i] = nxt[i];
+    }
+    a[3] = ((uint64_t)cur[1] << 32) | cur[0];
+}
+
 }  // namespace kzg

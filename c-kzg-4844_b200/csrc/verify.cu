@@ -404,18 +404,22 @@ __global__ void evaluate_zpow_kernel(Fr* __restrict__ zpow, const Fr* __restrict
     }
 }
 
+// one out-of-line Fr multiplier for the tree: 62 inlined products made the kernel 222 KB of straight-line
+// code (1.59 ms per 4096 blobs, r01v)
+static __device__ __noinline__ Fr fr_mul_nl(Fr a, Fr b) { return mul(a, b); }
+
 template <int LOG>
 __device__ __forceinline__ Fr evt_subtree(const uint8_t* __restrict__ src, int leaf0, const Fr* Z, const Fr* __restrict__ roots_brp, bool& bad) {
     if constexpr (LOG == 0) {
         Fr praw;
         load_fr_be(praw.l, src + 32 * leaf0);
         if (limbs_geq<8>(praw.l, FR_MOD)) bad = true;  // bytes_to_bls_field, bytes.c:67
-        return mul(praw, load_fr(roots_brp + leaf0));
+        return fr_mul_nl(praw, load_fr(roots_brp + leaf0));
     } else {
         Fr l = evt_subtree<LOG - 1>(src, leaf0, Z, roots_brp, bad);
         Fr r = evt_subtree<LOG - 1>(src, leaf0 + (1 << (LOG - 1)), Z, roots_brp, bad);
         Fr c = load_fr(roots_brp + 2 * (leaf0 >> LOG));
-        return add(mul(add(l, r), Z[LOG - 1]), mul(sub(l, r), c));
+        return add(fr_mul_nl(add(l, r), Z[LOG - 1]), fr_mul_nl(sub(l, r), c));
     }
 }
 
@@ -439,7 +443,7 @@ __global__ void __launch_bounds__(EV_THREADS) evaluate_tree_kernel(Fr* __restric
         Fr nv;
         if (t < active) {
             Fr l = sh[2 * t], r = sh[2 * t + 1];
-            nv = add(mul(add(l, r), load_fr(zp + k)), mul(sub(l, r), load_fr(roots_brp + 2 * t)));
+            nv = add(fr_mul_nl(add(l, r), load_fr(zp + k)), fr_mul_nl(sub(l, r), load_fr(roots_brp + 2 * t)));
         }
         __syncthreads();
         if (t < active) sh[t] = nv;
@@ -772,7 +776,7 @@ __global__ void g1_validate2_kernel(G1Affine* __restrict__ out_a, const uint8_t*
 // "placement", profiles/r01_summary.md r01q-r01s).
 __global__ void __launch_bounds__(128) stage1_fused_kernel(Fr* __restrict__ z_out, uint8_t* __restrict__ zy, const uint8_t* __restrict__ blobs, G1Affine* __restrict__ out_cm,
                                                            const uint8_t* __restrict__ in_cm, G1Affine* __restrict__ out_pf, const uint8_t* __restrict__ in_pf, uint64_t n,
-                                                           int* __restrict__ bad) {
+                                                           int* __restrict__ bad, G1* __restrict__ table) {
     __shared__ uint32_t kw[2][64][32];
     place_record(3);
     const int warp = threadIdx.x >> 5;
@@ -786,17 +790,44 @@ __global__ void __launch_bounds__(128) stage1_fused_kernel(Fr* __restrict__ z_ou
     uint8_t buf[48];
     for (int q = 0; q < 48; q++) buf[q] = src[q];
     G1Affine a;
-    if (!g1a_validate(a, buf)) {
+    // table columns: proofs 0..n-1, commitments n..2n-1 (vmsm.cu)
+    const bool ok = table ? g1a_validate_levels(a, buf, table + (warp == 2 ? n + i : i), 2 * n + 1) : g1a_validate(a, buf);
+    if (!ok) {
         *bad = 1;
         a = g1a_inf();
     }
     (warp == 2 ? out_cm : out_pf)[i] = a;
 }
-int launch_stage1_fused(Launch& L, Fr* z, uint8_t* zy, const uint8_t* blobs, G1Affine* out_cm, const uint8_t* in_cm, G1Affine* out_pf, const uint8_t* in_pf, uint64_t n, int* bad) {
+int launch_stage1_fused(Launch& L, Fr* z, uint8_t* zy, const uint8_t* blobs, G1Affine* out_cm, const uint8_t* in_cm, G1Affine* out_pf, const uint8_t* in_pf, uint64_t n, int* bad,
+                        G1* table) {
     if (!n) return RET_OK;
-    stage1_fused_kernel<<<blocks_for(n, 32), 128, 0, L.stream>>>(z, zy, blobs, out_cm, in_cm, out_pf, in_pf, n, bad);
+    stage1_fused_kernel<<<blocks_for(n, 32), 128, 0, L.stream>>>(z, zy, blobs, out_cm, in_cm, out_pf, in_pf, n, bad, table);
     KZG_CUDA_TRY(cudaGetLastError());
     L.count(1, "hash+validate");
+    return RET_OK;
+}
+// validation of n commitments (columns n..2n-1) and n proofs (columns 0..n-1) that also writes their table columns
+__global__ void g1_validate2_levels_kernel(G1Affine* __restrict__ out_cm, const uint8_t* __restrict__ in_cm, G1Affine* __restrict__ out_pf, const uint8_t* __restrict__ in_pf,
+                                           uint64_t n, int* __restrict__ bad, G1* __restrict__ table) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * n) return;
+    const bool is_cm = i >= n;
+    const uint64_t k = is_cm ? i - n : i;
+    const uint8_t* src = (is_cm ? in_cm : in_pf) + k * 48;
+    uint8_t buf[48];
+    for (int q = 0; q < 48; q++) buf[q] = src[q];
+    G1Affine a;
+    if (!g1a_validate_levels(a, buf, table + i, 2 * n + 1)) {
+        *bad = 1;
+        a = g1a_inf();
+    }
+    (is_cm ? out_cm : out_pf)[k] = a;
+}
+int launch_g1_validate2_levels(Launch& L, G1Affine* out_cm, const uint8_t* in_cm, G1Affine* out_pf, const uint8_t* in_pf, uint64_t n, int* bad, G1* table) {
+    if (!n) return RET_OK;
+    g1_validate2_levels_kernel<<<blocks_for(2 * n, 32), 32, 0, L.stream>>>(out_cm, in_cm, out_pf, in_pf, n, bad, table);
+    KZG_CUDA_TRY(cudaGetLastError());
+    L.count(1, "g1_validate");
     return RET_OK;
 }
 int debug_set_placement_buffer(uint32_t* dev_buf) {

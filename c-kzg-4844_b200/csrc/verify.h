@@ -34,7 +34,11 @@ int launch_g1_validate(Launch& L, G1Affine* out, const uint8_t* bytes48, uint64_
 // same for two arrays of n points in one launch (single shared flag)
 int launch_g1_validate2(Launch& L, G1Affine* out_a, const uint8_t* in_a, G1Affine* out_b, const uint8_t* in_b, uint64_t n, int* bad);
 // hash (z) of n blobs and validation of their n commitments + n proofs in one launch (4 warps per 32 blobs)
-int launch_stage1_fused(Launch& L, Fr* z, uint8_t* zy, const uint8_t* blobs, G1Affine* out_cm, const uint8_t* in_cm, G1Affine* out_pf, const uint8_t* in_pf, uint64_t n, int* bad);
+// table != nullptr: also leaves the vmsm table columns of the 2n points (layout above)
+int launch_stage1_fused(Launch& L, Fr* z, uint8_t* zy, const uint8_t* blobs, G1Affine* out_cm, const uint8_t* in_cm, G1Affine* out_pf, const uint8_t* in_pf, uint64_t n, int* bad,
+                        G1* table);
+// validation of n commitments + n proofs with the vmsm table columns
+int launch_g1_validate2_levels(Launch& L, G1Affine* out_cm, const uint8_t* in_cm, G1Affine* out_pf, const uint8_t* in_pf, uint64_t n, int* bad, G1* table);
 int debug_set_placement_buffer(uint32_t* dev_buf);
 int launch_g1_validate_ab(Launch& L, G1Affine* out_a, const uint8_t* in_a, uint64_t n, G1Affine* out_b, const uint8_t* in_b, uint64_t nb, int* bad);
 // r = hash_to_bls_field(digest): the batch transcript itself (eip4844.c:597-680) is hashed on the host
@@ -47,12 +51,14 @@ size_t rlc_scratch_bytes(uint64_t n_local);
 int launch_rlc(Launch& L, G1* out2, const G1Affine* commitments, const G1Affine* proofs, const Fr* z, const Fr* y, const Fr* r, bool use_r,
                uint64_t first, uint64_t n_local, void* scratch);
 // ---- vmsm.cu: the same linear combination as ONE pair of bucket MSMs over pre-shifted bases --------
-// Point array layout: pts[0..n) = proofs, pts[n..2n) = commitments, slot 2n = -G1 generator (filled by
-// the shift kernel).  table[j][i] = 2^(8j) * pts[i] (XYZZ), j < VMSM_LEVELS, is independent of the
-// challenge r, so it is built while the per-blob hashes / evaluations are still running.
-constexpr int VMSM_LEVELS = 17;
+// Point layout: column i < n = proof i, column n + i = commitment i, column 2n = -G1 generator.
+// table[j][col], j < 9: 2^(8j) P; j = 9..17: 2^(8(j-9)) [|z|]P (XYZZ) -- written by the validation
+// kernels themselves (g1.cuh g1a_validate_levels: the doubling chains of the subgroup test), i.e. before
+// the challenge r exists; the generator column is copied from the context.
+constexpr int VMSM_LEVELS = 18;
 size_t vmsm_table_points(uint64_t n);   // VMSM_LEVELS * (2n + 1)
-int launch_vmsm_shift(Launch& L, G1* table, const G1Affine* pts, uint64_t n);
+int launch_vmsm_generator_levels(Launch& L, G1* levels18);
+int vmsm_place_generator(Launch& L, G1* table, uint64_t n);
 size_t rlc_vmsm_scratch_bytes(uint64_t n);
 // out2[0] = A, out2[1] = B as launch_rlc (first = 0, use_r = true); r = hash_to_bls_field(digest32), digest32 a HOST pointer
 int launch_rlc_vmsm(Launch& L, G1* out2, const G1* table, const Fr* z, const Fr* y, const uint8_t* digest32, uint64_t n, void* scratch);

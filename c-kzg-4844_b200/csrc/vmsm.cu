@@ -8,13 +8,16 @@
 // Why not one scalar multiplication per point (rlc_points_kernel): a 255-bit multiplication is a chain
 // of ~2000 dependent Fp products on one lane (2.5 ms) and it can only start once the challenge r is
 // known, i.e. it sits in the serial tail of every call.  Here the part of that chain that does not
-// depend on r -- the doublings -- is moved in front of r:
-//   * vmsm_shift_kernel (runs beside the per-blob hash/evaluate stage, as soon as the points are
-//     validated): table[j][i] = 2^(8j) P_i for the 17 byte-levels of a 128-bit GLV half-scalar;
-//   * once r is known: scalars r^i, r^i z_i (rlc_vmsm_scalars_kernel) are split with the GLV
-//     endomorphism (k = k1 + q z^2, [z^2]P = -phi(P)) into 128-bit halves and recoded into signed
-//     bytes; every non-zero digit d of (point i, level j, half h) is one table entry that belongs in
-//     bucket |d| -- all levels share ONE set of 128 buckets because the shifts are already applied;
+// depend on r -- the doublings -- is taken from work that happens BEFORE r anyway:
+//   * the subgroup test of every commitment / proof multiplies by |z| twice; done LSB-first
+//     (g1.cuh g1a_validate_levels) it walks the doubling chains of P and of Q = [|z|]P and leaves
+//     table[j][i] = 2^(8j) P_i (j < 9) and 2^(8(j-9)) Q_i (j = 9..17) behind, for free;
+//   * once r is known: scalars r^i, r^i z_i (rlc_vmsm_scalars_kernel) are written in base |z|,
+//     k = a0 + a1|z| + a2|z|^2 + a3|z|^3 with 64-bit digits, so that
+//     [k]P = a0 P + a1 Q + a2 (-phi(P)) + a3 (-phi(Q))   (phi(x,y) = (beta x, y) acts as -z^2),
+//     and each 64-bit digit is recoded into signed bytes; every non-zero byte d of (point i, level j,
+//     quarter q) is one table entry that belongs in bucket |d| -- all levels share ONE set of 128
+//     buckets because the shifts are already applied;
 //   * vmsm_hist_kernel / vmsm_scatter_kernel: counting sort by bucket over 64 CTAs per MSM;
 //   * vmsm_accumulate_kernel: one thread per <= 8-entry slice of a bucket list (XYZZ + XYZZ adds);
 //   * vmsm_combine_kernel: one CTA per bucket folds its slices; vmsm_reduce_kernel: sum_b (b+1) B_b by
@@ -27,8 +30,9 @@
 
 namespace kzg {
 
-constexpr int VC = 8;                    // digit width (one byte of the half-scalar)
-constexpr int VW = VMSM_LEVELS;          // 16 bytes + the carry out of the top byte
+constexpr int VC = 8;                    // digit width (one byte of a 64-bit base-|z| digit)
+constexpr int VW = 9;                    // table levels per base: 8 bytes + the carry out of the top byte
+static_assert(VMSM_LEVELS == 2 * VW && VMSM_LEVELS == G1_LEVELS, "table layout: 9 levels of P, 9 levels of [|z|]P");
 constexpr int VNB = 1 << (VC - 1);       // 128 buckets (signed digits, magnitude 1..128)
 constexpr int VSORT_THREADS = 256;
 constexpr int VSORT_WARPS = VSORT_THREADS / 32;
@@ -38,7 +42,7 @@ constexpr int VACC_THREADS = 128;
 constexpr int VCOMB_THREADS = 128;
 
 struct VmsmJob {
-    const uint32_t* halves;  // [nh][4] 128-bit half-scalars, index h = 2 * point + phi
+    const uint32_t* halves;  // [nh][2] 64-bit base-|z| digits, index h = 4 * point + quarter
     uint32_t nh;
     uint32_t max_items;
     uint32_t* entries;       // [nh * VW]
@@ -69,33 +73,17 @@ __device__ __forceinline__ void vstore_g1(G1* p, const G1& a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// before r: shifted copies of every point
+// after r: scalars -> base-|z| digits
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) vmsm_shift_kernel(G1* __restrict__ table, const G1Affine* __restrict__ pts, uint32_t npts) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npts) return;
-    G1 q = (i == npts - 1) ? g1_from_affine(g1a_neg(g1a_generator())) : g1_from_affine(pts[i]);
-#pragma unroll 1
-    for (int j = 0; j < VW; j++) {
-        vstore_g1(table + (size_t)j * npts + i, q);
-        if (j + 1 < VW) {
-#pragma unroll 1
-            for (int s = 0; s < VC; s++) g1_dbl_to(q);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// after r: scalars -> GLV halves
-// ------------------------------------------------------------------------------------------------
-// hB layout (half index = 2 * point + phi): points 0..n-1 proofs with r^i z_i, points n..2n-1
-// commitments with r^i, point 2n = -G with sum r^i y_i.  MSM A reads the r^i segment with point base 0.
+// hB layout (index = 4 * point + quarter, 8 bytes each): points 0..n-1 proofs with r^i z_i, points
+// n..2n-1 commitments with r^i, point 2n = -G with sum r^i y_i.  MSM A reads the r^i segment with point
+// base 0.
 __device__ __forceinline__ void store_halves(uint32_t* hB, size_t point, const uint32_t k[8]) {
-    uint32_t k1[4], q[4];
-    glv_split(k1, q, k);
+    uint64_t a[4];
+    basez_split(a, k);
     uint4* dst = reinterpret_cast<uint4*>(hB) + 2 * point;
-    dst[0] = make_uint4(k1[0], k1[1], k1[2], k1[3]);
-    dst[1] = make_uint4(q[0], q[1], q[2], q[3]);
+    dst[0] = make_uint4((uint32_t)a[0], (uint32_t)(a[0] >> 32), (uint32_t)a[1], (uint32_t)(a[1] >> 32));
+    dst[1] = make_uint4((uint32_t)a[2], (uint32_t)(a[2] >> 32), (uint32_t)a[3], (uint32_t)(a[3] >> 32));
 }
 struct Digest8 {
     uint32_t h[8];  // big-endian words of the SHA-256 digest
@@ -158,20 +146,20 @@ __global__ void __launch_bounds__(256) rlc_vmsm_ysum_kernel(uint32_t* __restrict
 // ------------------------------------------------------------------------------------------------
 // counting sort of the digits by bucket: one CTA per MSM
 // ------------------------------------------------------------------------------------------------
-// calls f(level j, bucket b, negative) for every non-zero signed byte of the 128-bit value v
+// calls f(level j, bucket b, negative) for every non-zero signed byte of the 64-bit value v
 template <class Fn>
-__device__ __forceinline__ void for_each_byte_digit(const uint4 v, Fn f) {
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+__device__ __forceinline__ void for_each_byte_digit(const uint2 v, Fn f) {
+    const uint32_t w[2] = {v.x, v.y};
     uint32_t carry = 0;
 #pragma unroll
-    for (int j = 0; j < 16; j++) {
+    for (int j = 0; j < 8; j++) {
         uint32_t d = ((w[j >> 2] >> ((j & 3) * 8)) & 0xffu) + carry;
         const bool negd = d > (uint32_t)VNB;
         carry = negd ? 1u : 0u;
         const uint32_t mag = negd ? (256u - d) : d;  // 1..128 (or 0)
         if (mag != 0) f(j, mag - 1u, negd);
     }
-    if (carry) f(16, 0u, false);
+    if (carry) f(8, 0u, false);
 }
 
 // Two launches over VSORT_CTAS CTAs per MSM, each CTA owning a contiguous slice of the half-scalars:
@@ -197,7 +185,7 @@ __global__ void __launch_bounds__(VSORT_THREADS) vmsm_hist_kernel(const __grid_c
     __syncthreads();
     uint32_t h0, h1;
     vsort_slice(h0, h1, J.nh);
-    const uint4* hv = reinterpret_cast<const uint4*>(J.halves);
+    const uint2* hv = reinterpret_cast<const uint2*>(J.halves);
     for (uint32_t h = h0 + tid; h < h1; h += VSORT_THREADS) {
         for_each_byte_digit(hv[h], [&](int, uint32_t b, bool) { atomicAdd(&cnt[b], 1u); });
     }
@@ -238,7 +226,7 @@ __global__ void __launch_bounds__(VSORT_THREADS) vmsm_scatter_kernel(const __gri
     }
     uint32_t h0, h1;
     vsort_slice(h0, h1, J.nh);
-    const uint4* hv = reinterpret_cast<const uint4*>(J.halves);
+    const uint2* hv = reinterpret_cast<const uint2*>(J.halves);
     for (uint32_t h = h0 + tid; h < h1; h += VSORT_THREADS) {
         for_each_byte_digit(hv[h], [&](int, uint32_t b, bool) { atomicAdd(&cnt[warp][b], 1u); });
     }
@@ -259,11 +247,11 @@ __global__ void __launch_bounds__(VSORT_THREADS) vmsm_scatter_kernel(const __gri
         for (uint32_t k = istart[b] + tid; k < istart[b + 1]; k += VSORT_THREADS) J.item_bucket[k] = (uint32_t)b;
     __syncthreads();
     for (uint32_t h = h0 + tid; h < h1; h += VSORT_THREADS) {
-        const uint32_t pt = h >> 1, phi = h & 1u;
+        const uint32_t pt = h >> 2, qtr = h & 3u, phi = qtr >> 1, lvl0 = (qtr & 1u) * VW;
         for_each_byte_digit(hv[h], [&](int j, uint32_t b, bool negd) {
             const uint32_t pos = atomicAdd(&cnt[warp][b], 1u);
-            // second base is -phi(P): (beta X, -Y)
-            J.entries[pos] = ((uint32_t)j * npts + pt) | (phi ? 0x40000000u : 0u) | ((negd != (phi != 0)) ? 0x80000000u : 0u);
+            // quarters 2, 3 use the bases -phi(P), -phi(Q): (beta X, -Y)
+            J.entries[pos] = ((lvl0 + (uint32_t)j) * npts + pt) | (phi ? 0x40000000u : 0u) | ((negd != (phi != 0)) ? 0x80000000u : 0u);
         });
     }
 }
@@ -356,13 +344,25 @@ __global__ void __launch_bounds__(VNB) vmsm_reduce_kernel(G1* __restrict__ out2,
 static size_t val256(size_t x) { return (x + 255) & ~(size_t)255; }
 static uint32_t vmsm_max_items(uint64_t nh) { return (uint32_t)(VNB + (nh * VW + VCAP - 1) / VCAP); }
 
-size_t vmsm_table_points(uint64_t n) { return (size_t)VW * (2 * n + 1); }
+size_t vmsm_table_points(uint64_t n) { return (size_t)VMSM_LEVELS * (2 * n + 1); }
 
-int launch_vmsm_shift(Launch& L, G1* table, const G1Affine* pts, uint64_t n) {
-    const uint32_t npts = (uint32_t)(2 * n + 1);
-    vmsm_shift_kernel<<<(npts + 31) / 32, 32, 0, L.stream>>>(table, pts, npts);
+__global__ void vmsm_neg_generator_levels_kernel(G1* levels) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    G1 p = g1_from_affine(g1a_neg(g1a_generator()));
+    G1 q = g1_mul_bls_x_levels(p, levels, 1);
+    (void)g1_mul_bls_x_levels(q, levels + 9, 1);
+}
+// setup: the 18 table levels of -G1 (the base of the sum r^i y_i term)
+int launch_vmsm_generator_levels(Launch& L, G1* levels18) {
+    vmsm_neg_generator_levels_kernel<<<1, 1, 0, L.stream>>>(levels18);
     KZG_CUDA_TRY(cudaGetLastError());
-    L.count(1, "vmsm_shift");
+    L.count();
+    return RET_OK;
+}
+// per call: drop those levels into column 2n of the call's table
+int vmsm_place_generator(Launch& L, G1* table, uint64_t n) {
+    const size_t npts = 2 * n + 1;
+    KZG_CUDA_TRY(cudaMemcpy2DAsync(table + 2 * n, npts * sizeof(G1), L.ctx->g_levels, sizeof(G1), sizeof(G1), VMSM_LEVELS, cudaMemcpyDeviceToDevice, L.stream));
     return RET_OK;
 }
 
@@ -386,21 +386,21 @@ static uint8_t* vmsm_job_carve(VmsmJob& J, uint8_t* ws, const uint32_t* halves, 
 }
 
 size_t rlc_vmsm_scratch_bytes(uint64_t n) {
-    const uint64_t nhB = 2 * (2 * n + 1), nhA = 2 * n;
-    return val256(nhB * 16) + val256(n * sizeof(Fr)) + vmsm_job_bytes(nhA) + vmsm_job_bytes(nhB);
+    const uint64_t nhB = 4 * (2 * n + 1), nhA = 4 * n;
+    return val256(nhB * 8) + val256(n * sizeof(Fr)) + vmsm_job_bytes(nhA) + vmsm_job_bytes(nhB);
 }
 
 int launch_rlc_vmsm(Launch& L, G1* out2, const G1* table, const Fr* z, const Fr* y, const uint8_t* digest32, uint64_t n, void* scratch) {
     Digest8 dg;
     for (int i = 0; i < 8; i++)
         dg.h[i] = ((uint32_t)digest32[4 * i] << 24) | ((uint32_t)digest32[4 * i + 1] << 16) | ((uint32_t)digest32[4 * i + 2] << 8) | (uint32_t)digest32[4 * i + 3];
-    if (n == 0 || 2 * n + 1 >= (1ull << 30) / VW) return RET_ERROR;
-    const uint64_t nhB = 2 * (2 * n + 1), nhA = 2 * n;
+    if (n == 0 || 2 * n + 1 >= (1ull << 30) / VMSM_LEVELS) return RET_ERROR;
+    const uint64_t nhB = 4 * (2 * n + 1), nhA = 4 * n;
     uint8_t* ws = (uint8_t*)scratch;
-    uint32_t* hB = (uint32_t*)ws; ws += val256(nhB * 16);
+    uint32_t* hB = (uint32_t*)ws; ws += val256(nhB * 8);
     Fr* ty = (Fr*)ws; ws += val256(n * sizeof(Fr));
     VmsmJobs jobs;
-    ws = vmsm_job_carve(jobs.j[0], ws, hB + 4 * (2 * n), nhA);  // A: the r^i segment, points 0..n-1 (proofs)
+    ws = vmsm_job_carve(jobs.j[0], ws, hB + 8 * n, nhA);  // A: the r^i segment (32 bytes per point), points 0..n-1 (proofs)
     ws = vmsm_job_carve(jobs.j[1], ws, hB, nhB);
     const uint32_t npts = (uint32_t)(2 * n + 1);
 

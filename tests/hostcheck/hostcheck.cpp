@@ -52,6 +52,15 @@ int hc_g1_validate(uint8_t* out48, const uint8_t* in48) {
     if (ok) g1a_compress(out48, a);
     return ok;
 }
+// validation with table levels: 18 compressed points out (levels), returns the verdict
+int hc_g1_validate_levels(uint8_t* out48x18, const uint8_t* in48) {
+    G1Affine a;
+    G1 levels[G1_LEVELS];
+    int ok = g1a_validate_levels(a, in48, levels, 1);
+    for (int j = 0; j < G1_LEVELS; j++) g1a_compress(out48x18 + 48 * j, g1_to_affine(levels[j]));
+    return ok;
+}
+void hc_basez_split(uint64_t* a4, const uint32_t* k8) { basez_split(a4, k8); }
 int hc_g1_uncompress(uint8_t* out48, const uint8_t* in48) {
     G1Affine a;
     int ok = g1a_uncompress(a, in48);

@@ -160,6 +160,51 @@ def test_g1_validate_edge_cases(hc):
         assert hc.hc_g1_uncompress(out, enc) == 1 and out.raw == enc
 
 
+def test_g1_validate_levels_and_basez(hc):
+    """The table-producing validation (g1.cuh g1a_validate_levels): same verdict as g1a_validate, levels
+    = 2^(8j) P and 2^(8j) [|z|]P; base-|z| digits recompose the scalar; [k]P from the four bases."""
+    rnd = random.Random(11)
+    out = C.create_string_buffer(48 * 18)
+    Z = B.BLS_X
+    for trial in range(3):
+        p = rand_g1(rnd) if trial else B.G1_GEN_J
+        assert hc.hc_g1_validate_levels(out, B.g1_compress(p)) == 1
+        q = B.g1_mul(p, Z)
+        for j in range(9):
+            assert out.raw[48 * j : 48 * j + 48] == B.g1_compress(B.g1_mul(p, 1 << (8 * j))), j
+            assert out.raw[48 * (9 + j) : 48 * (10 + j)] == B.g1_compress(B.g1_mul(q, 1 << (8 * j))), j
+    # infinity: accepted, all levels infinity
+    inf = B.g1_compress(B.G1_INF)
+    assert hc.hc_g1_validate_levels(out, inf) == 1 and out.raw == inf * 18
+    # on the curve but outside G1: rejected
+    x = 5
+    while True:
+        x += 1
+        y = B.fp_sqrt((x**3 + 4) % P)
+        if y is not None and not B.g1_in_subgroup((x, y, 1)):
+            b = bytearray(x.to_bytes(48, "big")); b[0] |= 0x80
+            assert hc.hc_g1_validate_levels(out, bytes(b)) == 0
+            break
+    # base-|z| expansion
+    a = (C.c_uint64 * 4)()
+    for k in EDGE_R + [rnd.randrange(R) for _ in range(20)]:
+        hc.hc_basez_split(a, limbs(k, 8))
+        assert all(int(v) < Z for v in a)
+        assert sum(int(v) * Z**i for i, v in enumerate(a)) == k
+    # [k]P = a0 P + a1 Q - a2 phi(P) - a3 phi(Q) with phi(x, y) = (beta x, y), beta = FP_BETA_A
+    beta = pow(2, (P - 1) // 3, P)
+    p = rand_g1(rnd)
+    pa = B.g1_to_affine(p)
+    q = B.g1_mul(p, Z)
+    qa = B.g1_to_affine(q)
+    k = rnd.randrange(R)
+    hc.hc_basez_split(a, limbs(k, 8))
+    acc = B.g1_add(B.g1_mul(p, int(a[0])), B.g1_mul(q, int(a[1])))
+    acc = B.g1_add(acc, B.g1_neg(B.g1_mul((pa[0] * beta % P, pa[1], 1), int(a[2]))))
+    acc = B.g1_add(acc, B.g1_neg(B.g1_mul((qa[0] * beta % P, qa[1], 1), int(a[3]))))
+    assert B.g1_eq(acc, B.g1_mul(p, k))
+
+
 def g2_compress(q):
     """ZCash G2 compression of a Jacobian oracle point (test helper)."""
     a = B.g2_to_affine(q)
