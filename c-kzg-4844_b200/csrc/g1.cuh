@@ -339,10 +339,15 @@ KZG_HD_NOINLINE bool g1a_validate_levels(G1Affine& out, const uint8_t* in, G1* l
     return g1_is_inf(t);
 }
 
-// base-|z| digits of a scalar k < r (8 plain limbs): k = a[0] + a[1]|z| + a[2]|z|^2 + a[3]|z|^3, a[i] < |z| < 2^64
-KZG_HD void basez_split(uint64_t a[4], const uint32_t k[8]) {
-    const uint64_t Z = BLS_X_ABS;
+// Balanced base-|z| digits of a scalar k < r (8 plain limbs):
+//     k = s[0] + s[1]|z| + s[2]|z|^2 + s[3]|z|^3  (mod r),   |s[i]| <= |z|/2 + 1 < 2^62.8.
+// Plain digits a[i] < |z| by three long divisions, then a[i] > |z|/2 becomes a[i] - |z| with a carry
+// into the next digit; the carry out of the top digit is |z|^4 = |z|^2 - 1 (mod r = z^4 - z^2 + 1).
+// Balanced digits never carry out of their top byte when recoded into signed bytes (vmsm.cu).
+KZG_HD void basez_split(int64_t s[4], const uint32_t k[8]) {
+    const uint64_t Z = BLS_X_ABS, H = BLS_X_ABS / 2;
     uint32_t cur[8], nxt[8];
+    uint64_t a[4];
 #pragma unroll
     for (int i = 0; i < 8; i++) cur[i] = k[i];
 #pragma unroll 1
@@ -365,6 +370,20 @@ KZG_HD void basez_split(uint64_t a[4], const uint32_t k[8]) {
         for (int i = 0; i < 8; i++) cur[i] = nxt[i];
     }
     a[3] = ((uint64_t)cur[1] << 32) | cur[0];
+    uint64_t carry = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint64_t v = a[i] + carry;  // <= |z|: no overflow
+        if (v > H) {
+            s[i] = (int64_t)(v - Z);  // two's complement of a value in (-|z|/2, 0]
+            carry = 1;
+        } else {
+            s[i] = (int64_t)v;
+            carry = 0;
+        }
+    }
+    s[2] += (int64_t)carry;
+    s[0] -= (int64_t)carry;
 }
 
 }  // namespace kzg

@@ -1,0 +1,121 @@
+// Cooperative XYZZ addition on four lanes (a "quad"), device only.
+//
+// The tree sums at the end of a verifier's linear combination are pure latency: few additions, each
+// waiting for the previous level, and one addition on one lane is 14 dependent Fp products (~14 us).
+// add-2008-s has depth four: {U1, U2, S1, S2} -> {PP, RR, ZZ1*ZZ2, ZZZ1*ZZZ2} -> {PPP, Q, ZZ3} ->
+// {R*(Q - X3), S1*PPP, ZZZ3}.  Four consecutive lanes take one product of each level; every lane
+// picks its operands and then ALL lanes execute the same multiplier call, so the quad pays four
+// product latencies instead of fourteen.  Intermediates travel through a 576-byte scratch block in
+// shared memory.  Same group law as g1_add (g1.cuh), so the same results.
+#pragma once
+#include "g1.cuh"
+
+namespace kzg {
+
+struct QuadScratch {
+    Fp v[12];
+};
+
+__device__ __forceinline__ Fp quad_ld(const Fp* p) {
+    Fp a;
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4* d = reinterpret_cast<uint4*>(&a);
+#pragma unroll
+    for (int i = 0; i < 3; i++) d[i] = q[i];
+    return a;
+}
+__device__ __forceinline__ void quad_st(Fp* p, const Fp& a) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    const uint4* d = reinterpret_cast<const uint4*>(&a);
+#pragma unroll
+    for (int i = 0; i < 3; i++) q[i] = d[i];
+}
+__device__ __forceinline__ Fp quad_sel(bool c, const Fp& a, const Fp& b) {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = c ? a.l[i] : b.l[i];
+    return r;
+}
+
+// complete addition on one lane, for the rare equal-x case (kept out of line: it would otherwise set the
+// register budget of the fast path)
+static __device__ __noinline__ void g1_add_mem(G1* out, const G1* p, const G1* q) {
+    G1 a, b;
+    a.x = quad_ld(&p->x); a.y = quad_ld(&p->y); a.zz = quad_ld(&p->zz); a.zzz = quad_ld(&p->zzz);
+    b.x = quad_ld(&q->x); b.y = quad_ld(&q->y); b.zz = quad_ld(&q->zz); b.zzz = quad_ld(&q->zzz);
+    g1_add_to(a, b);
+    quad_st(&out->x, a.x); quad_st(&out->y, a.y); quad_st(&out->zz, a.zz); quad_st(&out->zzz, a.zzz);
+}
+
+// *out = *p + *q.  Called by the four lanes of a quad (lanes 4k..4k+3 of a warp) with identical
+// arguments; `out` may alias `p` or `q`.  The operands must be visible to all four lanes on entry
+// (plain loads: they may have been written earlier in the same kernel); `sc` is private to the quad.
+static __device__ __noinline__ void g1_add_quad(G1* out, const G1* p, const G1* q, QuadScratch* sc) {
+    const unsigned lane = threadIdx.x & 31u, ql = lane & 3u;
+    const unsigned mask = 0xFu << (lane & ~3u);
+    const Fp pzz = quad_ld(&p->zz), qzz = quad_ld(&q->zz);
+    const bool pinf = is_zero(pzz), qinf = is_zero(qzz);
+    if (pinf || qinf) {
+        __syncwarp(mask);
+        if (ql == 0) {
+            const G1* src = pinf ? q : p;
+            if (out != src) {
+                Fp a = quad_ld(&src->x), b = quad_ld(&src->y), c = quad_ld(&src->zz), d = quad_ld(&src->zzz);
+                quad_st(&out->x, a); quad_st(&out->y, b); quad_st(&out->zz, c); quad_st(&out->zzz, d);
+            }
+        }
+        __syncwarp(mask);
+        return;
+    }
+    // level 1: U1 = X1 ZZ2, U2 = X2 ZZ1, S1 = Y1 ZZZ2, S2 = Y2 ZZZ1
+    {
+        const Fp* ap = ql == 0 ? &p->x : ql == 1 ? &q->x : ql == 2 ? &p->y : &q->y;
+        const Fp* bp = ql == 0 ? &q->zz : ql == 1 ? &p->zz : ql == 2 ? &q->zzz : &p->zzz;
+        quad_st(&sc->v[ql], mul(quad_ld(ap), quad_ld(bp)));
+    }
+    __syncwarp(mask);
+    // (U1 and S1 are re-read from the scratch block where needed: fewer live registers)
+    const Fp Pd = sub(quad_ld(&sc->v[1]), quad_ld(&sc->v[0])), Rd = sub(quad_ld(&sc->v[3]), quad_ld(&sc->v[2]));
+    if (is_zero(Pd)) {  // same x: doubling or cancellation -- rare, one lane does the complete addition
+        __syncwarp(mask);
+        if (ql == 0) g1_add_mem(out, p, q);  // reads both operands completely before it writes
+        __syncwarp(mask);
+        return;
+    }
+    // level 2: PP = P^2, ZZ1 ZZ2, RR = R^2, ZZZ1 ZZZ2
+    {
+        const Fp* ap = (ql == 1) ? &p->zz : &p->zzz;
+        const Fp* bp = (ql == 1) ? &q->zz : &q->zzz;
+        const Fp la = quad_ld(ap), lb = quad_ld(bp);
+        const Fp d = quad_sel(ql == 0, Pd, Rd);
+        const bool even = (ql & 1u) == 0;
+        quad_st(&sc->v[4 + ql], mul(quad_sel(even, d, la), quad_sel(even, d, lb)));
+    }
+    __syncwarp(mask);  // from here on the inputs are dead: `out` may be written even if it aliases them
+    // level 3: PPP = P PP, Q = U1 PP, ZZ3 = (ZZ1 ZZ2) PP
+    {
+        const Fp a = quad_sel(ql == 1, quad_ld(&sc->v[0]), quad_sel(ql == 2, quad_ld(&sc->v[5]), Pd));
+        const Fp r3 = mul(a, quad_ld(&sc->v[4]));
+        if (ql == 0) quad_st(&sc->v[8], r3);
+        if (ql == 1) quad_st(&sc->v[9], r3);
+        if (ql == 2) quad_st(&out->zz, r3);
+    }
+    __syncwarp(mask);
+    // level 4: X3 = RR - PPP - 2Q;  R (Q - X3),  S1 PPP,  ZZZ3 = (ZZZ1 ZZZ2) PPP
+    const Fp PPP = quad_ld(&sc->v[8]), Qv = quad_ld(&sc->v[9]);
+    const Fp X3 = sub(sub(quad_ld(&sc->v[6]), PPP), dbl(Qv));
+    Fp r4;
+    {
+        const Fp a = quad_sel(ql == 1, quad_ld(&sc->v[2]), quad_sel(ql == 2, quad_ld(&sc->v[7]), Rd));
+        const Fp b = quad_sel(ql == 0 || ql == 3, sub(Qv, X3), PPP);
+        r4 = mul(a, b);
+        if (ql == 1) quad_st(&sc->v[10], r4);
+        if (ql == 2) quad_st(&out->zzz, r4);
+        if (ql == 0) quad_st(&out->x, X3);
+    }
+    __syncwarp(mask);
+    if (ql == 0) quad_st(&out->y, sub(r4, quad_ld(&sc->v[10])));
+    __syncwarp(mask);
+}
+
+}  // namespace kzg

@@ -26,12 +26,13 @@
 // doubling at all.
 #define KZG_FP_MUL_OUTLINE 1
 #include "g1_glv.cuh"
+#include "g1_quad.cuh"
 #include "verify.h"
 
 namespace kzg {
 
 constexpr int VC = 8;                    // digit width (one byte of a 64-bit base-|z| digit)
-constexpr int VW = 9;                    // table levels per base: 8 bytes + the carry out of the top byte
+constexpr int VW = 9;                    // table levels per base (the balanced digits use 8 of them)
 static_assert(VMSM_LEVELS == 2 * VW && VMSM_LEVELS == G1_LEVELS, "table layout: 9 levels of P, 9 levels of [|z|]P");
 constexpr int VNB = 1 << (VC - 1);       // 128 buckets (signed digits, magnitude 1..128)
 constexpr int VSORT_THREADS = 256;
@@ -52,6 +53,7 @@ struct VmsmJob {
     G1* partial;             // [max_items]
     G1* combined;            // [VNB]
     uint32_t* ctahist;       // [VSORT_CTAS][VNB]
+    G1* scan_tmp;            // [VNB]
 };
 struct VmsmJobs {
     VmsmJob j[2];
@@ -79,8 +81,11 @@ __device__ __forceinline__ void vstore_g1(G1* p, const G1& a) {
 // n..2n-1 commitments with r^i, point 2n = -G with sum r^i y_i.  MSM A reads the r^i segment with point
 // base 0.
 __device__ __forceinline__ void store_halves(uint32_t* hB, size_t point, const uint32_t k[8]) {
-    uint64_t a[4];
-    basez_split(a, k);
+    int64_t sd[4];
+    basez_split(sd, k);
+    uint64_t a[4];  // magnitude (< 2^63) | sign in bit 63
+#pragma unroll
+    for (int i = 0; i < 4; i++) a[i] = sd[i] < 0 ? ((uint64_t)(-sd[i]) | (1ull << 63)) : (uint64_t)sd[i];
     uint4* dst = reinterpret_cast<uint4*>(hB) + 2 * point;
     dst[0] = make_uint4((uint32_t)a[0], (uint32_t)(a[0] >> 32), (uint32_t)a[1], (uint32_t)(a[1] >> 32));
     dst[1] = make_uint4((uint32_t)a[2], (uint32_t)(a[2] >> 32), (uint32_t)a[3], (uint32_t)(a[3] >> 32));
@@ -146,10 +151,12 @@ __global__ void __launch_bounds__(256) rlc_vmsm_ysum_kernel(uint32_t* __restrict
 // ------------------------------------------------------------------------------------------------
 // counting sort of the digits by bucket: one CTA per MSM
 // ------------------------------------------------------------------------------------------------
-// calls f(level j, bucket b, negative) for every non-zero signed byte of the 64-bit value v
+// calls f(level j, bucket b, negative) for every non-zero signed byte of the balanced digit v
+// (magnitude below 0x6a00.. in bits 0..62, sign in bit 63: the top byte never carries out)
 template <class Fn>
 __device__ __forceinline__ void for_each_byte_digit(const uint2 v, Fn f) {
-    const uint32_t w[2] = {v.x, v.y};
+    const uint32_t w[2] = {v.x, v.y & 0x7fffffffu};
+    const bool sgn = (v.y >> 31) != 0;
     uint32_t carry = 0;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
@@ -157,9 +164,8 @@ __device__ __forceinline__ void for_each_byte_digit(const uint2 v, Fn f) {
         const bool negd = d > (uint32_t)VNB;
         carry = negd ? 1u : 0u;
         const uint32_t mag = negd ? (256u - d) : d;  // 1..128 (or 0)
-        if (mag != 0) f(j, mag - 1u, negd);
+        if (mag != 0) f(j, mag - 1u, negd != sgn);
     }
-    if (carry) f(8, 0u, false);
 }
 
 // Two launches over VSORT_CTAS CTAs per MSM, each CTA owning a contiguous slice of the half-scalars:
@@ -281,68 +287,60 @@ __global__ void __launch_bounds__(VACC_THREADS) vmsm_accumulate_kernel(const __g
     vstore_g1(J.partial + slot, acc);
 }
 
+// One CTA per bucket folds the bucket's partial sums pairwise, in place: round after round the upper half
+// of the list is added onto the lower half, one cooperative addition (g1_quad.cuh) per quad of lanes.
 __global__ void __launch_bounds__(VCOMB_THREADS) vmsm_combine_kernel(const __grid_constant__ VmsmJobs jobs) {
-    __shared__ G1 sh[VCOMB_THREADS];
+    __shared__ QuadScratch sc[VCOMB_THREADS / 4];
     const VmsmJob& J = jobs.j[blockIdx.y];
-    const int t = threadIdx.x, bucket = blockIdx.x;
-    const uint32_t it1 = J.item_start[bucket + 1];
-    G1 acc = g1_inf();
-#pragma unroll 1
-    for (uint32_t it = J.item_start[bucket] + t; it < it1; it += VCOMB_THREADS) {
-        G1 b = vload_g1(J.partial + it);
-        g1_add_to(acc, b);
-    }
-    sh[t] = acc;
-    __syncthreads();
-#pragma unroll 1
-    for (int s = VCOMB_THREADS / 2; s > 0; s >>= 1) {
-        if (t < s) {
-            G1 x = sh[t], yv = sh[t + s];
-            g1_add_to(x, yv);
-            sh[t] = x;
-        }
+    const int t = threadIdx.x, quad = t >> 2, bucket = blockIdx.x;
+    const uint32_t it0 = J.item_start[bucket];
+    uint32_t m = J.item_start[bucket + 1] - it0;
+    G1* base = J.partial + it0;
+    while (m > 1) {
+        const uint32_t half = (m + 1) >> 1, pairs = m - half;
+        for (uint32_t i = quad; i < pairs; i += VCOMB_THREADS / 4) g1_add_quad(base + i, base + i, base + i + half, &sc[quad]);
         __syncthreads();
+        m = half;
     }
-    if (t == 0) vstore_g1(J.combined + bucket, sh[0]);
+    if (t < 12) reinterpret_cast<uint4*>(J.combined + bucket)[t] = reinterpret_cast<const uint4*>(base)[t];
 }
 
-// sum_b (b+1) B_b = sum_b S_b with S_b = sum_{b' >= b} B_b'
-__global__ void __launch_bounds__(VNB) vmsm_reduce_kernel(G1* __restrict__ out2, const __grid_constant__ VmsmJobs jobs) {
-    __shared__ G1 sh[VNB];
+// sum_b (b+1) B_b = sum_b S_b with S_b = sum_{b' >= b} B_b': suffix scan (ping-pong between `combined`
+// and `scan_tmp`), then a tree, one quad per addition.
+constexpr int VRED_THREADS = 4 * VNB;
+__global__ void __launch_bounds__(VRED_THREADS) vmsm_reduce_kernel(G1* __restrict__ out2, const __grid_constant__ VmsmJobs jobs) {
+    extern __shared__ __align__(16) unsigned char vred_smem[];
+    QuadScratch* sc = reinterpret_cast<QuadScratch*>(vred_smem);
     const VmsmJob& J = jobs.j[blockIdx.x];
-    const int t = threadIdx.x;
-    G1 acc = vload_g1(J.combined + t);
-    sh[t] = acc;
-    __syncthreads();
+    const int t = threadIdx.x, b = t >> 2, ql = t & 3;
+    G1* cur = J.combined;
+    G1* nxt = J.scan_tmp;
 #pragma unroll 1
     for (int off = 1; off < VNB; off <<= 1) {
-        const bool has = t + off < VNB;
-        G1 o;
-        if (has) o = sh[t + off];
-        __syncthreads();
-        if (has) {
-            g1_add_to(acc, o);
-            sh[t] = acc;
+        if (b + off < VNB) {
+            g1_add_quad(nxt + b, cur + b, cur + b + off, &sc[b]);
+        } else {
+            // three 16-byte words per lane: a straight copy of the 192-byte point
+            for (int w = ql; w < 12; w += 4) reinterpret_cast<uint4*>(nxt + b)[w] = reinterpret_cast<const uint4*>(cur + b)[w];
         }
         __syncthreads();
+        G1* tmp = cur;
+        cur = nxt;
+        nxt = tmp;
     }
 #pragma unroll 1
     for (int s = VNB / 2; s > 0; s >>= 1) {
-        if (t < s) {
-            G1 x = sh[t], yv = sh[t + s];
-            g1_add_to(x, yv);
-            sh[t] = x;
-        }
+        if (b < s) g1_add_quad(cur + b, cur + b, cur + b + s, &sc[b]);
         __syncthreads();
     }
-    if (t == 0) vstore_g1(out2 + blockIdx.x, sh[0]);
+    if (t < 12) reinterpret_cast<uint4*>(out2 + blockIdx.x)[t] = reinterpret_cast<const uint4*>(cur)[t];
 }
 
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
 static size_t val256(size_t x) { return (x + 255) & ~(size_t)255; }
-static uint32_t vmsm_max_items(uint64_t nh) { return (uint32_t)(VNB + (nh * VW + VCAP - 1) / VCAP); }
+static uint32_t vmsm_max_items(uint64_t nh) { return (uint32_t)(VNB + (nh * 8 + VCAP - 1) / VCAP); }
 
 size_t vmsm_table_points(uint64_t n) { return (size_t)VMSM_LEVELS * (2 * n + 1); }
 
@@ -369,7 +367,7 @@ int vmsm_place_generator(Launch& L, G1* table, uint64_t n) {
 static size_t vmsm_job_bytes(uint64_t nh) {
     const uint32_t mi = vmsm_max_items(nh);
     return val256(nh * VW * sizeof(uint32_t)) + 2 * val256((VNB + 1) * sizeof(uint32_t)) + val256(mi * sizeof(uint32_t)) + val256((size_t)mi * sizeof(G1)) +
-           val256(VNB * sizeof(G1)) + val256(VSORT_CTAS * VNB * sizeof(uint32_t));
+           2 * val256(VNB * sizeof(G1)) + val256(VSORT_CTAS * VNB * sizeof(uint32_t));
 }
 static uint8_t* vmsm_job_carve(VmsmJob& J, uint8_t* ws, const uint32_t* halves, uint64_t nh) {
     J.halves = halves;
@@ -382,6 +380,7 @@ static uint8_t* vmsm_job_carve(VmsmJob& J, uint8_t* ws, const uint32_t* halves, 
     J.partial = (G1*)ws; ws += val256((size_t)J.max_items * sizeof(G1));
     J.combined = (G1*)ws; ws += val256(VNB * sizeof(G1));
     J.ctahist = (uint32_t*)ws; ws += val256(VSORT_CTAS * VNB * sizeof(uint32_t));
+    J.scan_tmp = (G1*)ws; ws += val256(VNB * sizeof(G1));
     return ws;
 }
 
@@ -420,7 +419,9 @@ int launch_rlc_vmsm(Launch& L, G1* out2, const G1* table, const Fr* z, const Fr*
     L.count(1, "vmsm_accumulate");
     vmsm_combine_kernel<<<dim3(VNB, 2), VCOMB_THREADS, 0, L.stream>>>(jobs);
     KZG_CUDA_TRY(cudaGetLastError());
-    vmsm_reduce_kernel<<<2, VNB, 0, L.stream>>>(out2, jobs);
+    static const cudaError_t attr = cudaFuncSetAttribute(vmsm_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(VNB * sizeof(QuadScratch)));
+    KZG_CUDA_TRY(attr);
+    vmsm_reduce_kernel<<<2, VRED_THREADS, VNB * sizeof(QuadScratch), L.stream>>>(out2, jobs);
     KZG_CUDA_TRY(cudaGetLastError());
     L.count(2, "vmsm_reduce");
     return RET_OK;

@@ -60,7 +60,7 @@ int hc_g1_validate_levels(uint8_t* out48x18, const uint8_t* in48) {
     for (int j = 0; j < G1_LEVELS; j++) g1a_compress(out48x18 + 48 * j, g1_to_affine(levels[j]));
     return ok;
 }
-void hc_basez_split(uint64_t* a4, const uint32_t* k8) { basez_split(a4, k8); }
+void hc_basez_split(int64_t* s4, const uint32_t* k8) { basez_split(s4, k8); }
 int hc_g1_uncompress(uint8_t* out48, const uint8_t* in48) {
     G1Affine a;
     int ok = g1a_uncompress(a, in48);

@@ -185,12 +185,12 @@ def test_g1_validate_levels_and_basez(hc):
             b = bytearray(x.to_bytes(48, "big")); b[0] |= 0x80
             assert hc.hc_g1_validate_levels(out, bytes(b)) == 0
             break
-    # base-|z| expansion
-    a = (C.c_uint64 * 4)()
-    for k in EDGE_R + [rnd.randrange(R) for _ in range(20)]:
+    # balanced base-|z| expansion (mod r)
+    a = (C.c_int64 * 4)()
+    for k in EDGE_R + [Z**3 * (Z // 2 + 5) % R, Z // 2, Z // 2 + 1, Z**2 * (Z // 2 + 1)] + [rnd.randrange(R) for _ in range(200)]:
         hc.hc_basez_split(a, limbs(k, 8))
-        assert all(int(v) < Z for v in a)
-        assert sum(int(v) * Z**i for i, v in enumerate(a)) == k
+        assert all(abs(int(v)) <= Z // 2 + 1 for v in a), k
+        assert sum(int(v) * Z**i for i, v in enumerate(a)) % R == k % R, k
     # [k]P = a0 P + a1 Q - a2 phi(P) - a3 phi(Q) with phi(x, y) = (beta x, y), beta = FP_BETA_A
     beta = pow(2, (P - 1) // 3, P)
     p = rand_g1(rnd)
@@ -199,9 +199,9 @@ def test_g1_validate_levels_and_basez(hc):
     qa = B.g1_to_affine(q)
     k = rnd.randrange(R)
     hc.hc_basez_split(a, limbs(k, 8))
-    acc = B.g1_add(B.g1_mul(p, int(a[0])), B.g1_mul(q, int(a[1])))
-    acc = B.g1_add(acc, B.g1_neg(B.g1_mul((pa[0] * beta % P, pa[1], 1), int(a[2]))))
-    acc = B.g1_add(acc, B.g1_neg(B.g1_mul((qa[0] * beta % P, qa[1], 1), int(a[3]))))
+    acc = B.g1_add(B.g1_mul(p, int(a[0]) % R), B.g1_mul(q, int(a[1]) % R))
+    acc = B.g1_add(acc, B.g1_neg(B.g1_mul((pa[0] * beta % P, pa[1], 1), int(a[2]) % R)))
+    acc = B.g1_add(acc, B.g1_neg(B.g1_mul((qa[0] * beta % P, qa[1], 1), int(a[3]) % R)))
     assert B.g1_eq(acc, B.g1_mul(p, k))
 
 
