@@ -38,9 +38,14 @@ METRIC = "blobs/sec: blob_to_kzg_commitment & verify_blob_kzg_proof_batch @1/2/4
 
 # algorithmic HBM bytes per blob for each kernel of the verify step (DESIGN.md "Roofline accounting")
 ALGO_BYTES_PER_BLOB = {
-    "evaluate": 131072 + 32 + 64,          # blob in, z in, z||y out (roots of unity are L2-resident constants)
+    "evaluate": 131072 + 12 * 32 + 64,     # blob in, powers of z in, z||y out (roots of unity are L2-resident constants)
+    "hash+validate": 131072 + 48 + 64 + 2 * (48 + 96) + 2 * 18 * 192,  # fused stage-1 kernel: blob + points in, z, affine points and table columns out
+    "vmsm_accumulate": 2 * 3 * 32 * (4 + 192) + 192 * 3 * 32 // 8,  # ~96 digit entries per blob: index + 192-byte table point in, one partial per 8 entries out
+    "vmsm_sort": 3 * 32 * 2 + 3 * 32 * 4 * 2,
+    "vmsm_reduce": 192 * 3 * 32 // 8,
+    "transcript(d2h,host_sha)": 160,
     "blob_challenge": 131072 + 48 + 64,    # blob + commitment in, z out
-    "g1_validate": 2 * (48 + 96),          # two points in, two affine points out
+    "g1_validate": 2 * (48 + 96) + 2 * 18 * 192,  # two points in, two affine points + their 18 table levels out
     "rlc_points": 3 * 96 + 64 + 3 * 192,   # 3 bases + 2 scalars in, 3 XYZZ out
     "rlc_scalars": 64 + 96,
     "g1_sum": 3 * 192,
@@ -54,13 +59,15 @@ ALGO_BYTES_PER_BLOB = {
 }
 # measured DRAM traffic per blob (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full`
 # capture, profiles/r01_summary.md "r01k"/"r01o"), for the kernels that were captured
-MEASURED_TRAFFIC_PER_BLOB = {"msm_accumulate": 596_000, "evaluate": 236_300, "rlc_points": 900}  # evaluate: r01o capture
+MEASURED_TRAFFIC_PER_BLOB = {"msm_accumulate": 596_000, "hash+validate": 135_400, "rlc_points": 900}  # hash+validate: r01t capture (539 MB + 15 MB per 4096 blobs)
 
 # algorithmic 32x32->64 multiply-accumulates per blob (SURVEY.md section 8(d) convention: Fp mul = 300, Fr mul = 136)
 ALGO_MAC_PER_BLOB = {
-    "evaluate": 112 * 256 * 136,
+    "evaluate": (4096 + 2 * 4095) * 136,   # tree evaluation: one product per leaf, two per node
     "g1_validate": 2 * 2200 * 300,
+    "hash+validate": 2 * 2200 * 300,
     "rlc_points": 3 * 3600 * 300,
+    "vmsm_accumulate": 3 * 32 * 14 * 300,  # ~32 non-zero signed bytes per scalar, three scalars per blob, 14 products per XYZZ addition
     "msm_accumulate": 98304 * 10 * 300,
 }
 
@@ -333,7 +340,7 @@ def run_b200(args):
     # The roofline kernel is the largest of the kernels that stream the per-blob bytes.  At n=4096 the
     # per-call tail (one pairing check, the transcript hash, the tree sums) is comparable in time but
     # moves no per-blob data, so an HBM figure for it would be meaningless; it is named separately.
-    per_call = ("pairing_check", "r_from_digest", "g1_sum")
+    per_call = ("pairing_check", "r_from_digest", "g1_sum", "transcript(d2h,host_sha)", "rlc_scalars", "vmsm_sort", "vmsm_accumulate", "vmsm_reduce")
     # "stream the per-blob bytes" = read the blob itself (131,168 B per blob for this path)
     streaming = [k for k in kern if k not in per_call and ALGO_BYTES_PER_BLOB.get(k, 0) >= 100_000] or list(kern)
     dom = max(streaming, key=lambda k: kern[k][0])

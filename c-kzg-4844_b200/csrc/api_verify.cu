@@ -104,7 +104,7 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
     TRY(call.alloc(&s.zy, n * 64));
     TRY(call.alloc(&s.bad, 1));
     KZG_CUDA_TRY(cudaMemsetAsync(s.bad, 0, sizeof(int), call.stream));
-    if (call.trace_kernels || (host && n < 64)) {  // serial form
+    if (host && (call.trace_kernels || n < 64)) {  // serial form
         if (host) KZG_CUDA_TRY(cudaMemcpyAsync(d_up, blobs, n * BLOB_BYTES, cudaMemcpyHostToDevice, call.stream));
         if (s.want_shift)
             TRY(launch_g1_validate2_levels(L, s.cm, d_cm, s.pf, d_pf, n, s.bad, s.table));
@@ -410,6 +410,7 @@ int ckzg_b200_verify_blob_kzg_proof_batch(ckzg_b200_ctx* ctx, int* ok, const uin
         const uint8_t* hc = (mem == CKZG_B200_DEVICE) ? h_c : commitments;
         const uint8_t* hp = (mem == CKZG_B200_DEVICE) ? h_p : proofs;
         transcript_digest(digest, hc, h_zy, hp, nullptr, n);
+        L.count(0, "transcript(d2h,host_sha)");
         if (!s.want_shift) {
             uint8_t* d_digest;
             TRY(call.alloc(&d_digest, 32));
