@@ -125,10 +125,13 @@ __device__ __forceinline__ void challenge_message_block(uint32_t w[16], int k, c
 
 // Runs on warps 0 and 1 of the CTA (they meet at named barrier 1, so other warps of the CTA are free
 // to do something else).
+// `lanes` (<= 32) blobs per CTA: the lanes above it leave at once (a partially filled warp still costs
+// the full issue slots, so this only helps to spread a small batch over more SMs).
 __device__ __forceinline__ void challenge_warp_pair(uint32_t (*kw)[64][32], Fr* __restrict__ z_out, uint8_t* __restrict__ zy, const uint8_t* __restrict__ blobs,
-                                                    const uint8_t* __restrict__ commitments, uint64_t n) {
+                                                    const uint8_t* __restrict__ commitments, uint64_t n, int lanes) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t i = (uint64_t)blockIdx.x * 32 + lane;
+    if (lane >= lanes) return;
+    const uint64_t i = (uint64_t)blockIdx.x * lanes + lane;
     const bool live = i < n;
     const uint64_t ii = live ? i : 0;  // dead lanes shadow blob 0 (reads only) so every thread reaches every barrier
     const uint4* blob = reinterpret_cast<const uint4*>(blobs + ii * BLOB_BYTES);
@@ -208,10 +211,10 @@ __device__ __forceinline__ void challenge_warp_pair(uint32_t (*kw)[64][32], Fr* 
 }
 
 __global__ void __launch_bounds__(64) blob_challenge_kernel(Fr* __restrict__ z_out, uint8_t* __restrict__ zy, const uint8_t* __restrict__ blobs,
-                                                          const uint8_t* __restrict__ commitments, uint64_t n) {
+                                                          const uint8_t* __restrict__ commitments, uint64_t n, int lanes) {
     __shared__ uint32_t kw[2][64][32];  // [buffer][round][lane] = K[t] + W[t]
     place_record(1);
-    challenge_warp_pair(kw, z_out, zy, blobs, commitments, n);
+    challenge_warp_pair(kw, z_out, zy, blobs, commitments, n, lanes);
 }
 
 __global__ void z_from_bytes_kernel(Fr* z_out, uint8_t* zy, const uint8_t* z_bytes, uint64_t n, int* bad) {
@@ -691,10 +694,18 @@ __global__ void __launch_bounds__(64) rlc_final_kernel(G1* __restrict__ out2, co
 // launchers
 // ------------------------------------------------------------------------------------------------
 static inline unsigned blocks_for(uint64_t n, unsigned per) { return (unsigned)((n + per - 1) / per); }
+// blobs per hash CTA (CKZG_B200_HASH_LANES overrides, for measurements)
+static int hash_lanes(uint64_t n) {
+    static const int forced = getenv("CKZG_B200_HASH_LANES") ? atoi(getenv("CKZG_B200_HASH_LANES")) : 0;
+    if (forced >= 1 && forced <= 32) return forced;
+    (void)n;
+    return 32;
+}
 
 int launch_blob_challenges(Launch& L, Fr* z, uint8_t* zy, const uint8_t* blobs, const uint8_t* commitments48, uint64_t n) {
     if (!n) return RET_OK;
-    blob_challenge_kernel<<<blocks_for(n, 32), 64, 0, L.stream>>>(z, zy, blobs, commitments48, n);
+    const int lanes = hash_lanes(n);
+    blob_challenge_kernel<<<blocks_for(n, lanes), 64, 0, L.stream>>>(z, zy, blobs, commitments48, n, lanes);
     KZG_CUDA_TRY(cudaGetLastError());
     L.count(1, "blob_challenge");
     return RET_OK;
@@ -776,15 +787,16 @@ __global__ void g1_validate2_kernel(G1Affine* __restrict__ out_a, const uint8_t*
 // "placement", profiles/r01_summary.md r01q-r01s).
 __global__ void __launch_bounds__(128) stage1_fused_kernel(Fr* __restrict__ z_out, uint8_t* __restrict__ zy, const uint8_t* __restrict__ blobs, G1Affine* __restrict__ out_cm,
                                                            const uint8_t* __restrict__ in_cm, G1Affine* __restrict__ out_pf, const uint8_t* __restrict__ in_pf, uint64_t n,
-                                                           int* __restrict__ bad, G1* __restrict__ table) {
+                                                           int* __restrict__ bad, G1* __restrict__ table, int lanes) {
     __shared__ uint32_t kw[2][64][32];
     place_record(3);
     const int warp = threadIdx.x >> 5;
     if (warp < 2) {
-        challenge_warp_pair(kw, z_out, zy, blobs, in_cm, n);
+        challenge_warp_pair(kw, z_out, zy, blobs, in_cm, n, lanes);
         return;
     }
-    const uint64_t i = (uint64_t)blockIdx.x * 32 + (threadIdx.x & 31);
+    if ((int)(threadIdx.x & 31) >= lanes) return;
+    const uint64_t i = (uint64_t)blockIdx.x * lanes + (threadIdx.x & 31);
     if (i >= n) return;
     const uint8_t* src = (warp == 2 ? in_cm : in_pf) + i * 48;
     uint8_t buf[48];
@@ -801,7 +813,8 @@ __global__ void __launch_bounds__(128) stage1_fused_kernel(Fr* __restrict__ z_ou
 int launch_stage1_fused(Launch& L, Fr* z, uint8_t* zy, const uint8_t* blobs, G1Affine* out_cm, const uint8_t* in_cm, G1Affine* out_pf, const uint8_t* in_pf, uint64_t n, int* bad,
                         G1* table) {
     if (!n) return RET_OK;
-    stage1_fused_kernel<<<blocks_for(n, 32), 128, 0, L.stream>>>(z, zy, blobs, out_cm, in_cm, out_pf, in_pf, n, bad, table);
+    const int lanes = hash_lanes(n);
+    stage1_fused_kernel<<<blocks_for(n, lanes), 128, 0, L.stream>>>(z, zy, blobs, out_cm, in_cm, out_pf, in_pf, n, bad, table, lanes);
     KZG_CUDA_TRY(cudaGetLastError());
     L.count(1, "hash+validate");
     return RET_OK;
