@@ -479,6 +479,26 @@ def run_b200(args):
         mod.profile_enable(ts, 0)
         extra["verify_cell_kernels_ms"] = {k: round(v[0] / 3, 3) for k, v in pv["kernels"].items() if k not in ("begin",)}
         extra["verify_cell_device_ms_per_call"] = pv["call_ms"] / 3
+        # larger batches through the C ABI with host pointers (row-major by blob, bindings/go/main_test.go:1016-1028):
+        # the whole input enters ONE serial transcript hash on the host (eip7594.c:405-474), 2112 B per cell
+        import ctypes
+
+        h_cm_rows = host_cms.view(-1, 48)[:m7].repeat_interleave(128, dim=0).contiguous().pin_memory()
+        for nb in (64, m7):
+            if nb > m7:
+                continue
+            idx_arr = (ctypes.c_uint64 * (nb * 128))(*([k for _ in range(nb) for k in range(128)]))
+            def vc_call():
+                return mod.verify_cell_kzg_proof_batch_ptr(h_cm_rows.data_ptr(), idx_arr, h_cells.data_ptr(), h_cprf.data_ptr(), nb * 128, ts)
+            assert vc_call()
+            mod.profile_enable(ts, 2)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                vc_call()
+            extra["verify_cell_kzg_proof_batch_%dx128_blobs_per_s" % nb] = nb * 3 / (time.perf_counter() - t0)
+            pv = mod.profile_dump(ts)
+            mod.profile_enable(ts, 0)
+            extra["verify_cell_%dx128_kernels_ms" % nb] = {k: round(v[0] / 3, 3) for k, v in pv["kernels"].items() if k not in ("begin",)}
         one = bytes(host_blobs[:BLOB].numpy().tobytes())
         for _ in range(2):
             mod.blob_to_kzg_commitment(one, ts)

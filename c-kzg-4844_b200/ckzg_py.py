@@ -329,3 +329,16 @@ def verify_blob_kzg_proof_batch_device(blobs_ptr, commitments_ptr, proofs_ptr, n
         "ckzg_b200_verify_blob_kzg_proof_batch",
     )
     return bool(ok.value)
+
+
+def verify_cell_kzg_proof_batch_ptr(commitments_ptr, cell_indices, cells_ptr, proofs_ptr, n, ts, mem=HOST):
+    """Raw-pointer form of verify_cell_kzg_proof_batch (host or device buffers; `cell_indices` is a ctypes
+    uint64 array or any sequence, always host memory as in the C ABI)."""
+    idx = cell_indices if isinstance(cell_indices, C.Array) else (C.c_uint64 * max(n, 1))(*cell_indices)
+    ok = C.c_int(0)
+    lib().ckzg_b200_verify_cell_kzg_proof_batch.restype = C.c_int
+    _raise(
+        lib().ckzg_b200_verify_cell_kzg_proof_batch(ts.engine, C.byref(ok), C.c_void_p(commitments_ptr), idx, C.c_void_p(cells_ptr), C.c_void_p(proofs_ptr), C.c_uint64(n), mem),
+        "ckzg_b200_verify_cell_kzg_proof_batch",
+    )
+    return bool(ok.value)

@@ -45,6 +45,7 @@ static int ctx_build(Ctx* c, const uint8_t* g1_mono, const uint8_t* g1_lag, cons
     TRY(setup_g2_and_lines(call.stream, L, c, g2_mono, d_bad));
     KZG_CUDA_TRY(cudaMalloc((void**)&c->g_levels, VMSM_LEVELS * sizeof(G1)));
     TRY(launch_vmsm_generator_levels(L, c->g_levels));
+    TRY(setup_verify_cells(L, c));
     TRY(fk20_setup(L, c));
     TRY(recover_setup(L, c));
 
@@ -73,6 +74,7 @@ static void ctx_free(Ctx* c) {
     cudaFree(c->g2_points);
     cudaFree(c->fk_table);
     cudaFree(c->g_levels);
+    cudaFree(c->mono_levels);
     cudaFree(c->rec_shiftA);
     cudaFree(c->rec_shiftB);
     for (auto& b : c->pin_free) cudaFreeHost(b.first);

@@ -235,6 +235,10 @@ int ckzg_b200_verify_cell_kzg_proof_batch(ckzg_b200_ctx* ctx, int* ok, const uin
         std::unordered_map<std::string, uint64_t> seen;
         seen.reserve(256);
         for (uint64_t i = 0; i < n; i++) {
+            if (i > 0 && memcmp(hc + 48 * i, hc + 48 * (i - 1), 48) == 0) {  // row-major by blob: the usual case
+                cm_index[i] = cm_index[i - 1];
+                continue;
+            }
             std::string key((const char*)hc + 48 * i, 48);
             auto it = seen.find(key);
             if (it == seen.end()) {
@@ -248,6 +252,19 @@ int ckzg_b200_verify_cell_kzg_proof_batch(ckzg_b200_ctx* ctx, int* ok, const uin
         }
     }
     const uint64_t u = uniq.size() / 48;
+
+    // Validation does not need the challenge: it starts now and runs under the host's transcript hash.
+    const uint8_t *d_cells, *d_pf, *d_uniq;
+    TRY(call.stage_in(&d_pf, proofs, n * 48, mem));
+    TRY(call.stage_in(&d_uniq, uniq.data(), uniq.size(), CKZG_B200_HOST));
+    G1* d_table;
+    int *d_flags;  // [0] bad input, [1] pairing verdict
+    TRY(call.alloc(&d_table, verify_cells_table_points(n, u)));
+    TRY(call.alloc(&d_flags, 2));
+    KZG_CUDA_TRY(cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), call.stream));
+    TRY(launch_verify_cells_validate(L, d_table, d_pf, n, d_uniq, u, d_flags));
+    TRY(call.stage_in(&d_cells, cells, n * CELL_BYTES, mem));
+
     // challenge transcript (eip7594.c:390-482)
     uint8_t digest[32];
     {
@@ -273,7 +290,9 @@ int ckzg_b200_verify_cell_kzg_proof_batch(ckzg_b200_ctx* ctx, int* ok, const uin
     }
     // CSR groupings: cells by column, cells by unique commitment
     std::vector<uint32_t> col_start(129, 0), col_items(n), cm_start(u + 1, 0), cm_items(n);
+    std::vector<uint8_t> col_of(n);
     for (uint64_t i = 0; i < n; i++) {
+        col_of[i] = (uint8_t)cell_indices[i];
         col_start[cell_indices[i] + 1]++;
         cm_start[cm_index[i] + 1]++;
     }
@@ -286,42 +305,28 @@ int ckzg_b200_verify_cell_kzg_proof_batch(ckzg_b200_ctx* ctx, int* ok, const uin
             cm_items[mc[cm_index[i]]++] = (uint32_t)i;
         }
     }
+    L.count(0, "transcript(host_sha)");  // what the host hash adds beyond the validation it runs beside
 
-    const uint8_t *d_cells, *d_pf, *d_uniq, *d_digest, *d_cs, *d_ci, *d_ms, *d_mi;
-    TRY(call.stage_in(&d_cells, cells, n * CELL_BYTES, mem));
-    TRY(call.stage_in(&d_pf, proofs, n * 48, mem));
-    TRY(call.stage_in(&d_uniq, uniq.data(), uniq.size(), CKZG_B200_HOST));
-    TRY(call.stage_in(&d_digest, digest, 32, CKZG_B200_HOST));
+    const uint8_t *d_cs, *d_ci, *d_ms, *d_mi, *d_col;
+    TRY(call.stage_in(&d_col, col_of.data(), col_of.size(), CKZG_B200_HOST));
     TRY(call.stage_in(&d_cs, (const uint8_t*)col_start.data(), col_start.size() * 4, CKZG_B200_HOST));
     TRY(call.stage_in(&d_ci, (const uint8_t*)col_items.data(), col_items.size() * 4, CKZG_B200_HOST));
     TRY(call.stage_in(&d_ms, (const uint8_t*)cm_start.data(), cm_start.size() * 4, CKZG_B200_HOST));
     TRY(call.stage_in(&d_mi, (const uint8_t*)cm_items.data(), cm_items.size() * 4, CKZG_B200_HOST));
-    G1Affine *d_pf_pts, *d_cm_pts;
-    Fr* d_r;
-    int *d_bad, *d_ok;
     G1* d_AB;
     uint8_t* scratch;
-    TRY(call.alloc(&d_pf_pts, n));
-    TRY(call.alloc(&d_cm_pts, u));
-    TRY(call.alloc(&d_r, 1));
-    TRY(call.alloc(&d_bad, 1));
-    TRY(call.alloc(&d_ok, 1));
     TRY(call.alloc(&d_AB, 2));
     TRY(call.alloc(&scratch, verify_cells_scratch_bytes(n, u)));
-    KZG_CUDA_TRY(cudaMemsetAsync(d_bad, 0, sizeof(int), call.stream));
-    TRY(launch_r_from_digest(L, d_r, d_digest));
-    // bytes_to_kzg_proof (eip7594.c:917-920) and bytes_to_kzg_commitment (:513) in one launch
-    TRY(launch_g1_validate_ab(L, d_pf_pts, d_pf, n, d_cm_pts, d_uniq, u, d_bad));
-    TRY(launch_verify_cells(L, d_AB, d_pf_pts, d_cm_pts, d_cells, d_r, (const uint32_t*)d_cs, (const uint32_t*)d_ci, (const uint32_t*)d_ms, (const uint32_t*)d_mi, n, u, d_bad,
+    TRY(launch_verify_cells(L, d_AB, d_table, d_cells, digest, d_col, (const uint32_t*)d_cs, (const uint32_t*)d_ci, (const uint32_t*)d_ms, (const uint32_t*)d_mi, n, u, d_flags,
                             scratch));
-    int bad = 0;
-    KZG_CUDA_TRY(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, call.stream));
+    // e(B, G2) == e(A, [tau^64]G2)   (eip7594.c:966); an invalid input leaves infinities behind, the
+    // verdict is then ignored
+    TRY(launch_pairing_check(L, d_flags + 1, d_AB + 0, d_AB + 1, nullptr, LINE_G2_TAU64, LINE_G2_GEN));
+    int flags[2] = {0, 0};
+    KZG_CUDA_TRY(cudaMemcpyAsync(flags, d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, call.stream));
     KZG_CUDA_TRY(cudaStreamSynchronize(call.stream));
-    if (bad) return RET_BADARGS;
-    // e(B, G2) == e(A, [tau^64]G2)   (eip7594.c:966)
-    TRY(launch_pairing_check(L, d_ok, d_AB + 0, d_AB + 1, nullptr, LINE_G2_TAU64, LINE_G2_GEN));
-    KZG_CUDA_TRY(cudaMemcpyAsync(ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, call.stream));
-    KZG_CUDA_TRY(cudaStreamSynchronize(call.stream));
+    if (flags[0]) return RET_BADARGS;
+    *ok = flags[1];
     return RET_OK;
 }
 

@@ -41,9 +41,17 @@ int launch_recover(Launch& L, uint8_t* cells_out, Fr* mono_out, const uint8_t* c
                    void* scratch);
 
 // ---- verify_cells.cu -----------------------------------------------------------------------------
+// Table columns of one call: proofs 0..n-1, unique commitments n..n+u-1, then the 64 (negated) setup
+// points of the interpolation commitment; VMSM_LEVELS rows (vmsm.cu layout).
+int setup_verify_cells(Launch& L, Ctx* c);  // Ctx::mono_levels
+size_t verify_cells_table_points(uint64_t n, uint64_t u);
+// before the challenge: decompress + subgroup-check proofs and unique commitments (bytes_to_kzg_proof
+// eip7594.c:917-920, bytes_to_kzg_commitment :513), leaving their table columns; copies the fixed columns
+int launch_verify_cells_validate(Launch& L, G1* table, const uint8_t* proofs48, uint64_t n, const uint8_t* uniq48, uint64_t u, int* d_bad);
 size_t verify_cells_scratch_bytes(uint64_t n, uint64_t u);
-// out2[0] = sum r^k pi_k, out2[1] = sum w_c C_c - [I] + sum r^k h_k^64 pi_k  (eip7594.c:825-974)
-int launch_verify_cells(Launch& L, G1* out2, const G1Affine* proofs, const G1Affine* commitments, const uint8_t* cells, const Fr* r, const uint32_t* col_start,
+// out2[0] = sum r^k pi_k, out2[1] = sum w_c C_c - [I] + sum r^k h_k^64 pi_k  (eip7594.c:825-974);
+// r = hash_to_bls_field(digest32) (HOST pointer); col_of[k] = cell index of cell k (device, n bytes)
+int launch_verify_cells(Launch& L, G1* out2, const G1* table, const uint8_t* cells, const uint8_t* digest32, const uint8_t* col_of, const uint32_t* col_start,
                         const uint32_t* col_items, const uint32_t* cm_start, const uint32_t* cm_items, uint64_t n, uint64_t u, int* d_bad, void* scratch);
 
 }  // namespace kzg

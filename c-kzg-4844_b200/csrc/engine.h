@@ -75,6 +75,7 @@ struct Ctx {
     void* rec_shiftB = nullptr;           // 7^-k / 8192
     void* fk_table = nullptr;             // FK20 fixed-base multiples, cells.h (3.2 GB)
     G1* g_levels = nullptr;               // [18] table levels of -G1 generator (vmsm.cu)
+    G1* mono_levels = nullptr;            // [18][64] table levels of -[tau^j]G1, j < 64 (verify_cells.cu)
     uint64_t precompute = 0;
 
     // Small pool of pinned host buffers for the device->host hops inside a call (a pageable destination

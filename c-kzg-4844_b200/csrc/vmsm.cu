@@ -27,37 +27,9 @@
 #define KZG_FP_MUL_OUTLINE 1
 #include "g1_glv.cuh"
 #include "g1_quad.cuh"
-#include "verify.h"
+#include "vmsm.cuh"
 
 namespace kzg {
-
-constexpr int VC = 8;                    // digit width (one byte of a 64-bit base-|z| digit)
-constexpr int VW = 9;                    // table levels per base (the balanced digits use 8 of them)
-static_assert(VMSM_LEVELS == 2 * VW && VMSM_LEVELS == G1_LEVELS, "table layout: 9 levels of P, 9 levels of [|z|]P");
-constexpr int VNB = 1 << (VC - 1);       // 128 buckets (signed digits, magnitude 1..128)
-constexpr int VSORT_THREADS = 256;
-constexpr int VSORT_WARPS = VSORT_THREADS / 32;
-constexpr int VSORT_CTAS = 64;           // CTAs per MSM in the counting sort
-constexpr uint32_t VCAP = 8;             // list entries folded by one accumulate thread
-constexpr int VACC_THREADS = 128;
-constexpr int VCOMB_THREADS = 128;
-
-struct VmsmJob {
-    const uint32_t* halves;  // [nh][2] 64-bit base-|z| digits, index h = 4 * point + quarter
-    uint32_t nh;
-    uint32_t max_items;
-    uint32_t* entries;       // [nh * VW]
-    uint32_t* starts;        // [VNB + 1]
-    uint32_t* item_start;    // [VNB + 1]
-    uint32_t* item_bucket;   // [max_items]
-    G1* partial;             // [max_items]
-    G1* combined;            // [VNB]
-    uint32_t* ctahist;       // [VSORT_CTAS][VNB]
-    G1* scan_tmp;            // [VNB]
-};
-struct VmsmJobs {
-    VmsmJob j[2];
-};
 
 __device__ __forceinline__ G1 vload_g1(const G1* p) {
     G1 a;
@@ -80,34 +52,6 @@ __device__ __forceinline__ void vstore_g1(G1* p, const G1& a) {
 // hB layout (index = 4 * point + quarter, 8 bytes each): points 0..n-1 proofs with r^i z_i, points
 // n..2n-1 commitments with r^i, point 2n = -G with sum r^i y_i.  MSM A reads the r^i segment with point
 // base 0.
-__device__ __forceinline__ void store_halves(uint32_t* hB, size_t point, const uint32_t k[8]) {
-    int64_t sd[4];
-    basez_split(sd, k);
-    uint64_t a[4];  // magnitude (< 2^63) | sign in bit 63
-#pragma unroll
-    for (int i = 0; i < 4; i++) a[i] = sd[i] < 0 ? ((uint64_t)(-sd[i]) | (1ull << 63)) : (uint64_t)sd[i];
-    uint4* dst = reinterpret_cast<uint4*>(hB) + 2 * point;
-    dst[0] = make_uint4((uint32_t)a[0], (uint32_t)(a[0] >> 32), (uint32_t)a[1], (uint32_t)(a[1] >> 32));
-    dst[1] = make_uint4((uint32_t)a[2], (uint32_t)(a[2] >> 32), (uint32_t)a[3], (uint32_t)(a[3] >> 32));
-}
-struct Digest8 {
-    uint32_t h[8];  // big-endian words of the SHA-256 digest
-};
-// r = hash_to_bls_field(digest) (src/common/bytes.c:123): the digest is below 2^256 < 3r
-__device__ __forceinline__ Fr fr_from_digest_words(const uint32_t h[8]) {
-    uint32_t t[8], s[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) t[i] = h[7 - i];
-#pragma unroll 1
-    for (int k = 0; k < 2; k++) {
-        uint32_t bw = limbs_sub<8>(s, t, FR_MOD);
-        if (!bw) {
-#pragma unroll
-            for (int i = 0; i < 8; i++) t[i] = s[i];
-        }
-    }
-    return to_mont<FrTag>(t);
-}
 __global__ void rlc_vmsm_scalars_kernel(uint32_t* __restrict__ hB, Fr* __restrict__ ty, const Fr* __restrict__ z, const Fr* __restrict__ y, const Digest8 digest,
                                         uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -357,6 +301,26 @@ int launch_vmsm_generator_levels(Launch& L, G1* levels18) {
     L.count();
     return RET_OK;
 }
+// table levels of n fixed affine bases (optionally negated): one thread per point, setup time only
+__global__ void vmsm_point_levels_kernel(G1* __restrict__ levels, const G1Affine* __restrict__ pts, uint32_t n, bool negate) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1Affine a = pts[i];
+    if (g1a_is_inf(a)) {
+        const G1 inf = g1_inf();
+        for (int j = 0; j < G1_LEVELS; j++) g1_store(levels + (size_t)j * n + i, inf);
+        return;
+    }
+    if (negate) a = g1a_neg(a);
+    G1 q = g1_mul_bls_x_levels(g1_from_affine(a), levels + i, n);
+    (void)g1_mul_bls_x_levels(q, levels + (size_t)9 * n + i, n);
+}
+int launch_vmsm_point_levels(Launch& L, G1* levels, const G1Affine* pts, uint32_t n, bool negate) {
+    vmsm_point_levels_kernel<<<(n + 31) / 32, 32, 0, L.stream>>>(levels, pts, n, negate);
+    KZG_CUDA_TRY(cudaGetLastError());
+    L.count();
+    return RET_OK;
+}
 // per call: drop those levels into column 2n of the call's table
 int vmsm_place_generator(Launch& L, G1* table, uint64_t n) {
     const size_t npts = 2 * n + 1;
@@ -364,12 +328,12 @@ int vmsm_place_generator(Launch& L, G1* table, uint64_t n) {
     return RET_OK;
 }
 
-static size_t vmsm_job_bytes(uint64_t nh) {
+size_t vmsm_job_bytes(uint64_t nh) {
     const uint32_t mi = vmsm_max_items(nh);
     return val256(nh * VW * sizeof(uint32_t)) + 2 * val256((VNB + 1) * sizeof(uint32_t)) + val256(mi * sizeof(uint32_t)) + val256((size_t)mi * sizeof(G1)) +
            2 * val256(VNB * sizeof(G1)) + val256(VSORT_CTAS * VNB * sizeof(uint32_t));
 }
-static uint8_t* vmsm_job_carve(VmsmJob& J, uint8_t* ws, const uint32_t* halves, uint64_t nh) {
+uint8_t* vmsm_job_carve(VmsmJob& J, uint8_t* ws, const uint32_t* halves, uint64_t nh) {
     J.halves = halves;
     J.nh = (uint32_t)nh;
     J.max_items = vmsm_max_items(nh);
@@ -382,6 +346,26 @@ static uint8_t* vmsm_job_carve(VmsmJob& J, uint8_t* ws, const uint32_t* halves, 
     J.ctahist = (uint32_t*)ws; ws += val256(VSORT_CTAS * VNB * sizeof(uint32_t));
     J.scan_tmp = (G1*)ws; ws += val256(VNB * sizeof(G1));
     return ws;
+}
+
+int launch_vmsm_jobs(Launch& L, G1* out2, const VmsmJobs& jobs, const G1* table, uint32_t npts) {
+    vmsm_hist_kernel<<<dim3(VSORT_CTAS, 2), VSORT_THREADS, 0, L.stream>>>(jobs);
+    KZG_CUDA_TRY(cudaGetLastError());
+    vmsm_scatter_kernel<<<dim3(VSORT_CTAS, 2), VSORT_THREADS, 0, L.stream>>>(jobs, npts);
+    KZG_CUDA_TRY(cudaGetLastError());
+    L.count(2, "vmsm_sort");
+    dim3 agrid((jobs.j[1].max_items + VACC_THREADS - 1) / VACC_THREADS, 2);
+    vmsm_accumulate_kernel<<<agrid, VACC_THREADS, 0, L.stream>>>(jobs, table);
+    KZG_CUDA_TRY(cudaGetLastError());
+    L.count(1, "vmsm_accumulate");
+    vmsm_combine_kernel<<<dim3(VNB, 2), VCOMB_THREADS, 0, L.stream>>>(jobs);
+    KZG_CUDA_TRY(cudaGetLastError());
+    static const cudaError_t attr = cudaFuncSetAttribute(vmsm_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(VNB * sizeof(QuadScratch)));
+    KZG_CUDA_TRY(attr);
+    vmsm_reduce_kernel<<<2, VRED_THREADS, VNB * sizeof(QuadScratch), L.stream>>>(out2, jobs);
+    KZG_CUDA_TRY(cudaGetLastError());
+    L.count(2, "vmsm_reduce");
+    return RET_OK;
 }
 
 size_t rlc_vmsm_scratch_bytes(uint64_t n) {
@@ -408,23 +392,7 @@ int launch_rlc_vmsm(Launch& L, G1* out2, const G1* table, const Fr* z, const Fr*
     rlc_vmsm_ysum_kernel<<<1, 256, 0, L.stream>>>(hB, ty, (uint32_t)n);
     KZG_CUDA_TRY(cudaGetLastError());
     L.count(2, "rlc_scalars");
-    vmsm_hist_kernel<<<dim3(VSORT_CTAS, 2), VSORT_THREADS, 0, L.stream>>>(jobs);
-    KZG_CUDA_TRY(cudaGetLastError());
-    vmsm_scatter_kernel<<<dim3(VSORT_CTAS, 2), VSORT_THREADS, 0, L.stream>>>(jobs, npts);
-    KZG_CUDA_TRY(cudaGetLastError());
-    L.count(2, "vmsm_sort");
-    dim3 agrid((jobs.j[1].max_items + VACC_THREADS - 1) / VACC_THREADS, 2);
-    vmsm_accumulate_kernel<<<agrid, VACC_THREADS, 0, L.stream>>>(jobs, table);
-    KZG_CUDA_TRY(cudaGetLastError());
-    L.count(1, "vmsm_accumulate");
-    vmsm_combine_kernel<<<dim3(VNB, 2), VCOMB_THREADS, 0, L.stream>>>(jobs);
-    KZG_CUDA_TRY(cudaGetLastError());
-    static const cudaError_t attr = cudaFuncSetAttribute(vmsm_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(VNB * sizeof(QuadScratch)));
-    KZG_CUDA_TRY(attr);
-    vmsm_reduce_kernel<<<2, VRED_THREADS, VNB * sizeof(QuadScratch), L.stream>>>(out2, jobs);
-    KZG_CUDA_TRY(cudaGetLastError());
-    L.count(2, "vmsm_reduce");
-    return RET_OK;
+    return launch_vmsm_jobs(L, out2, jobs, table, npts);
 }
 
 }  // namespace kzg

@@ -91,6 +91,60 @@ def test_cells_recover_roundtrip_batch(env):
     assert mod.verify_cell_kzg_proof_batch(cm_l, idx_l, cell_l, prf_l, ts) is False
 
 
+def test_verify_cells_batch8192_and_controls(env):
+    """verify_cell_kzg_proof_batch at 64 blobs x 128 cells (row-major by blob, bindings/go/main_test.go:1016-1028):
+    the bucket-MSM form must accept the engine's own (parity-checked) cells + proofs, in any order and with
+    duplicates, reject one wrong proof / cell / index, and report invalid encodings as BADARGS."""
+    import torch
+
+    from oracle import ref_lib
+
+    mod, ts, n, host, dev, cms, prs = env
+    m = 64
+    cells = torch.empty(m * 262144, dtype=torch.uint8, device="cuda")
+    cprf = torch.empty(m * 128 * 48, dtype=torch.uint8, device="cuda")
+    mod.compute_cells_and_kzg_proofs_device(cells.data_ptr(), cprf.data_ptr(), dev.data_ptr(), m, ts)
+    hc, hp, hcm = cells.cpu().numpy().tobytes(), cprf.cpu().numpy().tobytes(), cms.cpu().numpy().tobytes()
+    cm_l = [hcm[48 * b : 48 * b + 48] for b in range(m) for k in range(128)]
+    idx_l = [k for b in range(m) for k in range(128)]
+    cell_l = [hc[i * 2048 : (i + 1) * 2048] for i in range(m * 128)]
+    prf_l = [hp[i * 48 : (i + 1) * 48] for i in range(m * 128)]
+    assert mod.verify_cell_kzg_proof_batch(cm_l, idx_l, cell_l, prf_l, ts) is True
+    # shuffled, with duplicates (eip7594.c:345-376: dedup order follows first appearance)
+    order = list(range(m * 128))
+    random.Random(4).shuffle(order)
+    order = order[:3000] + order[:17]
+    pick = lambda l: [l[i] for i in order]
+    assert mod.verify_cell_kzg_proof_batch(pick(cm_l), pick(idx_l), pick(cell_l), pick(prf_l), ts) is True
+    if os.path.exists(ref_lib.REF_SO):  # the reference agrees on a 300-cell sample of the same data
+        ref = ref_lib.CKZG()
+        sub = order[:300]
+        assert ref.verify_cell_kzg_proof_batch(b"".join(cm_l[i] for i in sub), [idx_l[i] for i in sub], b"".join(cell_l[i] for i in sub), b"".join(prf_l[i] for i in sub)) is True
+    # negative controls
+    p2 = list(prf_l)
+    p2[4097], p2[4098] = p2[4098], p2[4097]
+    assert mod.verify_cell_kzg_proof_batch(cm_l, idx_l, cell_l, p2, ts) is False
+    c2 = list(cell_l)
+    c2[8000] = c2[8000][:2047] + bytes([c2[8000][2047] ^ 1])
+    assert mod.verify_cell_kzg_proof_batch(cm_l, idx_l, c2, prf_l, ts) is False
+    i2 = list(idx_l)
+    i2[77] = (i2[77] + 64) % 128
+    assert mod.verify_cell_kzg_proof_batch(cm_l, i2, cell_l, prf_l, ts) is False
+    k2 = list(cm_l)
+    k2[128 * 9 + 3] = cm_l[0]
+    assert mod.verify_cell_kzg_proof_batch(k2, idx_l, cell_l, prf_l, ts) is False
+    # invalid encodings
+    R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+    c3 = list(cell_l)
+    c3[5000] = c3[5000][:64] + R.to_bytes(32, "big") + c3[5000][96:]
+    with pytest.raises(Exception):
+        mod.verify_cell_kzg_proof_batch(cm_l, idx_l, c3, prf_l, ts)
+    p3 = list(prf_l)
+    p3[8191] = bytes(48)
+    with pytest.raises(Exception):
+        mod.verify_cell_kzg_proof_batch(cm_l, idx_l, cell_l, p3, ts)
+
+
 def test_concurrent_callers_share_one_settings(env):
     """The reference allows many threads on one const KZGSettings (bindings/rust/src/bindings/mod.rs:912,
     bindings/go/main_test.go:957-970): every call here owns its stream and pool allocations."""
