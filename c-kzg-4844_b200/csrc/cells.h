@@ -33,6 +33,11 @@ int launch_fk20_msm(Launch& L, G1* u_brp, const uint32_t* S, uint64_t n);
 // upper half, forward G1 FFT (fk20.c:257-269 + eip7594.c:133)
 int launch_fk20_g1_ffts(Launch& L, G1* proofs, G1* u_brp, uint64_t n);
 
+// ---- fk20_fft.cu ---------------------------------------------------------------------------------
+// in place, nvec vectors of 128 XYZZ points: [unscaled inverse FFT of bit-reversed input, lower half kept ->]
+// forward FFT with the upper half taken as infinity, output bit-reversed
+int g1_fft128_run(Launch& L, G1* data, uint64_t nvec, bool with_inverse);
+
 // ---- recover.cu ----------------------------------------------------------------------------------
 int recover_setup(Launch& L, Ctx* c);
 size_t recover_scratch_bytes(uint64_t n);

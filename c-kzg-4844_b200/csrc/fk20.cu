@@ -9,12 +9,11 @@
 // B200 design: the 8192 bases X^[j][i] are fixed, so setup stores every small multiple of every
 // window shift, T[p][w][m] = (m+1) 2^(8w) X^_p (3.2 GB of the 180 GB HBM).  An MSM(64) is then a
 // pure gather-and-add of 64 x 32 table points: one warp per MSM, two base points per lane, a
-// shared-memory tree at the end -- no buckets, no doublings, no sorting.  The G1 FFTs keep the
-// 128-point vector of a blob in shared memory, one butterfly per thread per stage; ordering is
-// arranged so that no permutation pass exists (MSM j stores to slot brp7(j); inverse DIT gives
-// natural order; forward DIF leaves the proofs in the bit-reversed order the API returns).
+// shared-memory tree at the end -- no buckets, no doublings, no sorting.  The G1 FFTs live in
+// fk20_fft.cu; ordering is arranged so that no permutation pass exists (MSM j stores to slot brp7(j);
+// inverse DIT gives natural order; forward DIF leaves the proofs in the bit-reversed order the API
+// returns).
 #include "cells.h"
-#include "fft_twiddles.cuh"
 #include "g1_hot.cuh"
 
 namespace kzg {
@@ -50,111 +49,6 @@ __device__ __forceinline__ Fr ld_fr2(const Fr* p) {
     return r;
 }
 __device__ __forceinline__ int brp7(int v) { return (int)(__brev((uint32_t)v) >> 25); }
-
-// [w128^e]P through the GLV split k = k1 + k2*lambda (both < 2^128, digits precomputed in
-// fft_twiddles.cuh): one table of odd multiples of P serves both halves because the second base is
-// -phi(P) = (beta*x, -y).  129 doublings + ~52 additions instead of 255 + 128.  Every lane of a warp
-// calls this with the SAME e (lanes span blobs, see g1_fft_stage_kernel), so the digit-dependent
-// branches are warp-uniform and the NAF sparsity is real.
-__device__ __noinline__ G1 g1_mul_twiddle(const G1& p, int e) {
-    if (e == 0) return p;
-    G1 tab[8];  // (2i+1) P
-    tab[0] = p;
-    G1 p2 = p;
-    g1_dbl_to(p2);
-#pragma unroll 1
-    for (int i = 1; i < 8; i++) {
-        tab[i] = tab[i - 1];
-        g1_add_to(tab[i], p2);
-    }
-    const Fp beta = Fp::from_limbs(FP_BETA_A);
-    const int8_t* d1 = FFT_TW_NAF[e][0];
-    const int8_t* d2 = FFT_TW_NAF[e][1];
-    G1 acc = g1_inf();
-#pragma unroll 1
-    for (int i = FFT_TW_TOP[e] - 1; i >= 0; i--) {
-        g1_dbl_to(acc);
-        int a = d1[i], b = d2[i];
-        if (a != 0) {
-            G1 t = tab[((a < 0 ? -a : a) - 1) >> 1];
-            if (a < 0) t.y = neg(t.y);
-            g1_add_to(acc, t);
-        }
-        if (b != 0) {
-            G1 t = tab[((b < 0 ? -b : b) - 1) >> 1];
-            t.x = mul(t.x, beta);
-            if (b > 0) t.y = neg(t.y);  // base is -phi(P)
-            g1_add_to(acc, t);
-        }
-    }
-    return acc;
-}
-
-// ------------------------------------------------------------------------------------------------
-// G1 FFT over 128 points per vector, one radix-2 stage per launch, data in global memory (L2).
-// Thread = (butterfly b, vector v) with the 32 lanes of a warp spanning 32 VECTORS of the same
-// butterfly: they share the twiddle, so control flow never diverges.
-// ------------------------------------------------------------------------------------------------
-constexpr int GS_WARPS = 4;
-enum { GS_INVERSE = 0, GS_FORWARD_FIRST = 1, GS_FORWARD = 2 };
-
-// mode GS_INVERSE (decimation in time, g1_ifft_unscaled fft.c:227): v' = [w^-j] v; (u+v', u-v'); the
-//   last stage (half = 64) keeps only the lower output (FK20 discards the upper half, fk20.c:264-266).
-// mode GS_FORWARD_FIRST: input upper half is infinity: (u, [w^j] u).
-// mode GS_FORWARD (decimation in frequency, g1_fft fft.c:199): (u+v, [w^j](u-v)).
-__global__ void __launch_bounds__(32 * GS_WARPS) g1_fft_stage_kernel(G1* __restrict__ data, uint64_t nvec, int half, int mode) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = blockIdx.x * GS_WARPS + warp;  // 0..63
-    const uint64_t vec = (uint64_t)blockIdx.y * 32 + lane;
-    if (vec >= nvec) return;
-    const int j = b & (half - 1);
-    const int i0 = ((b - j) << 1) + j, i1 = i0 + half;
-    const int step = 64 / half;                       // twiddle exponent of w128 per unit of j
-    G1* base = data + vec * 128;
-    if (mode == GS_FORWARD_FIRST) {
-        G1 u = ld_g1(base + i0);
-        st_g1(base + i1, g1_mul_twiddle(u, j * step));
-        return;
-    }
-    G1 u = ld_g1(base + i0), v = ld_g1(base + i1);
-    if (mode == GS_INVERSE) {
-        if (j != 0) v = g1_mul_twiddle(v, (128 - j * step) & 127);
-        G1 s = u;
-        g1_add_to(s, v);
-        st_g1(base + i0, s);
-        if (half != 64) {
-            G1 d = g1_neg(v);
-            g1_add_to(d, u);
-            st_g1(base + i1, d);
-        }
-    } else {
-        G1 s = u;
-        g1_add_to(s, v);
-        G1 d = g1_neg(v);
-        g1_add_to(d, u);
-        if (j != 0) d = g1_mul_twiddle(d, j * step);
-        st_g1(base + i0, s);
-        st_g1(base + i1, d);
-    }
-}
-
-// in place: [inverse DIT on bit-reversed input, lower half kept] -> forward DIF with upper half = infinity
-static int g1_fft128_run(Launch& L, G1* data, uint64_t nvec, bool with_inverse) {
-    dim3 grid(64 / GS_WARPS, (unsigned)((nvec + 31) / 32));
-    if (with_inverse) {
-        for (int half = 1; half <= 64; half <<= 1) {
-            g1_fft_stage_kernel<<<grid, 32 * GS_WARPS, 0, L.stream>>>(data, nvec, half, GS_INVERSE);
-            KZG_CUDA_TRY(cudaGetLastError());
-        }
-    }
-    g1_fft_stage_kernel<<<grid, 32 * GS_WARPS, 0, L.stream>>>(data, nvec, 64, GS_FORWARD_FIRST);
-    KZG_CUDA_TRY(cudaGetLastError());
-    for (int half = 32; half >= 1; half >>= 1) {
-        g1_fft_stage_kernel<<<grid, 32 * GS_WARPS, 0, L.stream>>>(data, nvec, half, GS_FORWARD);
-        KZG_CUDA_TRY(cudaGetLastError());
-    }
-    return RET_OK;
-}
 
 // ------------------------------------------------------------------------------------------------
 // setup: X^ columns and the window tables

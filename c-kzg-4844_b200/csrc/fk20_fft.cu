@@ -1,0 +1,149 @@
+// G1 FFTs of FK20 (128 points per vector) with every group operation spread over four lanes.
+//
+// Replaces (paths relative to the reference tree):
+//   g1_fft_fast / g1_fft / g1_ifft_unscaled ... src/eip7594/fft.c:164-240
+//   their use in compute_fk20_cell_proofs ..... src/eip7594/fk20.c:257-269
+//   and in init_fk20_multi_settings ........... src/setup/setup.c:284-289
+//
+// A radix-2 stage is 64 twiddle multiplications per vector, and the 14 stages of the two transforms are a
+// dependency chain: with one multiplication per thread (129 doublings + ~52 additions, ~2000 dependent Fp
+// products, 1.9 ms) a batch of 256 blobs put one warp on each SM sub-partition and waited 14 times for
+// that chain (r01y: 43 ms of the 71 ms per 256 blobs).  Here a QUAD of lanes shares each group operation
+// (g1_quad.cuh: doubling = 3 product levels instead of 9 products, addition = 4 instead of 14), which cuts
+// the chain to ~630 product latencies and puts four times as many warps on the multiplier.
+//
+// Thread layout: CTA = 4 warps = 4 butterflies; the 8 quads of a warp take the SAME butterfly of 8
+// different vectors, so the GLV + width-4-NAF digit strings of the twiddle (fft_twiddles.cuh) are
+// warp-uniform.  Per quad, shared memory holds the table of odd multiples, the beta-twisted x
+// coordinates (second GLV base -phi(P) = (beta x, -y)), the accumulator and the scratch of the
+// cooperative operations.
+#define KZG_FP_MUL_OUTLINE 1
+#include "cells.h"
+#include "fft_twiddles.cuh"
+#include "g1_quad.cuh"
+
+namespace kzg {
+
+struct QuadWork {
+    G1 tab[8];  // (2i+1) P
+    Fp bx[8];   // beta * tab[i].x
+    G1 acc;
+    G1 t;
+    QuadScratch sc;
+};
+constexpr int GQ_WARPS = 4;
+constexpr int GQ_QUADS = GQ_WARPS * 8;
+constexpr size_t GQ_SMEM = GQ_QUADS * sizeof(QuadWork);
+
+// W->acc = [w128^e] *src   (e != 0; src may be W->t)
+static __device__ __noinline__ void g1_mul_twiddle_quad(QuadWork* W, const G1* src, int e) {
+    const unsigned lane = threadIdx.x & 31u, ql = lane & 3u;
+    const unsigned mask = 0xFu << (lane & ~3u);
+    quad_copy_g1(&W->tab[0], src);
+    __syncwarp(mask);
+    g1_dbl_quad(&W->t, &W->tab[0], &W->sc);
+#pragma unroll 1
+    for (int i = 1; i < 8; i++) g1_add_quad(&W->tab[i], &W->tab[i - 1], &W->t, &W->sc);
+    {
+        const Fp beta = Fp::from_limbs(FP_BETA_A);
+#pragma unroll 1
+        for (int i = (int)ql; i < 8; i += 4) quad_st(&W->bx[i], mul(quad_ld(&W->tab[i].x), beta));
+        if (ql == 0) {
+            const Fp z = Fp::zero();
+            quad_st(&W->acc.x, z); quad_st(&W->acc.y, z); quad_st(&W->acc.zz, z); quad_st(&W->acc.zzz, z);
+        }
+    }
+    __syncwarp(mask);
+    const int8_t* d1 = FFT_TW_NAF[e][0];
+    const int8_t* d2 = FFT_TW_NAF[e][1];
+#pragma unroll 1
+    for (int i = FFT_TW_TOP[e] - 1; i >= 0; i--) {
+        g1_dbl_quad(&W->acc, &W->acc, &W->sc);
+        const int a = d1[i], b = d2[i];
+        if (a != 0) {
+            const G1* t = &W->tab[((a < 0 ? -a : a) - 1) >> 1];
+            g1_add_quad_q(&W->acc, &W->acc, &t->x, t, a < 0, &W->sc);
+        }
+        if (b != 0) {  // base -phi(P): (beta x, -y)
+            const int idx = ((b < 0 ? -b : b) - 1) >> 1;
+            g1_add_quad_q(&W->acc, &W->acc, &W->bx[idx], &W->tab[idx], b > 0, &W->sc);
+        }
+    }
+}
+
+enum { GS_INVERSE = 0, GS_FORWARD_FIRST = 1, GS_FORWARD = 2 };
+
+// One radix-2 stage, data in global memory (L2).
+// mode GS_INVERSE (decimation in time, g1_ifft_unscaled fft.c:227): v' = [w^-j] v; (u+v', u-v'); the
+//   last stage (half = 64) keeps only the lower output (FK20 discards the upper half, fk20.c:264-266).
+// mode GS_FORWARD_FIRST: input upper half is infinity: (u, [w^j] u).
+// mode GS_FORWARD (decimation in frequency, g1_fft fft.c:199): (u+v, [w^j](u-v)).
+__global__ void __launch_bounds__(32 * GQ_WARPS) g1_fft_stage_quad_kernel(G1* __restrict__ data, uint64_t nvec, int half, int mode) {
+    extern __shared__ __align__(16) unsigned char gq_smem[];
+    QuadWork* W = reinterpret_cast<QuadWork*>(gq_smem) + (threadIdx.x >> 2);
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned mask = 0xFu << (lane & ~3u);
+    const int b = blockIdx.x * GQ_WARPS + warp;  // butterfly 0..63
+    const uint64_t vec = (uint64_t)blockIdx.y * 8 + (lane >> 2);
+    if (vec >= nvec) return;
+    const int j = b & (half - 1);
+    const int i0 = ((b - j) << 1) + j;
+    const int step = 64 / half;  // twiddle exponent of w128 per unit of j
+    G1* P0 = data + vec * 128 + i0;
+    G1* P1 = P0 + half;
+    if (mode == GS_FORWARD_FIRST) {
+        const G1* r = P0;
+        if (j != 0) {
+            g1_mul_twiddle_quad(W, P0, j * step);
+            r = &W->acc;
+        }
+        quad_copy_g1(P1, r);
+        return;
+    }
+    if (mode == GS_INVERSE) {
+        const G1* v = P1;
+        if (j != 0) {
+            g1_mul_twiddle_quad(W, P1, (128 - j * step) & 127);
+            v = &W->acc;
+        }
+        if (half != 64) {
+            g1_add_quad_q(&W->t, P0, &v->x, v, true, &W->sc);  // u - v'
+            g1_add_quad(P0, P0, v, &W->sc);                    // u + v'
+            quad_copy_g1(P1, &W->t);
+        } else {
+            g1_add_quad(P0, P0, v, &W->sc);
+        }
+        return;
+    }
+    g1_add_quad_q(&W->t, P0, &P1->x, P1, true, &W->sc);  // u - v
+    g1_add_quad(P0, P0, P1, &W->sc);                     // u + v
+    const G1* r = &W->t;
+    if (j != 0) {
+        g1_mul_twiddle_quad(W, &W->t, j * step);
+        r = &W->acc;
+    }
+    __syncwarp(mask);
+    quad_copy_g1(P1, r);
+}
+
+// in place: [inverse DIT on bit-reversed input, lower half kept] -> forward DIF with upper half = infinity
+int g1_fft128_run(Launch& L, G1* data, uint64_t nvec, bool with_inverse) {
+    static const cudaError_t attr = cudaFuncSetAttribute(g1_fft_stage_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GQ_SMEM);
+    KZG_CUDA_TRY(attr);
+    dim3 grid(64 / GQ_WARPS, (unsigned)((nvec + 7) / 8));
+    if (with_inverse) {
+        for (int half = 1; half <= 64; half <<= 1) {
+            g1_fft_stage_quad_kernel<<<grid, 32 * GQ_WARPS, GQ_SMEM, L.stream>>>(data, nvec, half, GS_INVERSE);
+            KZG_CUDA_TRY(cudaGetLastError());
+        }
+    }
+    g1_fft_stage_quad_kernel<<<grid, 32 * GQ_WARPS, GQ_SMEM, L.stream>>>(data, nvec, 64, GS_FORWARD_FIRST);
+    KZG_CUDA_TRY(cudaGetLastError());
+    for (int half = 32; half >= 1; half >>= 1) {
+        g1_fft_stage_quad_kernel<<<grid, 32 * GQ_WARPS, GQ_SMEM, L.stream>>>(data, nvec, half, GS_FORWARD);
+        KZG_CUDA_TRY(cudaGetLastError());
+    }
+    return RET_OK;
+}
+
+}  // namespace kzg

@@ -118,4 +118,158 @@ static __device__ __noinline__ void g1_add_quad(G1* out, const G1* p, const G1* 
     __syncwarp(mask);
 }
 
+// ---- general form: q given as (x = *qx, y = +-q->y, zz, zzz of *q) -----------------------------------
+// *out = *p + Q with Q = (*qx, negq ? -q->y : q->y, q->zz, q->zzz): lets a caller add -T or the
+// endomorphism image (beta x, y) of a table entry T without first building it in memory.
+static __device__ __noinline__ void g1_add_mem_q(G1* out, const G1* p, const Fp* qx, const G1* q, bool negq) {
+    G1 a, b;
+    a.x = quad_ld(&p->x); a.y = quad_ld(&p->y); a.zz = quad_ld(&p->zz); a.zzz = quad_ld(&p->zzz);
+    b.x = quad_ld(qx); b.y = quad_ld(&q->y); b.zz = quad_ld(&q->zz); b.zzz = quad_ld(&q->zzz);
+    if (negq) b.y = neg(b.y);
+    g1_add_to(a, b);
+    quad_st(&out->x, a.x); quad_st(&out->y, a.y); quad_st(&out->zz, a.zz); quad_st(&out->zzz, a.zzz);
+}
+
+static __device__ __noinline__ void g1_add_quad_q(G1* out, const G1* p, const Fp* qx, const G1* q, bool negq, QuadScratch* sc) {
+    const unsigned lane = threadIdx.x & 31u, ql = lane & 3u;
+    const unsigned mask = 0xFu << (lane & ~3u);
+    const Fp pzz = quad_ld(&p->zz), qzz = quad_ld(&q->zz);
+    const bool pinf = is_zero(pzz), qinf = is_zero(qzz);
+    if (pinf || qinf) {
+        __syncwarp(mask);
+        if (ql == 0) {
+            if (pinf) {
+                Fp a = quad_ld(qx), b = quad_ld(&q->y), c = quad_ld(&q->zz), d = quad_ld(&q->zzz);
+                if (negq) b = neg(b);
+                quad_st(&out->x, a); quad_st(&out->y, b); quad_st(&out->zz, c); quad_st(&out->zzz, d);
+            } else if (out != p) {
+                Fp a = quad_ld(&p->x), b = quad_ld(&p->y), c = quad_ld(&p->zz), d = quad_ld(&p->zzz);
+                quad_st(&out->x, a); quad_st(&out->y, b); quad_st(&out->zz, c); quad_st(&out->zzz, d);
+            }
+        }
+        __syncwarp(mask);
+        return;
+    }
+    // level 1: U1 = X1 ZZ2, U2 = X2 ZZ1, S1 = Y1 ZZZ2, S2 = Y2 ZZZ1
+    {
+        const Fp* ap = ql == 0 ? &p->x : ql == 1 ? qx : ql == 2 ? &p->y : &q->y;
+        const Fp* bp = ql == 0 ? &q->zz : ql == 1 ? &p->zz : ql == 2 ? &q->zzz : &p->zzz;
+        Fp a = quad_ld(ap);
+        if (ql == 3 && negq) a = neg(a);
+        quad_st(&sc->v[ql], mul(a, quad_ld(bp)));
+    }
+    __syncwarp(mask);
+    const Fp Pd = sub(quad_ld(&sc->v[1]), quad_ld(&sc->v[0])), Rd = sub(quad_ld(&sc->v[3]), quad_ld(&sc->v[2]));
+    if (is_zero(Pd)) {  // same x: doubling or cancellation -- rare, one lane does the complete addition
+        __syncwarp(mask);
+        if (ql == 0) g1_add_mem_q(out, p, qx, q, negq);
+        __syncwarp(mask);
+        return;
+    }
+    // level 2: PP = P^2, ZZ1 ZZ2, RR = R^2, ZZZ1 ZZZ2
+    {
+        const Fp* ap = (ql == 1) ? &p->zz : &p->zzz;
+        const Fp* bp = (ql == 1) ? &q->zz : &q->zzz;
+        const Fp la = quad_ld(ap), lb = quad_ld(bp);
+        const Fp d = quad_sel(ql == 0, Pd, Rd);
+        const bool even = (ql & 1u) == 0;
+        quad_st(&sc->v[4 + ql], mul(quad_sel(even, d, la), quad_sel(even, d, lb)));
+    }
+    __syncwarp(mask);  // from here on the inputs are dead: `out` may be written even if it aliases them
+    // level 3: PPP = P PP, Q = U1 PP, ZZ3 = (ZZ1 ZZ2) PP
+    {
+        const Fp a = quad_sel(ql == 1, quad_ld(&sc->v[0]), quad_sel(ql == 2, quad_ld(&sc->v[5]), Pd));
+        const Fp r3 = mul(a, quad_ld(&sc->v[4]));
+        if (ql == 0) quad_st(&sc->v[8], r3);
+        if (ql == 1) quad_st(&sc->v[9], r3);
+        if (ql == 2) quad_st(&out->zz, r3);
+    }
+    __syncwarp(mask);
+    // level 4: X3 = RR - PPP - 2Q;  R (Q - X3),  S1 PPP,  ZZZ3 = (ZZZ1 ZZZ2) PPP
+    const Fp PPP = quad_ld(&sc->v[8]), Qv = quad_ld(&sc->v[9]);
+    const Fp X3 = sub(sub(quad_ld(&sc->v[6]), PPP), dbl(Qv));
+    Fp r4;
+    {
+        const Fp a = quad_sel(ql == 1, quad_ld(&sc->v[2]), quad_sel(ql == 2, quad_ld(&sc->v[7]), Rd));
+        const Fp b = quad_sel(ql == 0 || ql == 3, sub(Qv, X3), PPP);
+        r4 = mul(a, b);
+        if (ql == 1) quad_st(&sc->v[10], r4);
+        if (ql == 2) quad_st(&out->zzz, r4);
+        if (ql == 0) quad_st(&out->x, X3);
+    }
+    __syncwarp(mask);
+    if (ql == 0) quad_st(&out->y, sub(r4, quad_ld(&sc->v[10])));
+    __syncwarp(mask);
+}
+
+// *out = 2 * *p on the four lanes of a quad (dbl-2008-s-1 has depth three: {V = (2Y)^2, X^2} ->
+// {W = 2Y V, S = X V, ZZ3 = V ZZ, M^2} -> {M (S - X3), W Y, ZZZ3 = W ZZZ}); `out` may alias `p`.
+static __device__ __noinline__ void g1_dbl_quad(G1* out, const G1* p, QuadScratch* sc) {
+    const unsigned lane = threadIdx.x & 31u, ql = lane & 3u;
+    const unsigned mask = 0xFu << (lane & ~3u);
+    const Fp pzz = quad_ld(&p->zz);
+    if (is_zero(pzz)) {  // infinity stays infinity
+        __syncwarp(mask);
+        if (ql == 0 && out != p) {
+            const Fp z = Fp::zero();
+            quad_st(&out->x, z); quad_st(&out->y, z); quad_st(&out->zz, z); quad_st(&out->zzz, z);
+        }
+        __syncwarp(mask);
+        return;
+    }
+    const Fp x = quad_ld(&p->x), y = quad_ld(&p->y);
+    const Fp U = dbl(y);
+    // level 1 (two distinct products; lanes 2, 3 repeat them)
+    {
+        const Fp a = quad_sel((ql & 1u) == 0, U, x);
+        const Fp r1 = mul(a, a);
+        if (ql < 2) quad_st(&sc->v[ql], r1);  // v[0] = V, v[1] = X^2
+    }
+    __syncwarp(mask);
+    const Fp V = quad_ld(&sc->v[0]);
+    Fp M = quad_ld(&sc->v[1]);
+    M = add(dbl(M), M);
+    // level 2
+    Fp r2;
+    {
+        const Fp a = quad_sel(ql == 0, U, quad_sel(ql == 1, x, quad_sel(ql == 2, pzz, M)));
+        const Fp b = quad_sel(ql == 3, M, V);
+        r2 = mul(a, b);
+        if (ql == 0) quad_st(&sc->v[2], r2);  // W
+        if (ql == 1) quad_st(&sc->v[3], r2);  // S
+        if (ql == 3) quad_st(&sc->v[4], r2);  // M^2
+    }
+    const Fp pzzz = quad_ld(&p->zzz);
+    __syncwarp(mask);
+    // level 3
+    const Fp W = quad_ld(&sc->v[2]), S = quad_ld(&sc->v[3]);
+    const Fp X3 = sub(quad_ld(&sc->v[4]), dbl(S));
+    Fp r3;
+    {
+        const Fp a = quad_sel(ql == 0, M, W);
+        const Fp b = quad_sel(ql == 0, sub(S, X3), quad_sel(ql == 1, y, pzzz));
+        r3 = mul(a, b);
+        if (ql == 1) quad_st(&sc->v[5], r3);  // W Y
+    }
+    __syncwarp(mask);  // every lane has read what it needs of *p
+    if (ql == 2) {
+        quad_st(&out->zz, r2);
+        quad_st(&out->zzz, r3);
+    }
+    if (ql == 0) {
+        quad_st(&out->x, X3);
+        quad_st(&out->y, sub(r3, quad_ld(&sc->v[5])));
+    }
+    __syncwarp(mask);
+}
+
+// *dst = *src, the twelve 16-byte words spread over the quad; callers synchronise
+__device__ __forceinline__ void quad_copy_g1(G1* dst, const G1* src) {
+    const unsigned ql = threadIdx.x & 3u;
+    const uint4* s = reinterpret_cast<const uint4*>(src);
+    uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int i = 0; i < 3; i++) d[ql * 3 + i] = s[ql * 3 + i];
+}
+
 }  // namespace kzg
