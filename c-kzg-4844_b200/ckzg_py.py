@@ -342,3 +342,15 @@ def verify_cell_kzg_proof_batch_ptr(commitments_ptr, cell_indices, cells_ptr, pr
         "ckzg_b200_verify_cell_kzg_proof_batch",
     )
     return bool(ok.value)
+
+
+def coalesce_stats(ts):
+    """{op: (requests, batches, largest batch)} of the call-coalescing front end (ckzg_b200_coalesce_stats)."""
+    out = (C.c_uint64 * 15)()
+    _raise(lib().ckzg_b200_coalesce_stats(ts.engine, out), "ckzg_b200_coalesce_stats")
+    names = ("blob_to_kzg_commitment", "compute_blob_kzg_proof", "compute_kzg_proof", "compute_cells_and_kzg_proofs", "recover_cells_and_kzg_proofs")
+    return {n: (int(out[3 * i]), int(out[3 * i + 1]), int(out[3 * i + 2])) for i, n in enumerate(names)}
+
+
+def coalesce_enable(ts, on=True):
+    _raise(lib().ckzg_b200_coalesce_enable(ts.engine, C.c_int(1 if on else 0)), "ckzg_b200_coalesce_enable")

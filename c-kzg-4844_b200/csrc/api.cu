@@ -62,6 +62,7 @@ static int ctx_build(Ctx* c, const uint8_t* g1_mono, const uint8_t* g1_lag, cons
 
 static void ctx_free(Ctx* c) {
     if (!c) return;
+    coalescer_destroy(c);
     int prev = -1;
     cudaGetDevice(&prev);
     cudaSetDevice(c->device);
@@ -131,6 +132,7 @@ int ckzg_b200_ctx_create(ckzg_b200_ctx** out, const uint8_t* g1_monomial_bytes, 
         ctx_free(c);
         return rc;
     }
+    coalescer_create(c);
     *out = reinterpret_cast<ckzg_b200_ctx*>(c);
     return RET_OK;
 }

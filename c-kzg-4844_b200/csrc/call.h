@@ -118,6 +118,10 @@ struct Call {
     } while (0)
 
 
+// call-coalescing front end of the per-blob entry points (coalesce.cu)
+void coalescer_create(Ctx* c);
+void coalescer_destroy(Ctx* c);
+
 // n x 4096 scalars (wire blobs or plain limbs) -> n compressed commitments (api.cu)
 int commit_scalars_batch(Call& call, uint8_t* out_dev48, const uint8_t* d_scalars, bool big_endian, uint64_t n, int* d_bad);
 

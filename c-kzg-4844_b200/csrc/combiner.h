@@ -1,0 +1,84 @@
+// Call-coalescing front end for the per-blob API: concurrent callers of
+// blob_to_kzg_commitment / compute_*_proof / compute_cells_and_kzg_proofs / recover_cells_and_kzg_proofs
+// (the reference is re-entrant and its consumers call it from many threads: bindings/go/main_test.go:957-970,
+// bindings/rust/src/bindings/mod.rs:912) are merged into ONE batched engine call.
+//
+// Group commit, no timers: a caller that finds no batch running becomes the leader and runs at once --
+// a lone caller pays nothing; callers that arrive while a batch is running queue up and are taken
+// together, in arrival order, by the next leader.  Up to `max_inflight` batches run concurrently so
+// that one batch's upload overlaps another's kernels.
+//
+// Pure host C++ (no CUDA): tests/hostcheck compiles it with g++ against a mock executor.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <vector>
+
+namespace kzg {
+
+struct CoReq {
+    const void* in[3] = {nullptr, nullptr, nullptr};
+    void* out[2] = {nullptr, nullptr};
+    uint64_t aux = 0;  // compatibility class: only requests with equal aux share a batch
+    int rc = 0;
+    bool done = false;
+};
+
+struct CombinerStats {
+    uint64_t requests = 0, batches = 0, largest = 0;
+};
+
+class Combiner {
+public:
+    explicit Combiner(size_t max_batch, int max_inflight = 2) : max_batch_(max_batch ? max_batch : 1), max_inflight_(max_inflight < 1 ? 1 : max_inflight) {}
+
+    // Runs `r` through `run(std::vector<CoReq*>&)`, which must set rc of every request it is given.
+    // Returns r.rc.  Blocks until r has been served (by this thread as a leader or by another one).
+    template <class Run>
+    int submit(CoReq& r, Run&& run) {
+        std::unique_lock<std::mutex> lk(mu_);
+        q_.push_back(&r);
+        stats_.requests++;
+        for (;;) {
+            while (!r.done && (inflight_ >= max_inflight_ || q_.empty())) cv_.wait(lk);
+            if (r.done) return r.rc;
+            // lead one batch: the longest prefix of the queue that shares the head's class
+            std::vector<CoReq*> batch;
+            const uint64_t cls = q_.front()->aux;
+            while (!q_.empty() && batch.size() < max_batch_ && q_.front()->aux == cls) {
+                batch.push_back(q_.front());
+                q_.pop_front();
+            }
+            inflight_++;
+            stats_.batches++;
+            if (batch.size() > stats_.largest) stats_.largest = batch.size();
+            lk.unlock();
+            run(batch);
+            lk.lock();
+            inflight_--;
+            for (CoReq* b : batch) b->done = true;
+            cv_.notify_all();
+            if (r.done) return r.rc;
+            // r was not in that batch (it sat behind max_batch others or another class): lead again / wait
+        }
+    }
+    CombinerStats stats() {
+        std::lock_guard<std::mutex> g(mu_);
+        return stats_;
+    }
+
+private:
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<CoReq*> q_;
+    size_t max_batch_;
+    int max_inflight_;
+    int inflight_ = 0;
+    CombinerStats stats_;
+};
+
+}  // namespace kzg

@@ -77,6 +77,7 @@ struct Ctx {
     G1* g_levels = nullptr;               // [18] table levels of -G1 generator (vmsm.cu)
     G1* mono_levels = nullptr;            // [18][64] table levels of -[tau^j]G1, j < 64 (verify_cells.cu)
     uint64_t precompute = 0;
+    void* coalescer = nullptr;            // call-coalescing front end (coalesce.cu)
 
     // Small pool of pinned host buffers for the device->host hops inside a call (a pageable destination
     // makes cudaMemcpyAsync stage through the driver and block).  Buffers are reused across calls and

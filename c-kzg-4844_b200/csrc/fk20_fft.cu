@@ -24,30 +24,32 @@
 
 namespace kzg {
 
-struct QuadWork {
-    G1 tab[8];  // (2i+1) P
-    Fp bx[8];   // beta * tab[i].x
+struct QuadWork {  // shared memory, per quad
     G1 acc;
     G1 t;
     QuadScratch sc;
+};
+struct QuadTab {  // global scratch (L2), per quad: read once per addition, so its latency hardly shows,
+    G1 tab[8];    // (2i+1) P                    and leaving it out of shared memory lets a whole 256-blob
+    Fp bx[8];     // beta * tab[i].x             stage be resident at once (7 CTAs per SM instead of 2)
 };
 constexpr int GQ_WARPS = 4;
 constexpr int GQ_QUADS = GQ_WARPS * 8;
 constexpr size_t GQ_SMEM = GQ_QUADS * sizeof(QuadWork);
 
 // W->acc = [w128^e] *src   (e != 0; src may be W->t)
-static __device__ __noinline__ void g1_mul_twiddle_quad(QuadWork* W, const G1* src, int e) {
+static __device__ __noinline__ void g1_mul_twiddle_quad(QuadWork* W, QuadTab* T, const G1* src, int e) {
     const unsigned lane = threadIdx.x & 31u, ql = lane & 3u;
     const unsigned mask = 0xFu << (lane & ~3u);
-    quad_copy_g1(&W->tab[0], src);
+    quad_copy_g1(&T->tab[0], src);
     __syncwarp(mask);
-    g1_dbl_quad(&W->t, &W->tab[0], &W->sc);
+    g1_dbl_quad(&W->t, &T->tab[0], &W->sc);
 #pragma unroll 1
-    for (int i = 1; i < 8; i++) g1_add_quad(&W->tab[i], &W->tab[i - 1], &W->t, &W->sc);
+    for (int i = 1; i < 8; i++) g1_add_quad(&T->tab[i], &T->tab[i - 1], &W->t, &W->sc);
     {
         const Fp beta = Fp::from_limbs(FP_BETA_A);
 #pragma unroll 1
-        for (int i = (int)ql; i < 8; i += 4) quad_st(&W->bx[i], mul(quad_ld(&W->tab[i].x), beta));
+        for (int i = (int)ql; i < 8; i += 4) quad_st(&T->bx[i], mul(quad_ld(&T->tab[i].x), beta));
         if (ql == 0) {
             const Fp z = Fp::zero();
             quad_st(&W->acc.x, z); quad_st(&W->acc.y, z); quad_st(&W->acc.zz, z); quad_st(&W->acc.zzz, z);
@@ -61,12 +63,12 @@ static __device__ __noinline__ void g1_mul_twiddle_quad(QuadWork* W, const G1* s
         g1_dbl_quad(&W->acc, &W->acc, &W->sc);
         const int a = d1[i], b = d2[i];
         if (a != 0) {
-            const G1* t = &W->tab[((a < 0 ? -a : a) - 1) >> 1];
+            const G1* t = &T->tab[((a < 0 ? -a : a) - 1) >> 1];
             g1_add_quad_q(&W->acc, &W->acc, &t->x, t, a < 0, &W->sc);
         }
         if (b != 0) {  // base -phi(P): (beta x, -y)
             const int idx = ((b < 0 ? -b : b) - 1) >> 1;
-            g1_add_quad_q(&W->acc, &W->acc, &W->bx[idx], &W->tab[idx], b > 0, &W->sc);
+            g1_add_quad_q(&W->acc, &W->acc, &T->bx[idx], &T->tab[idx], b > 0, &W->sc);
         }
     }
 }
@@ -78,9 +80,10 @@ enum { GS_INVERSE = 0, GS_FORWARD_FIRST = 1, GS_FORWARD = 2 };
 //   last stage (half = 64) keeps only the lower output (FK20 discards the upper half, fk20.c:264-266).
 // mode GS_FORWARD_FIRST: input upper half is infinity: (u, [w^j] u).
 // mode GS_FORWARD (decimation in frequency, g1_fft fft.c:199): (u+v, [w^j](u-v)).
-__global__ void __launch_bounds__(32 * GQ_WARPS) g1_fft_stage_quad_kernel(G1* __restrict__ data, uint64_t nvec, int half, int mode) {
+__global__ void __launch_bounds__(32 * GQ_WARPS, 4) g1_fft_stage_quad_kernel(G1* __restrict__ data, QuadTab* __restrict__ tabs, uint64_t nvec, int half, int mode) {
     extern __shared__ __align__(16) unsigned char gq_smem[];
     QuadWork* W = reinterpret_cast<QuadWork*>(gq_smem) + (threadIdx.x >> 2);
+    QuadTab* T = tabs + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * GQ_QUADS + (threadIdx.x >> 2));
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned mask = 0xFu << (lane & ~3u);
     const int b = blockIdx.x * GQ_WARPS + warp;  // butterfly 0..63
@@ -94,7 +97,7 @@ __global__ void __launch_bounds__(32 * GQ_WARPS) g1_fft_stage_quad_kernel(G1* __
     if (mode == GS_FORWARD_FIRST) {
         const G1* r = P0;
         if (j != 0) {
-            g1_mul_twiddle_quad(W, P0, j * step);
+            g1_mul_twiddle_quad(W, T, P0, j * step);
             r = &W->acc;
         }
         quad_copy_g1(P1, r);
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__(32 * GQ_WARPS) g1_fft_stage_quad_kernel(G1* __
     if (mode == GS_INVERSE) {
         const G1* v = P1;
         if (j != 0) {
-            g1_mul_twiddle_quad(W, P1, (128 - j * step) & 127);
+            g1_mul_twiddle_quad(W, T, P1, (128 - j * step) & 127);
             v = &W->acc;
         }
         if (half != 64) {
@@ -119,7 +122,7 @@ __global__ void __launch_bounds__(32 * GQ_WARPS) g1_fft_stage_quad_kernel(G1* __
     g1_add_quad(P0, P0, P1, &W->sc);                     // u + v
     const G1* r = &W->t;
     if (j != 0) {
-        g1_mul_twiddle_quad(W, &W->t, j * step);
+        g1_mul_twiddle_quad(W, T, &W->t, j * step);
         r = &W->acc;
     }
     __syncwarp(mask);
@@ -131,18 +134,21 @@ int g1_fft128_run(Launch& L, G1* data, uint64_t nvec, bool with_inverse) {
     static const cudaError_t attr = cudaFuncSetAttribute(g1_fft_stage_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GQ_SMEM);
     KZG_CUDA_TRY(attr);
     dim3 grid(64 / GQ_WARPS, (unsigned)((nvec + 7) / 8));
+    QuadTab* tabs = nullptr;
+    KZG_CUDA_TRY(cudaMallocAsync((void**)&tabs, (size_t)grid.x * grid.y * GQ_QUADS * sizeof(QuadTab), L.stream));
     if (with_inverse) {
         for (int half = 1; half <= 64; half <<= 1) {
-            g1_fft_stage_quad_kernel<<<grid, 32 * GQ_WARPS, GQ_SMEM, L.stream>>>(data, nvec, half, GS_INVERSE);
+            g1_fft_stage_quad_kernel<<<grid, 32 * GQ_WARPS, GQ_SMEM, L.stream>>>(data, tabs, nvec, half, GS_INVERSE);
             KZG_CUDA_TRY(cudaGetLastError());
         }
     }
-    g1_fft_stage_quad_kernel<<<grid, 32 * GQ_WARPS, GQ_SMEM, L.stream>>>(data, nvec, 64, GS_FORWARD_FIRST);
+    g1_fft_stage_quad_kernel<<<grid, 32 * GQ_WARPS, GQ_SMEM, L.stream>>>(data, tabs, nvec, 64, GS_FORWARD_FIRST);
     KZG_CUDA_TRY(cudaGetLastError());
     for (int half = 32; half >= 1; half >>= 1) {
-        g1_fft_stage_quad_kernel<<<grid, 32 * GQ_WARPS, GQ_SMEM, L.stream>>>(data, nvec, half, GS_FORWARD);
+        g1_fft_stage_quad_kernel<<<grid, 32 * GQ_WARPS, GQ_SMEM, L.stream>>>(data, tabs, nvec, half, GS_FORWARD);
         KZG_CUDA_TRY(cudaGetLastError());
     }
+    KZG_CUDA_TRY(cudaFreeAsync(tabs, L.stream));
     return RET_OK;
 }
 

@@ -110,7 +110,7 @@ out:
 C_KZG_RET blob_to_kzg_commitment(KZGCommitment *out, const Blob *blob, const KZGSettings *s) {
     ckzg_b200_ctx *e = engine_of(s);
     if (e == NULL) return C_KZG_BADARGS;
-    return (C_KZG_RET)ckzg_b200_blob_to_kzg_commitment_batch(e, out->bytes, blob->bytes, 1, CKZG_B200_HOST, NULL);
+    return (C_KZG_RET)ckzg_b200_blob_to_kzg_commitment_coalesced(e, out->bytes, blob->bytes);
 }
 
 C_KZG_RET compute_kzg_proof(
@@ -118,9 +118,7 @@ C_KZG_RET compute_kzg_proof(
 ) {
     ckzg_b200_ctx *e = engine_of(s);
     if (e == NULL) return C_KZG_BADARGS;
-    return (C_KZG_RET)ckzg_b200_compute_kzg_proof_batch(
-        e, proof_out->bytes, y_out->bytes, blob->bytes, z_bytes->bytes, 1, CKZG_B200_HOST, NULL
-    );
+    return (C_KZG_RET)ckzg_b200_compute_kzg_proof_coalesced(e, proof_out->bytes, y_out->bytes, blob->bytes, z_bytes->bytes);
 }
 
 C_KZG_RET compute_blob_kzg_proof(
@@ -128,9 +126,7 @@ C_KZG_RET compute_blob_kzg_proof(
 ) {
     ckzg_b200_ctx *e = engine_of(s);
     if (e == NULL) return C_KZG_BADARGS;
-    return (C_KZG_RET)ckzg_b200_compute_blob_kzg_proof_batch(
-        e, out->bytes, blob->bytes, commitment_bytes->bytes, 1, CKZG_B200_HOST, NULL
-    );
+    return (C_KZG_RET)ckzg_b200_compute_blob_kzg_proof_coalesced(e, out->bytes, blob->bytes, commitment_bytes->bytes);
 }
 
 C_KZG_RET verify_kzg_proof(
@@ -189,9 +185,7 @@ C_KZG_RET compute_cells_and_kzg_proofs(Cell *cells, KZGProof *proofs, const Blob
     if (cells == NULL && proofs == NULL) return C_KZG_BADARGS; /* eip7594.c:72-74 */
     ckzg_b200_ctx *e = engine_of(s);
     if (e == NULL) return C_KZG_BADARGS;
-    return (C_KZG_RET)ckzg_b200_compute_cells_and_kzg_proofs_batch(
-        e, (uint8_t *)cells, (uint8_t *)proofs, blob->bytes, 1, CKZG_B200_HOST, NULL
-    );
+    return (C_KZG_RET)ckzg_b200_compute_cells_and_kzg_proofs_coalesced(e, (uint8_t *)cells, (uint8_t *)proofs, blob->bytes);
 }
 
 C_KZG_RET recover_cells_and_kzg_proofs(
@@ -210,9 +204,8 @@ C_KZG_RET recover_cells_and_kzg_proofs(
     }
     ckzg_b200_ctx *e = engine_of(s);
     if (e == NULL) return C_KZG_BADARGS;
-    return (C_KZG_RET)ckzg_b200_recover_cells_and_kzg_proofs_batch(
-        e, (uint8_t *)recovered_cells, (uint8_t *)recovered_proofs, cell_indices, (const uint8_t *)cells, num_cells, 1,
-        CKZG_B200_HOST, NULL
+    return (C_KZG_RET)ckzg_b200_recover_cells_and_kzg_proofs_coalesced(
+        e, (uint8_t *)recovered_cells, (uint8_t *)recovered_proofs, cell_indices, (const uint8_t *)cells, num_cells
     );
 }
 

@@ -126,6 +126,26 @@ int ckzg_b200_verify_cell_kzg_proof_batch(
     const uint8_t *proofs, uint64_t num_cells, int mem
 );
 
+/*
+ * Per-blob entry points with call coalescing: what the frozen per-blob API
+ * (blob_to_kzg_commitment src/eip4844/eip4844.c:264, compute_kzg_proof :382, compute_blob_kzg_proof :506,
+ * compute_cells_and_kzg_proofs src/eip7594/eip7594.c:61, recover_cells_and_kzg_proofs :177) calls.  Host
+ * pointers, synchronous, re-entrant: callers that arrive while a batch is running are merged into the next
+ * batched engine call; a lone caller runs at once.  Results and return codes per caller are those of the
+ * corresponding n = 1 call.
+ */
+int ckzg_b200_blob_to_kzg_commitment_coalesced(ckzg_b200_ctx *ctx, uint8_t *out48, const uint8_t *blob);
+int ckzg_b200_compute_blob_kzg_proof_coalesced(ckzg_b200_ctx *ctx, uint8_t *proof48, const uint8_t *blob, const uint8_t *commitment48);
+int ckzg_b200_compute_kzg_proof_coalesced(ckzg_b200_ctx *ctx, uint8_t *proof48, uint8_t *y32, const uint8_t *blob, const uint8_t *z32);
+int ckzg_b200_compute_cells_and_kzg_proofs_coalesced(ckzg_b200_ctx *ctx, uint8_t *cells, uint8_t *proofs, const uint8_t *blob);
+int ckzg_b200_recover_cells_and_kzg_proofs_coalesced(
+    ckzg_b200_ctx *ctx, uint8_t *recovered_cells, uint8_t *recovered_proofs, const uint64_t *cell_indices, const uint8_t *cells, uint64_t num_cells
+);
+/* {requests, batches, largest batch} x {commitment, blob proof, kzg proof, cells, recover} since context creation */
+int ckzg_b200_coalesce_stats(ckzg_b200_ctx *ctx, uint64_t out15[15]);
+/* on = 0: every call runs alone; default on (environment CKZG_B200_COALESCE=0 disables at context creation) */
+int ckzg_b200_coalesce_enable(ckzg_b200_ctx *ctx, int on);
+
 /* Internal Fiat-Shamir challenge, exposed for the vectors in tests/compute_challenge
  * (src/eip4844/eip4844.c:147; commitment given in its canonical 48-byte form). out = 32 bytes BE.
  * ctx may be NULL (the hash needs no setup; the current CUDA device is used). */

@@ -173,3 +173,62 @@ def test_concurrent_callers_share_one_settings(env):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_coalesced_per_blob_api_matches_batched_results(env):
+    """concurrent callers of the frozen per-blob API are merged into batched engine calls.  Every
+    caller must get exactly the bytes (and the return code) its own n = 1 call would have produced."""
+    import threading
+
+    import torch
+
+    mod, ts, n, host, dev, cms, prs = env
+    m = 24
+    hb, hc, hp = host.numpy().tobytes(), cms.cpu().numpy().tobytes(), prs.cpu().numpy().tobytes()
+    cells = torch.empty(m * 262144, dtype=torch.uint8, device="cuda")
+    cprf = torch.empty(m * 128 * 48, dtype=torch.uint8, device="cuda")
+    mod.compute_cells_and_kzg_proofs_device(cells.data_ptr(), cprf.data_ptr(), dev.data_ptr(), m, ts)
+    want_cells, want_cprf = cells.cpu().numpy().tobytes(), cprf.cpu().numpy().tobytes()
+    R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+    bad_blob = R.to_bytes(32, "big") + hb[32:131072]
+    before = mod.coalesce_stats(ts)
+    errors = []
+
+    def worker(i):
+        try:
+            blob = hb[131072 * i : 131072 * (i + 1)]
+            cm, pf = hc[48 * i : 48 * i + 48], hp[48 * i : 48 * i + 48]
+            for _ in range(2):
+                assert mod.blob_to_kzg_commitment(blob, ts) == cm
+                assert mod.compute_blob_kzg_proof(blob, cm, ts) == pf
+                c, p = mod.compute_cells_and_kzg_proofs(blob, ts)
+                assert b"".join(c) == want_cells[262144 * i : 262144 * (i + 1)]
+                assert b"".join(p) == want_cprf[6144 * i : 6144 * (i + 1)]
+                idx = list(range(i % 2, 128, 2)) if i % 3 else list(range(60, 128))
+                rc, rp = mod.recover_cells_and_kzg_proofs(idx, [c[k] for k in idx], ts)
+                assert rc == c and rp == p
+                if i % 5 == 0:  # an invalid blob inside a batch fails alone
+                    with pytest.raises(Exception):
+                        mod.blob_to_kzg_commitment(bad_blob, ts)
+                    with pytest.raises(Exception):
+                        mod.compute_cells_and_kzg_proofs(bad_blob, ts)
+        except Exception as e:  # noqa: BLE001
+            errors.append((i, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(m)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
+    after = mod.coalesce_stats(ts)
+    merged = {k: (after[k][0] - before[k][0], after[k][1] - before[k][1], after[k][2]) for k in after}
+    # 24 concurrent callers: far fewer engine calls than requests for the long-running operations
+    assert merged["compute_cells_and_kzg_proofs"][0] >= 2 * m and merged["compute_cells_and_kzg_proofs"][1] < merged["compute_cells_and_kzg_proofs"][0]
+    assert merged["compute_cells_and_kzg_proofs"][2] > 1
+    # switched off, the same calls still work (every call alone)
+    mod.coalesce_enable(ts, False)
+    try:
+        assert mod.blob_to_kzg_commitment(hb[:131072], ts) == hc[:48]
+    finally:
+        mod.coalesce_enable(ts, True)
