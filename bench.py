@@ -501,22 +501,15 @@ def run_b200(args):
             extra["verify_cell_%dx128_kernels_ms" % nb] = {k: round(v[0] / 3, 3) for k, v in pv["kernels"].items() if k not in ("begin",)}
         # per-blob frozen API from concurrent host threads (bindings/go/main_test.go:957-970 shape), with and
         # without the call-coalescing front end
-        hb_all = host_blobs.numpy()
-        blob_bytes = [bytes(hb_all[BLOB * i : BLOB * (i + 1)].tobytes()) for i in range(64)]
-        def _per_blob_callers(fn, nthreads, reps):
-            th = [threading.Thread(target=lambda w=w: [fn(blob_bytes[(w * reps + k) % 64]) for k in range(reps)]) for w in range(nthreads)]
-            t0 = time.perf_counter()
-            for t in th:
-                t.start()
-            for t in th:
-                t.join()
-            return nthreads * reps / (time.perf_counter() - t0)
+        # (native host threads: Python threads would serialise on the interpreter lock around each call)
+        blob_bytes = [bytes(host_blobs[:BLOB].numpy().tobytes())]
         for on in (True, False):
             mod.coalesce_enable(ts, on)
             tag = "coalesced" if on else "uncoalesced"
-            _per_blob_callers(lambda b: mod.compute_cells_and_kzg_proofs(b, ts), 8, 1)
-            extra["compute_cells_and_kzg_proofs_per_blob_api_32_threads_%s_blobs_per_s" % tag] = _per_blob_callers(lambda b: mod.compute_cells_and_kzg_proofs(b, ts), 32, 4)
-            extra["blob_to_kzg_commitment_per_blob_api_32_threads_%s_blobs_per_s" % tag] = _per_blob_callers(lambda b: mod.blob_to_kzg_commitment(b, ts), 32, 8)
+            mod.bench_per_blob_callers(ts, 1, 8, 1, host_blobs.data_ptr(), 64)
+            for nthreads in (8, 64):
+                extra["compute_cells_and_kzg_proofs_per_blob_api_%d_threads_%s_blobs_per_s" % (nthreads, tag)] = mod.bench_per_blob_callers(ts, 1, nthreads, 6, host_blobs.data_ptr(), 64)
+                extra["blob_to_kzg_commitment_per_blob_api_%d_threads_%s_blobs_per_s" % (nthreads, tag)] = mod.bench_per_blob_callers(ts, 0, nthreads, 24, host_blobs.data_ptr(), 64)
         mod.coalesce_enable(ts, True)
         extra["coalesce_stats(requests,batches,largest)"] = mod.coalesce_stats(ts)
         t0 = time.perf_counter()

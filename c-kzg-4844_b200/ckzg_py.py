@@ -354,3 +354,10 @@ def coalesce_stats(ts):
 
 def coalesce_enable(ts, on=True):
     _raise(lib().ckzg_b200_coalesce_enable(ts.engine, C.c_int(1 if on else 0)), "ckzg_b200_coalesce_enable")
+
+
+def bench_per_blob_callers(ts, op, threads, reps, blobs_ptr, n_blobs):
+    """blobs/s of `threads` native host threads calling the per-blob API (0 = commitment, 1 = cells + proofs)."""
+    sec = C.c_double(0)
+    _raise(lib().ckzg_b200_bench_per_blob_callers(ts.engine, C.c_int(op), C.c_int(threads), C.c_int(reps), C.c_void_p(blobs_ptr), C.c_uint64(n_blobs), C.byref(sec)), "ckzg_b200_bench_per_blob_callers")
+    return threads * reps / sec.value

@@ -9,14 +9,23 @@ constexpr int CELL_FR = 64;           // FIELD_ELEMENTS_PER_CELL (cell.h:28)
 constexpr int CELL_BYTES = 2048;      // BYTES_PER_CELL
 constexpr int FK_POINTS = CELLS_EXT * CELL_FR;  // 8192 fixed bases X^[j][i] (x_ext_fft_columns, setup.c:272-289)
 
-// Fixed-base tables for the 128 x MSM(64) of FK20: T[p][w][m] = (m+1) * 2^(8w) * X^_p, affine,
-// p = j*64 + i, w < 32 windows of 8 signed bits, m < 128.  3.2 GB of HBM buys a pure
-// gather-and-add MSM: 2048 mixed additions, no buckets, no doublings (the role the reference gives
-// to `precompute`, setup.c:291-323 / README.md:110-143 -- 96 MiB at precompute=8).
-constexpr int FK_C = 8;
-constexpr int FK_W = 32;
-constexpr int FK_M = 1 << (FK_C - 1);  // 128 multiples per window
-constexpr size_t FK_TABLE_POINTS = (size_t)FK_POINTS * FK_W * FK_M;
+// Fixed-base tables for the 128 x MSM(64) of FK20: T[p][w][m] = (m+1) * 2^(c w) * X^_p, affine,
+// p = j*64 + i, w < ceil(256 / c) windows of c signed bits, m < 2^(c-1).  HBM buys a pure gather-and-add
+// MSM: 64 * ceil(256 / c) mixed additions, no buckets, no doublings (the role the reference gives to
+// `precompute`, setup.c:291-323 / README.md:110-143 -- 96 MiB at precompute=8).  The window width is
+// chosen per context from the free device memory (fk20.cu fk20_pick_window): c = 12 -> 22 windows,
+// 35 GB (1408 additions per MSM); c = 10 -> 26 windows, 10.5 GB; c = 8 -> 32 windows, 3.2 GB (2048).
+struct FkGeom {
+    int c = 8, w = 32, m = 128;
+    size_t table_points() const { return (size_t)FK_POINTS * w * m; }
+};
+inline FkGeom fk_geom(int c) {
+    FkGeom g;
+    g.c = c;
+    g.w = (256 + c - 1) / c;
+    g.m = 1 << (c - 1);
+    return g;
+}
 
 // ---- cells.cu ------------------------------------------------------------------------------------
 // cells (n x 128 x 2048 B, may be null) and/or monomial coefficients (n x 4096 Fr, may be null)

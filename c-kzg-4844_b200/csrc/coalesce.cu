@@ -6,6 +6,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
+#include <thread>
 #include <vector>
 
 #include "call.h"
@@ -258,6 +260,31 @@ int ckzg_b200_coalesce_enable(ckzg_b200_ctx* ctx, int on) {
     Coalescer* co = reinterpret_cast<Coalescer*>(reinterpret_cast<Ctx*>(ctx)->coalescer);
     if (!co) return RET_ERROR;
     co->enabled = on != 0;
+    return RET_OK;
+}
+
+// Measurement hook (bench.py): `threads` native host threads call the per-blob entry point `op`
+// (0 = blob_to_kzg_commitment, 1 = compute_cells_and_kzg_proofs) `reps` times each on blobs taken from a host
+// array, exactly as concurrent users of the frozen API do; *seconds = wall time of the whole run.
+int ckzg_b200_bench_per_blob_callers(ckzg_b200_ctx* ctx, int op, int threads, int reps, const uint8_t* blobs, uint64_t n_blobs, double* seconds) {
+    if (!ctx || !blobs || !seconds || threads < 1 || reps < 1 || n_blobs == 0 || op < 0 || op > 1) return RET_BADARGS;
+    std::vector<int> rcs((size_t)threads, RET_OK);
+    std::vector<std::thread> th;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int t = 0; t < threads; t++)
+        th.emplace_back([=, &rcs] {
+            std::vector<uint8_t> cells(op == 1 ? 2 * (size_t)BLOB_BYTES : 0), proofs(op == 1 ? CELLS_EXT * 48 : 48);
+            for (int k = 0; k < reps; k++) {
+                const uint8_t* blob = blobs + (((uint64_t)t * (uint64_t)reps + (uint64_t)k) % n_blobs) * BLOB_BYTES;
+                int rc = op == 0 ? ckzg_b200_blob_to_kzg_commitment_coalesced(ctx, proofs.data(), blob)
+                                 : ckzg_b200_compute_cells_and_kzg_proofs_coalesced(ctx, cells.data(), proofs.data(), blob);
+                if (rc) rcs[(size_t)t] = rc;
+            }
+        });
+    for (auto& x : th) x.join();
+    *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    for (int rc : rcs)
+        if (rc) return rc;
     return RET_OK;
 }
 

@@ -73,7 +73,8 @@ struct Ctx {
     void* g2_points = nullptr;            // [65] affine G2 (Fp2 coordinates)
     void* rec_shiftA = nullptr;           // 7^k / 8192   (recover.cu)
     void* rec_shiftB = nullptr;           // 7^-k / 8192
-    void* fk_table = nullptr;             // FK20 fixed-base multiples, cells.h (3.2 GB)
+    void* fk_table = nullptr;             // FK20 fixed-base multiples, cells.h (3.2 - 35 GB)
+    int fk_c = 8;                         // window width of fk_table
     G1* g_levels = nullptr;               // [18] table levels of -G1 generator (vmsm.cu)
     G1* mono_levels = nullptr;            // [18][64] table levels of -[tau^j]G1, j < 64 (verify_cells.cu)
     uint64_t precompute = 0;

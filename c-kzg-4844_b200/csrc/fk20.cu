@@ -7,12 +7,14 @@
 //   blst_p1s_mult_wbits(_precompute) ...... blst/src/multi_scalar.c:133-262
 //
 // B200 design: the 8192 bases X^[j][i] are fixed, so setup stores every small multiple of every
-// window shift, T[p][w][m] = (m+1) 2^(8w) X^_p (3.2 GB of the 180 GB HBM).  An MSM(64) is then a
-// pure gather-and-add of 64 x 32 table points: one warp per MSM, two base points per lane, a
+// window shift, T[p][w][m] = (m+1) 2^(cw) X^_p (c = 12: 35 GB of the 180 GB HBM).  An MSM(64) is then a
+// pure gather-and-add of 64 x ceil(256/c) table points: one warp per MSM, two base points per lane, a
 // shared-memory tree at the end -- no buckets, no doublings, no sorting.  The G1 FFTs live in
 // fk20_fft.cu; ordering is arranged so that no permutation pass exists (MSM j stores to slot brp7(j);
 // inverse DIT gives natural order; forward DIF leaves the proofs in the bit-reversed order the API
 // returns).
+#include <stdlib.h>
+
 #include "cells.h"
 #include "g1_hot.cuh"
 
@@ -70,30 +72,31 @@ __global__ void fk_xhat_affine_kernel(G1Affine* __restrict__ xhat, const G1* __r
     G1 p = ld_g1(fft_out + e);
     xhat[brp7(q) * 64 + offset] = g1_to_affine(p);
 }
-// bases[p][w] = 2^(8w) * xhat[p], affine
-__global__ void fk_bases_kernel(G1Affine* __restrict__ bases, const G1Affine* __restrict__ xhat) {
+// bases[p][w] = 2^(cw) * xhat[p], affine
+__global__ void fk_bases_kernel(G1Affine* __restrict__ bases, const G1Affine* __restrict__ xhat, const FkGeom g) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= FK_POINTS) return;
     G1Affine a = xhat[p];
-    bases[(size_t)p * FK_W] = a;
+    bases[(size_t)p * g.w] = a;
     G1 acc = g1_from_affine(a);
 #pragma unroll 1
-    for (int w = 1; w < FK_W; w++) {
+    for (int w = 1; w < g.w; w++) {
 #pragma unroll 1
-        for (int k = 0; k < FK_C; k++) g1_dbl_to(acc);
+        for (int k = 0; k < g.c; k++) g1_dbl_to(acc);
         G1Affine q = g1_to_affine(acc);
-        bases[(size_t)p * FK_W + w] = q;
+        bases[(size_t)p * g.w + w] = q;
         acc = g1_from_affine(q);
     }
 }
-// table[(p*32 + w)*128 + m] = (m+1) * bases[p][w], affine; one thread per (p, w), batches of 16
+// table[(p*W + w)*M + m] = (m+1) * bases[p][w], affine; one thread per (p, w), batches of 16
 // converted with one inversion each (Montgomery's trick)
 constexpr int FK_BATCH = 16;
-__global__ void __launch_bounds__(64) fk_multiples_kernel(G1Affine* __restrict__ table, const G1Affine* __restrict__ bases) {
+__global__ void __launch_bounds__(64) fk_multiples_kernel(G1Affine* __restrict__ table, const G1Affine* __restrict__ bases, const FkGeom g) {
     size_t pw = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pw >= (size_t)FK_POINTS * FK_W) return;
+    if (pw >= (size_t)FK_POINTS * g.w) return;
     const G1Affine base = bases[pw];
-    G1Affine* dst = table + pw * FK_M;
+    G1Affine* dst = table + pw * g.m;
+    const int FK_M = g.m;
     G1 run = g1_from_affine(base);
     G1 pts[FK_BATCH];
     Fp pre[FK_BATCH];
@@ -126,14 +129,32 @@ __global__ void __launch_bounds__(64) fk_multiples_kernel(G1Affine* __restrict__
     }
 }
 
+// Window width of the fixed-base tables: the widest that leaves the device comfortable (several contexts
+// may live in one process), or CKZG_B200_FK_WINDOW = 8 | 10 | 12.
+static int fk20_pick_window() {
+    const char* env = getenv("CKZG_B200_FK_WINDOW");
+    if (env) {
+        int v = atoi(env);
+        if (v == 8 || v == 10 || v == 12) return v;
+    }
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return 8;
+    const size_t GB = (size_t)1 << 30;
+    if (free_b >= 100 * GB) return 12;
+    if (free_b >= 40 * GB) return 10;
+    return 8;
+}
+
 int fk20_setup(Launch& L, Ctx* c) {
-    KZG_CUDA_TRY(cudaMalloc((void**)&c->fk_table, FK_TABLE_POINTS * sizeof(G1Affine)));
+    c->fk_c = fk20_pick_window();
+    const FkGeom g = fk_geom(c->fk_c);
+    KZG_CUDA_TRY(cudaMalloc((void**)&c->fk_table, g.table_points() * sizeof(G1Affine)));
     G1 *xin = nullptr, *xout = nullptr;
     G1Affine *xhat = nullptr, *bases = nullptr;
     KZG_CUDA_TRY(cudaMallocAsync((void**)&xin, 64 * 128 * sizeof(G1), L.stream));
     KZG_CUDA_TRY(cudaMallocAsync((void**)&xout, 64 * 128 * sizeof(G1), L.stream));
     KZG_CUDA_TRY(cudaMallocAsync((void**)&xhat, FK_POINTS * sizeof(G1Affine), L.stream));
-    KZG_CUDA_TRY(cudaMallocAsync((void**)&bases, (size_t)FK_POINTS * FK_W * sizeof(G1Affine), L.stream));
+    KZG_CUDA_TRY(cudaMallocAsync((void**)&bases, (size_t)FK_POINTS * g.w * sizeof(G1Affine), L.stream));
     fk_gather_x_kernel<<<64 * 128 / 128, 128, 0, L.stream>>>(xin, c->g1_monomial);
     KZG_CUDA_TRY(cudaGetLastError());
     {
@@ -143,9 +164,9 @@ int fk20_setup(Launch& L, Ctx* c) {
     (void)xout;
     fk_xhat_affine_kernel<<<64 * 128 / 64, 64, 0, L.stream>>>(xhat, xin);
     KZG_CUDA_TRY(cudaGetLastError());
-    fk_bases_kernel<<<FK_POINTS / 64, 64, 0, L.stream>>>(bases, xhat);
+    fk_bases_kernel<<<FK_POINTS / 64, 64, 0, L.stream>>>(bases, xhat, g);
     KZG_CUDA_TRY(cudaGetLastError());
-    fk_multiples_kernel<<<(unsigned)((size_t)FK_POINTS * FK_W / 64), 64, 0, L.stream>>>((G1Affine*)c->fk_table, bases);
+    fk_multiples_kernel<<<(unsigned)(((size_t)FK_POINTS * g.w + 63) / 64), 64, 0, L.stream>>>((G1Affine*)c->fk_table, bases, g);
     KZG_CUDA_TRY(cudaGetLastError());
     KZG_CUDA_TRY(cudaFreeAsync(xin, L.stream));
     KZG_CUDA_TRY(cudaFreeAsync(xout, L.stream));
@@ -160,7 +181,8 @@ int fk20_setup(Launch& L, Ctx* c) {
 // ------------------------------------------------------------------------------------------------
 constexpr int FM_WARPS = 4;
 
-__global__ void __launch_bounds__(32 * FM_WARPS) fk20_msm_kernel(G1* __restrict__ u_brp, const uint32_t* __restrict__ S, const G1Affine* __restrict__ table, uint64_t total) {
+__global__ void __launch_bounds__(32 * FM_WARPS) fk20_msm_kernel(G1* __restrict__ u_brp, const uint32_t* __restrict__ S, const G1Affine* __restrict__ table, uint64_t total,
+                                                                 const FkGeom g) {
     __shared__ G1 sh[FM_WARPS][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t msm = (uint64_t)blockIdx.x * FM_WARPS + warp;  // = blob * 128 + j
@@ -173,17 +195,19 @@ __global__ void __launch_bounds__(32 * FM_WARPS) fk20_msm_kernel(G1* __restrict_
             const int i = lane + 32 * h;
             const uint4* sp = reinterpret_cast<const uint4*>(S + (msm * 64 + i) * 8);
             uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
-            uint32_t s[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-            const G1Affine* tp = table + ((size_t)(j * 64 + i) * FK_W) * FK_M;
+            uint32_t s[9] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w, 0u};
+            const G1Affine* tp = table + ((size_t)(j * 64 + i) * g.w) * g.m;
+            const uint32_t dmask = (1u << g.c) - 1u, dfull = 1u << g.c;
             uint32_t carry = 0;
 #pragma unroll 1
-            for (int w = 0; w < FK_W; w++) {
-                uint32_t d = ((s[w >> 2] >> ((w & 3) * 8)) & 0xffu) + carry;
-                bool negd = d > (uint32_t)FK_M;
+            for (int w = 0; w < g.w; w++) {
+                const int o = w * g.c;  // signed c-bit digit at bit o (the scalar is below 2^255: the top digit absorbs the carry)
+                uint32_t d = (__funnelshift_r(s[o >> 5], s[(o >> 5) + 1], o & 31) & dmask) + carry;
+                bool negd = d > (uint32_t)g.m;
                 carry = negd ? 1u : 0u;
-                uint32_t mag = negd ? (256u - d) : d;
+                uint32_t mag = negd ? (dfull - d) : d;
                 if (mag != 0) {
-                    G1Affine a = ld_affine(tp + (size_t)w * FK_M + (mag - 1));
+                    G1Affine a = ld_affine(tp + (size_t)w * g.m + (mag - 1));
                     g1_madd_nl(acc, a, negd);
                 }
             }
@@ -209,7 +233,7 @@ __global__ void __launch_bounds__(32 * FM_WARPS) fk20_msm_kernel(G1* __restrict_
 int launch_fk20_msm(Launch& L, G1* u_brp, const uint32_t* S, uint64_t n) {
     if (!n) return RET_OK;
     uint64_t total = n * 128;
-    fk20_msm_kernel<<<(unsigned)((total + FM_WARPS - 1) / FM_WARPS), 32 * FM_WARPS, 0, L.stream>>>(u_brp, S, (const G1Affine*)L.ctx->fk_table, total);
+    fk20_msm_kernel<<<(unsigned)((total + FM_WARPS - 1) / FM_WARPS), 32 * FM_WARPS, 0, L.stream>>>(u_brp, S, (const G1Affine*)L.ctx->fk_table, total, fk_geom(L.ctx->fk_c));
     KZG_CUDA_TRY(cudaGetLastError());
     L.count(1, "fk20_msm");
     return RET_OK;

@@ -146,6 +146,10 @@ int ckzg_b200_coalesce_stats(ckzg_b200_ctx *ctx, uint64_t out15[15]);
 /* on = 0: every call runs alone; default on (environment CKZG_B200_COALESCE=0 disables at context creation) */
 int ckzg_b200_coalesce_enable(ckzg_b200_ctx *ctx, int on);
 
+/* Measurement hook: `threads` native host threads call per-blob entry point `op` (0 = blob_to_kzg_commitment,
+ * 1 = compute_cells_and_kzg_proofs) `reps` times each on blobs from a HOST array; *seconds = wall time. */
+int ckzg_b200_bench_per_blob_callers(ckzg_b200_ctx *ctx, int op, int threads, int reps, const uint8_t *blobs, uint64_t n_blobs, double *seconds);
+
 /* Internal Fiat-Shamir challenge, exposed for the vectors in tests/compute_challenge
  * (src/eip4844/eip4844.c:147; commitment given in its canonical 48-byte form). out = 32 bytes BE.
  * ctx may be NULL (the hash needs no setup; the current CUDA device is used). */
