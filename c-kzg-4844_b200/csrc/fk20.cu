@@ -180,8 +180,9 @@ int fk20_setup(Launch& L, Ctx* c) {
 // 128 x MSM(64) per blob: one warp per MSM
 // ------------------------------------------------------------------------------------------------
 constexpr int FM_WARPS = 4;
+constexpr int FM_AHEAD = 4;  // table entries requested ahead of the addition that uses them
 
-__global__ void __launch_bounds__(32 * FM_WARPS) fk20_msm_kernel(G1* __restrict__ u_brp, const uint32_t* __restrict__ S, const G1Affine* __restrict__ table, uint64_t total,
+__global__ void __launch_bounds__(32 * FM_WARPS, 3) fk20_msm_kernel(G1* __restrict__ u_brp, const uint32_t* __restrict__ S, const G1Affine* __restrict__ table, uint64_t total,
                                                                  const FkGeom g) {
     __shared__ G1 sh[FM_WARPS][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -190,26 +191,50 @@ __global__ void __launch_bounds__(32 * FM_WARPS) fk20_msm_kernel(G1* __restrict_
     G1 acc = g1_inf();
     if (active) {
         const int j = (int)(msm & 127);
+        // digits of the lane's two scalars first (signed c-bit, the carry runs up the windows), so that the
+        // table entry of step t + FM_AHEAD can be pulled into L2 while step t is being added: the gathers are
+        // random 96-byte reads over a table of up to 35 GB
+        uint16_t dig[64];  // magnitude | sign << 15, index = half * W + window
+        const G1Affine* tp[2];
+        const uint32_t dmask = (1u << g.c) - 1u, dfull = 1u << g.c;
 #pragma unroll 1
         for (int h = 0; h < 2; h++) {
             const int i = lane + 32 * h;
             const uint4* sp = reinterpret_cast<const uint4*>(S + (msm * 64 + i) * 8);
             uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
             uint32_t s[9] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w, 0u};
-            const G1Affine* tp = table + ((size_t)(j * 64 + i) * g.w) * g.m;
-            const uint32_t dmask = (1u << g.c) - 1u, dfull = 1u << g.c;
+            tp[h] = table + ((size_t)(j * 64 + i) * g.w) * g.m;
             uint32_t carry = 0;
 #pragma unroll 1
             for (int w = 0; w < g.w; w++) {
-                const int o = w * g.c;  // signed c-bit digit at bit o (the scalar is below 2^255: the top digit absorbs the carry)
+                const int o = w * g.c;  // the scalar is below 2^255: the top digit absorbs the carry
                 uint32_t d = (__funnelshift_r(s[o >> 5], s[(o >> 5) + 1], o & 31) & dmask) + carry;
                 bool negd = d > (uint32_t)g.m;
                 carry = negd ? 1u : 0u;
                 uint32_t mag = negd ? (dfull - d) : d;
-                if (mag != 0) {
-                    G1Affine a = ld_affine(tp + (size_t)w * g.m + (mag - 1));
-                    g1_madd_nl(acc, a, negd);
-                }
+                dig[h * g.w + w] = (uint16_t)(mag | (negd ? 0x8000u : 0u));
+            }
+        }
+        const int steps = 2 * g.w;
+        auto entry = [&](int t) -> const G1Affine* {
+            const int h = t >= g.w ? 1 : 0;
+            return tp[h] + (size_t)(t - h * g.w) * g.m + ((dig[t] & 0x7fffu) - 1u);
+        };
+        auto pull = [&](int t) {
+            if (t < steps && (dig[t] & 0x7fffu) != 0) {
+                const char* e = reinterpret_cast<const char*>(entry(t));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(e));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(e + 64));
+            }
+        };
+#pragma unroll 1
+        for (int t = 0; t < FM_AHEAD; t++) pull(t);
+#pragma unroll 1
+        for (int t = 0; t < steps; t++) {
+            pull(t + FM_AHEAD);
+            if ((dig[t] & 0x7fffu) != 0) {
+                G1Affine a = ld_affine(entry(t));
+                g1_madd_nl(acc, a, (dig[t] & 0x8000u) != 0);
             }
         }
     }
