@@ -19,6 +19,41 @@ void note_cuda_error(cudaError_t e, const char* file, int line) {
     if (getenv("CKZG_B200_DEBUG")) fprintf(stderr, "[ckzg_b200] CUDA error %d (%s) at %s:%d\n", (int)e, cudaGetErrorString(e), file, line);
 }
 
+// How much HBM the fixed-base tables may take, decided once per context from the memory that is free when it
+// is created (several contexts can live in one process; each plans against what is left):
+//   FK20 table (cells.h):        c = 12 -> 35 GB | 10 -> 10.5 GB | 8 -> 3.2 GB
+//   commitment table (msm_direct.cu): c = 14 -> 61 GB | 13 -> 32 GB | 12 -> 18 GB | none (bucket MSM)
+// CKZG_B200_FK_WINDOW / CKZG_B200_COMMIT_WINDOW (0 = none) override.
+static void plan_tables(Ctx* c) {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;
+    const double gb = (double)free_b / (double)(1ull << 30);
+    if (gb >= 150) {
+        c->fk_c = 12;
+        c->commit_c = 14;
+    } else if (gb >= 110) {
+        c->fk_c = 12;
+        c->commit_c = 13;
+    } else if (gb >= 70) {
+        c->fk_c = 12;
+        c->commit_c = 0;
+    } else if (gb >= 40) {
+        c->fk_c = 10;
+        c->commit_c = 0;
+    } else {
+        c->fk_c = 8;
+        c->commit_c = 0;
+    }
+    if (const char* env = getenv("CKZG_B200_FK_WINDOW")) {
+        const int v = atoi(env);
+        if (v == 8 || v == 10 || v == 12) c->fk_c = v;
+    }
+    if (const char* env = getenv("CKZG_B200_COMMIT_WINDOW")) {
+        const int v = atoi(env);
+        if (v == 0 || (v >= 10 && v <= 14)) c->commit_c = v;
+    }
+}
+
 static int ctx_build(Ctx* c, const uint8_t* g1_mono, const uint8_t* g1_lag, const uint8_t* g2_mono) {
     Call call(c);
     if (!call.ok) return RET_ERROR;
@@ -46,7 +81,9 @@ static int ctx_build(Ctx* c, const uint8_t* g1_mono, const uint8_t* g1_lag, cons
     KZG_CUDA_TRY(cudaMalloc((void**)&c->g_levels, VMSM_LEVELS * sizeof(G1)));
     TRY(launch_vmsm_generator_levels(L, c->g_levels));
     TRY(setup_verify_cells(L, c));
+    plan_tables(c);
     TRY(fk20_setup(L, c));
+    TRY(msm_direct_setup(L, c));
     TRY(recover_setup(L, c));
 
     int bad = 0;
@@ -74,6 +111,7 @@ static void ctx_free(Ctx* c) {
     cudaFree(c->g2_lines);
     cudaFree(c->g2_points);
     cudaFree(c->fk_table);
+    cudaFree(c->commit_table);
     cudaFree(c->g_levels);
     cudaFree(c->mono_levels);
     cudaFree(c->rec_shiftA);
@@ -147,13 +185,20 @@ namespace kzg {
 int commit_scalars_batch(Call& call, uint8_t* out_dev48, const uint8_t* d_scalars, bool big_endian, uint64_t n, int* d_bad) {
     Ctx* c = call.ctx;
     Launch L = call.launch();
+    G1* d_res;
+    TRY(call.alloc(&d_res, n));
+    if (c->commit_table) {  // direct table: no sort lists, no buckets
+        uint8_t* ws;
+        TRY(call.alloc(&ws, msm_direct_workspace_bytes(n)));
+        TRY(launch_msm_direct(L, d_res, d_scalars, big_endian, n, d_bad, ws));
+        TRY(launch_g1_compress(L, out_dev48, d_res, n));
+        return RET_OK;
+    }
     const uint64_t CHUNK = 2048;
     uint64_t chunk = n < CHUNK ? n : CHUNK;
     int parts = msm_pick_parts(chunk);
     uint8_t* ws;
-    G1* d_res;
     TRY(call.alloc(&ws, msm_workspace_bytes(chunk, parts)));
-    TRY(call.alloc(&d_res, n));
     for (uint64_t off = 0; off < n; off += chunk) {
         uint64_t m = (n - off < chunk) ? n - off : chunk;
         TRY(launch_msm(L, d_res + off, d_scalars + off * BLOB_BYTES, big_endian, m, c->msm_table, d_bad ? d_bad + off : nullptr, ws, parts));

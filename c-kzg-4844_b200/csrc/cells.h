@@ -18,6 +18,7 @@ constexpr int FK_POINTS = CELLS_EXT * CELL_FR;  // 8192 fixed bases X^[j][i] (x_
 struct FkGeom {
     int c = 8, w = 32, m = 128;
     size_t table_points() const { return (size_t)FK_POINTS * w * m; }
+    size_t points_for(size_t npts) const { return npts * (size_t)w * m; }
 };
 inline FkGeom fk_geom(int c) {
     FkGeom g;
@@ -34,8 +35,10 @@ int launch_blob_to_cells(Launch& L, uint8_t* cells, Fr* mono, const uint8_t* blo
 int launch_fk20_scalars(Launch& L, uint32_t* S, const Fr* mono, uint64_t n);
 
 // ---- fk20.cu -------------------------------------------------------------------------------------
-// setup: X^ columns (init_fk20_multi_settings, setup.c:238-330) + the window tables
+// setup: X^ columns (init_fk20_multi_settings, setup.c:238-330) + the window tables (width Ctx::fk_c)
 int fk20_setup(Launch& L, Ctx* c);
+// table[(p*W + w)*M + m] = (m+1) 2^(cw) pts[p], affine, for npts fixed bases
+int launch_fixed_base_table(Launch& L, G1Affine* table, const G1Affine* pts, int npts, const FkGeom& g);
 // u_brp[blob][brp7(j)] = sum_i S[blob][j][i] * X^[j][i]
 int launch_fk20_msm(Launch& L, G1* u_brp, const uint32_t* S, uint64_t n);
 // proofs[blob][128] (XYZZ, final bit-reversed order) from u_brp: unscaled inverse G1 FFT, zero the

@@ -75,6 +75,8 @@ struct Ctx {
     void* rec_shiftB = nullptr;           // 7^-k / 8192
     void* fk_table = nullptr;             // FK20 fixed-base multiples, cells.h (3.2 - 35 GB)
     int fk_c = 8;                         // window width of fk_table
+    void* commit_table = nullptr;         // direct (bucket-free) multiples of the Lagrange points, msm_direct.cu (18 - 61 GB)
+    int commit_c = 0;                     // its window width; 0 = not built, the bucket MSM (msm_table) serves
     G1* g_levels = nullptr;               // [18] table levels of -G1 generator (vmsm.cu)
     G1* mono_levels = nullptr;            // [18][64] table levels of -[tau^j]G1, j < 64 (verify_cells.cu)
     uint64_t precompute = 0;
@@ -174,6 +176,10 @@ struct MsmWorkspace {
 size_t msm_workspace_bytes(uint64_t n, int parts);
 int msm_pick_parts(uint64_t n);
 int launch_msm(Launch& L, G1* result, const uint8_t* scalars, bool big_endian_bytes, uint64_t n, const G1Affine* table, int* d_bad, void* workspace, int parts);
+// ---- msm_direct.cu: the same sums from the direct table (Ctx::commit_table), no sort / buckets ----------
+int msm_direct_setup(Launch& L, Ctx* c);
+size_t msm_direct_workspace_bytes(uint64_t n);
+int launch_msm_direct(Launch& L, G1* result, const uint8_t* scalars, bool big_endian_bytes, uint64_t n, int* d_bad, void* workspace);
 // points -> canonical 48-byte compression (one thread per point)
 int launch_g1_compress(Launch& L, uint8_t* out48, const G1* pts, uint64_t n);
 

@@ -73,9 +73,9 @@ __global__ void fk_xhat_affine_kernel(G1Affine* __restrict__ xhat, const G1* __r
     xhat[brp7(q) * 64 + offset] = g1_to_affine(p);
 }
 // bases[p][w] = 2^(cw) * xhat[p], affine
-__global__ void fk_bases_kernel(G1Affine* __restrict__ bases, const G1Affine* __restrict__ xhat, const FkGeom g) {
+__global__ void fk_bases_kernel(G1Affine* __restrict__ bases, const G1Affine* __restrict__ xhat, int npts, const FkGeom g) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= FK_POINTS) return;
+    if (p >= npts) return;
     G1Affine a = xhat[p];
     bases[(size_t)p * g.w] = a;
     G1 acc = g1_from_affine(a);
@@ -91,9 +91,9 @@ __global__ void fk_bases_kernel(G1Affine* __restrict__ bases, const G1Affine* __
 // table[(p*W + w)*M + m] = (m+1) * bases[p][w], affine; one thread per (p, w), batches of 16
 // converted with one inversion each (Montgomery's trick)
 constexpr int FK_BATCH = 16;
-__global__ void __launch_bounds__(64) fk_multiples_kernel(G1Affine* __restrict__ table, const G1Affine* __restrict__ bases, const FkGeom g) {
+__global__ void __launch_bounds__(64) fk_multiples_kernel(G1Affine* __restrict__ table, const G1Affine* __restrict__ bases, int npts, const FkGeom g) {
     size_t pw = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pw >= (size_t)FK_POINTS * g.w) return;
+    if (pw >= (size_t)npts * g.w) return;
     const G1Affine base = bases[pw];
     G1Affine* dst = table + pw * g.m;
     const int FK_M = g.m;
@@ -129,50 +129,42 @@ __global__ void __launch_bounds__(64) fk_multiples_kernel(G1Affine* __restrict__
     }
 }
 
-// Window width of the fixed-base tables: the widest that leaves the device comfortable (several contexts
-// may live in one process), or CKZG_B200_FK_WINDOW = 8 | 10 | 12.
-static int fk20_pick_window() {
-    const char* env = getenv("CKZG_B200_FK_WINDOW");
-    if (env) {
-        int v = atoi(env);
-        if (v == 8 || v == 10 || v == 12) return v;
-    }
-    size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return 8;
-    const size_t GB = (size_t)1 << 30;
-    if (free_b >= 100 * GB) return 12;
-    if (free_b >= 40 * GB) return 10;
-    return 8;
+// table[(p*W + w)*M + m] = (m+1) 2^(cw) pts[p] for npts affine points (fixed-base tables of FK20 and of the
+// direct commitment MSM, msm_direct.cu)
+int launch_fixed_base_table(Launch& L, G1Affine* table, const G1Affine* pts, int npts, const FkGeom& g) {
+    G1Affine* bases = nullptr;
+    KZG_CUDA_TRY(cudaMallocAsync((void**)&bases, (size_t)npts * g.w * sizeof(G1Affine), L.stream));
+    fk_bases_kernel<<<(npts + 63) / 64, 64, 0, L.stream>>>(bases, pts, npts, g);
+    KZG_CUDA_TRY(cudaGetLastError());
+    fk_multiples_kernel<<<(unsigned)(((size_t)npts * g.w + 63) / 64), 64, 0, L.stream>>>(table, bases, npts, g);
+    KZG_CUDA_TRY(cudaGetLastError());
+    KZG_CUDA_TRY(cudaFreeAsync(bases, L.stream));
+    L.count(2, "fixed_base_table");
+    return RET_OK;
 }
 
 int fk20_setup(Launch& L, Ctx* c) {
-    c->fk_c = fk20_pick_window();
     const FkGeom g = fk_geom(c->fk_c);
     KZG_CUDA_TRY(cudaMalloc((void**)&c->fk_table, g.table_points() * sizeof(G1Affine)));
-    G1 *xin = nullptr, *xout = nullptr;
-    G1Affine *xhat = nullptr, *bases = nullptr;
+    G1* xin = nullptr;
+    G1Affine* xhat = nullptr;
     KZG_CUDA_TRY(cudaMallocAsync((void**)&xin, 64 * 128 * sizeof(G1), L.stream));
-    KZG_CUDA_TRY(cudaMallocAsync((void**)&xout, 64 * 128 * sizeof(G1), L.stream));
     KZG_CUDA_TRY(cudaMallocAsync((void**)&xhat, FK_POINTS * sizeof(G1Affine), L.stream));
-    KZG_CUDA_TRY(cudaMallocAsync((void**)&bases, (size_t)FK_POINTS * g.w * sizeof(G1Affine), L.stream));
     fk_gather_x_kernel<<<64 * 128 / 128, 128, 0, L.stream>>>(xin, c->g1_monomial);
     KZG_CUDA_TRY(cudaGetLastError());
     {
         int rc = g1_fft128_run(L, xin, 64, false);
         if (rc) return rc;
     }
-    (void)xout;
     fk_xhat_affine_kernel<<<64 * 128 / 64, 64, 0, L.stream>>>(xhat, xin);
     KZG_CUDA_TRY(cudaGetLastError());
-    fk_bases_kernel<<<FK_POINTS / 64, 64, 0, L.stream>>>(bases, xhat, g);
-    KZG_CUDA_TRY(cudaGetLastError());
-    fk_multiples_kernel<<<(unsigned)(((size_t)FK_POINTS * g.w + 63) / 64), 64, 0, L.stream>>>((G1Affine*)c->fk_table, bases, g);
-    KZG_CUDA_TRY(cudaGetLastError());
+    {
+        int rc = launch_fixed_base_table(L, (G1Affine*)c->fk_table, xhat, FK_POINTS, g);
+        if (rc) return rc;
+    }
     KZG_CUDA_TRY(cudaFreeAsync(xin, L.stream));
-    KZG_CUDA_TRY(cudaFreeAsync(xout, L.stream));
     KZG_CUDA_TRY(cudaFreeAsync(xhat, L.stream));
-    KZG_CUDA_TRY(cudaFreeAsync(bases, L.stream));
-    L.count(5, "fk20_setup");
+    L.count(2, "fk20_setup");
     return RET_OK;
 }
 

@@ -93,6 +93,27 @@ def test_commitment_batch_entry(gpu, ref):
             assert out.raw[48 * i : 48 * i + 48] == ref.blob_to_kzg_commitment(blobs[i])
 
 
+def test_table_plans_agree(gpu, ref, monkeypatch):
+    """The fixed-base tables are sized from the free HBM when a context is created (api.cu plan_tables):
+    the bucket MSM / 8-bit FK20 windows that serve when memory is short must give the same bytes as the
+    direct commitment table / 12-bit windows (and as the reference)."""
+    from gpu_common import product
+
+    blobs = [synth_blob(300 + b) for b in range(3)]
+    want = [ref.blob_to_kzg_commitment(b) for b in blobs]
+    want_cp = gpu.compute_cells_and_kzg_proofs(blobs[0])
+    for commit_w, fk_w in (("0", "8"), ("12", "10")):
+        monkeypatch.setenv("CKZG_B200_COMMIT_WINDOW", commit_w)
+        monkeypatch.setenv("CKZG_B200_FK_WINDOW", fk_w)
+        small = product()
+        try:
+            assert [small.blob_to_kzg_commitment(b) for b in blobs] == want
+            assert small.compute_blob_kzg_proof(blobs[1], want[1]) == ref.compute_blob_kzg_proof(blobs[1], want[1])
+            assert small.compute_cells_and_kzg_proofs(blobs[0]) == want_cp
+        finally:
+            small.close() if hasattr(small, "close") else None
+
+
 def _engine(gpu):
     import ctypes as C
 
