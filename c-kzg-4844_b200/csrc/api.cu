@@ -19,39 +19,31 @@ void note_cuda_error(cudaError_t e, const char* file, int line) {
     if (getenv("CKZG_B200_DEBUG")) fprintf(stderr, "[ckzg_b200] CUDA error %d (%s) at %s:%d\n", (int)e, cudaGetErrorString(e), file, line);
 }
 
-// How much HBM the fixed-base tables may take, decided once per context from the memory that is free when it
-// is created (several contexts can live in one process; each plans against what is left):
-//   FK20 table (cells.h):        c = 12 -> 35 GB | 10 -> 10.5 GB | 8 -> 3.2 GB
-//   commitment table (msm_direct.cu): c = 14 -> 61 GB | 13 -> 32 GB | 12 -> 18 GB | none (bucket MSM)
-// CKZG_B200_FK_WINDOW / CKZG_B200_COMMIT_WINDOW (0 = none) override.
-static void plan_tables(Ctx* c) {
+// The two big fixed-base tables are built on FIRST USE of the API that needs them (a verifier never pays for
+// them) and sized from the HBM that is free at that moment -- several contexts can share a device:
+//   commitment table (msm_direct.cu): c = 14 -> 61 GB | 13 -> 32 GB | 12 -> 18 GB | none (bucket MSM, msm.cu)
+//   FK20 table (fk20.cu):             c = 12 -> 35 GB | 10 -> 10.5 GB | 8 -> 3.2 GB
+// CKZG_B200_COMMIT_WINDOW (0 = none, 10..14) / CKZG_B200_FK_WINDOW (8, 10, 12) pin the choice.
+static double free_gb() {
     size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;
-    const double gb = (double)free_b / (double)(1ull << 30);
-    if (gb >= 150) {
-        c->fk_c = 12;
-        c->commit_c = 14;
-    } else if (gb >= 110) {
-        c->fk_c = 12;
-        c->commit_c = 13;
-    } else if (gb >= 70) {
-        c->fk_c = 12;
-        c->commit_c = 0;
-    } else if (gb >= 40) {
-        c->fk_c = 10;
-        c->commit_c = 0;
-    } else {
-        c->fk_c = 8;
-        c->commit_c = 0;
-    }
-    if (const char* env = getenv("CKZG_B200_FK_WINDOW")) {
-        const int v = atoi(env);
-        if (v == 8 || v == 10 || v == 12) c->fk_c = v;
-    }
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return 0;
+    return (double)free_b / (double)(1ull << 30);
+}
+int plan_commit_window() {
     if (const char* env = getenv("CKZG_B200_COMMIT_WINDOW")) {
         const int v = atoi(env);
-        if (v == 0 || (v >= 10 && v <= 14)) c->commit_c = v;
+        if (v == 0 || (v >= 10 && v <= 14)) return v;
     }
+    const double gb = free_gb();
+    return gb >= 150 ? 14 : gb >= 90 ? 13 : gb >= 60 ? 12 : 0;
+}
+int plan_fk_window() {
+    if (const char* env = getenv("CKZG_B200_FK_WINDOW")) {
+        const int v = atoi(env);
+        if (v == 8 || v == 10 || v == 12) return v;
+    }
+    const double gb = free_gb();
+    return gb >= 70 ? 12 : gb >= 30 ? 10 : 8;
 }
 
 static int ctx_build(Ctx* c, const uint8_t* g1_mono, const uint8_t* g1_lag, const uint8_t* g2_mono) {
@@ -81,9 +73,6 @@ static int ctx_build(Ctx* c, const uint8_t* g1_mono, const uint8_t* g1_lag, cons
     KZG_CUDA_TRY(cudaMalloc((void**)&c->g_levels, VMSM_LEVELS * sizeof(G1)));
     TRY(launch_vmsm_generator_levels(L, c->g_levels));
     TRY(setup_verify_cells(L, c));
-    plan_tables(c);
-    TRY(fk20_setup(L, c));
-    TRY(msm_direct_setup(L, c));
     TRY(recover_setup(L, c));
 
     int bad = 0;
@@ -187,6 +176,7 @@ int commit_scalars_batch(Call& call, uint8_t* out_dev48, const uint8_t* d_scalar
     Launch L = call.launch();
     G1* d_res;
     TRY(call.alloc(&d_res, n));
+    TRY(msm_direct_ensure(c));
     if (c->commit_table) {  // direct table: no sort lists, no buckets
         uint8_t* ws;
         TRY(call.alloc(&ws, msm_direct_workspace_bytes(n)));

@@ -13,7 +13,7 @@ constexpr int FK_POINTS = CELLS_EXT * CELL_FR;  // 8192 fixed bases X^[j][i] (x_
 // p = j*64 + i, w < ceil(256 / c) windows of c signed bits, m < 2^(c-1).  HBM buys a pure gather-and-add
 // MSM: 64 * ceil(256 / c) mixed additions, no buckets, no doublings (the role the reference gives to
 // `precompute`, setup.c:291-323 / README.md:110-143 -- 96 MiB at precompute=8).  The window width is
-// chosen per context from the free device memory (fk20.cu fk20_pick_window): c = 12 -> 22 windows,
+// chosen from the device memory that is free when the table is first needed (api.cu plan_fk_window): c = 12 -> 22 windows,
 // 35 GB (1408 additions per MSM); c = 10 -> 26 windows, 10.5 GB; c = 8 -> 32 windows, 3.2 GB (2048).
 struct FkGeom {
     int c = 8, w = 32, m = 128;
@@ -35,8 +35,8 @@ int launch_blob_to_cells(Launch& L, uint8_t* cells, Fr* mono, const uint8_t* blo
 int launch_fk20_scalars(Launch& L, uint32_t* S, const Fr* mono, uint64_t n);
 
 // ---- fk20.cu -------------------------------------------------------------------------------------
-// setup: X^ columns (init_fk20_multi_settings, setup.c:238-330) + the window tables (width Ctx::fk_c)
-int fk20_setup(Launch& L, Ctx* c);
+// X^ columns (init_fk20_multi_settings, setup.c:238-330) + the window tables, built on first use
+int fk20_ensure(Ctx* c);
 // table[(p*W + w)*M + m] = (m+1) 2^(cw) pts[p], affine, for npts fixed bases
 int launch_fixed_base_table(Launch& L, G1Affine* table, const G1Affine* pts, int npts, const FkGeom& g);
 // u_brp[blob][brp7(j)] = sum_i S[blob][j][i] * X^[j][i]

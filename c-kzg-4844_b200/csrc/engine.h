@@ -77,6 +77,8 @@ struct Ctx {
     int fk_c = 8;                         // window width of fk_table
     void* commit_table = nullptr;         // direct (bucket-free) multiples of the Lagrange points, msm_direct.cu (18 - 61 GB)
     int commit_c = 0;                     // its window width; 0 = not built, the bucket MSM (msm_table) serves
+    std::once_flag fk_once, commit_once;  // both tables are built on first use (api.cu plan_*_window)
+    int fk_rc = 0, commit_rc = 0;
     G1* g_levels = nullptr;               // [18] table levels of -G1 generator (vmsm.cu)
     G1* mono_levels = nullptr;            // [18][64] table levels of -[tau^j]G1, j < 64 (verify_cells.cu)
     uint64_t precompute = 0;
@@ -177,7 +179,10 @@ size_t msm_workspace_bytes(uint64_t n, int parts);
 int msm_pick_parts(uint64_t n);
 int launch_msm(Launch& L, G1* result, const uint8_t* scalars, bool big_endian_bytes, uint64_t n, const G1Affine* table, int* d_bad, void* workspace, int parts);
 // ---- msm_direct.cu: the same sums from the direct table (Ctx::commit_table), no sort / buckets ----------
-int msm_direct_setup(Launch& L, Ctx* c);
+// builds Ctx::commit_table on first use if the free HBM allows (else leaves it null: bucket form)
+int msm_direct_ensure(Ctx* c);
+int plan_commit_window();
+int plan_fk_window();
 size_t msm_direct_workspace_bytes(uint64_t n);
 int launch_msm_direct(Launch& L, G1* result, const uint8_t* scalars, bool big_endian_bytes, uint64_t n, int* d_bad, void* workspace);
 // points -> canonical 48-byte compression (one thread per point)

@@ -15,6 +15,7 @@
 // returns).
 #include <stdlib.h>
 
+#include "call.h"
 #include "cells.h"
 #include "g1_hot.cuh"
 
@@ -143,9 +144,21 @@ int launch_fixed_base_table(Launch& L, G1Affine* table, const G1Affine* pts, int
     return RET_OK;
 }
 
-int fk20_setup(Launch& L, Ctx* c) {
+static int fk20_build(Launch& L, Ctx* c) {
+    static const int widths[3] = {12, 10, 8};
+    c->fk_c = plan_fk_window();
+    for (int k = 0; k < 3; k++) {  // a failed allocation falls back to the next smaller table
+        if (widths[k] > c->fk_c) continue;
+        const FkGeom g = fk_geom(widths[k]);
+        if (cudaMalloc((void**)&c->fk_table, g.table_points() * sizeof(G1Affine)) == cudaSuccess) {
+            c->fk_c = widths[k];
+            break;
+        }
+        (void)cudaGetLastError();
+        c->fk_table = nullptr;
+    }
+    if (!c->fk_table) return RET_MALLOC;
     const FkGeom g = fk_geom(c->fk_c);
-    KZG_CUDA_TRY(cudaMalloc((void**)&c->fk_table, g.table_points() * sizeof(G1Affine)));
     G1* xin = nullptr;
     G1Affine* xhat = nullptr;
     KZG_CUDA_TRY(cudaMallocAsync((void**)&xin, 64 * 128 * sizeof(G1), L.stream));
@@ -165,7 +178,23 @@ int fk20_setup(Launch& L, Ctx* c) {
     KZG_CUDA_TRY(cudaFreeAsync(xin, L.stream));
     KZG_CUDA_TRY(cudaFreeAsync(xhat, L.stream));
     L.count(2, "fk20_setup");
+    KZG_CUDA_TRY(cudaStreamSynchronize(L.stream));
     return RET_OK;
+}
+
+// X^ columns (init_fk20_multi_settings, setup.c:238-330) + the window tables, on first use of an API that
+// computes cell proofs
+int fk20_ensure(Ctx* c) {
+    std::call_once(c->fk_once, [c] {
+        Call call(c);
+        if (!call.ok) {
+            c->fk_rc = RET_ERROR;
+            return;
+        }
+        Launch L = call.launch();
+        c->fk_rc = fk20_build(L, c);
+    });
+    return c->fk_rc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -249,6 +278,10 @@ __global__ void __launch_bounds__(32 * FM_WARPS, 3) fk20_msm_kernel(G1* __restri
 
 int launch_fk20_msm(Launch& L, G1* u_brp, const uint32_t* S, uint64_t n) {
     if (!n) return RET_OK;
+    {
+        int rc = fk20_ensure(L.ctx);
+        if (rc) return rc;
+    }
     uint64_t total = n * 128;
     fk20_msm_kernel<<<(unsigned)((total + FM_WARPS - 1) / FM_WARPS), 32 * FM_WARPS, 0, L.stream>>>(u_brp, S, (const G1Affine*)L.ctx->fk_table, total, fk_geom(L.ctx->fk_c));
     KZG_CUDA_TRY(cudaGetLastError());

@@ -9,12 +9,14 @@
 // Against the bucket form (msm.cu: 24 windows x 4096 additions, a counting sort before and a 1024-bucket
 // reduction after): c = 14 needs 19 x 4096 additions and no sort / reduction at all, for 61 GB of the
 // 180 GB HBM; c = 13: 20 windows, 32 GB; c = 12: 22 windows, 18 GB.  The width is chosen per context from
-// the free device memory (api.cu plan_tables); without room the bucket form stays in use.
+// the device memory that is free when the table is first needed (api.cu plan_commit_window); without room the
+// bucket form stays in use.
 //
 // Layout: 8 CTAs of 128 threads per blob (32 when fewer than 64 blobs must fill the GPU); a thread owns 4
 // (1) scalars (coalesced 32-byte loads), walks their windows with one XYZZ accumulator (table entries pulled
 // into L2 a few steps ahead), the CTA folds its 128 accumulators through shared memory, and a second small
 // kernel adds the partial sums of a blob (one warp per blob).
+#include "call.h"
 #include "cells.h"
 #include "g1_hot.cuh"
 
@@ -141,11 +143,27 @@ int launch_msm_direct(Launch& L, G1* result, const uint8_t* scalars, bool big_en
     return RET_OK;
 }
 
-int msm_direct_setup(Launch& L, Ctx* c) {
-    if (c->commit_c == 0) return RET_OK;  // no room: the bucket form (msm.cu) serves
-    const FkGeom g = fk_geom(c->commit_c);
-    KZG_CUDA_TRY(cudaMalloc((void**)&c->commit_table, g.points_for(N_BLOB) * sizeof(G1Affine)));
-    return launch_fixed_base_table(L, (G1Affine*)c->commit_table, c->g1_lagrange_brp, N_BLOB, g);
+int msm_direct_ensure(Ctx* c) {
+    std::call_once(c->commit_once, [c] {
+        c->commit_c = plan_commit_window();
+        if (c->commit_c == 0) return;  // no room: the bucket form (msm.cu) serves
+        const FkGeom g = fk_geom(c->commit_c);
+        if (cudaMalloc((void**)&c->commit_table, g.points_for(N_BLOB) * sizeof(G1Affine)) != cudaSuccess) {
+            (void)cudaGetLastError();
+            c->commit_table = nullptr;
+            c->commit_c = 0;
+            return;
+        }
+        Call call(c);
+        if (!call.ok) {
+            c->commit_rc = RET_ERROR;
+            return;
+        }
+        Launch L = call.launch();
+        c->commit_rc = launch_fixed_base_table(L, (G1Affine*)c->commit_table, c->g1_lagrange_brp, N_BLOB, g);
+        if (c->commit_rc == RET_OK && cudaStreamSynchronize(call.stream) != cudaSuccess) c->commit_rc = RET_ERROR;
+    });
+    return c->commit_rc;
 }
 
 }  // namespace kzg
