@@ -272,4 +272,80 @@ __device__ __forceinline__ void quad_copy_g1(G1* dst, const G1* src) {
     for (int i = 0; i < 3; i++) d[ql * 3 + i] = s[ql * 3 + i];
 }
 
+// ---- validation on a quad: decompression on lane 0, the two |z| chains of the subgroup test shared ------
+// Same result as g1a_validate_levels (g1.cuh): decompress, accept infinity, else require phi(P) + [z^2]P = inf,
+// and leave the 18 table levels (2^(8j) P, 2^(8j) [|z|]P) behind.  The chains are 2 x (63 doublings + 5
+// additions): 1.2 ms of dependent products on one lane, 0.4 ms on a quad.
+struct QuadValidate {
+    G1 p;    // the point (zz = zzz = 1)
+    G1 q;    // [|z|] P
+    G1 d;    // running doubling chain
+    G1 acc;
+    Fp bx;   // beta * x
+    QuadScratch sc;
+    int state;  // 0 invalid encoding, 1 finite point, 2 infinity
+    int pad[3];
+};
+
+// *acc = [|z|] *src, storing 2^(8j) *src (j = 0..8) at levels[j * stride]; *d is scratch
+static __device__ __noinline__ void g1_mul_bls_x_levels_quad(G1* acc, G1* d, const G1* src, G1* levels, size_t stride, QuadScratch* sc) {
+    const unsigned lane = threadIdx.x & 31u, ql = lane & 3u;
+    const unsigned mask = 0xFu << (lane & ~3u);
+    quad_copy_g1(d, src);
+    if (ql == 0) {
+        const Fp z = Fp::zero();
+        quad_st(&acc->x, z); quad_st(&acc->y, z); quad_st(&acc->zz, z); quad_st(&acc->zzz, z);
+    }
+    __syncwarp(mask);
+    const uint64_t x = BLS_X_ABS;
+#pragma unroll 1
+    for (int i = 0; i < 64; i++) {
+        if ((i & 7) == 0) {
+            quad_copy_g1(levels + (size_t)(i >> 3) * stride, d);
+            __syncwarp(mask);
+        }
+        if ((x >> i) & 1ull) g1_add_quad(acc, acc, d, sc);
+        g1_dbl_quad(d, d, sc);
+    }
+    quad_copy_g1(levels + (size_t)8 * stride, d);
+    __syncwarp(mask);
+}
+
+// Called by the four lanes of a quad with identical arguments; returns the verdict to all of them.
+// out_affine (may be null) receives the decompressed point (infinity when invalid).
+static __device__ __noinline__ bool g1a_validate_levels_quad(G1Affine* out_affine, const uint8_t* in48, G1* levels, size_t stride, QuadValidate* W) {
+    const unsigned lane = threadIdx.x & 31u, ql = lane & 3u;
+    const unsigned mask = 0xFu << (lane & ~3u);
+    if (ql == 0) {
+        uint8_t buf[48];
+        for (int i = 0; i < 48; i++) buf[i] = in48[i];
+        G1Affine a;
+        const bool ok = g1a_uncompress(a, buf);
+        const int st = !ok ? 0 : (g1a_is_inf(a) ? 2 : 1);
+        if (st == 1) {
+            const Fp one = Fp::one();
+            quad_st(&W->p.x, a.x); quad_st(&W->p.y, a.y); quad_st(&W->p.zz, one); quad_st(&W->p.zzz, one);
+            quad_st(&W->bx, mul(a.x, Fp::from_limbs(FP_BETA_A)));
+        }
+        if (out_affine) *out_affine = (st == 1) ? a : g1a_inf();
+        W->state = st;
+    }
+    __syncwarp(mask);
+    const int st = W->state;
+    if (st != 1) {
+        const G1 inf = g1_inf();
+        for (int j = (int)ql; j < G1_LEVELS; j += 4) g1_store(levels + (size_t)j * stride, inf);
+        __syncwarp(mask);
+        return st == 2;
+    }
+    g1_mul_bls_x_levels_quad(&W->acc, &W->d, &W->p, levels, stride, &W->sc);
+    quad_copy_g1(&W->q, &W->acc);
+    __syncwarp(mask);
+    g1_mul_bls_x_levels_quad(&W->acc, &W->d, &W->q, levels + (size_t)9 * stride, stride, &W->sc);
+    g1_add_quad_q(&W->acc, &W->acc, &W->bx, &W->p, false, &W->sc);  // phi(P) + [z^2]P
+    const bool in_group = is_zero(quad_ld(&W->acc.zz));
+    __syncwarp(mask);
+    return in_group;
+}
+
 }  // namespace kzg

@@ -17,6 +17,7 @@
 
 #define KZG_FP_MUL_OUTLINE 1
 #include "g1_glv.cuh"
+#include "g1_quad.cuh"
 #include "sha256.cuh"
 #include "verify.h"
 
@@ -810,6 +811,40 @@ __global__ void __launch_bounds__(128) stage1_fused_kernel(Fr* __restrict__ z_ou
     }
     (warp == 2 ? out_cm : out_pf)[i] = a;
 }
+// (A variant of this kernel with the validations on quads of lanes -- 8 more warps per CTA -- was measured in
+// r02l: the extra warps share the sub-partitions of the hash pair and the stage went 2.35 -> 3.45 ms.  The
+// hash is the floor of this stage; the quad validator below serves where no hash runs beside it.)
+// n_a + n_b points (two byte arrays) on QUADS of lanes (g1_quad.cuh g1a_validate_levels_quad), 32 per CTA; table
+// columns col_a + k / col_b + k of `npts`.  The two |z| chains of the subgroup test take a third of the time on a
+// quad; more total work than one lane per point, so callers use it while the batch fits one wave.
+constexpr int VQ_QUADS = 32;
+__global__ void __launch_bounds__(4 * VQ_QUADS) g1_validate_levels_quad_kernel(G1Affine* __restrict__ out_a, const uint8_t* __restrict__ in_a, uint64_t na, uint64_t col_a,
+                                                                               G1Affine* __restrict__ out_b, const uint8_t* __restrict__ in_b, uint64_t nb, uint64_t col_b,
+                                                                               G1* __restrict__ table, uint64_t npts, int* __restrict__ bad) {
+    extern __shared__ __align__(16) unsigned char vq_smem[];
+    const uint64_t g = (uint64_t)blockIdx.x * VQ_QUADS + (threadIdx.x >> 2);
+    if (g >= na + nb) return;
+    const bool second = g >= na;
+    const uint64_t k = second ? g - na : g;
+    QuadValidate* W = reinterpret_cast<QuadValidate*>(vq_smem) + (threadIdx.x >> 2);
+    G1Affine* out = second ? out_b : out_a;
+    G1Affine* oa = out ? out + k : nullptr;
+    const bool ok = g1a_validate_levels_quad(oa, (second ? in_b : in_a) + k * 48, table + (second ? col_b : col_a) + k, npts, W);
+    if (!ok && (threadIdx.x & 3) == 0) {
+        *bad = 1;
+        if (oa) *oa = g1a_inf();
+    }
+}
+int launch_g1_validate_levels_ab(Launch& L, G1Affine* out_a, const uint8_t* in_a, uint64_t na, uint64_t col_a, G1Affine* out_b, const uint8_t* in_b, uint64_t nb, uint64_t col_b,
+                                 G1* table, uint64_t npts, int* bad) {
+    if (!(na + nb)) return RET_OK;
+    g1_validate_levels_quad_kernel<<<blocks_for(na + nb, VQ_QUADS), 4 * VQ_QUADS, VQ_QUADS * sizeof(QuadValidate), L.stream>>>(out_a, in_a, na, col_a, out_b, in_b, nb, col_b, table,
+                                                                                                                           npts, bad);
+    KZG_CUDA_TRY(cudaGetLastError());
+    L.count(1, "g1_validate");
+    return RET_OK;
+}
+
 int launch_stage1_fused(Launch& L, Fr* z, uint8_t* zy, const uint8_t* blobs, G1Affine* out_cm, const uint8_t* in_cm, G1Affine* out_pf, const uint8_t* in_pf, uint64_t n, int* bad,
                         G1* table) {
     if (!n) return RET_OK;

@@ -39,6 +39,10 @@ int launch_stage1_fused(Launch& L, Fr* z, uint8_t* zy, const uint8_t* blobs, G1A
                         G1* table);
 // validation of n commitments + n proofs with the vmsm table columns
 int launch_g1_validate2_levels(Launch& L, G1Affine* out_cm, const uint8_t* in_cm, G1Affine* out_pf, const uint8_t* in_pf, uint64_t n, int* bad, G1* table);
+// n_a + n_b points on quads of lanes (g1_quad.cuh); table columns col_a + k / col_b + k of a table of npts columns;
+// out_a / out_b (affine points) may be null
+int launch_g1_validate_levels_ab(Launch& L, G1Affine* out_a, const uint8_t* in_a, uint64_t na, uint64_t col_a, G1Affine* out_b, const uint8_t* in_b, uint64_t nb, uint64_t col_b,
+                                 G1* table, uint64_t npts, int* bad);
 int debug_set_placement_buffer(uint32_t* dev_buf);
 int launch_g1_validate_ab(Launch& L, G1Affine* out_a, const uint8_t* in_a, uint64_t n, G1Affine* out_b, const uint8_t* in_b, uint64_t nb, int* bad);
 // r = hash_to_bls_field(digest): the batch transcript itself (eip4844.c:597-680) is hashed on the host
