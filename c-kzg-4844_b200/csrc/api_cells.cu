@@ -1,4 +1,5 @@
 // C ABI, EIP-7594 entry points (include/ckzg_b200.h): cells + FK20 proofs, batched over blobs.
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -23,7 +24,8 @@ int fk20_proofs_from_mono(Call& call, uint8_t* d_out48, const Fr* d_mono, uint64
     TRY(call.alloc(&d_S, n * 128 * 64 * 8));
     TRY(call.alloc(&d_u, n * 128));
     TRY(call.alloc(&d_proofs, n * 128));
-    const int parts = (call.trace_kernels || n < 32) ? 1 : (n < 128 ? 2 : 4);
+    static const int forced_parts = getenv("CKZG_B200_FK_PARTS") ? atoi(getenv("CKZG_B200_FK_PARTS")) : 0;  // measurements
+    const int parts = forced_parts >= 1 && forced_parts <= 4 ? forced_parts : ((call.trace_kernels || n < 32) ? 1 : (n < 128 ? 2 : 4));
     if (parts == 1) {
         Launch L = call.launch();
         TRY(launch_fk20_scalars(L, d_S, d_mono, n));
