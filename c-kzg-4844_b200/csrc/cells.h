@@ -41,6 +41,9 @@ int fk20_ensure(Ctx* c);
 int launch_fixed_base_table(Launch& L, G1Affine* table, const G1Affine* pts, int npts, const FkGeom& g);
 // u_brp[blob][brp7(j)] = sum_i S[blob][j][i] * X^[j][i]
 int launch_fk20_msm(Launch& L, G1* u_brp, const uint32_t* S, uint64_t n);
+// the same sums by pairwise affine additions with batched inversions (msm_affine.cu), for batches
+size_t fk20_msm_affine_workspace_bytes(uint64_t n, int c);
+int launch_fk20_msm_affine(Launch& L, G1* u_brp, const uint32_t* S, uint64_t n, void* workspace);
 // proofs[blob][128] (XYZZ, final bit-reversed order) from u_brp: unscaled inverse G1 FFT, zero the
 // upper half, forward G1 FFT (fk20.c:257-269 + eip7594.c:133)
 int launch_fk20_g1_ffts(Launch& L, G1* proofs, G1* u_brp, uint64_t n);

@@ -185,6 +185,9 @@ int plan_commit_window();
 int plan_fk_window();
 size_t msm_direct_workspace_bytes(uint64_t n);
 int launch_msm_direct(Launch& L, G1* result, const uint8_t* scalars, bool big_endian_bytes, uint64_t n, int* d_bad, void* workspace);
+// ---- msm_affine.cu: the same table sums added pairwise in affine coordinates with batched inversions (batches) ----
+size_t msm_affine_workspace_bytes(uint64_t n, int c);
+int launch_msm_affine(Launch& L, G1* result, const uint8_t* scalars, bool big_endian_bytes, uint64_t n, int* d_bad, void* workspace);
 // points -> canonical 48-byte compression (one thread per point)
 int launch_g1_compress(Launch& L, uint8_t* out48, const G1* pts, uint64_t n);
 

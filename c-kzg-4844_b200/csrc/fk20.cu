@@ -282,6 +282,14 @@ int launch_fk20_msm(Launch& L, G1* u_brp, const uint32_t* S, uint64_t n) {
         int rc = fk20_ensure(L.ctx);
         if (rc) return rc;
     }
+    static const int affine_min = getenv("CKZG_B200_FK_AFFINE_MIN") ? atoi(getenv("CKZG_B200_FK_AFFINE_MIN")) : 8;  // 0 = never
+    if (affine_min > 0 && n >= (uint64_t)affine_min) {
+        void* ws = nullptr;
+        KZG_CUDA_TRY(cudaMallocAsync(&ws, fk20_msm_affine_workspace_bytes(n, L.ctx->fk_c), L.stream));
+        int rc = launch_fk20_msm_affine(L, u_brp, S, n, ws);
+        cudaFreeAsync(ws, L.stream);
+        return rc;
+    }
     uint64_t total = n * 128;
     fk20_msm_kernel<<<(unsigned)((total + FM_WARPS - 1) / FM_WARPS), 32 * FM_WARPS, 0, L.stream>>>(u_brp, S, (const G1Affine*)L.ctx->fk_table, total, fk_geom(L.ctx->fk_c));
     KZG_CUDA_TRY(cudaGetLastError());

@@ -232,3 +232,40 @@ def test_coalesced_per_blob_api_matches_batched_results(env):
         assert mod.blob_to_kzg_commitment(hb[:131072], ts) == hc[:48]
     finally:
         mod.coalesce_enable(ts, True)
+
+
+def test_fk20_affine_batch_matches_single_blob_path(env):
+    """Batches of >= 8 blobs add the FK20 table points pairwise in affine coordinates with batched inversions
+    (msm_affine.cu); single blobs use XYZZ accumulators (fk20.cu).  Both must give the same bytes, also for blobs
+    whose digits are mostly zero (infinity operands), all equal, or extreme."""
+    import torch
+
+    mod, ts, n, host, dev, cms, prs = env
+    R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+    z, one, top = (0).to_bytes(32, "big"), (1).to_bytes(32, "big"), (R - 1).to_bytes(32, "big")
+    hb = host.numpy().tobytes()
+    special = [
+        z * 4096,
+        one * 4096,
+        top * 4096,
+        z * 4000 + top + z * 95,
+        b"".join(i.to_bytes(32, "big") for i in range(4096)),
+        (one + top) * 2048,
+        z * 64 + one * 64 + z * 3968,
+        b"".join(((1 << 254) + 7 * i).to_bytes(32, "big") for i in range(4096)),
+    ]
+    blobs = special + [hb[131072 * i : 131072 * (i + 1)] for i in range(8)]
+    m = len(blobs)
+    d_in = torch.frombuffer(bytearray(b"".join(blobs)), dtype=torch.uint8).cuda()
+    cells = torch.empty(m * 262144, dtype=torch.uint8, device="cuda")
+    cprf = torch.empty(m * 128 * 48, dtype=torch.uint8, device="cuda")
+    mod.compute_cells_and_kzg_proofs_device(cells.data_ptr(), cprf.data_ptr(), d_in.data_ptr(), m, ts)
+    got_c, got_p = cells.cpu().numpy().tobytes(), cprf.cpu().numpy().tobytes()
+    mod.coalesce_enable(ts, False)  # every call below runs alone: the n = 1 path
+    try:
+        for i, blob in enumerate(blobs):
+            c, p = mod.compute_cells_and_kzg_proofs(blob, ts)
+            assert b"".join(c) == got_c[262144 * i : 262144 * (i + 1)], i
+            assert b"".join(p) == got_p[6144 * i : 6144 * (i + 1)], i
+    finally:
+        mod.coalesce_enable(ts, True)
