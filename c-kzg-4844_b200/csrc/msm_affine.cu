@@ -21,8 +21,8 @@
 // quotient commitment, like msm_direct.cu; used when a batch has at least BAM_MIN_BLOBS blobs (a single blob
 // is faster through the one-kernel XYZZ form: every level here is a latency chain of its own).
 #define KZG_FP_MUL_OUTLINE 1
+#include "affine_batch.cuh"
 #include "cells.h"
-#include "g1.cuh"
 
 namespace kzg {
 
@@ -45,59 +45,6 @@ __device__ __forceinline__ void bam_st_fp(Fp* p, const Fp& a) {
 #pragma unroll
     for (int i = 0; i < 3; i++) q[i] = d[i];
 }
-
-// What one pair contributes to the batched inversion, and how its sum is finished afterwards.
-enum { BAM_ADD = 0, BAM_DBL = 1, BAM_TAKE_A = 2, BAM_TAKE_B = 3, BAM_INF = 4 };
-
-// denominator of the pair (never zero) and the kind of the pair.  ya / yb are loaded only when needed.
-template <class LoadYA, class LoadYB>
-__device__ __forceinline__ int bam_plan(Fp& d, const Fp& xa, const Fp& xb, bool inf_a, bool inf_b, LoadYA load_ya, LoadYB load_yb) {
-    d = Fp::one();
-    if (inf_a && inf_b) return BAM_INF;
-    if (inf_b) return BAM_TAKE_A;
-    if (inf_a) return BAM_TAKE_B;
-    const Fp t = sub(xb, xa);
-    if (!is_zero(t)) {
-        d = t;
-        return BAM_ADD;
-    }
-    const Fp ya = load_ya(), yb = load_yb();
-    if (eq(ya, yb) && !is_zero(ya)) {  // the same point: doubling, slope 3 x^2 / (2 y)
-        d = dbl(ya);
-        return BAM_DBL;
-    }
-    return BAM_INF;  // opposite points (or a 2-torsion point, which the subgroup does not contain)
-}
-
-// the sum of the pair given 1 / d
-__device__ __forceinline__ void bam_finish(Fp& x3, Fp& y3, int kind, const Fp& xa, const Fp& ya, const Fp& xb, const Fp& yb, const Fp& dinv) {
-    if (kind == BAM_TAKE_A) {
-        x3 = xa;
-        y3 = ya;
-        return;
-    }
-    if (kind == BAM_TAKE_B) {
-        x3 = xb;
-        y3 = yb;
-        return;
-    }
-    if (kind == BAM_INF) {
-        x3 = Fp::zero();
-        y3 = Fp::zero();
-        return;
-    }
-    Fp num;
-    if (kind == BAM_DBL) {
-        const Fp xx = sqr(xa);
-        num = add(dbl(xx), xx);
-    } else {
-        num = sub(yb, ya);
-    }
-    const Fp lam = mul(num, dinv);
-    x3 = sub(sub(sqr(lam), xa), xb);
-    y3 = sub(mul(lam, sub(xa, x3)), ya);
-}
-
 
 // 1 / run for every thread of the CTA with ONE inversion: all lanes of one warp invert the same value -- the
 // product of all segment products -- so the branchy binary-Euclid loop runs without divergence (with 32

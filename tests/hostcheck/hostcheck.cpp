@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include "g1.cuh"
+#include "affine_batch.cuh"
 #ifdef HOSTCHECK_PAIRING
 #include "pairing.cuh"
 #include "pairing_coop.cuh"
@@ -93,6 +94,17 @@ int hc_g1_madd(uint8_t* out48, const uint8_t* p48, const uint8_t* q48, int negat
     }
     g1_madd(acc, q, negate != 0);
     g1a_compress(out48, g1_to_affine(acc));
+    return 1;
+}
+
+// out[i] = a[i] + b[i] for n <= 64 pairs of compressed points through the batched affine addition (one inversion)
+int hc_affine_batch_add(uint8_t* out48, const uint8_t* a48, const uint8_t* b48, int n) {
+    G1Affine a[64], b[64], o[64];
+    if (n < 0 || n > 64) return 0;
+    for (int i = 0; i < n; i++)
+        if (!g1a_uncompress(a[i], a48 + 48 * i) || !g1a_uncompress(b[i], b48 + 48 * i)) return 0;
+    affine_batch_add(o, a, b, n);
+    for (int i = 0; i < n; i++) g1a_compress(out48 + 48 * i, o[i]);
     return 1;
 }
 

@@ -113,6 +113,37 @@ def test_g1_madd_special_cases(hc):
         assert out.raw == B.g1_compress(want)
 
 
+def test_affine_batch_add_every_branch(hc):
+    """The pair logic of the batched affine additions (csrc/affine_batch.cuh, used by msm_affine.cu): generic sums,
+    P + P (doubling slope through the shared inversion), P + (-P), infinity on either or both sides, all inside ONE
+    batch with one inversion, against the integer oracle."""
+    rnd = random.Random(11)
+    inf = B.G1_INF
+    pts = [rand_g1(rnd) for _ in range(40)]
+    a, b = [], []
+    for i in range(16):
+        a.append(pts[i]), b.append(pts[16 + i])
+    a += [pts[0], pts[1], inf, pts[2], inf, pts[3], B.g1_neg(pts[4])]
+    b += [pts[0], B.g1_neg(pts[1]), pts[5], inf, inf, pts[3], pts[4]]
+    for _ in range(20):
+        p = pts[rnd.randrange(40)]
+        q = [pts[rnd.randrange(40)], p, B.g1_neg(p), inf][rnd.randrange(4)]
+        a.append(p), b.append(q)
+    n = len(a)
+    assert n <= 64
+    out = C.create_string_buffer(48 * n)
+    assert hc.hc_affine_batch_add(out, b"".join(B.g1_compress(x) for x in a), b"".join(B.g1_compress(x) for x in b), n) == 1
+    for i in range(n):
+        assert out.raw[48 * i : 48 * i + 48] == B.g1_compress(B.g1_add(a[i], b[i])), i
+    # a batch of one, and a batch whose pairs are all exceptional
+    one = C.create_string_buffer(48)
+    assert hc.hc_affine_batch_add(one, B.g1_compress(pts[7]), B.g1_compress(pts[7]), 1) == 1
+    assert one.raw == B.g1_compress(B.g1_dbl(pts[7]))
+    exc = C.create_string_buffer(48 * 3)
+    assert hc.hc_affine_batch_add(exc, b"".join(B.g1_compress(x) for x in (inf, pts[8], pts[9])), b"".join(B.g1_compress(x) for x in (inf, B.g1_neg(pts[8]), inf)), 3) == 1
+    assert exc.raw == B.g1_compress(inf) * 2 + B.g1_compress(pts[9])
+
+
 def test_g1_validate_edge_cases(hc):
     """The encoding edge cases of src/test/tests.c:536-745 (validate_kzg_g1)."""
     rnd = random.Random(6)
