@@ -71,3 +71,40 @@ def verify_batch_replicas(verify_local, device, group=None):
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
     return bool(ok.item())
+
+
+# ---- EIP-7594 paths -------------------------------------------------------------------
+# compute_cells_and_kzg_proofs / recover_cells_and_kzg_proofs / blob_to_kzg_commitment are independent per blob:
+# replicas only, no data-path collective; the helper below just hands every rank its block of blobs and (if asked)
+# gathers the fixed-size per-blob outputs.  verify_cell_kzg_proof_batch shards by ranges of (commitment, index,
+# cell, proof) tuples: every rank runs an independent batch verification of its range (own Fiat-Shamir challenge)
+# and the verdicts meet in ONE all-reduce(MIN) -- the sub-batching the reference's own parallel benchmark uses
+# (bindings/go/main_test.go:1037-1101); a batch is valid iff each of its sub-batches is.
+
+
+def map_blobs_sharded(process_local, n_total, out_bytes_per_blob=0, device="cpu", group=None):
+    """process_local(first, count) -> bytes (count x out_bytes_per_blob) for this rank's block of blobs.
+    Returns the concatenated outputs of all ranks in blob order when out_bytes_per_blob > 0 (all-gather),
+    else this rank's own output."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    ranges = [shard_range(n_total, r, world) for r in range(world)]
+    first, count = ranges[rank]
+    local = process_local(first, count) if count else b""
+    if not out_bytes_per_blob or world == 1:
+        return local
+    assert len(local) == count * out_bytes_per_blob
+    t = torch.frombuffer(bytearray(local), dtype=torch.uint8).to(device) if count else torch.zeros(0, dtype=torch.uint8, device=device)
+    return bytes(_all_gather_bytes(t, [c * out_bytes_per_blob for _, c in ranges], group).cpu().numpy().tobytes())
+
+
+def verify_cells_sharded(verify_local, n_tuples, device="cpu", group=None):
+    """verify_local(first, count) -> bool for the tuples [first, first + count) (an empty range is valid,
+    src/eip7594/eip7594.c:852-855).  One all-reduce(MIN) of the verdicts."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    first, count = shard_range(n_tuples, rank, world)
+    ok = torch.tensor([1 if (count == 0 or verify_local(first, count)) else 0], dtype=torch.int32, device=device)
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    return bool(ok.item())

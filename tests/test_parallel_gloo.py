@@ -86,3 +86,76 @@ def test_shard_range_properties():
             assert sum(c for _, c in rs) == n
             assert all(rs[i][0] + rs[i][1] == rs[i + 1][0] for i in range(w - 1))
             assert max(c for _, c in rs) - min(c for _, c in rs) <= 1
+
+
+def _cells_worker(rank, world, port, q):
+    """EIP-7594 sharding with the unmodified reference (oracle/_ref) as every rank's engine: the sharded verdict must
+    equal the reference's verdict on the whole batch, for a valid batch and for one with a single bad proof."""
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    entry.load_package()
+    import importlib
+
+    from oracle import ref_lib
+    from gpu_common import synth_blob
+
+    par = importlib.import_module("ckzg_b200.parallel")
+    ref = ref_lib.CKZG()
+    nblobs = 3
+    blobs = [synth_blob(700 + b) for b in range(nblobs)]
+
+    # replicas: every rank computes the cells + proofs of its block of blobs; outputs gathered in blob order
+    def process(first, count):
+        out = b""
+        for b in range(first, first + count):
+            cells, proofs = ref.compute_cells_and_kzg_proofs(blobs[b])
+            out += cells + proofs
+        return out
+
+    per_blob = 128 * 2048 + 128 * 48
+    gathered = par.map_blobs_sharded(process, nblobs, per_blob)
+    assert len(gathered) == nblobs * per_blob
+    cms = [ref.blob_to_kzg_commitment(b) for b in blobs]
+    tuples = []  # row-major by blob, every third cell
+    for b in range(nblobs):
+        blk = gathered[b * per_blob : (b + 1) * per_blob]
+        for k in range(0, 128, 3):
+            tuples.append((cms[b], k, blk[2048 * k : 2048 * (k + 1)], blk[128 * 2048 + 48 * k : 128 * 2048 + 48 * (k + 1)]))
+
+    def verdict(ts):
+        def local(first, count):
+            part = ts[first : first + count]
+            return ref.verify_cell_kzg_proof_batch(b"".join(t[0] for t in part), [t[1] for t in part], b"".join(t[2] for t in part), b"".join(t[3] for t in part))
+
+        return par.verify_cells_sharded(local, len(ts))
+
+    good = verdict(tuples)
+    bad_tuples = list(tuples)
+    j = len(tuples) - 2  # lands in the last rank's range
+    bad_tuples[j] = (bad_tuples[j][0], bad_tuples[j][1], bad_tuples[j][2], tuples[j - 1][3])
+    bad = verdict(bad_tuples)
+    whole_good = ref.verify_cell_kzg_proof_batch(b"".join(t[0] for t in tuples), [t[1] for t in tuples], b"".join(t[2] for t in tuples), b"".join(t[3] for t in tuples))
+    whole_bad = ref.verify_cell_kzg_proof_batch(b"".join(t[0] for t in bad_tuples), [t[1] for t in bad_tuples], b"".join(t[2] for t in bad_tuples), b"".join(t[3] for t in bad_tuples))
+    q.put((rank, good, bad, whole_good, whole_bad, hashlib.sha256(gathered).hexdigest()))
+    dist.destroy_process_group()
+
+
+def test_cells_sharding_matches_reference_verdicts():
+    from oracle import ref_lib
+
+    if not os.path.exists(ref_lib.REF_SO):
+        pytest.skip("oracle/_ref not built")
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_cells_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    assert len({r[5] for r in res}) == 1  # every rank holds the same gathered outputs
+    for rank, good, bad, whole_good, whole_bad, _ in res:
+        assert good is True and whole_good is True
+        assert bad is False and whole_bad is False
