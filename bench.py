@@ -376,7 +376,7 @@ def run_b200(args):
     }
 
     extra = {}
-    if rank == 0 and not args.no_extra:
+    if rank == 0 and world == 1 and not args.no_extra:  # the other configs / APIs: single-GPU runs only
         # configs[1]: n = 64 in one call (latency-bound case), and commitments
         def v64():
             return mod.verify_blob_kzg_proof_batch_device(d_blobs.data_ptr(), d_cms.data_ptr(), d_prs.data_ptr(), 64, ts)
