@@ -16,14 +16,15 @@
 
 #include <string.h>
 
-#if defined(__x86_64__) && defined(__GNUC__)
+/* CKZG_HOST_SHA_PORTABLE forces the portable rounds (tests/test_host_sha256.py checks both forms) */
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(CKZG_HOST_SHA_PORTABLE)
 #include <immintrin.h>
 #define HAVE_X86_SHA 1
 #else
 #define HAVE_X86_SHA 0
 #endif
 
-static const uint32_t K[64] = {
+static const uint32_t K[64] __attribute__((aligned(16))) = {
     0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u,
     0xd807aa98u, 0x12835b01u, 0x243185beu, 0x550c7dc3u, 0x72be5d74u, 0x80deb1feu, 0x9bdc06a7u, 0xc19bf174u,
     0xe49b69c1u, 0xefbe4786u, 0x0fc19dc6u, 0x240ca1ccu, 0x2de92c6fu, 0x4a7484aau, 0x5cb0a9dcu, 0x76f988dau,
@@ -56,6 +57,20 @@ static void blocks_portable(uint32_t h[8], const uint8_t *p, size_t nblocks) {
 }
 
 #if HAVE_X86_SHA
+/* Four rounds: the two sha256rnds2 of one 128-bit group of message words + constants. */
+#define SHA_RNDS4(MSG, KIDX)                                                            \
+    do {                                                                                \
+        __m128i wk_ = _mm_add_epi32((MSG), _mm_load_si128((const __m128i *)&K[KIDX])); \
+        s1 = _mm_sha256rnds2_epu32(s1, s0, wk_);                                        \
+        wk_ = _mm_shuffle_epi32(wk_, 0x0E);                                             \
+        s0 = _mm_sha256rnds2_epu32(s0, s1, wk_);                                        \
+    } while (0)
+/* Next four schedule words from the previous sixteen: M0 <- f(M0, M1, M2, M3). */
+#define SHA_SCHED(M0, M1, M2, M3) M0 = _mm_sha256msg2_epu32(_mm_add_epi32(_mm_sha256msg1_epu32(M0, M1), _mm_alignr_epi8(M3, M2, 4)), M3)
+
+/* Fully unrolled, message words in four named registers (the rolled form kept them in an indexed array on the
+ * stack: 15-20 % slower).  The serial transcript hash of verify_cell_kzg_proof_batch is 2112 bytes per cell --
+ * 69 MB for 256 blobs x 128 cells -- and is the largest single item of that call. */
 __attribute__((target("sha,sse4.1,ssse3"))) static void blocks_shani(uint32_t h[8], const uint8_t *p, size_t nblocks) {
     const __m128i shuf = _mm_set_epi64x(0x0c0d0e0f08090a0bULL, 0x0405060700010203ULL);
     __m128i t = _mm_loadu_si128((const __m128i *)&h[0]);   /* a b c d */
@@ -65,21 +80,27 @@ __attribute__((target("sha,sse4.1,ssse3"))) static void blocks_shani(uint32_t h[
     __m128i s0 = _mm_alignr_epi8(t, s1, 8);                 /* a b e f */
     s1 = _mm_blend_epi16(s1, t, 0xF0);                      /* c d g h */
     while (nblocks--) {
-        __m128i save0 = s0, save1 = s1, m[4], msg;
-        for (int i = 0; i < 4; i++) m[i] = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i *)(p + 16 * i)), shuf);
-        for (int r = 0; r < 16; r++) {
-            __m128i cur = m[r & 3];
-            msg = _mm_add_epi32(cur, _mm_loadu_si128((const __m128i *)&K[4 * r]));
-            s1 = _mm_sha256rnds2_epu32(s1, s0, msg);
-            msg = _mm_shuffle_epi32(msg, 0x0E);
-            s0 = _mm_sha256rnds2_epu32(s0, s1, msg);
-            if (r < 12) { /* next schedule words: W[4(r+4) .. 4(r+4)+3] replaces m[r&3] */
-                __m128i w0 = m[r & 3], w1 = m[(r + 1) & 3], w2 = m[(r + 2) & 3], w3 = m[(r + 3) & 3];
-                __m128i x = _mm_sha256msg1_epu32(w0, w1);
-                x = _mm_add_epi32(x, _mm_alignr_epi8(w3, w2, 4));
-                m[r & 3] = _mm_sha256msg2_epu32(x, w3);
-            }
-        }
+        const __m128i save0 = s0, save1 = s1;
+        __m128i m0 = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i *)(p + 0)), shuf);
+        __m128i m1 = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i *)(p + 16)), shuf);
+        __m128i m2 = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i *)(p + 32)), shuf);
+        __m128i m3 = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i *)(p + 48)), shuf);
+        SHA_RNDS4(m0, 0);  SHA_SCHED(m0, m1, m2, m3);
+        SHA_RNDS4(m1, 4);  SHA_SCHED(m1, m2, m3, m0);
+        SHA_RNDS4(m2, 8);  SHA_SCHED(m2, m3, m0, m1);
+        SHA_RNDS4(m3, 12); SHA_SCHED(m3, m0, m1, m2);
+        SHA_RNDS4(m0, 16); SHA_SCHED(m0, m1, m2, m3);
+        SHA_RNDS4(m1, 20); SHA_SCHED(m1, m2, m3, m0);
+        SHA_RNDS4(m2, 24); SHA_SCHED(m2, m3, m0, m1);
+        SHA_RNDS4(m3, 28); SHA_SCHED(m3, m0, m1, m2);
+        SHA_RNDS4(m0, 32); SHA_SCHED(m0, m1, m2, m3);
+        SHA_RNDS4(m1, 36); SHA_SCHED(m1, m2, m3, m0);
+        SHA_RNDS4(m2, 40); SHA_SCHED(m2, m3, m0, m1);
+        SHA_RNDS4(m3, 44); SHA_SCHED(m3, m0, m1, m2);
+        SHA_RNDS4(m0, 48);
+        SHA_RNDS4(m1, 52);
+        SHA_RNDS4(m2, 56);
+        SHA_RNDS4(m3, 60);
         s0 = _mm_add_epi32(s0, save0);
         s1 = _mm_add_epi32(s1, save1);
         p += 64;
@@ -91,6 +112,8 @@ __attribute__((target("sha,sse4.1,ssse3"))) static void blocks_shani(uint32_t h[
     _mm_storeu_si128((__m128i *)&h[0], s0);
     _mm_storeu_si128((__m128i *)&h[4], s1);
 }
+#undef SHA_RNDS4
+#undef SHA_SCHED
 #endif
 
 static void blocks(uint32_t h[8], const uint8_t *p, size_t n) {
