@@ -34,6 +34,7 @@ struct CombinerStats {
 
 class Combiner {
 public:
+    static constexpr int kUnserved = 3;  // C_KZG_MALLOC: what a caller sees if the executor could not run its batch
     explicit Combiner(size_t max_batch, int max_inflight = 2) : max_batch_(max_batch ? max_batch : 1), max_inflight_(max_inflight < 1 ? 1 : max_inflight) {}
 
     // Runs `r` through `run(std::vector<CoReq*>&)`, which must set rc of every request it is given.
@@ -57,7 +58,14 @@ public:
             stats_.batches++;
             if (batch.size() > stats_.largest) stats_.largest = batch.size();
             lk.unlock();
-            run(batch);
+            // a request is never reported as served unless the executor said so: an executor that throws
+            // (allocation failure while gathering a batch) fails the batch instead of wedging the queue
+            for (CoReq* b : batch) b->rc = kUnserved;
+            try {
+                run(batch);
+            } catch (...) {
+                for (CoReq* b : batch) b->rc = kUnserved;
+            }
             lk.lock();
             inflight_--;
             for (CoReq* b : batch) b->done = true;

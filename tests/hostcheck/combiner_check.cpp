@@ -1,6 +1,7 @@
 // TEST-ONLY harness for the call-coalescing front end (c-kzg-4844_b200/csrc/combiner.h) with a mock
 // executor: `threads` callers submit `per_thread` requests each; the executor sleeps `exec_us` per batch
-// and answers request x with 3x + 1, or with rc = 1 when x is odd and `fail_odd` is set.
+// and answers request x with 3x + 1, or with rc = 1 when x is odd and `fail_odd` is set (fail_odd = 2: the executor
+// throws on every batch that contains a multiple of 7 -- those callers must all see Combiner::kUnserved).
 #include <atomic>
 #include <chrono>
 #include <thread>
@@ -20,9 +21,16 @@ extern "C" int combiner_selftest(int threads, int per_thread, int max_batch, int
         for (CoReq* r : b)
             if (r->aux != b[0]->aux) mixed++;
         std::this_thread::sleep_for(std::chrono::microseconds(exec_us));
+        if (fail_odd == 2) {
+            for (CoReq* r : b)
+                if (*(const uint64_t*)r->in[0] % 7 == 0) {
+                    --concurrent;
+                    throw 1;
+                }
+        }
         for (CoReq* r : b) {
             uint64_t x = *(const uint64_t*)r->in[0];
-            if (fail_odd && (x & 1)) {
+            if (fail_odd == 1 && (x & 1)) {
                 r->rc = 1;
             } else {
                 *(uint64_t*)r->out[0] = 3 * x + 1;
@@ -41,7 +49,10 @@ extern "C" int combiner_selftest(int threads, int per_thread, int max_batch, int
                 r.out[0] = &y;
                 r.aux = classes > 1 ? (x % (uint64_t)classes) : 0;
                 int rc = comb.submit(r, run);
-                if (fail_odd && (x & 1)) {
+                if (fail_odd == 2) {  // either served correctly or reported as unserved, never a silent wrong answer
+                    if (!((rc == 0 && y == 3 * x + 1) || (rc == Combiner::kUnserved && y == 0))) errors++;
+                    if (x % 7 == 0 && rc != Combiner::kUnserved) errors++;
+                } else if (fail_odd == 1 && (x & 1)) {
                     if (rc != 1) errors++;
                 } else if (rc != 0 || y != 3 * x + 1) {
                     errors++;

@@ -55,3 +55,10 @@ def test_per_request_return_codes_survive_batching(lib):
 def test_classes_never_share_a_batch(lib):
     rc, (req, batches, largest, peak) = run(lib, 24, 20, 64, 2, 1000, classes=3)
     assert rc == 0 and req == 480
+
+
+def test_executor_failure_fails_the_batch_not_the_queue(lib):
+    """An executor that throws (e.g. an allocation failure while gathering a batch) must surface as an error code to
+    exactly the callers of that batch; later batches keep flowing and nobody gets a silent wrong answer."""
+    rc, (req, batches, largest, peak) = run(lib, 16, 30, 8, 2, 300, fail_odd=2)
+    assert rc == 0 and req == 480
