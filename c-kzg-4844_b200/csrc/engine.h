@@ -92,13 +92,16 @@ struct Ctx {
     void* pin_acquire(size_t bytes, size_t* got) {
         {
             std::lock_guard<std::mutex> g(pin_mu);
+            // best fit: a 48-byte request must not walk off with the 16 MB staging block of a coalesced batch
+            size_t best = pin_free.size();
             for (size_t i = 0; i < pin_free.size(); i++)
-                if (pin_free[i].second >= bytes) {
-                    void* p = pin_free[i].first;
-                    *got = pin_free[i].second;
-                    pin_free.erase(pin_free.begin() + i);
-                    return p;
-                }
+                if (pin_free[i].second >= bytes && (best == pin_free.size() || pin_free[i].second < pin_free[best].second)) best = i;
+            if (best != pin_free.size()) {
+                void* p = pin_free[best].first;
+                *got = pin_free[best].second;
+                pin_free.erase(pin_free.begin() + best);
+                return p;
+            }
         }
         void* p = nullptr;
         size_t cap = bytes < 4096 ? 4096 : bytes;
@@ -108,7 +111,7 @@ struct Ctx {
     }
     void pin_release(void* p, size_t cap) {
         std::lock_guard<std::mutex> g(pin_mu);
-        if (pin_free.size() < 8) {
+        if (pin_free.size() < 16) {
             pin_free.push_back({p, cap});
             return;
         }
