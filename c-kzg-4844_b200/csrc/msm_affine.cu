@@ -18,8 +18,11 @@
 // points give infinity.
 //
 // Replaces g1_lincomb_fast (src/common/lincomb.c:65) for the fixed bases of blob_to_kzg_commitment and of the
-// quotient commitment, like msm_direct.cu; used when a batch has at least BAM_MIN_BLOBS blobs (a single blob
-// is faster through the one-kernel XYZZ form: every level here is a latency chain of its own).
+// quotient commitment, like msm_direct.cu -- behind CKZG_B200_AFFINE_MIN (off by default: with the 61 GB table
+// level 1 is bound by its two passes of random HBM reads and the form only reaches parity, r02p) -- and, in
+// the second half of this file, the 128 x MSM(64) of FK20 for batches of >= 8 blobs, where it is 20 % faster
+// than the XYZZ kernel (r02q).  A single blob stays on the one-kernel XYZZ forms: every level here is a
+// latency chain of its own.
 #define KZG_FP_MUL_OUTLINE 1
 #include "affine_batch.cuh"
 #include "cells.h"

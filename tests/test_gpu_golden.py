@@ -94,7 +94,7 @@ def test_commitment_batch_entry(gpu, ref):
 
 
 def test_table_plans_agree(gpu, ref, monkeypatch):
-    """The fixed-base tables are sized from the free HBM when a context is created (api.cu plan_tables):
+    """The fixed-base tables are sized from the free HBM when they are first needed (api.cu plan_commit_window / plan_fk_window):
     the bucket MSM / 8-bit FK20 windows that serve when memory is short must give the same bytes as the
     direct commitment table / 12-bit windows (and as the reference)."""
     from gpu_common import product
