@@ -26,7 +26,9 @@ extern "C" {
 
 typedef struct ckzg_b200_ctx ckzg_b200_ctx; /* opaque: device-resident trusted setup + tables */
 
-/* where a caller buffer lives */
+/* where a caller buffer lives.  HOST buffers need no alignment (the frozen API takes byte pointers from Go slices,
+ * Python bytes, ...: they are copied to aligned device staging); DEVICE buffers must be 16-byte aligned (the kernels
+ * read field elements as two 128-bit words), which cudaMalloc / torch allocations always are. */
 enum { CKZG_B200_HOST = 0, CKZG_B200_DEVICE = 1 };
 
 /*
