@@ -43,23 +43,32 @@ def lib():
             "load_trusted_setup blob_to_kzg_commitment compute_kzg_proof compute_blob_kzg_proof verify_kzg_proof "
             "verify_blob_kzg_proof verify_blob_kzg_proof_batch ckzg_b200_blob_to_kzg_commitment_batch "
             "ckzg_b200_compute_blob_kzg_proof_batch ckzg_b200_compute_kzg_proof_batch ckzg_b200_verify_blob_kzg_proof_batch "
-            "ckzg_b200_verify_kzg_proof ckzg_b200_verify_blob_batch_stage1 ckzg_b200_verify_blob_batch_stage2 "
-            "ckzg_b200_verify_blob_batch_finish ckzg_b200_compute_challenge ckzg_b200_selftest_field ckzg_b200_selftest_g1"
+            "ckzg_b200_verify_kzg_proof ckzg_b200_verify_shard_stage1 ckzg_b200_verify_shard_stage2 "
+            "ckzg_b200_verify_shard_finish ckzg_b200_pack_verify_tuples ckzg_b200_compute_challenge ckzg_b200_selftest_field ckzg_b200_selftest_g1"
         ).split():
             getattr(_lib, name).restype = C.c_int
         _lib.ckzg_b200_launch_count.restype = C.c_uint64
         _lib.ckzg_b200_launch_count.argtypes = [C.c_void_p]
         _lib.free_trusted_setup.restype = None
+        _lib.ckzg_b200_verify_shard_free.restype = None
+        _lib.ckzg_b200_verify_shard_free.argtypes = [C.c_void_p]
+        _lib.ckzg_b200_set_caller_stream.restype = None
+        _lib.ckzg_b200_set_caller_stream.argtypes = [C.c_void_p]
     return _lib
 
 
 def _raise(code, fn):
+    """C_KZG_RET -> exception; the code rides along as `.code` (parallel.py agrees on it across ranks)."""
+    if code == 0:
+        return
     if code == 1:
-        raise ValueError("%s: invalid argument (C_KZG_BADARGS)" % fn)
-    if code == 3:
-        raise MemoryError("%s: C_KZG_MALLOC" % fn)
-    if code != 0:
-        raise RuntimeError("%s: C_KZG_ERROR (code %d) -- CUDA device/engine failure; there is no CPU path" % (fn, code))
+        e = ValueError("%s: invalid argument (C_KZG_BADARGS)" % fn)
+    elif code == 3:
+        e = MemoryError("%s: C_KZG_MALLOC" % fn)
+    else:
+        e = RuntimeError("%s: C_KZG_ERROR (code %d) -- CUDA device/engine failure; there is no CPU path" % (fn, code))
+    e.code = code
+    raise e
 
 
 class TrustedSetup:
@@ -206,38 +215,54 @@ def verify_blob_kzg_proof_batch_host(blobs_ptr, commitments_ptr, proofs_ptr, n, 
     return bool(ok.value)
 
 
-def verify_stage1(blobs_ptr, commitments_ptr, proofs_ptr, n, ts, mem=DEVICE):
-    """Per-blob stage of the sharded verifier -> n x 64 bytes (z || y), see parallel.py."""
-    out = C.create_string_buffer(64 * max(n, 1))
-    if mem == DEVICE:
-        import torch
+class VerifyShard:
+    """One rank's shard of a sharded verify_blob_kzg_proof_batch (include/ckzg_b200.h, parallel.py): the per-blob
+    stage runs in the constructor (-> self.zy, n x 64 bytes of z || y), the validated points, their vmsm table, z and y
+    stay on the device until stage2()."""
 
-        dev_out = torch.empty(64 * max(n, 1), dtype=torch.uint8, device="cuda")
+    def __init__(self, blobs_ptr, commitments_ptr, proofs_ptr, n, ts, mem=DEVICE):
+        self.n = n
+        self._h = C.c_void_p(None)
+        out = C.create_string_buffer(64 * max(n, 1))
         _raise(
-            lib().ckzg_b200_verify_blob_batch_stage1(ts.engine, C.c_void_p(dev_out.data_ptr()), C.c_void_p(blobs_ptr), C.c_void_p(commitments_ptr), C.c_void_p(proofs_ptr), C.c_uint64(n), DEVICE),
-            "ckzg_b200_verify_blob_batch_stage1",
+            lib().ckzg_b200_verify_shard_stage1(ts.engine, C.byref(self._h), out, C.c_void_p(blobs_ptr), C.c_void_p(commitments_ptr), C.c_void_p(proofs_ptr), C.c_uint64(n), mem),
+            "ckzg_b200_verify_shard_stage1",
         )
-        return bytes(dev_out.cpu().numpy().tobytes())[: 64 * n]
-    _raise(
-        lib().ckzg_b200_verify_blob_batch_stage1(ts.engine, out, C.c_void_p(blobs_ptr), C.c_void_p(commitments_ptr), C.c_void_p(proofs_ptr), C.c_uint64(n), HOST),
-        "ckzg_b200_verify_blob_batch_stage1",
-    )
-    return out.raw[: 64 * n]
+        self.zy = out.raw[: 64 * n]
+
+    def stage2(self, tuples, n_total, first):
+        part = C.create_string_buffer(384)
+        _raise(lib().ckzg_b200_verify_shard_stage2(self._h, part, bytes(tuples), C.c_uint64(n_total), C.c_uint64(first)), "ckzg_b200_verify_shard_stage2")
+        return part.raw
+
+    def close(self):
+        if self._h:
+            lib().ckzg_b200_verify_shard_free(self._h)
+            self._h = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
-def verify_stage2(tuples, n_total, first, n_local, ts):
-    part = C.create_string_buffer(144)
-    _raise(
-        lib().ckzg_b200_verify_blob_batch_stage2(ts.engine, part, bytes(tuples), C.c_uint64(n_total), C.c_uint64(first), C.c_uint64(n_local), HOST),
-        "ckzg_b200_verify_blob_batch_stage2",
-    )
-    return part.raw
+def pack_verify_tuples(commitments, zy, proofs, n):
+    """n x 160-byte records C || z || y || proof (eip4844.c:648-660), assembled in C."""
+    out = C.create_string_buffer(160 * max(n, 1))
+    _raise(lib().ckzg_b200_pack_verify_tuples(out, bytes(commitments), bytes(zy), bytes(proofs), C.c_uint64(n)), "ckzg_b200_pack_verify_tuples")
+    return out.raw[: 160 * n]
 
 
-def verify_finish(partials, n_ranks, ts):
+def verify_shard_finish(partials, n_ranks, ts):
     ok = C.c_int(0)
-    _raise(lib().ckzg_b200_verify_blob_batch_finish(ts.engine, C.byref(ok), bytes(partials), C.c_uint64(n_ranks)), "ckzg_b200_verify_blob_batch_finish")
+    _raise(lib().ckzg_b200_verify_shard_finish(ts.engine, C.byref(ok), bytes(partials), C.c_uint64(n_ranks)), "ckzg_b200_verify_shard_finish")
     return bool(ok.value)
+
+
+def set_caller_stream(cuda_stream_ptr):
+    """DEVICE-mode ordering (include/ckzg_b200.h): this thread's engine calls wait for work enqueued on this stream."""
+    lib().ckzg_b200_set_caller_stream(C.c_void_p(cuda_stream_ptr or None))
 
 
 def compute_cells_and_kzg_proofs(blob, ts):

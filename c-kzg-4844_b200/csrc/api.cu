@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <thread>
 #include <vector>
 
 #include "../../include/ckzg_b200.h"
@@ -14,6 +15,11 @@
 #include "call.h"
 
 namespace kzg {
+
+cudaStream_t& caller_stream_tls() {
+    static thread_local cudaStream_t s = nullptr;
+    return s;
+}
 
 void note_cuda_error(cudaError_t e, const char* file, int line) {
     if (getenv("CKZG_B200_DEBUG")) fprintf(stderr, "[ckzg_b200] CUDA error %d (%s) at %s:%d\n", (int)e, cudaGetErrorString(e), file, line);
@@ -88,7 +94,11 @@ static int ctx_build(Ctx* c, const uint8_t* g1_mono, const uint8_t* g1_lag, cons
 
 static void ctx_free(Ctx* c) {
     if (!c) return;
+    for (size_t d = 1; d < c->peers.size(); d++) ctx_free(c->peers[d]);  // peers[0] is the context itself
+    c->peers.clear();
     coalescer_destroy(c);
+    delete c->pool;
+    c->pool = nullptr;
     int prev = -1;
     cudaGetDevice(&prev);
     cudaSetDevice(c->device);
@@ -121,23 +131,8 @@ struct ckzg_b200_ctx {
 
 extern "C" {
 
-int ckzg_b200_ctx_create(ckzg_b200_ctx** out, const uint8_t* g1_monomial_bytes, const uint8_t* g1_lagrange_bytes, const uint8_t* g2_monomial_bytes, uint64_t precompute, int device) {
-    if (!out || !g1_monomial_bytes || !g1_lagrange_bytes || !g2_monomial_bytes) return RET_BADARGS;
-    *out = nullptr;
-    if (precompute > 15) return RET_BADARGS;  // setup.c:411
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-        note_cuda_error(cudaErrorNoDevice, __FILE__, __LINE__);
-        return RET_ERROR;  // no CPU fallback, by design
-    }
-    if (device < 0) {
-        const char* env = getenv("CKZG_B200_DEVICE");
-        if (env)
-            device = atoi(env);
-        else if (cudaGetDevice(&device) != cudaSuccess)
-            return RET_ERROR;
-    }
-    if (device >= ndev) return RET_BADARGS;
+// one ordinary context on one device
+static int ctx_create_single(Ctx** out, const uint8_t* g1_monomial_bytes, const uint8_t* g1_lagrange_bytes, const uint8_t* g2_monomial_bytes, uint64_t precompute, int device) {
     Ctx* c = new (std::nothrow) Ctx();
     if (!c) return RET_MALLOC;
     {
@@ -160,13 +155,92 @@ int ckzg_b200_ctx_create(ckzg_b200_ctx** out, const uint8_t* g1_monomial_bytes, 
         return rc;
     }
     coalescer_create(c);
+    *out = c;
+    return RET_OK;
+}
+
+// CKZG_B200_DEVICES = "all" | "0,1,2,3": the devices one context spans (multi.cu).  Empty / unset: one device.
+static std::vector<int> devices_from_env(int ndev) {
+    std::vector<int> v;
+    const char* env = getenv("CKZG_B200_DEVICES");
+    if (!env || !*env) return v;
+    if (strcmp(env, "all") == 0) {
+        for (int d = 0; d < ndev; d++) v.push_back(d);
+        return v;
+    }
+    for (const char* p = env; *p;) {
+        char* end = nullptr;
+        long d = strtol(p, &end, 10);
+        if (end == p) break;
+        bool dup = false;
+        for (int x : v) dup = dup || x == (int)d;
+        if (d >= 0 && d < ndev && !dup) v.push_back((int)d);
+        p = (*end == ',') ? end + 1 : end;
+        if (*end && *end != ',') break;
+    }
+    return v;
+}
+
+int ckzg_b200_ctx_create(ckzg_b200_ctx** out, const uint8_t* g1_monomial_bytes, const uint8_t* g1_lagrange_bytes, const uint8_t* g2_monomial_bytes, uint64_t precompute, int device) {
+    if (!out || !g1_monomial_bytes || !g1_lagrange_bytes || !g2_monomial_bytes) return RET_BADARGS;
+    *out = nullptr;
+    if (precompute > 15) return RET_BADARGS;  // setup.c:411
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        note_cuda_error(cudaErrorNoDevice, __FILE__, __LINE__);
+        return RET_ERROR;  // no CPU fallback, by design
+    }
+    std::vector<int> devs;
+    if (device < 0) {
+        devs = devices_from_env(ndev);
+        const char* env = getenv("CKZG_B200_DEVICE");
+        if (!devs.empty())
+            device = devs[0];
+        else if (env)
+            device = atoi(env);
+        else if (cudaGetDevice(&device) != cudaSuccess)
+            return RET_ERROR;
+    }
+    if (device >= ndev || device < 0) return RET_BADARGS;
+    Ctx* c = nullptr;
+    int rc = ctx_create_single(&c, g1_monomial_bytes, g1_lagrange_bytes, g2_monomial_bytes, precompute, device);
+    if (rc) return rc;
+    if (devs.size() > 1) {
+        // one ordinary context per further device, built concurrently (each decompresses the setup on its own GPU)
+        std::vector<Ctx*> peers(devs.size(), nullptr);
+        std::vector<int> rcs(devs.size(), RET_OK);
+        std::vector<std::thread> th;
+        peers[0] = c;
+        for (size_t d = 1; d < devs.size(); d++)
+            th.emplace_back([&, d] { rcs[d] = ctx_create_single(&peers[d], g1_monomial_bytes, g1_lagrange_bytes, g2_monomial_bytes, precompute, devs[d]); });
+        for (auto& t : th) t.join();
+        for (size_t d = 1; d < devs.size() && !rc; d++) rc = rcs[d];
+        if (rc) {
+            for (size_t d = 1; d < devs.size(); d++)
+                if (peers[d]) ctx_free(peers[d]);
+            ctx_free(c);
+            return rc;
+        }
+        c->peers = peers;
+    }
     *out = reinterpret_cast<ckzg_b200_ctx*>(c);
     return RET_OK;
 }
 
 void ckzg_b200_ctx_destroy(ckzg_b200_ctx* ctx) { ctx_free(reinterpret_cast<Ctx*>(ctx)); }
 int ckzg_b200_ctx_device(const ckzg_b200_ctx* ctx) { return reinterpret_cast<const Ctx*>(ctx)->device; }
-uint64_t ckzg_b200_launch_count(const ckzg_b200_ctx* ctx) { return reinterpret_cast<const Ctx*>(ctx)->launches.load(); }
+int ckzg_b200_ctx_device_count(const ckzg_b200_ctx* ctx) {
+    const Ctx* c = reinterpret_cast<const Ctx*>(ctx);
+    return c->peers.empty() ? 1 : (int)c->peers.size();
+}
+void ckzg_b200_set_caller_stream(void* cuda_stream) { caller_stream_tls() = (cudaStream_t)cuda_stream; }
+
+uint64_t ckzg_b200_launch_count(const ckzg_b200_ctx* ctx) {
+    const Ctx* c = reinterpret_cast<const Ctx*>(ctx);
+    uint64_t total = c->launches.load();
+    for (size_t d = 1; d < c->peers.size(); d++) total += c->peers[d]->launches.load();
+    return total;
+}
 
 }  // extern "C" (reopened below)
 namespace kzg {
@@ -218,6 +292,14 @@ extern "C" {
 int ckzg_b200_blob_to_kzg_commitment_batch(ckzg_b200_ctx* ctx, uint8_t* out, const uint8_t* blobs, uint64_t n, int mem, int* status) {
     if (!ctx || !out || !blobs) return RET_BADARGS;
     if (n == 0) return RET_OK;
+    if (mem == CKZG_B200_HOST) {  // a context spanning devices: contiguous ranges of blobs, one per device
+        Ctx* mc = reinterpret_cast<Ctx*>(ctx);
+        const int parts = multi_parts(mc, n, 16);
+        if (parts > 1)
+            return multi_map(mc, n, parts, [&](ckzg_b200_ctx* dc, uint64_t f, uint64_t m) {
+                return ckzg_b200_blob_to_kzg_commitment_batch(dc, out + 48 * f, blobs + f * BLOB_BYTES, m, mem, status ? status + f : nullptr);
+            });
+    }
     Call call(reinterpret_cast<Ctx*>(ctx));
     if (!call.ok) return RET_ERROR;
     const uint8_t* d_blobs;

@@ -2,6 +2,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <string>
 #include <unordered_map>
 
@@ -45,6 +46,15 @@ int ckzg_b200_compute_cells_and_kzg_proofs_batch(ckzg_b200_ctx* ctx, uint8_t* ce
     if (!ctx || !blobs) return RET_BADARGS;
     if (!cells && !proofs) return RET_BADARGS;  // eip7594.c:72-74
     if (n == 0) return RET_OK;
+    if (mem == CKZG_B200_HOST) {  // a context spanning devices: contiguous ranges of blobs, one per device
+        Ctx* mc = reinterpret_cast<Ctx*>(ctx);
+        const int parts = multi_parts(mc, n, 8);
+        if (parts > 1)
+            return multi_map(mc, n, parts, [&](ckzg_b200_ctx* dc, uint64_t f, uint64_t m) {
+                return ckzg_b200_compute_cells_and_kzg_proofs_batch(dc, cells ? cells + f * 2 * BLOB_BYTES : nullptr, proofs ? proofs + f * 128 * 48 : nullptr,
+                                                                    blobs + f * BLOB_BYTES, m, mem, status ? status + f : nullptr);
+            });
+    }
     Call call(reinterpret_cast<Ctx*>(ctx));
     if (!call.ok) return RET_ERROR;
     Launch L = call.launch();
@@ -101,6 +111,23 @@ int ckzg_b200_recover_cells_and_kzg_proofs_batch(ckzg_b200_ctx* ctx, uint8_t* re
     if (n == 0) return RET_OK;
     // eip7594.c:191-213: count and index checks (host side, before anything else)
     if (num_cells > 128 || num_cells < 64) return RET_BADARGS;
+    if (mem == CKZG_B200_HOST) {
+        Ctx* mc = reinterpret_cast<Ctx*>(ctx);
+        const int parts = multi_parts(mc, n, 8);
+        if (parts > 1) {
+            // index errors are BADARGS for the whole call before any work (eip7594.c:191-213): check all ranges first
+            for (uint64_t b = 0; b < n; b++)
+                for (uint64_t i = 0; i < num_cells; i++) {
+                    const uint64_t v = cell_indices[b * num_cells + i];
+                    if (v >= 128 || (i > 0 && v <= cell_indices[b * num_cells + i - 1])) return RET_BADARGS;
+                }
+            return multi_map(mc, n, parts, [&](ckzg_b200_ctx* dc, uint64_t f, uint64_t m) {
+                return ckzg_b200_recover_cells_and_kzg_proofs_batch(dc, recovered_cells + f * 2 * BLOB_BYTES, recovered_proofs ? recovered_proofs + f * 128 * 48 : nullptr,
+                                                                    cell_indices + f * num_cells, cells + f * num_cells * CELL_BYTES, num_cells, m, mem,
+                                                                    status ? status + f : nullptr);
+            });
+        }
+    }
     std::vector<int16_t> slot(n * 128, (int16_t)-1);
     std::vector<uint8_t> present(n * 128, 0);
     for (uint64_t b = 0; b < n; b++) {
@@ -175,6 +202,33 @@ int ckzg_b200_verify_cell_kzg_proof_batch(ckzg_b200_ctx* ctx, int* ok, const uin
     if (!commitments || !cell_indices || !cells || !proofs) return RET_BADARGS;
     for (uint64_t i = 0; i < n; i++)
         if (cell_indices[i] >= 128) return RET_BADARGS;  // eip7594.c:861-864
+    if (mem == CKZG_B200_HOST && !multi_inside_fanout()) {
+        // Large batches are verified as independent SUB-BATCHES -- contiguous ranges of cells, each with its own
+        // Fiat-Shamir challenge (each exactly the reference's verification of that range), verdicts AND-ed, any
+        // invalid encoding -> BADARGS: a batch is valid iff every sub-batch is, so (return code, *ok) are the
+        // reference's.  It is the reference's own parallel pattern (bindings/go/main_test.go:1037-1101), applied
+        // inside the call: the one serial transcript hash (2112 B per cell, eip7594.c:405-474; 85 % of a 256-blob call
+        // on one host core) becomes one hash per sub-batch on its own host thread, and the sub-batches spread over
+        // the context's devices.  CKZG_B200_CELL_SUBBATCH=0 restores one challenge per call; =k sets the count per device.
+        Ctx* mc = reinterpret_cast<Ctx*>(ctx);
+        static const int sub_env = getenv("CKZG_B200_CELL_SUBBATCH") ? atoi(getenv("CKZG_B200_CELL_SUBBATCH")) : -1;
+        const int per_dev = sub_env >= 0 ? sub_env : host_threads_default();
+        const uint64_t want = (uint64_t)multi_device_count(mc) * (uint64_t)(per_dev < 1 ? 1 : per_dev);
+        const uint64_t by_size = n / 4096;  // at least 32 blobs' worth of cells per sub-batch
+        const uint64_t parts = sub_env == 0 ? (uint64_t)multi_parts(mc, n, 4096) : (by_size < want ? by_size : want);
+        if (parts >= 2) {
+            std::atomic<int> all_ok{1};
+            int rc = multi_map(mc, n, (int)parts, [&](ckzg_b200_ctx* dc, uint64_t f, uint64_t m) {
+                int o = 0;
+                int r = ckzg_b200_verify_cell_kzg_proof_batch(dc, &o, commitments + 48 * f, cell_indices + f, cells + f * CELL_BYTES, proofs + 48 * f, m, mem);
+                if (!o) all_ok.store(0);
+                return r;
+            });
+            if (rc) return rc;
+            *ok = all_ok.load();
+            return RET_OK;
+        }
+    }
     Call call(reinterpret_cast<Ctx*>(ctx));
     if (!call.ok) return RET_ERROR;
     Launch L = call.launch();

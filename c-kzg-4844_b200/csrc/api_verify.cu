@@ -5,12 +5,19 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <memory>
+#include <thread>
 
 #include "../src/host_sha256.h"
 #include "call.h"
 #include "verify.h"
 
 using namespace kzg;
+
+namespace kzg {
+int verify_blob_batch_multi(Ctx* c, int* ok, const uint8_t* blobs, const uint8_t* commitments, const uint8_t* proofs, uint64_t n, int D);
+}
 
 namespace {
 
@@ -105,7 +112,7 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
     TRY(call.alloc(&s.bad, 1));
     KZG_CUDA_TRY(cudaMemsetAsync(s.bad, 0, sizeof(int), call.stream));
     if (host && (call.trace_kernels || n < 64)) {  // serial form
-        if (host) KZG_CUDA_TRY(cudaMemcpyAsync(d_up, blobs, n * BLOB_BYTES, cudaMemcpyHostToDevice, call.stream));
+        if (host) TRY(call.upload(d_up, blobs, n * BLOB_BYTES, call.stream));
         if (s.want_shift)
             TRY(launch_g1_validate2_levels(L, s.cm, d_cm, s.pf, d_pf, n, s.bad, s.table));
         else
@@ -132,20 +139,13 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
     const uint64_t CH = host ? 512 : n;
     const int nchunks = (int)((n + CH - 1) / CH);
     const int nside = std::min(8, nchunks);
+    // side streams are forked from (ordered after) the call stream and joined / destroyed by the Call on
+    // every exit path, so no early return below can leave a kernel reading released scratch
     cudaStream_t side[8], copy = nullptr;
-    cudaEvent_t ev;
-    KZG_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    KZG_CUDA_TRY(cudaEventRecord(ev, call.stream));
     int rc = RET_OK;
-    for (int i = 0; i < nside; i++) {
-        if (cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking) != cudaSuccess) return RET_ERROR;
-        cudaStreamWaitEvent(side[i], ev, 0);
-    }
-    if (host) {
-        if (cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking) != cudaSuccess) return RET_ERROR;
-        cudaStreamWaitEvent(copy, ev, 0);
-    }
-    cudaEventDestroy(ev);
+    for (int i = 0; i < nside; i++)
+        if (!(side[i] = call.fork())) return RET_ERROR;
+    if (host && !(copy = call.fork())) return RET_ERROR;
     std::vector<cudaEvent_t> hashed(nchunks, nullptr);
     int c = 0;
     for (uint64_t off = 0; off < n && rc == RET_OK; off += CH, c++) {
@@ -153,7 +153,8 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
         cudaStream_t st = side[c % nside];
         if (host) {
             cudaEvent_t landed;
-            if (cudaMemcpyAsync(d_up + off * BLOB_BYTES, blobs + off * BLOB_BYTES, m * BLOB_BYTES, cudaMemcpyHostToDevice, copy) != cudaSuccess ||
+            // pinned sources: one DMA per chunk; pageable sources: staged through the pinned ring by the host threads
+            if (call.upload(d_up + off * BLOB_BYTES, blobs + off * BLOB_BYTES, m * BLOB_BYTES, copy) != RET_OK ||
                 cudaEventCreateWithFlags(&landed, cudaEventDisableTiming) != cudaSuccess) {
                 rc = RET_ERROR;
                 break;
@@ -184,8 +185,6 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
         cudaEventDestroy(hashed[c]);
         if (rc == RET_OK) rc = launch_evaluate(L, s.y + off, s.zy + off * 64, nullptr, nullptr, d_blobs + off * BLOB_BYTES, s.z + off, m, s.bad, 0);
     }
-    for (int i = 0; i < nside; i++) cudaStreamDestroy(side[i]);
-    if (copy) cudaStreamDestroy(copy);
     return rc;
 }
 
@@ -213,18 +212,6 @@ void transcript_digest(uint8_t digest[32], const uint8_t* cm, const uint8_t* zy,
     }
     ckzg_host_sha256_final(&h, digest);
 }
-int r_from_transcript(Call& call, Fr* d_r, const uint8_t* cm, const uint8_t* zy, const uint8_t* pf, const uint8_t* tuples, uint64_t n) {
-    Launch L = call.launch();
-    uint8_t digest[32];
-    transcript_digest(digest, cm, zy, pf, tuples, n);
-    uint8_t* d_digest;
-    TRY(call.alloc(&d_digest, 32));
-    KZG_CUDA_TRY(cudaMemcpyAsync(d_digest, digest, 32, cudaMemcpyHostToDevice, call.stream));
-    KZG_CUDA_TRY(cudaStreamSynchronize(call.stream));  // `digest` is a stack buffer
-    TRY(launch_r_from_digest(L, d_r, d_digest));
-    return RET_OK;
-}
-
 int read_flag(Call& call, const int* d_flag, int* out) {
     KZG_CUDA_TRY(cudaMemcpyAsync(out, d_flag, sizeof(int), cudaMemcpyDeviceToHost, call.stream));
     KZG_CUDA_TRY(cudaStreamSynchronize(call.stream));
@@ -238,6 +225,14 @@ extern "C" {
 int ckzg_b200_compute_kzg_proof_batch(ckzg_b200_ctx* ctx, uint8_t* proofs, uint8_t* ys, const uint8_t* blobs, const uint8_t* zs, uint64_t n, int mem, int* status) {
     if (!ctx || !proofs || !ys || !blobs || !zs) return RET_BADARGS;
     if (n == 0) return RET_OK;
+    if (mem == CKZG_B200_HOST) {
+        Ctx* mc = reinterpret_cast<Ctx*>(ctx);
+        const int parts = multi_parts(mc, n, 16);
+        if (parts > 1)
+            return multi_map(mc, n, parts, [&](ckzg_b200_ctx* dc, uint64_t f, uint64_t m) {
+                return ckzg_b200_compute_kzg_proof_batch(dc, proofs + 48 * f, ys + 32 * f, blobs + f * BLOB_BYTES, zs + 32 * f, m, mem, status ? status + f : nullptr);
+            });
+    }
     Call call(reinterpret_cast<Ctx*>(ctx));
     if (!call.ok) return RET_ERROR;
     Launch L = call.launch();
@@ -257,6 +252,14 @@ int ckzg_b200_compute_kzg_proof_batch(ckzg_b200_ctx* ctx, uint8_t* proofs, uint8
 int ckzg_b200_compute_blob_kzg_proof_batch(ckzg_b200_ctx* ctx, uint8_t* proofs, const uint8_t* blobs, const uint8_t* commitments, uint64_t n, int mem, int* status) {
     if (!ctx || !proofs || !blobs || !commitments) return RET_BADARGS;
     if (n == 0) return RET_OK;
+    if (mem == CKZG_B200_HOST) {
+        Ctx* mc = reinterpret_cast<Ctx*>(ctx);
+        const int parts = multi_parts(mc, n, 16);
+        if (parts > 1)
+            return multi_map(mc, n, parts, [&](ckzg_b200_ctx* dc, uint64_t f, uint64_t m) {
+                return ckzg_b200_compute_blob_kzg_proof_batch(dc, proofs + 48 * f, blobs + f * BLOB_BYTES, commitments + 48 * f, m, mem, status ? status + f : nullptr);
+            });
+    }
     Call call(reinterpret_cast<Ctx*>(ctx));
     if (!call.ok) return RET_ERROR;
     Launch L = call.launch();
@@ -280,16 +283,24 @@ int ckzg_b200_compute_blob_kzg_proof_batch(ckzg_b200_ctx* ctx, uint8_t* proofs, 
 
 // context-free calls (hash / encoding helpers of the reference that take no KZGSettings) run on a bare
 // context bound to the current device
+// (one immutable bare context per device, created once under a lock: concurrent callers with different current
+// devices never see each other's device -- the reference's helpers are re-entrant and so are these)
 static Ctx* bare_ctx() {
-    static Ctx bare;
+    static std::mutex mu;
+    static Ctx* table[64] = {nullptr};
     int dev = 0;
     const char* env = getenv("CKZG_B200_DEVICE");
     if (env)
         dev = atoi(env);
-    else
-        cudaGetDevice(&dev);
-    bare.device = dev;
-    return &bare;
+    else if (cudaGetDevice(&dev) != cudaSuccess)
+        dev = 0;
+    if (dev < 0 || dev >= 64) dev = 0;
+    std::lock_guard<std::mutex> g(mu);
+    if (!table[dev]) {
+        table[dev] = new Ctx();
+        table[dev]->device = dev;
+    }
+    return table[dev];
 }
 
 int ckzg_b200_hash_to_bls_field(uint8_t* out32, const uint8_t* digest32) {
@@ -357,6 +368,12 @@ int ckzg_b200_verify_blob_kzg_proof_batch(ckzg_b200_ctx* ctx, int* ok, const uin
         return RET_OK;
     }
     if (!blobs || !commitments || !proofs) return RET_BADARGS;
+    {
+        // a context that spans devices (CKZG_B200_DEVICES) shards HOST batches: >= 256 blobs per device
+        Ctx* c = reinterpret_cast<Ctx*>(ctx);
+        const uint64_t D = multi_inside_fanout() ? 1 : std::min<uint64_t>(c->peers.size(), n / 256);
+        if (mem == CKZG_B200_HOST && D >= 2) return verify_blob_batch_multi(c, ok, blobs, commitments, proofs, n, (int)D);
+    }
     Call call(reinterpret_cast<Ctx*>(ctx));
     if (!call.ok) return RET_ERROR;
     Launch L = call.launch();
@@ -375,12 +392,11 @@ int ckzg_b200_verify_blob_kzg_proof_batch(ckzg_b200_ctx* ctx, int* ok, const uin
     uint8_t *h_zy = pin, *h_c = pin + n * 64, *h_p = pin + n * 112;
     int* h_bad = (int*)(pin + n * 160);
     if (use_r && mem == CKZG_B200_DEVICE) {
-        cudaStream_t cp = nullptr;
-        if (cudaStreamCreateWithFlags(&cp, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&fetched, cudaEventDisableTiming) != cudaSuccess) return RET_ERROR;
+        cudaStream_t cp = call.fork();  // ordered after the caller's producer through the call stream
+        if (!cp || cudaEventCreateWithFlags(&fetched, cudaEventDisableTiming) != cudaSuccess) return RET_ERROR;
         cudaMemcpyAsync(h_c, d_cm, n * 48, cudaMemcpyDeviceToHost, cp);
         cudaMemcpyAsync(h_p, d_pf, n * 48, cudaMemcpyDeviceToHost, cp);
         cudaEventRecord(fetched, cp);
-        cudaStreamDestroy(cp);
     }
     int rc1 = verify_stage1(call, s, blobs, d_cm, d_pf, n, mem);
     if (rc1) {
@@ -427,7 +443,7 @@ int ckzg_b200_verify_blob_kzg_proof_batch(ckzg_b200_ctx* ctx, int* ok, const uin
     TRY(call.alloc((uint8_t**)&scratch, s.want_shift ? rlc_vmsm_scratch_bytes(n) : rlc_scratch_bytes(n)));
     TRY(call.alloc(&d_ok, 1));
     if (s.want_shift)
-        TRY(launch_rlc_vmsm(L, d_AB, s.table, s.z, s.y, digest, n, scratch));  // the digest travels as a kernel argument
+        TRY(launch_rlc_vmsm(L, d_AB, s.table, s.z, s.y, digest, 0, n, scratch));  // the digest travels as a kernel argument
     else
         TRY(launch_rlc(L, d_AB, s.cm, s.pf, s.z, s.y, d_r, use_r, 0, n, scratch));
     if (stage_marks) call.mark("stage:linear_combination");
@@ -481,126 +497,201 @@ int ckzg_b200_verify_kzg_proof(ckzg_b200_ctx* ctx, int* ok, const uint8_t* commi
 }
 
 // ---- multi-GPU split -----------------------------------------------------------
+// One GLOBAL batch, one Fiat-Shamir challenge, sharded by blob ranges (exact reference semantics for the whole
+// batch, eip4844.c:697-765).  A shard keeps its device state -- validated points, the vmsm table its validation left
+// behind, z_i, y_i -- between the per-blob stage and the linear combination, so nothing is decompressed or
+// validated twice and the combination is the same pair of bucket MSMs as the single-GPU call, with weights
+// r^(first + i).  Two front ends share it: the ckzg_b200_verify_shard_* entry points (one process per GPU,
+// the exchange steps are the caller's collectives: c-kzg-4844_b200/parallel.py) and the in-library
+// multi-device path below (CKZG_B200_DEVICES, exchange through pinned host memory).
+}  // extern "C"
 
-int ckzg_b200_verify_blob_batch_stage1(ckzg_b200_ctx* ctx, uint8_t* zy, const uint8_t* blobs, const uint8_t* commitments, const uint8_t* proofs, uint64_t n, int mem) {
-    if (!ctx || !zy || !blobs || !commitments || !proofs) return RET_BADARGS;
-    if (n == 0) return RET_OK;
-    Call call(reinterpret_cast<Ctx*>(ctx));
-    if (!call.ok) return RET_ERROR;
-    const uint8_t *d_blobs, *d_cm, *d_pf;
-    (void)d_blobs;
+namespace kzg {
+struct VerifyShard {
+    Call call;
+    Stage1 s;
+    uint64_t n = 0;
+    explicit VerifyShard(Ctx* c) : call(c) {}
+};
+
+// per-blob stage of a shard; zy_host (n x 64, HOST) receives z || y.  BADARGS for an invalid blob / point.
+static int shard_stage1(VerifyShard& sh, uint8_t* zy_host, const uint8_t* blobs, const uint8_t* commitments, const uint8_t* proofs, uint64_t n, int mem) {
+    Call& call = sh.call;
+    sh.n = n;
+    const uint8_t *d_cm, *d_pf;
     TRY(call.stage_in(&d_cm, commitments, n * 48, mem));
     TRY(call.stage_in(&d_pf, proofs, n * 48, mem));
-    Stage1 s;
-    TRY(verify_stage1(call, s, blobs, d_cm, d_pf, n, mem));
-    int bad = 0;
-    TRY(read_flag(call, s.bad, &bad));
-    if (bad) return RET_BADARGS;
-    cudaMemcpyKind kind = (mem == CKZG_B200_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-    KZG_CUDA_TRY(cudaMemcpyAsync(zy, s.zy, n * 64, kind, call.stream));
+    sh.s.want_shift = true;
+    TRY(verify_stage1(call, sh.s, blobs, d_cm, d_pf, n, mem));
+    uint8_t* pin = nullptr;
+    TRY(call.pin(&pin, 64));
+    int* h_bad = (int*)pin;
+    KZG_CUDA_TRY(cudaMemcpyAsync(zy_host, sh.s.zy, n * 64, cudaMemcpyDeviceToHost, call.stream));
+    KZG_CUDA_TRY(cudaMemcpyAsync(h_bad, sh.s.bad, sizeof(int), cudaMemcpyDeviceToHost, call.stream));
     KZG_CUDA_TRY(cudaStreamSynchronize(call.stream));
-    return RET_OK;
+    return *h_bad ? RET_BADARGS : RET_OK;
 }
-
-int ckzg_b200_verify_blob_batch_stage2(ckzg_b200_ctx* ctx, uint8_t* partial144, const uint8_t* tuples, uint64_t n_total, uint64_t first, uint64_t n_local, int mem) {
-    if (!ctx || !partial144 || !tuples || first + n_local > n_total) return RET_BADARGS;
-    Call call(reinterpret_cast<Ctx*>(ctx));
-    if (!call.ok) return RET_ERROR;
+// this shard's share of A and B (2 XYZZ points, 384 bytes of Montgomery limbs: an opaque exchange format) -> HOST
+static int shard_stage2(VerifyShard& sh, uint8_t* partial384_host, const uint8_t digest[32], uint64_t first) {
+    Call& call = sh.call;
     Launch L = call.launch();
-    const uint8_t* d_tuples;
-    TRY(call.stage_in(&d_tuples, tuples, n_total * 160, mem));
-    Fr* d_r;
-    TRY(call.alloc(&d_r, 1));
-    {
-        std::vector<uint8_t> h_t;
-        const uint8_t* ht = tuples;
-        if (mem == CKZG_B200_DEVICE) {
-            h_t.resize(n_total * 160);
-            KZG_CUDA_TRY(cudaMemcpyAsync(h_t.data(), d_tuples, n_total * 160, cudaMemcpyDeviceToHost, call.stream));
-            KZG_CUDA_TRY(cudaStreamSynchronize(call.stream));
-            ht = h_t.data();
-        }
-        TRY(r_from_transcript(call, d_r, nullptr, nullptr, nullptr, ht, n_total));
-    }
     G1* d_AB;
-    uint8_t* d_out;
-    TRY(call.alloc(&d_AB, 3));
-    TRY(call.alloc(&d_out, 144));
-    KZG_CUDA_TRY(cudaMemsetAsync(d_AB, 0, 3 * sizeof(G1), call.stream));  // zz == 0: infinity
-    if (n_local) {
-        // this rank's slice: unpack points and scalars from the 160-byte records (already validated in stage 1)
-        uint8_t *d_cm48, *d_pf48;
-        G1Affine *d_cm, *d_pf;
-        Fr *d_z, *d_y;
-        int* d_bad;
-        void* scratch;
-        TRY(call.alloc(&d_cm48, n_local * 48));
-        TRY(call.alloc(&d_pf48, n_local * 48));
-        TRY(call.alloc(&d_cm, n_local));
-        TRY(call.alloc(&d_pf, n_local));
-        TRY(call.alloc(&d_z, n_local));
-        TRY(call.alloc(&d_y, n_local));
-        TRY(call.alloc(&d_bad, 1));
-        TRY(call.alloc((uint8_t**)&scratch, rlc_scratch_bytes(n_local)));
-        KZG_CUDA_TRY(cudaMemsetAsync(d_bad, 0, sizeof(int), call.stream));
-        const uint8_t* base = d_tuples + first * 160;
-        KZG_CUDA_TRY(cudaMemcpy2DAsync(d_cm48, 48, base, 160, 48, n_local, cudaMemcpyDeviceToDevice, call.stream));
-        KZG_CUDA_TRY(cudaMemcpy2DAsync(d_pf48, 48, base + 112, 160, 48, n_local, cudaMemcpyDeviceToDevice, call.stream));
-        TRY(launch_g1_validate(L, d_cm, d_cm48, n_local, d_bad, 0));
-        TRY(launch_g1_validate(L, d_pf, d_pf48, n_local, d_bad, 0));
-        TRY(launch_fr_from_bytes(L, d_z, base + 48, 160, n_local, nullptr));
-        TRY(launch_fr_from_bytes(L, d_y, base + 80, 160, n_local, nullptr));
-        TRY(launch_rlc(L, d_AB, d_cm, d_pf, d_z, d_y, d_r, true, first, n_local, scratch));
-        int bad = 0;
-        TRY(read_flag(call, d_bad, &bad));
-        if (bad) return RET_BADARGS;
-    }
-    TRY(launch_g1_compress(L, d_out, d_AB, 2));
-    KZG_CUDA_TRY(cudaMemcpyAsync(partial144, d_out, 96, cudaMemcpyDeviceToHost, call.stream));
+    uint8_t* scratch;
+    TRY(call.alloc(&d_AB, 2));
+    TRY(call.alloc(&scratch, rlc_vmsm_scratch_bytes(sh.n)));
+    TRY(launch_rlc_vmsm(L, d_AB, sh.s.table, sh.s.z, sh.s.y, digest, first, sh.n, scratch));
+    KZG_CUDA_TRY(cudaMemcpyAsync(partial384_host, d_AB, 2 * sizeof(G1), cudaMemcpyDeviceToHost, call.stream));
     KZG_CUDA_TRY(cudaStreamSynchronize(call.stream));
-    memset(partial144 + 96, 0, 48);
-    partial144[96] = 0xC0;  // third slot reserved (infinity)
     return RET_OK;
 }
-
-int ckzg_b200_verify_blob_batch_finish(ckzg_b200_ctx* ctx, int* ok, const uint8_t* partials, uint64_t n_ranks) {
-    if (!ctx || !ok || !partials || n_ranks == 0) return RET_BADARGS;
-    *ok = 0;
-    Call call(reinterpret_cast<Ctx*>(ctx));
+// sum of the shards' partial points, one pairing check
+static int shards_finish(Ctx* c, int* ok, const uint8_t* partials, uint64_t n_ranks) {
+    Call call(c);
     if (!call.ok) return RET_ERROR;
     Launch L = call.launch();
-    // gather A_k and B_k (compressed) -> points -> two sums -> pairing
-    std::vector<uint8_t> a48(n_ranks * 48), b48(n_ranks * 48);
+    static_assert(sizeof(G1) == 192, "exchange format: 2 x 192-byte XYZZ points per shard");
+    std::vector<G1> h(2 * n_ranks);
     for (uint64_t k = 0; k < n_ranks; k++) {
-        memcpy(&a48[k * 48], partials + k * 144, 48);
-        memcpy(&b48[k * 48], partials + k * 144 + 48, 48);
+        memcpy(&h[k], partials + k * 384, 192);
+        memcpy(&h[n_ranks + k], partials + k * 384 + 192, 192);
     }
-    const uint8_t *d_a48, *d_b48;
-    TRY(call.stage_in(&d_a48, a48.data(), a48.size(), CKZG_B200_HOST));
-    TRY(call.stage_in(&d_b48, b48.data(), b48.size(), CKZG_B200_HOST));
-    G1Affine *d_a, *d_b;
-    int *d_bad, *d_ok;
-    TRY(call.alloc(&d_a, n_ranks));
-    TRY(call.alloc(&d_b, n_ranks));
-    TRY(call.alloc(&d_bad, 1));
-    TRY(call.alloc(&d_ok, 1));
-    KZG_CUDA_TRY(cudaMemsetAsync(d_bad, 0, sizeof(int), call.stream));
-    TRY(launch_g1_validate(L, d_a, d_a48, n_ranks, d_bad, 0));
-    TRY(launch_g1_validate(L, d_b, d_b48, n_ranks, d_bad, 0));
-    // sum with unit weights: reuse the RLC machinery with z = 0, y = 0 is wasteful; lift + tree-sum instead
-    G1 *d_pts, *d_AB;
-    TRY(call.alloc(&d_pts, 2 * n_ranks + 8));
+    G1 *d_a, *d_b, *d_AB;
+    int* d_ok;
+    TRY(call.alloc(&d_a, 2 * n_ranks + 8));
+    TRY(call.alloc(&d_b, 2 * n_ranks + 8));
     TRY(call.alloc(&d_AB, 2));
-    TRY(launch_lift_affine(L, d_pts, d_a, n_ranks));
-    TRY(launch_g1_sum(L, d_AB + 0, d_pts, n_ranks));
-    TRY(launch_lift_affine(L, d_pts, d_b, n_ranks));
-    TRY(launch_g1_sum(L, d_AB + 1, d_pts, n_ranks));
-    int bad = 0;
-    TRY(read_flag(call, d_bad, &bad));
-    if (bad) return RET_BADARGS;
+    TRY(call.alloc(&d_ok, 1));
+    KZG_CUDA_TRY(cudaMemcpyAsync(d_a, h.data(), n_ranks * sizeof(G1), cudaMemcpyHostToDevice, call.stream));
+    KZG_CUDA_TRY(cudaMemcpyAsync(d_b, h.data() + n_ranks, n_ranks * sizeof(G1), cudaMemcpyHostToDevice, call.stream));
+    KZG_CUDA_TRY(cudaStreamSynchronize(call.stream));  // `h` is pageable: the copies above are done with it now
+    TRY(launch_g1_sum(L, d_AB + 0, d_a, n_ranks));
+    TRY(launch_g1_sum(L, d_AB + 1, d_b, n_ranks));
     TRY(launch_pairing_check(L, d_ok, d_AB + 0, d_AB + 1, nullptr, LINE_G2_TAU, LINE_G2_GEN));
     TRY(read_flag(call, d_ok, ok));
     return RET_OK;
+}
+
+namespace {
+struct Rendezvous {
+    std::mutex m;
+    std::condition_variable cv;
+    int n, count = 0, gen = 0;
+    explicit Rendezvous(int n_) : n(n_) {}
+    void wait() {
+        std::unique_lock<std::mutex> lk(m);
+        const int g = gen;
+        if (++count == n) {
+            count = 0;
+            gen++;
+            cv.notify_all();
+        } else {
+            cv.wait(lk, [&] { return gen != g; });
+        }
+    }
+};
+}  // namespace
+
+// In-library multi-device verify_blob_kzg_proof_batch (HOST pointers): one host thread per device runs the
+// per-blob stage of its contiguous range of blobs; z||y meets in pinned host memory, where ONE thread hashes the
+// batch transcript (it is hashed on the host on a single GPU too); every device forms its partial sums with the
+// weights r^(first + i); device 0 adds the 2 x D partial points and runs the one pairing check.
+int verify_blob_batch_multi(Ctx* c, int* ok, const uint8_t* blobs, const uint8_t* commitments, const uint8_t* proofs, uint64_t n, int D) {
+    std::vector<uint64_t> first(D + 1);
+    for (int d = 0; d <= D; d++) first[d] = n * (uint64_t)d / (uint64_t)D;
+    size_t cap = 0;
+    uint8_t* pin = (uint8_t*)c->pin_acquire(n * 64 + (size_t)D * 384, &cap);
+    if (!pin) return RET_MALLOC;
+    uint8_t *zy = pin, *parts = pin + n * 64;
+    uint8_t digest[32];
+    std::vector<int> rc(D, RET_OK);
+    Rendezvous bar(D);
+    auto all_ok = [&] {
+        for (int d = 0; d < D; d++)
+            if (rc[d]) return false;
+        return true;
+    };
+    auto body = [&](int d) {
+        const uint64_t f = first[d], cnt = first[d + 1] - first[d];
+        VerifyShard sh(c->peers[d]);
+        rc[d] = sh.call.ok ? shard_stage1(sh, zy + 64 * f, blobs + f * BLOB_BYTES, commitments + 48 * f, proofs + 48 * f, cnt, CKZG_B200_HOST) : RET_ERROR;
+        bar.wait();
+        const bool go = all_ok();
+        if (go && d == 0) transcript_digest(digest, commitments, zy, proofs, nullptr, n);
+        bar.wait();
+        if (go) rc[d] = shard_stage2(sh, parts + 384 * (size_t)d, digest, f);
+    };
+    std::vector<std::thread> th;
+    for (int d = 1; d < D; d++) th.emplace_back(body, d);
+    body(0);
+    for (auto& t : th) t.join();
+    int out = RET_OK;
+    for (int d = 0; d < D && !out; d++) out = rc[d];  // the reference reports the first invalid input; any BADARGS is BADARGS
+    if (!out) out = shards_finish(c, ok, parts, (uint64_t)D);
+    c->pin_release(pin, cap);
+    return out;
+}
+}  // namespace kzg
+
+struct ckzg_b200_verify_shard {
+    VerifyShard v;
+    explicit ckzg_b200_verify_shard(Ctx* c) : v(c) {}
+};
+
+extern "C" {
+
+// 160-byte records (C || z || y || proof) of compute_r_powers_for_verify_kzg_proof_batch, eip4844.c:648-660
+int ckzg_b200_pack_verify_tuples(uint8_t* tuples, const uint8_t* commitments, const uint8_t* zy, const uint8_t* proofs, uint64_t n) {
+    if (!tuples || !commitments || !zy || !proofs) return n ? RET_BADARGS : RET_OK;
+    for (uint64_t i = 0; i < n; i++) {
+        uint8_t* t = tuples + 160 * i;
+        memcpy(t, commitments + 48 * i, 48);
+        memcpy(t + 48, zy + 64 * i, 64);
+        memcpy(t + 112, proofs + 48 * i, 48);
+    }
+    return RET_OK;
+}
+
+int ckzg_b200_verify_shard_stage1(ckzg_b200_ctx* ctx, ckzg_b200_verify_shard** shard, uint8_t* zy, const uint8_t* blobs, const uint8_t* commitments, const uint8_t* proofs,
+                                  uint64_t n_local, int mem) {
+    if (!ctx || !shard) return RET_BADARGS;
+    *shard = nullptr;
+    if (n_local && (!zy || !blobs || !commitments || !proofs)) return RET_BADARGS;
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    auto* sh = new (std::nothrow) ckzg_b200_verify_shard(c);
+    if (!sh) return RET_MALLOC;
+    int rc = sh->v.call.ok ? RET_OK : RET_ERROR;
+    if (!rc && n_local) rc = shard_stage1(sh->v, zy, blobs, commitments, proofs, n_local, mem);
+    if (rc) {
+        delete sh;
+        return rc;
+    }
+    *shard = sh;
+    return RET_OK;
+}
+
+int ckzg_b200_verify_shard_stage2(ckzg_b200_verify_shard* shard, uint8_t* partial384, const uint8_t* tuples, uint64_t n_total, uint64_t first) {
+    if (!shard || !partial384 || (!tuples && n_total) || first + shard->v.n > n_total) return RET_BADARGS;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (cudaSetDevice(shard->v.call.ctx->device) != cudaSuccess) return RET_ERROR;
+    int rc = RET_OK;
+    if (shard->v.n == 0) {
+        memset(partial384, 0, 384);  // zz = zzz = 0: two points at infinity
+    } else {
+        uint8_t digest[32];
+        transcript_digest(digest, nullptr, nullptr, nullptr, tuples, n_total);
+        rc = shard_stage2(shard->v, partial384, digest, first);
+    }
+    if (prev >= 0) cudaSetDevice(prev);
+    return rc;
+}
+
+void ckzg_b200_verify_shard_free(ckzg_b200_verify_shard* shard) { delete shard; }
+
+int ckzg_b200_verify_shard_finish(ckzg_b200_ctx* ctx, int* ok, const uint8_t* partials, uint64_t n_ranks) {
+    if (!ctx || !ok || !partials || n_ranks == 0) return RET_BADARGS;
+    *ok = 0;
+    return shards_finish(reinterpret_cast<Ctx*>(ctx), ok, partials, n_ranks);
 }
 
 }  // extern "C"

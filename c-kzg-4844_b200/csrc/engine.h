@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "g1.cuh"
+#include "hostpool.h"
 
 namespace kzg {
 
@@ -77,12 +78,26 @@ struct Ctx {
     int fk_c = 8;                         // window width of fk_table
     void* commit_table = nullptr;         // direct (bucket-free) multiples of the Lagrange points, msm_direct.cu (18 - 61 GB)
     int commit_c = 0;                     // its window width; 0 = not built, the bucket MSM (msm_table) serves
-    std::once_flag fk_once, commit_once;  // both tables are built on first use (api.cu plan_*_window)
-    int fk_rc = 0, commit_rc = 0;
+    std::once_flag commit_once;           // both tables are built on first use (api.cu plan_*_window)
+    std::mutex fk_mu;
+    std::atomic<bool> fk_ready{false};
     G1* g_levels = nullptr;               // [18] table levels of -G1 generator (vmsm.cu)
     G1* mono_levels = nullptr;            // [18][64] table levels of -[tau^j]G1, j < 64 (verify_cells.cu)
     uint64_t precompute = 0;
     void* coalescer = nullptr;            // call-coalescing front end (coalesce.cu)
+
+    // In-library multi-device (multi.cu): with CKZG_B200_DEVICES=0,1,... the context returned to the caller is the
+    // PRIMARY (peers[0] == this) and owns one ordinary context per further device; the batched entry points shard
+    // HOST-memory batches over them.  Empty for a single-device context and for the peers themselves.
+    std::vector<Ctx*> peers;
+    // host worker threads (parallel memcpy into pinned staging, per-device / per-sub-batch fan-out); created on demand
+    std::mutex pool_mu;
+    HostPool* pool = nullptr;
+    HostPool* host_pool() {
+        std::lock_guard<std::mutex> g(pool_mu);
+        if (!pool) pool = new HostPool(host_threads_default() - 1);  // the caller is the last worker
+        return pool;
+    }
 
     // Small pool of pinned host buffers for the device->host hops inside a call (a pageable destination
     // makes cudaMemcpyAsync stage through the driver and block).  Buffers are reused across calls and
@@ -105,7 +120,8 @@ struct Ctx {
         }
         void* p = nullptr;
         size_t cap = bytes < 4096 ? 4096 : bytes;
-        if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+        // portable: the multi-device paths hand one staging block to copies issued on several devices
+        if (cudaHostAlloc(&p, cap, cudaHostAllocPortable) != cudaSuccess) return nullptr;
         *got = cap;
         return p;
     }

@@ -144,11 +144,12 @@ int launch_fixed_base_table(Launch& L, G1Affine* table, const G1Affine* pts, int
     return RET_OK;
 }
 
-static int fk20_build(Launch& L, Ctx* c) {
+// `max_c`: widest window to try; a failed allocation falls back to the next smaller table
+static int fk20_build(Launch& L, Ctx* c, int max_c) {
     static const int widths[3] = {12, 10, 8};
-    c->fk_c = plan_fk_window();
-    for (int k = 0; k < 3; k++) {  // a failed allocation falls back to the next smaller table
-        if (widths[k] > c->fk_c) continue;
+    c->fk_table = nullptr;
+    for (int k = 0; k < 3; k++) {
+        if (widths[k] > max_c) continue;
         const FkGeom g = fk_geom(widths[k]);
         if (cudaMalloc((void**)&c->fk_table, g.table_points() * sizeof(G1Affine)) == cudaSuccess) {
             c->fk_c = widths[k];
@@ -184,17 +185,30 @@ static int fk20_build(Launch& L, Ctx* c) {
 
 // X^ columns (init_fk20_multi_settings, setup.c:238-330) + the window tables, on first use of an API that
 // computes cell proofs
+// A failed build (not only a failed allocation) releases the table and retries with the next smaller window;
+// if even the 8-bit table cannot be built the error is reported but NOT remembered: the next call tries again.
 int fk20_ensure(Ctx* c) {
-    std::call_once(c->fk_once, [c] {
-        Call call(c);
-        if (!call.ok) {
-            c->fk_rc = RET_ERROR;
-            return;
+    if (c->fk_ready.load(std::memory_order_acquire)) return RET_OK;
+    std::lock_guard<std::mutex> g(c->fk_mu);
+    if (c->fk_ready.load(std::memory_order_relaxed)) return RET_OK;
+    int rc = RET_ERROR;
+    for (int max_c = plan_fk_window(); max_c >= 8; max_c = c->fk_c - 2) {
+        {
+            Call call(c);
+            if (!call.ok) return RET_ERROR;
+            Launch L = call.launch();
+            rc = fk20_build(L, c, max_c);
         }
-        Launch L = call.launch();
-        c->fk_rc = fk20_build(L, c);
-    });
-    return c->fk_rc;
+        if (rc == RET_OK) {
+            c->fk_ready.store(true, std::memory_order_release);
+            return RET_OK;
+        }
+        (void)cudaGetLastError();
+        if (!c->fk_table) break;  // nothing could be allocated at all
+        cudaFree(c->fk_table);
+        c->fk_table = nullptr;
+    }
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------

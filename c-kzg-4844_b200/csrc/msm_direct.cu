@@ -143,6 +143,9 @@ int launch_msm_direct(Launch& L, G1* result, const uint8_t* scalars, bool big_en
     return RET_OK;
 }
 
+// Never fails the caller: when the table cannot be allocated OR its build fails (a transient error of a
+// co-tenant, say) the table is released and the bucket form (msm.cu, msm_table) serves this context, as
+// include/ckzg_b200.h promises.
 int msm_direct_ensure(Ctx* c) {
     std::call_once(c->commit_once, [c] {
         c->commit_c = plan_commit_window();
@@ -154,16 +157,23 @@ int msm_direct_ensure(Ctx* c) {
             c->commit_c = 0;
             return;
         }
-        Call call(c);
-        if (!call.ok) {
-            c->commit_rc = RET_ERROR;
-            return;
+        int rc = RET_ERROR;
+        {
+            Call call(c);
+            if (call.ok) {
+                Launch L = call.launch();
+                rc = launch_fixed_base_table(L, (G1Affine*)c->commit_table, c->g1_lagrange_brp, N_BLOB, g);
+                if (rc == RET_OK && cudaStreamSynchronize(call.stream) != cudaSuccess) rc = RET_ERROR;
+            }
         }
-        Launch L = call.launch();
-        c->commit_rc = launch_fixed_base_table(L, (G1Affine*)c->commit_table, c->g1_lagrange_brp, N_BLOB, g);
-        if (c->commit_rc == RET_OK && cudaStreamSynchronize(call.stream) != cudaSuccess) c->commit_rc = RET_ERROR;
+        if (rc != RET_OK) {
+            (void)cudaGetLastError();
+            cudaFree(c->commit_table);
+            c->commit_table = nullptr;
+            c->commit_c = 0;
+        }
     });
-    return c->commit_rc;
+    return RET_OK;
 }
 
 }  // namespace kzg

@@ -64,8 +64,8 @@ size_t vmsm_table_points(uint64_t n);   // VMSM_LEVELS * (2n + 1)
 int launch_vmsm_generator_levels(Launch& L, G1* levels18);
 int vmsm_place_generator(Launch& L, G1* table, uint64_t n);
 size_t rlc_vmsm_scratch_bytes(uint64_t n);
-// out2[0] = A, out2[1] = B as launch_rlc (first = 0, use_r = true); r = hash_to_bls_field(digest32), digest32 a HOST pointer
-int launch_rlc_vmsm(Launch& L, G1* out2, const G1* table, const Fr* z, const Fr* y, const uint8_t* digest32, uint64_t n, void* scratch);
+// out2[0] = A, out2[1] = B as launch_rlc (use_r = true, weights r^(first + i)); r = hash_to_bls_field(digest32), digest32 a HOST pointer
+int launch_rlc_vmsm(Launch& L, G1* out2, const G1* table, const Fr* z, const Fr* y, const uint8_t* digest32, uint64_t first, uint64_t n, void* scratch);
 // sum of n XYZZ points -> out (device); in is clobbered
 int launch_g1_sum(Launch& L, G1* out, G1* in, uint64_t n);
 // canonical 32-byte big-endian encodings of n field elements

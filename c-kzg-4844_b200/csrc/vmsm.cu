@@ -52,14 +52,15 @@ __device__ __forceinline__ void vstore_g1(G1* p, const G1& a) {
 // hB layout (index = 4 * point + quarter, 8 bytes each): points 0..n-1 proofs with r^i z_i, points
 // n..2n-1 commitments with r^i, point 2n = -G with sum r^i y_i.  MSM A reads the r^i segment with point
 // base 0.
+// `first`: this call's points are tuples [first, first + n) of a larger batch (sharded verification): weights r^(first + i)
 __global__ void rlc_vmsm_scalars_kernel(uint32_t* __restrict__ hB, Fr* __restrict__ ty, const Fr* __restrict__ z, const Fr* __restrict__ y, const Digest8 digest,
-                                        uint32_t n) {
+                                        uint32_t n, uint64_t first) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Fr p = Fr::one();
     {
         Fr base = fr_from_digest_words(digest.h);
-        uint32_t e = i;
+        uint64_t e = first + i;
         while (e) {
             if (e & 1) p = mul(p, base);
             base = sqr(base);
@@ -373,7 +374,7 @@ size_t rlc_vmsm_scratch_bytes(uint64_t n) {
     return val256(nhB * 8) + val256(n * sizeof(Fr)) + vmsm_job_bytes(nhA) + vmsm_job_bytes(nhB);
 }
 
-int launch_rlc_vmsm(Launch& L, G1* out2, const G1* table, const Fr* z, const Fr* y, const uint8_t* digest32, uint64_t n, void* scratch) {
+int launch_rlc_vmsm(Launch& L, G1* out2, const G1* table, const Fr* z, const Fr* y, const uint8_t* digest32, uint64_t first, uint64_t n, void* scratch) {
     Digest8 dg;
     for (int i = 0; i < 8; i++)
         dg.h[i] = ((uint32_t)digest32[4 * i] << 24) | ((uint32_t)digest32[4 * i + 1] << 16) | ((uint32_t)digest32[4 * i + 2] << 8) | (uint32_t)digest32[4 * i + 3];
@@ -387,7 +388,7 @@ int launch_rlc_vmsm(Launch& L, G1* out2, const G1* table, const Fr* z, const Fr*
     ws = vmsm_job_carve(jobs.j[1], ws, hB, nhB);
     const uint32_t npts = (uint32_t)(2 * n + 1);
 
-    rlc_vmsm_scalars_kernel<<<(unsigned)((n + 63) / 64), 64, 0, L.stream>>>(hB, ty, z, y, dg, (uint32_t)n);
+    rlc_vmsm_scalars_kernel<<<(unsigned)((n + 63) / 64), 64, 0, L.stream>>>(hB, ty, z, y, dg, (uint32_t)n, first);
     KZG_CUDA_TRY(cudaGetLastError());
     rlc_vmsm_ysum_kernel<<<1, 256, 0, L.stream>>>(hB, ty, (uint32_t)n);
     KZG_CUDA_TRY(cudaGetLastError());

@@ -3,7 +3,7 @@
 SURVEY.md section 8(e): the per-blob stage (point validation, Fiat-Shamir challenge z_i, evaluation
 y_i) shards freely by blob; the batch challenge r hashes every (C_i, z_i, y_i, proof_i), so the only
 data-path exchange is an all-gather of 64 bytes per blob (z_i || y_i) followed by an all-gather of each
-rank's two partial linear combinations (2 x 48 bytes) -- the "single small collective" of the
+rank's two partial linear combinations (2 x 192 bytes, XYZZ) -- the "single small collective" of the
 north-star.  NCCL has no elliptic-curve reduction op, hence all-gather + local add instead of
 all-reduce.  Any rank (here: every rank, redundantly) finishes with one pairing check.
 
@@ -39,29 +39,71 @@ def _all_gather_bytes(local: torch.Tensor, counts, group=None):
     return torch.cat([b[:c] for b, c in zip(bufs, counts)])
 
 
-def verify_batch_sharded(stage1, stage2, finish, commitments: bytes, proofs: bytes, n_total, device, group=None):
+class ShardError(RuntimeError):
+    """Raised on EVERY rank when a stage failed on any rank (code = the largest C_KZG_RET seen)."""
+
+    def __init__(self, code, stage, rank_failed):
+        super().__init__("%s failed on rank %d with code %d" % (stage, rank_failed, code))
+        self.code, self.stage, self.rank_failed = code, stage, rank_failed
+
+
+def _agree_on_status(local_exc, stage, device, group=None):
+    """All-reduce(MAX) of a status word BEFORE any data collective, so that a stage that raised on one rank
+    raises ShardError on all of them instead of leaving the others blocked in the next all_gather.
+    The word packs (code, rank) so every rank names the same failing rank."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    code = 0
+    if local_exc is not None:
+        code = int(getattr(local_exc, "code", 2) or 2)
+    word = torch.tensor([code * 65536 + (rank if code else 0)], dtype=torch.int64, device=device)
+    if world > 1:
+        dist.all_reduce(word, op=dist.ReduceOp.MAX, group=group)
+    w = int(word.item())
+    if w:
+        raise ShardError(w // 65536, stage, w % 65536) from local_exc
+
+
+def verify_batch_sharded(stage1, stage2, finish, commitments: bytes, proofs: bytes, n_total, device, group=None, pack=None):
     """One global batch sharded over the process group.
 
     stage1() -> bytes (n_local x 64: z||y of this rank's blobs; raises on invalid input)
-    stage2(tuples: bytes, n_total, first, n_local) -> bytes (144: this rank's partial sums)
+    stage2(tuples: bytes, n_total, first, n_local) -> bytes (this rank's partial sums; 384 bytes from the engine,
+           the same length on every rank)
     finish(partials: bytes, n_ranks) -> bool
     commitments / proofs: the FULL batch's 48-byte encodings (tiny: replicated on every rank).
+    pack(commitments, zy, proofs, n) -> bytes: assembles the 160-byte records (the engine's C helper
+    ckzg_b200_pack_verify_tuples; default = a pure-Python join, for the CPU tests).
+
+    A stage that raises on any rank (an invalid blob or proof in its shard: C_KZG_BADARGS) makes EVERY rank raise
+    ShardError with the same code before the next collective -- no rank is left waiting.
     """
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     ranges = [shard_range(n_total, r, world) for r in range(world)]
     first, n_local = ranges[rank]
-    zy_local = stage1()
-    assert len(zy_local) == 64 * n_local
+    zy_local, exc = b"", None
+    try:
+        zy_local = stage1()
+        assert len(zy_local) == 64 * n_local
+    except Exception as e:  # noqa: BLE001 -- re-raised on every rank below
+        exc = e
+    _agree_on_status(exc, "stage1", device, group)
     t = torch.frombuffer(bytearray(zy_local), dtype=torch.uint8).to(device) if n_local else torch.zeros(0, dtype=torch.uint8, device=device)
     zy_all = bytes(_all_gather_bytes(t, [64 * c for _, c in ranges], group).cpu().numpy().tobytes())
     # the 160-byte records the batch challenge hashes (src/eip4844/eip4844.c:648-660)
-    tuples = b"".join(
-        commitments[48 * i : 48 * i + 48] + zy_all[64 * i : 64 * i + 64] + proofs[48 * i : 48 * i + 48] for i in range(n_total)
-    )
-    part = stage2(tuples, n_total, first, n_local)
-    assert len(part) == 144
+    if pack is not None:
+        tuples = pack(commitments, zy_all, proofs, n_total)
+    else:
+        tuples = b"".join(
+            commitments[48 * i : 48 * i + 48] + zy_all[64 * i : 64 * i + 64] + proofs[48 * i : 48 * i + 48] for i in range(n_total)
+        )
+    part, exc = b"", None
+    try:
+        part = stage2(tuples, n_total, first, n_local)
+    except Exception as e:  # noqa: BLE001
+        exc = e
+    _agree_on_status(exc, "stage2", device, group)
     pt = torch.frombuffer(bytearray(part), dtype=torch.uint8).to(device)
-    parts = bytes(_all_gather_bytes(pt, [144] * world, group).cpu().numpy().tobytes())
+    parts = bytes(_all_gather_bytes(pt, [len(part)] * world, group).cpu().numpy().tobytes())
     return finish(parts, world)
 
 

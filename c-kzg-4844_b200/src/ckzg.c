@@ -18,6 +18,7 @@
 #include "host_sha256.h"
 
 #include <inttypes.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -281,8 +282,15 @@ void bytes_from_g1(Bytes48 *out, const g1_t *in) { memcpy(out->bytes, in, 48); }
 
 void compute_challenge(fr_t *eval_challenge_out, const Blob *blob, const g1_t *commitment) { /* eip4844.c:147 */
     uint8_t z[32];
+    /* the reference's signature has no error channel: a failed device call must not come back as a zero
+     * challenge that looks like a result */
+    int rc = ckzg_b200_compute_challenge(NULL, z, blob->bytes, (const uint8_t *)commitment);
+    if (rc != 0) {
+        fprintf(stderr, "ckzg_b200: compute_challenge failed on the device (code %d); no CPU fallback exists\n", rc);
+        abort();
+    }
     memset(eval_challenge_out, 0, sizeof(*eval_challenge_out));
-    if (ckzg_b200_compute_challenge(NULL, z, blob->bytes, (const uint8_t *)commitment) == 0) memcpy(eval_challenge_out, z, 32);
+    memcpy(eval_challenge_out, z, 32);
 }
 
 C_KZG_RET compute_verify_cell_kzg_proof_batch_challenge( /* eip7594.c:390-482 */

@@ -32,6 +32,17 @@ typedef struct ckzg_b200_ctx ckzg_b200_ctx; /* opaque: device-resident trusted s
 enum { CKZG_B200_HOST = 0, CKZG_B200_DEVICE = 1 };
 
 /*
+ * DEVICE-mode ordering contract.  Every engine call runs on its own BLOCKING CUDA stream (plus side streams forked
+ * from it), so it is ordered after everything the caller enqueued earlier on the legacy default stream -- the stream
+ * torch uses unless told otherwise: `t[...] = x; engine_call(t.data_ptr())` needs no synchronize.  A caller that
+ * produces its device buffers on ANOTHER stream (a non-blocking stream, a torch side stream, a per-thread default
+ * stream) must either synchronise that stream first or name it here: the calling THREAD's subsequent engine calls
+ * then wait for an event recorded on `cuda_stream` (a cudaStream_t) when they start.  NULL restores the default.
+ * Calls are synchronous: outputs (HOST or DEVICE) are complete when a call returns, so no ordering is needed after it.
+ */
+void ckzg_b200_set_caller_stream(void *cuda_stream);
+
+/*
  * Device-side load_trusted_setup (replaces src/setup/setup.c:392-505).
  * Inputs are the three byte arrays of load_trusted_setup(): 4096x48 G1 monomial, 4096x48 G1 Lagrange,
  * 65x96 G2 monomial.  Decompresses on the GPU (no subgroup check, as setup.c:447-477), rejects a
@@ -49,6 +60,16 @@ int ckzg_b200_ctx_create(
 );
 void ckzg_b200_ctx_destroy(ckzg_b200_ctx *ctx);
 int ckzg_b200_ctx_device(const ckzg_b200_ctx *ctx);
+/*
+ * One context can span several GPUs of the node: with the environment variable CKZG_B200_DEVICES="0,1,2,3" (or "all")
+ * and `device` < 0 -- which is how load_trusted_setup (include/ckzg.h) creates its context -- the returned context owns
+ * one replica of the setup per listed device, and every batched entry point below shards HOST-memory batches over them
+ * inside the call: contiguous ranges of blobs for commitments / proofs / cells / recovery (no exchange), the per-blob
+ * stage + partial sums + one pairing for verify_blob_kzg_proof_batch (one challenge; z||y and the partial points meet in
+ * pinned host memory), independently verified sub-batches for verify_cell_kzg_proof_batch.  So a binding that links the
+ * frozen API unchanged drives all listed GPUs.  DEVICE-memory inputs always run on the device that owns them.
+ */
+int ckzg_b200_ctx_device_count(const ckzg_b200_ctx *ctx);
 
 /*
  * Batched blob_to_kzg_commitment (src/eip4844/eip4844.c:264 applied to n blobs).
@@ -87,22 +108,31 @@ int ckzg_b200_verify_kzg_proof(
 );
 
 /*
- * Multi-GPU split of verify_blob_kzg_proof_batch: stage 1 is per blob and shards
- * freely; the challenge needs every (C, z, y, proof) (all-gathered by the caller, 160 B/blob); stage 2
- * forms this rank's share of the three linear combinations; the caller all-gathers the 3 partial
- * points (3 x 48 B per rank) and any rank finishes with one pairing.
- *   stage1: zy out = n_local x 64 bytes (z || y, canonical big-endian), `mem` space.
- *   stage2: tuples = N_total x 160 bytes (C48 || z32 || y32 || proof48) in `mem` space; this rank owns
- *           [first, first + n_local).  partial out = 3 x 48 compressed points, HOST memory.
- *   finish: partials = n_ranks x 144 bytes, HOST memory.
+ * Multi-GPU split of verify_blob_kzg_proof_batch for one process per GPU: ONE global batch of
+ * n_total blobs, one Fiat-Shamir challenge, exact reference semantics for the whole batch (eip4844.c:697-765).
+ *   stage1: the per-blob stage of this rank's n_local blobs (validation, z_i, y_i).  zy out = n_local x 64 bytes
+ *           (z || y, canonical big-endian), HOST memory.  The shard object keeps the validated points, the table
+ *           their validation left behind, z and y ON THE DEVICE for stage 2.  BADARGS (no shard) for an invalid input.
+ *   (caller: all-gather zy, 64 B per blob; ckzg_b200_pack_verify_tuples builds the 160-byte records)
+ *   stage2: tuples = n_total x 160 bytes (C48 || z32 || y32 || proof48), HOST memory, hashed here into the challenge r
+ *           (eip4844.c:612-668); this rank owns [first, first + n_local) and forms its share of
+ *           A = sum r^i proof_i and B = sum r^i z_i proof_i + sum r^i C_i - [sum r^i y_i]G as one pair of bucket
+ *           MSMs with weights r^(first + i).  partial out = 384 bytes (two XYZZ points; an opaque exchange format).
+ *   (caller: all-gather the partials, 384 B per rank -- NCCL has no elliptic-curve reduction op)
+ *   finish: partials = n_ranks x 384 bytes, HOST memory: sums them, one pairing check.
+ * A shard must be freed (verify_shard_free) by the thread's process that created it; n_local may be 0.
+ * The same code runs inside the library when a context spans several devices (ckzg_b200_ctx_create, CKZG_B200_DEVICES).
  */
-int ckzg_b200_verify_blob_batch_stage1(
-    ckzg_b200_ctx *ctx, uint8_t *zy, const uint8_t *blobs, const uint8_t *commitments, const uint8_t *proofs, uint64_t n_local, int mem
+typedef struct ckzg_b200_verify_shard ckzg_b200_verify_shard;
+int ckzg_b200_verify_shard_stage1(
+    ckzg_b200_ctx *ctx, ckzg_b200_verify_shard **shard, uint8_t *zy, const uint8_t *blobs, const uint8_t *commitments,
+    const uint8_t *proofs, uint64_t n_local, int mem
 );
-int ckzg_b200_verify_blob_batch_stage2(
-    ckzg_b200_ctx *ctx, uint8_t *partial144, const uint8_t *tuples, uint64_t n_total, uint64_t first, uint64_t n_local, int mem
-);
-int ckzg_b200_verify_blob_batch_finish(ckzg_b200_ctx *ctx, int *ok, const uint8_t *partials, uint64_t n_ranks);
+/* host helper between the stages: tuples[i] = commitments[i] || zy[i] || proofs[i] (160 B).  All HOST memory. */
+int ckzg_b200_pack_verify_tuples(uint8_t *tuples, const uint8_t *commitments, const uint8_t *zy, const uint8_t *proofs, uint64_t n);
+int ckzg_b200_verify_shard_stage2(ckzg_b200_verify_shard *shard, uint8_t *partial384, const uint8_t *tuples, uint64_t n_total, uint64_t first);
+void ckzg_b200_verify_shard_free(ckzg_b200_verify_shard *shard);
+int ckzg_b200_verify_shard_finish(ckzg_b200_ctx *ctx, int *ok, const uint8_t *partials, uint64_t n_ranks);
 
 /*
  * EIP-7594.  Batched compute_cells_and_kzg_proofs (src/eip7594/eip7594.c:61): per blob 128 cells

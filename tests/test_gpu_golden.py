@@ -200,29 +200,41 @@ def test_verify_batch_sharded_stages(gpu, batch64):
     shards = [(0, 10), (10, 9), (19, 5)]
 
     def run(proofs):
-        zy = {}
+        zy, handles = {}, []
         for first, cnt in shards:
             out = C.create_string_buffer(64 * cnt)
-            rc = gpu.lib.ckzg_b200_verify_blob_batch_stage1(
-                e, out, b"".join(blobs[first : first + cnt]), b"".join(cms[first : first + cnt]), b"".join(proofs[first : first + cnt]), C.c_uint64(cnt), 0
+            h = C.c_void_p(None)
+            rc = gpu.lib.ckzg_b200_verify_shard_stage1(
+                e, C.byref(h), out, b"".join(blobs[first : first + cnt]), b"".join(cms[first : first + cnt]), b"".join(proofs[first : first + cnt]), C.c_uint64(cnt), 0
             )
-            assert rc == 0
+            assert rc == 0 and h.value
+            handles.append(h)
             for k in range(cnt):
                 zy[first + k] = out.raw[64 * k : 64 * k + 64]
-        tuples = b"".join(cms[i] + zy[i] + proofs[i] for i in range(n))  # the all-gathered 160-byte records
+        # the all-gathered 160-byte records, assembled by the C helper
+        tuples = C.create_string_buffer(160 * n)
+        assert gpu.lib.ckzg_b200_pack_verify_tuples(tuples, b"".join(cms[:n]), b"".join(zy[i] for i in range(n)), b"".join(proofs[:n]), C.c_uint64(n)) == 0
+        assert tuples.raw == b"".join(cms[i] + zy[i] + proofs[i] for i in range(n))
         partials = b""
-        for first, cnt in shards:
-            part = C.create_string_buffer(144)
-            assert gpu.lib.ckzg_b200_verify_blob_batch_stage2(e, part, tuples, C.c_uint64(n), C.c_uint64(first), C.c_uint64(cnt), 0) == 0
+        gpu.lib.ckzg_b200_verify_shard_free.restype = None
+        for (first, cnt), h in zip(shards, handles):
+            part = C.create_string_buffer(384)
+            assert gpu.lib.ckzg_b200_verify_shard_stage2(h, part, tuples, C.c_uint64(n), C.c_uint64(first)) == 0
+            gpu.lib.ckzg_b200_verify_shard_free(h)
             partials += part.raw
         ok = C.c_int(0)
-        assert gpu.lib.ckzg_b200_verify_blob_batch_finish(e, C.byref(ok), partials, C.c_uint64(len(shards))) == 0
+        assert gpu.lib.ckzg_b200_verify_shard_finish(e, C.byref(ok), partials, C.c_uint64(len(shards))) == 0
         return bool(ok.value)
 
     assert run(prs) is True
     bad = list(prs)
     bad[20] = prs[21]
     assert run(bad) is False
+    # an invalid proof encoding in one shard: BADARGS from that shard's stage 1, no shard object
+    h = C.c_void_p(None)
+    out = C.create_string_buffer(64 * 5)
+    rc = gpu.lib.ckzg_b200_verify_shard_stage1(e, C.byref(h), out, b"".join(blobs[19:24]), b"".join(cms[19:24]), b"".join(prs[19:23]) + bytes(48), C.c_uint64(5), 0)
+    assert rc == 1 and not h.value
 
 
 def test_verify_batch_pipelined_upload_path(gpu, batch64):

@@ -75,6 +75,58 @@ def test_sharded_verify_host_logic(world, n_total):
     assert covered == list(range(n_total))
 
 
+def _worker_failing(rank, world, port, n_total, fail_stage, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    import datetime
+
+    dist.init_process_group("gloo", rank=rank, world_size=world, timeout=datetime.timedelta(seconds=60))
+    entry.load_package()
+    import importlib
+
+    par = importlib.import_module("ckzg_b200.parallel")
+    first, cnt = par.shard_range(n_total, rank, world)
+
+    def bad_args():
+        e = ValueError("C_KZG_BADARGS")
+        e.code = 1
+        raise e
+
+    def stage1():
+        if fail_stage == 1 and rank == world - 1:
+            bad_args()
+        return b"\0" * (64 * cnt)
+
+    def stage2(tuples, n, f, c):
+        if fail_stage == 2 and rank == 0:
+            bad_args()
+        return b"\0" * 144
+
+    try:
+        par.verify_batch_sharded(stage1, stage2, lambda parts, nr: True, b"\0" * (48 * n_total), b"\0" * (48 * n_total), n_total, torch.device("cpu"))
+        q.put((rank, "returned", None, None))
+    except par.ShardError as e:
+        q.put((rank, "ShardError", e.code, e.rank_failed))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fail_stage", [1, 2])
+def test_sharded_verify_failure_on_one_rank_raises_everywhere(fail_stage):
+    """a stage raising on one rank used to leave the others blocked in all_gather.  Now every rank
+    raises ShardError with the failing rank's C_KZG_RET before the next collective."""
+    world, n_total = 2, 6
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_failing, args=(r, world, port, n_total, fail_stage, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    failing = world - 1 if fail_stage == 1 else 0
+    assert res == [(r, "ShardError", 1, failing) for r in range(world)]
+
+
 def test_shard_range_properties():
     entry.load_package()
     import importlib

@@ -28,6 +28,10 @@ def main():
             for k in KEYS:
                 if k in d:
                     print("  %-75s %s %s" % (k, d[k], u.get(k, "")))
+            # every pipe-utilisation percentage of the capture (integer work sits on fma / fmaheavy / alu)
+            for k in sorted(d):
+                if k not in KEYS and (k.startswith("sm__inst_executed_pipe_") or k.startswith("sm__pipe_")) and "pct_of_peak_sustained_active" in k and d[k] not in ("", "n/a", "0"):
+                    print("  %-75s %s %s" % (k, d[k], u.get(k, "")))
             stalls = [(float(v.replace(",", "")), k) for k, v in d.items() if "average_warp" in k and "issue_stalled" in k and k.endswith("_per_warp_active.pct") is False and v not in ("", "n/a")]
             st = []
             for k, v in d.items():

@@ -1,0 +1,79 @@
+#!/usr/bin/env python3
+"""Driver for ONE ncu --set full pass over every kernel that carries a path (round-2 VERDICT item 3/7):
+warm everything up (tables, pools) with the profiler off, then run each API once between
+cudaProfilerStart/Stop so `--profile-from-start off` captures exactly one call of each.
+
+  ncu --set full --clock-control none --import-source on --profile-from-start off \
+      -k regex:'<kernels>' -o gpurun_out/prof_all python tools/prof_all.py
+
+Sizes: commitments 1024 blobs, cells+proofs / recovery 256 blobs, blob verification 4096, cell verification 64 x 128."""
+import ctypes
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import __graft_entry__ as entry  # noqa: E402
+import bench  # noqa: E402
+
+BLOB = 131072
+nv = int(os.environ.get("PROF_VERIFY_N", "4096"))
+nc = int(os.environ.get("PROF_COMMIT_N", "1024"))
+n7 = int(os.environ.get("PROF_CELLS_N", "256"))
+nvc = int(os.environ.get("PROF_VCELL_N", "64"))
+mod = entry.load_package()
+ts = mod.load_trusted_setup()
+blobs = torch.from_numpy(bench.synth_blobs(nv, 9)).cuda()
+cms = torch.empty(48 * nv, dtype=torch.uint8, device="cuda")
+prs = torch.empty(48 * nv, dtype=torch.uint8, device="cuda")
+cells = torch.empty(n7 * 2 * BLOB, dtype=torch.uint8, device="cuda")
+cprf = torch.empty(n7 * 128 * 48, dtype=torch.uint8, device="cuda")
+rec_c = torch.empty_like(cells)
+rec_p = torch.empty_like(cprf)
+out_c = torch.empty(48 * nc, dtype=torch.uint8, device="cuda")
+idx = list(range(0, 128, 2)) * n7
+
+
+def commit():
+    mod.blob_to_kzg_commitment_device(out_c.data_ptr(), blobs.data_ptr(), nc, ts)
+
+
+def cells_proofs():
+    mod.compute_cells_and_kzg_proofs_device(cells.data_ptr(), cprf.data_ptr(), blobs.data_ptr(), n7, ts)
+
+
+def verify():
+    assert mod.verify_blob_kzg_proof_batch_device(blobs.data_ptr(), cms.data_ptr(), prs.data_ptr(), nv, ts)
+
+
+mod.blob_to_kzg_commitment_device(cms.data_ptr(), blobs.data_ptr(), nv, ts)
+mod.compute_blob_kzg_proof_device(prs.data_ptr(), blobs.data_ptr(), cms.data_ptr(), nv, ts)
+cells_proofs()
+given = cells.view(n7, 128, 2048)[:, 0::2, :].contiguous()
+
+
+def recover():
+    mod.recover_cells_and_kzg_proofs_device(rec_c.data_ptr(), rec_p.data_ptr(), idx, given.data_ptr(), 64, n7, ts)
+
+
+h_cells = cells[: nvc * 2 * BLOB].cpu().pin_memory()
+h_cprf = cprf[: nvc * 128 * 48].cpu().pin_memory()
+h_cm_rows = cms.cpu().view(-1, 48)[:nvc].repeat_interleave(128, dim=0).contiguous().pin_memory()
+idx_arr = (ctypes.c_uint64 * (nvc * 128))(*([k for _ in range(nvc) for k in range(128)]))
+
+
+def verify_cells():
+    assert mod.verify_cell_kzg_proof_batch_ptr(h_cm_rows.data_ptr(), idx_arr, h_cells.data_ptr(), h_cprf.data_ptr(), nvc * 128, ts)
+
+
+steps = [commit, cells_proofs, recover, verify, verify_cells]
+for f in steps:  # warm-up, profiler off
+    f()
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
+for f in steps:
+    f()
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
+print("ok")
