@@ -172,9 +172,8 @@ static std::vector<int> devices_from_env(int ndev) {
         char* end = nullptr;
         long d = strtol(p, &end, 10);
         if (end == p) break;
-        bool dup = false;
-        for (int x : v) dup = dup || x == (int)d;
-        if (d >= 0 && d < ndev && !dup) v.push_back((int)d);
+        // a device may be listed twice (two replicas on one GPU): the one-GPU way to exercise the multi-device paths
+        if (d >= 0 && d < ndev && v.size() < 16) v.push_back((int)d);
         p = (*end == ',') ? end + 1 : end;
         if (*end && *end != ',') break;
     }
@@ -222,6 +221,11 @@ int ckzg_b200_ctx_create(ckzg_b200_ctx** out, const uint8_t* g1_monomial_bytes, 
             return rc;
         }
         c->peers = peers;
+        if (getenv("CKZG_B200_DEBUG")) {
+            fprintf(stderr, "[ckzg_b200] context spans %zu devices:", devs.size());
+            for (int d : devs) fprintf(stderr, " %d", d);
+            fprintf(stderr, "\n");
+        }
     }
     *out = reinterpret_cast<ckzg_b200_ctx*>(c);
     return RET_OK;

@@ -1,5 +1,6 @@
 // C ABI, EIP-4844 proof and verification entry points (include/ckzg_b200.h), composed from the
 // kernels of verify.cu / msm.cu / pairing.cu.  Host code here only sequences launches and copies.
+#include <stdio.h>
 #include <string.h>
 
 #include <stdlib.h>
@@ -598,6 +599,7 @@ struct Rendezvous {
 int verify_blob_batch_multi(Ctx* c, int* ok, const uint8_t* blobs, const uint8_t* commitments, const uint8_t* proofs, uint64_t n, int D) {
     std::vector<uint64_t> first(D + 1);
     for (int d = 0; d <= D; d++) first[d] = n * (uint64_t)d / (uint64_t)D;
+    if (getenv("CKZG_B200_DEBUG")) fprintf(stderr, "[ckzg_b200] verify_blob_kzg_proof_batch: %llu blobs over %d devices\n", (unsigned long long)n, D);
     size_t cap = 0;
     uint8_t* pin = (uint8_t*)c->pin_acquire(n * 64 + (size_t)D * 384, &cap);
     if (!pin) return RET_MALLOC;

@@ -56,3 +56,19 @@ def test_c_consumer_runs_every_api_entry():
     exe = build()
     r = subprocess.run([exe, os.path.join(LIBDIR, "data", "trusted_setup.txt")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "c_consumer: ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
+
+
+@pytest.mark.gpu
+def test_c_consumer_batch_phase_on_a_multi_device_context():
+    """The same C program, unchanged, with the library told to span two devices (CKZG_B200_DEVICES; on a one-GPU box
+    two replicas share device 0 -- same code path): the 640-blob verify_blob_kzg_proof_batch and the 64 x 128-cell
+    verify_cell_kzg_proof_batch are sharded inside the library and give the same verdicts, incl. negative controls."""
+    import torch
+
+    exe = build()
+    devs = "0,1" if torch.cuda.device_count() >= 2 else "0,0"
+    env = dict(os.environ, CKZG_B200_DEVICES=devs, CKZG_B200_DEBUG="1")
+    r = subprocess.run([exe, os.path.join(LIBDIR, "data", "trusted_setup.txt"), "640"], capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0 and "c_consumer: ok" in r.stdout and "batch phase n=640 (8192 cells) ok" in r.stdout, (r.returncode, r.stdout, r.stderr[-2000:])
+    assert "context spans 2 devices" in r.stderr, r.stderr[-2000:]
+    assert "verify_blob_kzg_proof_batch: 640 blobs over 2 devices" in r.stderr, r.stderr[-2000:]

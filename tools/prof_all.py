@@ -53,8 +53,8 @@ cells_proofs()
 given = cells.view(n7, 128, 2048)[:, 0::2, :].contiguous()
 
 
-def recover():
-    mod.recover_cells_and_kzg_proofs_device(rec_c.data_ptr(), rec_p.data_ptr(), idx, given.data_ptr(), 64, n7, ts)
+def recover():  # cells only: the FK20 kernels are captured once, in cells_proofs
+    mod.recover_cells_and_kzg_proofs_device(rec_c.data_ptr(), 0, idx, given.data_ptr(), 64, n7, ts)
 
 
 h_cells = cells[: nvc * 2 * BLOB].cpu().pin_memory()
