@@ -198,6 +198,21 @@ def blob_to_kzg_commitment_device(out_ptr, blobs_ptr, n, ts):
     )
 
 
+def blob_to_kzg_commitment_batch_host(out_ptr, blobs_ptr, n, ts):
+    """Same engine call with HOST pointers given as integers (pinned torch tensors, numpy arrays)."""
+    _raise(
+        lib().ckzg_b200_blob_to_kzg_commitment_batch(ts.engine, C.c_void_p(out_ptr), C.c_void_p(blobs_ptr), C.c_uint64(n), HOST, None),
+        "ckzg_b200_blob_to_kzg_commitment_batch",
+    )
+
+
+def mulbench(ilp, iters, blocks, threads):
+    """Fp Montgomery-multiplier throughput probe (include/ckzg_b200.h): ms for blocks x threads x ilp x iters products."""
+    ms = C.c_float(0)
+    _raise(lib().ckzg_b200_selftest_mulbench(C.c_int(ilp), C.c_int(iters), C.c_int(blocks), C.c_int(threads), C.byref(ms)), "ckzg_b200_selftest_mulbench")
+    return float(ms.value)
+
+
 def compute_blob_kzg_proof_device(out_ptr, blobs_ptr, commitments_ptr, n, ts):
     _raise(
         lib().ckzg_b200_compute_blob_kzg_proof_batch(ts.engine, C.c_void_p(out_ptr), C.c_void_p(blobs_ptr), C.c_void_p(commitments_ptr), C.c_uint64(n), DEVICE, None),

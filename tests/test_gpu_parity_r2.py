@@ -158,7 +158,7 @@ def test_verify_cells_256x128_and_controls_mirrored_on_reference(env, ref):
         return a
 
     def wrong_index(cm2, idx2, cells2, prf2):
-        a = 77
+        a = 128 * 50 + 77  # a random blob (blob 0 is the zero polynomial: every index verifies, also in the reference)
         idx2[a] = (idx2[a] + 64) % 128
         return a
 
