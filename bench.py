@@ -536,7 +536,8 @@ def run_b200(args):
 
         tv_ms, _, _ = timed(vcells, 3, 1)
         v_prf2 = v_prf.clone()
-        v_prf2[48 * 70000 : 48 * 70001] = v_prf[48 * 70001 : 48 * 70002] if nb * 128 > 70001 else v_prf[0:48]
+        ci = nb * 128 - 5  # a proof of the last blob replaced by its neighbour's
+        v_prf2[48 * ci : 48 * ci + 48] = v_prf[48 * (ci + 1) : 48 * (ci + 2)]
         assert not mod.verify_cell_kzg_proof_batch_ptr(v_cm.data_ptr(), v_idx, v_cells.data_ptr(), v_prf2.data_ptr(), nb * 128, ts), "cell-proof negative control accepted"
         configs["verify_cell_kzg_proof_batch_512x128_per_gpu"] = {
             "baseline_config": "configs[4]: verify_cell_kzg_proof_batch, 512 blobs x 128 cells per GPU (4096 x 128 at 8 GPUs), host pointers",
