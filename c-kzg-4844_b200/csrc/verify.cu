@@ -91,6 +91,11 @@ __device__ __forceinline__ void place_record(uint32_t kernel_id) {
     const uint32_t k = atomicAdd(buf, 1u);
     if (k < buf[1]) buf[2 + k] = (kernel_id << 28) | ((threadIdx.x >> 5) << 24) | (smid << 8) | (warpid & 0xffu);
 }
+// CKZG_B200_SHA_ADDS=alu restores the all-ALU rounds (A/B measurements); default: additions on the FMA pipe
+static bool sha_fma_adds() {
+    static const bool on = !(getenv("CKZG_B200_SHA_ADDS") && strcmp(getenv("CKZG_B200_SHA_ADDS"), "alu") == 0);
+    return on;
+}
 __device__ __forceinline__ void pair_barrier() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
 
 // message block `k` of the transcript "FSBLOBVERIFY_V1_" || u64be(0) || u64be(4096) || blob || commitment
@@ -128,6 +133,18 @@ __device__ __forceinline__ void challenge_message_block(uint32_t w[16], int k, c
 // to do something else).
 // `lanes` (<= 32) blobs per CTA: the lanes above it leave at once (a partially filled warp still costs
 // the full issue slots, so this only helps to spread a small batch over more SMs).
+//
+// FMA_ADDS: the rounds warp is bound by the 16-lane ALU pipe, not by latency -- every warp instruction holds its pipe
+// for two cycles and a round was 6 SHF + 4 LOP3 + 3 IADD3 on the ALU pipe (13 x 2 = 26 of the 31 cycles measured per
+// round) against 2 IMAD.IADD on the FMA pipe.  With FMA_ADDS every addition of the round is written as x * one + y with
+// a run-time `one` (%nsmid clamped to 1), which ptxas cannot turn back into IADD3: 10 ALU + 8 FMA instructions per
+// round, and the e-recurrence is still three dependent instructions (SHF -> LOP3 -> IMAD).
+__device__ __forceinline__ uint32_t fma_add(uint32_t x, uint32_t one, uint32_t y) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(one), "r"(y));
+    return r;
+}
+template <bool FMA_ADDS>
 __device__ __forceinline__ void challenge_warp_pair(uint32_t (*kw)[64][32], Fr* __restrict__ z_out, uint8_t* __restrict__ zy, const uint8_t* __restrict__ blobs,
                                                     const uint8_t* __restrict__ commitments, uint64_t n, int lanes) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -179,10 +196,33 @@ __device__ __forceinline__ void challenge_warp_pair(uint32_t (*kw)[64][32], Fr* 
         } else if (k > 0) {
             const uint32_t(*src)[32] = kw[(k - 1) & 1];
             uint32_t a = st.h[0], b = st.h[1], c = st.h[2], d = st.h[3], e = st.h[4], f = st.h[5], g = st.h[6], h = st.h[7];
+            uint32_t one = 1u;
+            if (FMA_ADDS) {  // a value neither the front end nor ptxas can fold: min(number of SMs, 1)
+                asm volatile("mov.u32 %0, %%nsmid;" : "=r"(one));
+                one = one < 1u ? one : 1u;
+            }
 #pragma unroll 1
             for (int tt = 0; tt < 64; tt += 16) {
 #pragma unroll
                 for (int t = 0; t < 16; t++) {
+                    if (FMA_ADDS) {
+                        const uint32_t kwv = src[tt + t][lane];
+                        const uint32_t ch = (e & f) ^ (~e & g);
+                        const uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+                        const uint32_t pa = fma_add(h, one, kwv);
+                        const uint32_t pe = fma_add(pa, one, d);
+                        const uint32_t u = fma_add(ch, one, pe);       // everything of e' except Sigma1
+                        const uint32_t S0 = sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22);
+                        const uint32_t q1 = fma_add(S0, one, pa);
+                        const uint32_t q2 = fma_add(mj, one, q1);
+                        const uint32_t w2 = fma_add(ch, one, q2);      // everything of a' except Sigma1
+                        const uint32_t S1 = sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25);
+                        const uint32_t en = fma_add(S1, one, u);
+                        const uint32_t an = fma_add(S1, one, w2);
+                        h = g; g = f; f = e; e = en;
+                        d = c; c = b; b = a; a = an;
+                        continue;
+                    }
                     // the recurrence through e is the critical path: everything that does not depend on the
                     // current e or a (h, d, K+W) is summed first, so e' is ONE three-input add behind
                     // Sigma1/Ch -- rotate, xor, add: three dependent instructions per round instead of five
@@ -211,11 +251,12 @@ __device__ __forceinline__ void challenge_warp_pair(uint32_t (*kw)[64][32], Fr* 
     }
 }
 
+template <bool FMA_ADDS>
 __global__ void __launch_bounds__(64) blob_challenge_kernel(Fr* __restrict__ z_out, uint8_t* __restrict__ zy, const uint8_t* __restrict__ blobs,
                                                           const uint8_t* __restrict__ commitments, uint64_t n, int lanes) {
     __shared__ uint32_t kw[2][64][32];  // [buffer][round][lane] = K[t] + W[t]
     place_record(1);
-    challenge_warp_pair(kw, z_out, zy, blobs, commitments, n, lanes);
+    challenge_warp_pair<FMA_ADDS>(kw, z_out, zy, blobs, commitments, n, lanes);
 }
 
 __global__ void z_from_bytes_kernel(Fr* z_out, uint8_t* zy, const uint8_t* z_bytes, uint64_t n, int* bad) {
@@ -706,7 +747,10 @@ static int hash_lanes(uint64_t n) {
 int launch_blob_challenges(Launch& L, Fr* z, uint8_t* zy, const uint8_t* blobs, const uint8_t* commitments48, uint64_t n) {
     if (!n) return RET_OK;
     const int lanes = hash_lanes(n);
-    blob_challenge_kernel<<<blocks_for(n, lanes), 64, 0, L.stream>>>(z, zy, blobs, commitments48, n, lanes);
+    if (sha_fma_adds())
+        blob_challenge_kernel<true><<<blocks_for(n, lanes), 64, 0, L.stream>>>(z, zy, blobs, commitments48, n, lanes);
+    else
+        blob_challenge_kernel<false><<<blocks_for(n, lanes), 64, 0, L.stream>>>(z, zy, blobs, commitments48, n, lanes);
     KZG_CUDA_TRY(cudaGetLastError());
     L.count(1, "blob_challenge");
     return RET_OK;
@@ -786,6 +830,7 @@ __global__ void g1_validate2_kernel(G1Affine* __restrict__ out_a, const uint8_t*
 // the sub-partition they run on: as separate concurrent kernels the block scheduler stacked them on the
 // same sub-partitions and each took as long as running them back to back (tools/gpu_probe.py
 // "placement", profiles/r01_summary.md r01q-r01s).
+template <bool FMA_ADDS>
 __global__ void __launch_bounds__(128) stage1_fused_kernel(Fr* __restrict__ z_out, uint8_t* __restrict__ zy, const uint8_t* __restrict__ blobs, G1Affine* __restrict__ out_cm,
                                                            const uint8_t* __restrict__ in_cm, G1Affine* __restrict__ out_pf, const uint8_t* __restrict__ in_pf, uint64_t n,
                                                            int* __restrict__ bad, G1* __restrict__ table, int lanes) {
@@ -793,7 +838,7 @@ __global__ void __launch_bounds__(128) stage1_fused_kernel(Fr* __restrict__ z_ou
     place_record(3);
     const int warp = threadIdx.x >> 5;
     if (warp < 2) {
-        challenge_warp_pair(kw, z_out, zy, blobs, in_cm, n, lanes);
+        challenge_warp_pair<FMA_ADDS>(kw, z_out, zy, blobs, in_cm, n, lanes);
         return;
     }
     if ((int)(threadIdx.x & 31) >= lanes) return;
@@ -849,7 +894,10 @@ int launch_stage1_fused(Launch& L, Fr* z, uint8_t* zy, const uint8_t* blobs, G1A
                         G1* table) {
     if (!n) return RET_OK;
     const int lanes = hash_lanes(n);
-    stage1_fused_kernel<<<blocks_for(n, lanes), 128, 0, L.stream>>>(z, zy, blobs, out_cm, in_cm, out_pf, in_pf, n, bad, table, lanes);
+    if (sha_fma_adds())
+        stage1_fused_kernel<true><<<blocks_for(n, lanes), 128, 0, L.stream>>>(z, zy, blobs, out_cm, in_cm, out_pf, in_pf, n, bad, table, lanes);
+    else
+        stage1_fused_kernel<false><<<blocks_for(n, lanes), 128, 0, L.stream>>>(z, zy, blobs, out_cm, in_cm, out_pf, in_pf, n, bad, table, lanes);
     KZG_CUDA_TRY(cudaGetLastError());
     L.count(1, "hash+validate");
     return RET_OK;
