@@ -15,6 +15,7 @@
 //     and a decimation-in-frequency transform of natural input leaves its output bit-reversed.
 // So cells 0..63 are the (validated) input bytes and cells 64..127 one 4096-point DIF transform.
 #include "cells.h"
+#include "tma.cuh"
 
 namespace kzg {
 
@@ -70,18 +71,40 @@ __device__ __forceinline__ void ntt4096_dif_forward(Fr* sh, const Fr* __restrict
 }
 
 // blob -> monomial coefficients (global, Montgomery) and/or cells (bytes).
+// TMA: the 128 KiB of the blob arrive in shared memory through ONE bulk asynchronous copy (cp.async.bulk + mbarrier,
+// tma.cuh) into the buffer the transforms work in; every thread then converts its elements in place (raw big-endian
+// bytes -> Montgomery form, same 32-byte slot).  Otherwise: two LDG.128 per element through registers.
+template <bool TMA>
 __global__ void __launch_bounds__(NTT_THREADS) blob_to_cells_kernel(uint8_t* __restrict__ cells, Fr* __restrict__ mono, const uint8_t* __restrict__ blobs,
                                                                     const Fr* __restrict__ roots, int* __restrict__ bad) {
     extern __shared__ uint4 smem_raw[];
     Fr* sh = reinterpret_cast<Fr*>(smem_raw);
     __shared__ int s_bad;
+    __shared__ __align__(8) uint64_t s_bar;
     const int blob = blockIdx.x, tid = threadIdx.x;
     const uint8_t* src = blobs + (size_t)blob * BLOB_BYTES;
-    if (tid == 0) s_bad = 0;
+    if (tid == 0) {
+        s_bad = 0;
+        if (TMA) tma_mbar_init(&s_bar, 1);
+    }
     __syncthreads();
+    if (TMA) {
+        if (tid == 0) {
+            tma_mbar_expect_tx(&s_bar, BLOB_BYTES);
+            tma_load_1d(smem_raw, src, BLOB_BYTES, &s_bar);
+        }
+        tma_mbar_wait(&s_bar, 0);
+    }
     for (int i = tid; i < NTT_N; i += NTT_THREADS) {
-        const uint4* q = reinterpret_cast<const uint4*>(src + 32 * i);
-        uint4 hi = __ldg(q), lo = __ldg(q + 1);
+        uint4 hi, lo;
+        if (TMA) {
+            hi = smem_raw[2 * i];
+            lo = smem_raw[2 * i + 1];
+        } else {
+            const uint4* q = reinterpret_cast<const uint4*>(src + 32 * i);
+            hi = __ldg(q);
+            lo = __ldg(q + 1);
+        }
         uint32_t s[8] = {bswap32c(lo.w), bswap32c(lo.z), bswap32c(lo.y), bswap32c(lo.x), bswap32c(hi.w), bswap32c(hi.z), bswap32c(hi.y), bswap32c(hi.x)};
         if (limbs_geq<8>(s, FR_MOD)) s_bad = 1;  // bytes_to_bls_field, src/common/bytes.c:67
         sh[i] = to_mont<FrTag>(s);
@@ -172,13 +195,15 @@ __global__ void __launch_bounds__(FKS_THREADS) fk20_scalars_kernel(uint32_t* __r
 
 int launch_blob_to_cells(Launch& L, uint8_t* cells, Fr* mono, const uint8_t* blobs, uint64_t n, int* d_bad) {
     if (!n) return RET_OK;
-    static bool attr_done = false;
-    if (!attr_done) {
-        KZG_CUDA_TRY(cudaFuncSetAttribute(blob_to_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_N * (int)sizeof(Fr)));
-        KZG_CUDA_TRY(cudaFuncSetAttribute(fk20_scalars_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FKS_GROUP * 128 * (int)sizeof(Fr)));
-        attr_done = true;
+    // CKZG_B200_CELLS_LOAD=ldg: register loads instead of the bulk copy (A/B measurements, profiles/)
+    static const bool use_tma = !(getenv("CKZG_B200_CELLS_LOAD") && strcmp(getenv("CKZG_B200_CELLS_LOAD"), "ldg") == 0);
+    if (use_tma) {
+        KZG_FUNC_ATTR_PER_DEVICE(blob_to_cells_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_N * (int)sizeof(Fr));
+        blob_to_cells_kernel<true><<<(unsigned)n, NTT_THREADS, NTT_N * sizeof(Fr), L.stream>>>(cells, mono, blobs, L.ctx->roots, d_bad);
+    } else {
+        KZG_FUNC_ATTR_PER_DEVICE(blob_to_cells_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_N * (int)sizeof(Fr));
+        blob_to_cells_kernel<false><<<(unsigned)n, NTT_THREADS, NTT_N * sizeof(Fr), L.stream>>>(cells, mono, blobs, L.ctx->roots, d_bad);
     }
-    blob_to_cells_kernel<<<(unsigned)n, NTT_THREADS, NTT_N * sizeof(Fr), L.stream>>>(cells, mono, blobs, L.ctx->roots, d_bad);
     KZG_CUDA_TRY(cudaGetLastError());
     L.count(1, "blob_to_cells");
     return RET_OK;
@@ -186,11 +211,7 @@ int launch_blob_to_cells(Launch& L, uint8_t* cells, Fr* mono, const uint8_t* blo
 
 int launch_fk20_scalars(Launch& L, uint32_t* S, const Fr* mono, uint64_t n) {
     if (!n) return RET_OK;
-    static bool attr_done = false;
-    if (!attr_done) {
-        KZG_CUDA_TRY(cudaFuncSetAttribute(fk20_scalars_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FKS_GROUP * 128 * (int)sizeof(Fr)));
-        attr_done = true;
-    }
+    KZG_FUNC_ATTR_PER_DEVICE(fk20_scalars_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FKS_GROUP * 128 * (int)sizeof(Fr));
     dim3 grid(64 / FKS_GROUP, (unsigned)n);
     fk20_scalars_kernel<<<grid, FKS_THREADS, FKS_GROUP * 128 * sizeof(Fr), L.stream>>>(S, mono, L.ctx->roots);
     KZG_CUDA_TRY(cudaGetLastError());

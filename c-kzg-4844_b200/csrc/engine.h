@@ -178,6 +178,20 @@ struct Launch {
 
 void note_cuda_error(cudaError_t e, const char* file, int line);
 
+// cudaFuncSetAttribute acts on the CURRENT device only: a process that drives several devices (multi.cu, or several
+// contexts) must opt in on each of them, so the "done once" flag is one bit per device.
+#define KZG_FUNC_ATTR_PER_DEVICE(kernel, attr, value)                    \
+    do {                                                                 \
+        static std::atomic<uint64_t> _done{0};                           \
+        int _dev = 0;                                                    \
+        cudaGetDevice(&_dev);                                            \
+        const uint64_t _bit = 1ull << (_dev & 63);                       \
+        if (!(_done.load(std::memory_order_acquire) & _bit)) {           \
+            KZG_CUDA_TRY(cudaFuncSetAttribute(kernel, attr, value));     \
+            _done.fetch_or(_bit, std::memory_order_release);             \
+        }                                                                \
+    } while (0)
+
 // ---- setup.cu ----------------------------------------------------------------------------------
 // out[i] = uncompress(bytes[48*perm(i)]) ; ok_flag (device int) is cleared on any failure.
 int launch_g1_uncompress(Launch& L, G1Affine* out, const uint8_t* bytes, int n, bool bit_reverse, bool check_subgroup, int* d_bad);

@@ -131,8 +131,7 @@ __global__ void __launch_bounds__(32 * GQ_WARPS, 4) g1_fft_stage_quad_kernel(G1*
 
 // in place: [inverse DIT on bit-reversed input, lower half kept] -> forward DIF with upper half = infinity
 int g1_fft128_run(Launch& L, G1* data, uint64_t nvec, bool with_inverse) {
-    static const cudaError_t attr = cudaFuncSetAttribute(g1_fft_stage_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GQ_SMEM);
-    KZG_CUDA_TRY(attr);
+    KZG_FUNC_ATTR_PER_DEVICE(g1_fft_stage_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GQ_SMEM);
     dim3 grid(64 / GQ_WARPS, (unsigned)((nvec + 7) / 8));
     QuadTab* tabs = nullptr;
     KZG_CUDA_TRY(cudaMallocAsync((void**)&tabs, (size_t)grid.x * grid.y * GQ_QUADS * sizeof(QuadTab), L.stream));

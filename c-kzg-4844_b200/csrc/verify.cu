@@ -91,9 +91,13 @@ __device__ __forceinline__ void place_record(uint32_t kernel_id) {
     const uint32_t k = atomicAdd(buf, 1u);
     if (k < buf[1]) buf[2 + k] = (kernel_id << 28) | ((threadIdx.x >> 5) << 24) | (smid << 8) | (warpid & 0xffu);
 }
-// CKZG_B200_SHA_ADDS=alu restores the all-ALU rounds (A/B measurements); default: additions on the FMA pipe
+// CKZG_B200_SHA_ADDS=fma selects the variant with every addition of a round on the FMA pipe (A/B measurements).
+// Measured on B200 (profiles/R2_summary.md, R2e): hash+validate 2.28 ms with ptxas' own split (13 ALU + 2 IMAD.IADD
+// per round) against 2.50 ms with 10 ALU + 8 IMAD -- integer multiply-adds issue at a quarter warp per clock here
+// (the same 32 lanes/clk/SM the Montgomery multiplier measures), so moving a two-cycle ALU addition to the FMA pipe
+// costs four cycles there.  The default stays ptxas' split.
 static bool sha_fma_adds() {
-    static const bool on = !(getenv("CKZG_B200_SHA_ADDS") && strcmp(getenv("CKZG_B200_SHA_ADDS"), "alu") == 0);
+    static const bool on = getenv("CKZG_B200_SHA_ADDS") && strcmp(getenv("CKZG_B200_SHA_ADDS"), "fma") == 0;
     return on;
 }
 __device__ __forceinline__ void pair_barrier() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
@@ -134,9 +138,10 @@ __device__ __forceinline__ void challenge_message_block(uint32_t w[16], int k, c
 // `lanes` (<= 32) blobs per CTA: the lanes above it leave at once (a partially filled warp still costs
 // the full issue slots, so this only helps to spread a small batch over more SMs).
 //
-// FMA_ADDS: the rounds warp is bound by the 16-lane ALU pipe, not by latency -- every warp instruction holds its pipe
-// for two cycles and a round was 6 SHF + 4 LOP3 + 3 IADD3 on the ALU pipe (13 x 2 = 26 of the 31 cycles measured per
-// round) against 2 IMAD.IADD on the FMA pipe.  With FMA_ADDS every addition of the round is written as x * one + y with
+// FMA_ADDS (experiment, off by default: see sha_fma_adds): the rounds warp is bound by the 16-lane ALU pipe, not by
+// latency -- every warp instruction holds its pipe for two cycles and a round is 6 SHF + 4 LOP3 + 3 IADD3 on the ALU
+// pipe (13 x 2 = 26 of the 31 cycles measured per round) against 2 IMAD.IADD on the FMA pipe.  With FMA_ADDS every
+// addition of the round is written as x * one + y with
 // a run-time `one` (%nsmid clamped to 1), which ptxas cannot turn back into IADD3: 10 ALU + 8 FMA instructions per
 // round, and the e-recurrence is still three dependent instructions (SHF -> LOP3 -> IMAD).
 __device__ __forceinline__ uint32_t fma_add(uint32_t x, uint32_t one, uint32_t y) {

@@ -361,8 +361,7 @@ int launch_vmsm_jobs(Launch& L, G1* out2, const VmsmJobs& jobs, const G1* table,
     L.count(1, "vmsm_accumulate");
     vmsm_combine_kernel<<<dim3(VNB, 2), VCOMB_THREADS, 0, L.stream>>>(jobs);
     KZG_CUDA_TRY(cudaGetLastError());
-    static const cudaError_t attr = cudaFuncSetAttribute(vmsm_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(VNB * sizeof(QuadScratch)));
-    KZG_CUDA_TRY(attr);
+    KZG_FUNC_ATTR_PER_DEVICE(vmsm_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(VNB * sizeof(QuadScratch)));
     vmsm_reduce_kernel<<<2, VRED_THREADS, VNB * sizeof(QuadScratch), L.stream>>>(out2, jobs);
     KZG_CUDA_TRY(cudaGetLastError());
     L.count(2, "vmsm_reduce");
