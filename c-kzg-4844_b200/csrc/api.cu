@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -346,6 +347,34 @@ int ckzg_b200_profile_dump(ckzg_b200_ctx* ctx, char* buf, size_t cap) {
         n += snprintf(buf + n, cap - n, "%s\"%s\": [%.6f, %llu]", i ? ", " : "", c->prof.names[i], c->prof.ms[i], (unsigned long long)c->prof.cnt[i]);
     if (n > 0 && (size_t)n < cap) n += snprintf(buf + n, cap - n, "}}");
     return n;
+}
+
+// measurement hook (tools/upload_probe.py): `reps` uploads of `bytes` from `host` through Call::stage_in -- the staged
+// path for pageable memory, one DMA for pinned memory; mode 1 = cudaHostRegister + direct DMA + unregister instead
+int ckzg_b200_debug_upload(ckzg_b200_ctx* ctx, const uint8_t* host, uint64_t bytes, int reps, int mode, double* ms_best) {
+    if (!ctx || !host || !ms_best || reps < 1) return RET_BADARGS;
+    double best = 1e30;
+    for (int r = 0; r < reps; r++) {
+        Call call(reinterpret_cast<Ctx*>(ctx));
+        if (!call.ok) return RET_ERROR;
+        uint8_t* d = nullptr;
+        TRY(call.alloc(&d, bytes));
+        KZG_CUDA_TRY(cudaStreamSynchronize(call.stream));
+        const auto t0 = std::chrono::steady_clock::now();
+        if (mode == 1) {
+            KZG_CUDA_TRY(cudaHostRegister((void*)host, bytes, cudaHostRegisterDefault));
+            KZG_CUDA_TRY(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, call.stream));
+            KZG_CUDA_TRY(cudaStreamSynchronize(call.stream));
+            KZG_CUDA_TRY(cudaHostUnregister((void*)host));
+        } else {
+            TRY(call.upload(d, host, bytes, call.stream));
+            KZG_CUDA_TRY(cudaStreamSynchronize(call.stream));
+        }
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (ms < best) best = ms;
+    }
+    *ms_best = best;
+    return RET_OK;
 }
 
 int ckzg_b200_debug_placement(uint32_t* dev_buf) { return debug_set_placement_buffer(dev_buf); }

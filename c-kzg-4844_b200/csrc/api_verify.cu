@@ -84,6 +84,16 @@ struct Stage1 {
     // validation kernels as a by-product of the subgroup test
     bool want_shift = false;
     G1* table = nullptr;
+    // Streamed z||y (batch verification): when h_zy (pinned, n x 64) is set, the evaluations run in chunks and every
+    // chunk's z||y is copied to h_zy on a side stream as soon as it exists; zy_done[k] fires when chunk k (blobs
+    // [k * zy_chunk, ...)) has landed, so the host hashes the batch transcript BEHIND the GPU instead of after it.
+    uint8_t* h_zy = nullptr;
+    uint64_t zy_chunk = 0;
+    std::vector<cudaEvent_t> zy_done;
+    ~Stage1() {
+        for (cudaEvent_t e : zy_done)
+            if (e) cudaEventDestroy(e);
+    }
 };
 // CKZG_B200_RLC=points forces the one-multiplication-per-point linear combination (A/B comparison)
 bool rlc_use_vmsm() {
@@ -95,8 +105,25 @@ bool rlc_use_vmsm() {
 // concurrently with the point validations; HOST blobs are uploaded in chunks on a copy stream and every
 // chunk's (hash -> evaluate) chain starts as soon as its bytes have landed (copy engine || SMs).
 // With per-kernel profiling on (level 2) everything runs on the call's stream so event attribution is exact.
+// after the evaluation of blobs [off, off + m) has been enqueued on the call stream: copy their z||y to the host on `cpz`
+static int stage1_stream_zy(Call& call, Stage1& s, cudaStream_t cpz, uint64_t off, uint64_t m) {
+    cudaEvent_t ready = nullptr, done = nullptr;
+    KZG_CUDA_TRY(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    cudaEventRecord(ready, call.stream);
+    cudaStreamWaitEvent(cpz, ready, 0);
+    cudaEventDestroy(ready);
+    KZG_CUDA_TRY(cudaMemcpyAsync(s.h_zy + off * 64, s.zy + off * 64, m * 64, cudaMemcpyDeviceToHost, cpz));
+    KZG_CUDA_TRY(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    cudaEventRecord(done, cpz);
+    s.zy_done.push_back(done);
+    return RET_OK;
+}
+
 int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_cm, const uint8_t* d_pf, uint64_t n, int mem) {
     Launch L = call.launch();
+    const bool stream_zy = s.h_zy != nullptr && !call.trace_kernels && n >= 1024;
+    cudaStream_t cpz = nullptr;
+    if (stream_zy && !(cpz = call.fork())) return RET_ERROR;
     const bool host = (mem == CKZG_B200_HOST);
     uint8_t* d_up = nullptr;
     if (host) TRY(call.alloc(&d_up, n * BLOB_BYTES));
@@ -128,7 +155,17 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
         // evaluations follow on the same stream.
         TRY(launch_stage1_fused(L, s.z, s.zy, d_blobs, s.cm, d_cm, s.pf, d_pf, n, s.bad, s.table));
         call.mark_on(call.stream, "stage:t_hash_done");
-        int rc = launch_evaluate(L, s.y, s.zy, nullptr, nullptr, d_blobs, s.z, n, s.bad, 0);
+        int rc = RET_OK;
+        if (stream_zy) {
+            s.zy_chunk = (n + 3) / 4;  // four chunks: the host hashes chunk k while the GPU evaluates chunk k + 1
+            for (uint64_t off = 0; off < n && rc == RET_OK; off += s.zy_chunk) {
+                const uint64_t m = (n - off < s.zy_chunk) ? n - off : s.zy_chunk;
+                rc = launch_evaluate(L, s.y + off, s.zy + off * 64, nullptr, nullptr, d_blobs + off * BLOB_BYTES, s.z + off, m, s.bad, 0);
+                if (rc == RET_OK) rc = stage1_stream_zy(call, s, cpz, off, m);
+            }
+        } else {
+            rc = launch_evaluate(L, s.y, s.zy, nullptr, nullptr, d_blobs, s.z, n, s.bad, 0);
+        }
         call.mark_on(call.stream, "stage:t_evaluate_done");
         return rc;
     }
@@ -185,6 +222,10 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
         cudaStreamWaitEvent(call.stream, hashed[c], 0);
         cudaEventDestroy(hashed[c]);
         if (rc == RET_OK) rc = launch_evaluate(L, s.y + off, s.zy + off * 64, nullptr, nullptr, d_blobs + off * BLOB_BYTES, s.z + off, m, s.bad, 0);
+        if (rc == RET_OK && stream_zy) {
+            s.zy_chunk = CH;
+            rc = stage1_stream_zy(call, s, cpz, off, m);
+        }
     }
     return rc;
 }
@@ -193,6 +234,26 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
 // (compute_r_powers_for_verify_kzg_proof_batch, eip4844.c:612-668).  The transcript is one serial hash
 // chain: hashed on the host (src/host_sha256.c explains why); the 32-byte digest goes back to the
 // device, which reduces it mod r.  Inputs are host pointers; zy is n x 64 (z || y).
+struct TranscriptHasher {
+    ckzg_host_sha256 h;
+    void begin(uint64_t n) {
+        ckzg_host_sha256_init(&h);
+        uint8_t head[32] = {'R', 'C', 'K', 'Z', 'G', 'B', 'A', 'T', 'C', 'H', '_', '_', '_', 'V', '1', '_'};
+        for (int i = 0; i < 8; i++) {
+            head[16 + i] = (uint8_t)((uint64_t)N_BLOB >> (56 - 8 * i));
+            head[24 + i] = (uint8_t)(n >> (56 - 8 * i));
+        }
+        ckzg_host_sha256_update(&h, head, 32);
+    }
+    void feed(const uint8_t* cm, const uint8_t* zy, const uint8_t* pf, uint64_t first, uint64_t count) {
+        for (uint64_t i = first; i < first + count; i++) {
+            ckzg_host_sha256_update(&h, cm + 48 * i, 48);
+            ckzg_host_sha256_update(&h, zy + 64 * i, 64);
+            ckzg_host_sha256_update(&h, pf + 48 * i, 48);
+        }
+    }
+    void finish(uint8_t digest[32]) { ckzg_host_sha256_final(&h, digest); }
+};
 void transcript_digest(uint8_t digest[32], const uint8_t* cm, const uint8_t* zy, const uint8_t* pf, const uint8_t* tuples, uint64_t n) {
     ckzg_host_sha256 h;
     ckzg_host_sha256_init(&h);
@@ -399,6 +460,7 @@ int ckzg_b200_verify_blob_kzg_proof_batch(ckzg_b200_ctx* ctx, int* ok, const uin
         cudaMemcpyAsync(h_p, d_pf, n * 48, cudaMemcpyDeviceToHost, cp);
         cudaEventRecord(fetched, cp);
     }
+    if (use_r) s.h_zy = h_zy;  // stream z||y to the host chunk by chunk (n >= 1024), hashed behind the evaluations
     int rc1 = verify_stage1(call, s, blobs, d_cm, d_pf, n, mem);
     if (rc1) {
         if (fetched) {
@@ -410,23 +472,36 @@ int ckzg_b200_verify_blob_kzg_proof_batch(ckzg_b200_ctx* ctx, int* ok, const uin
     const bool stage_marks = call.profiling && !call.trace_kernels;  // level 1: stage boundaries of the concurrent form
     if (stage_marks) call.mark("stage:per_blob(validate|hash,evaluate)");
     // the reference stops at the first invalid input (eip4844.c:813-831) before any pairing work
-    if (use_r) cudaMemcpyAsync(h_zy, s.zy, n * 64, cudaMemcpyDeviceToHost, call.stream);
+    const bool streamed = !s.zy_done.empty();
+    if (use_r && !streamed) cudaMemcpyAsync(h_zy, s.zy, n * 64, cudaMemcpyDeviceToHost, call.stream);
     cudaMemcpyAsync(h_bad, s.bad, sizeof(int), cudaMemcpyDeviceToHost, call.stream);
-    cudaError_t se = cudaStreamSynchronize(call.stream);
+    const uint8_t* hc = (mem == CKZG_B200_DEVICE) ? h_c : commitments;
+    const uint8_t* hp = (mem == CKZG_B200_DEVICE) ? h_p : proofs;
+    uint8_t digest[32] = {0};
+    cudaError_t se = cudaSuccess;
     if (fetched) {
-        if (se == cudaSuccess) se = cudaEventSynchronize(fetched);
+        se = cudaEventSynchronize(fetched);
         cudaEventDestroy(fetched);
     }
+    if (streamed && se == cudaSuccess) {
+        // the batch transcript (eip4844.c:612-668), hashed chunk by chunk as the chunks' z||y land
+        TranscriptHasher th;
+        th.begin(n);
+        for (size_t k = 0; k < s.zy_done.size() && se == cudaSuccess; k++) {
+            se = cudaEventSynchronize(s.zy_done[k]);
+            const uint64_t off = k * s.zy_chunk;
+            if (se == cudaSuccess) th.feed(hc, h_zy, hp, off, (n - off < s.zy_chunk) ? n - off : s.zy_chunk);
+        }
+        th.finish(digest);
+    }
+    if (se == cudaSuccess) se = cudaStreamSynchronize(call.stream);
     KZG_CUDA_TRY(se);
     if (*h_bad) return RET_BADARGS;
 
     Fr* d_r;
     TRY(call.alloc(&d_r, 1));
-    uint8_t digest[32] = {0};
     if (use_r) {
-        const uint8_t* hc = (mem == CKZG_B200_DEVICE) ? h_c : commitments;
-        const uint8_t* hp = (mem == CKZG_B200_DEVICE) ? h_p : proofs;
-        transcript_digest(digest, hc, h_zy, hp, nullptr, n);
+        if (!streamed) transcript_digest(digest, hc, h_zy, hp, nullptr, n);
         L.count(0, "transcript(d2h,host_sha)");
         if (!s.want_shift) {
             uint8_t* d_digest;

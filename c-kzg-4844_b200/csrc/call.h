@@ -166,7 +166,8 @@ struct Call {
             KZG_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
             return RET_OK;
         }
-        constexpr size_t SLOT = 8u << 20;
+        // CKZG_B200_STAGE_SLOT_MB: size of one of the four pinned staging slots (default 8 MiB)
+        static const size_t SLOT = ((getenv("CKZG_B200_STAGE_SLOT_MB") && atoi(getenv("CKZG_B200_STAGE_SLOT_MB")) > 0) ? (size_t)atoi(getenv("CKZG_B200_STAGE_SLOT_MB")) : 8u) << 20;
         constexpr int NSLOT = 4;
         if (!ring) {
             TRY(pin(&ring, SLOT * NSLOT));

@@ -38,6 +38,11 @@ struct PairingSmem {
     G1 pts[2];
     int dec_ok[2];
 };
+// pairing_check_kernel: two cooperative machines (one per pairing of the product)
+struct PairingSmem2 {
+    CoopWS ws[2];
+    G1 pts[2];
+};
 extern __shared__ __align__(16) unsigned char pairing_smem_raw[];
 
 __global__ void __launch_bounds__(COOP_LANES) monomial_form_kernel(int* out, const uint8_t* lag01, const G2Lines* lines) {
@@ -59,9 +64,14 @@ __global__ void __launch_bounds__(COOP_LANES) monomial_form_kernel(int* out, con
 }
 
 // ok = [ e(A, Q_a) == e(B + B_extra, Q_b) ] = [ e(-A, Q_a) * e(B + B_extra, Q_b) == 1 ];  A, B XYZZ sums.
-__global__ void __launch_bounds__(COOP_LANES) pairing_check_kernel(int* ok, const G1* A, const G1* B, const G1* B_extra, const G2Lines* lines, int line_a, int line_b) {
-    PairingSmem& sm = *reinterpret_cast<PairingSmem*>(pairing_smem_raw);
-    CoopWS& ws = sm.ws;
+// 128 threads = TWO cooperative machines: the Miller loops of the two pairings are independent chains (63 squarings +
+// 68 line products each), so they run side by side on the two halves of the CTA -- 131 dependent tower operations
+// instead of the 199 of the shared-squaring loop on one machine -- and machine 0 multiplies the two values and runs
+// the final exponentiation (the Miller value of a product of pairings is the product of the Miller values).
+__global__ void __launch_bounds__(2 * COOP_LANES) pairing_check_kernel(int* ok, const G1* A, const G1* B, const G1* B_extra, const G2Lines* lines, int line_a, int line_b) {
+    PairingSmem2& sm = *reinterpret_cast<PairingSmem2*>(pairing_smem_raw);
+    const int g = threadIdx.x >> 6;
+    CoopWS& ws = sm.ws[g];
     G1* pts = sm.pts;
     if (threadIdx.x == 0) {
         pts[0] = *A;
@@ -73,14 +83,27 @@ __global__ void __launch_bounds__(COOP_LANES) pairing_check_kernel(int* ok, cons
         pts[1] = b;
     }
     __syncthreads();
-    coop_pairing_product_is_one(ws, pts[0], &lines[line_a], pts[1], &lines[line_b], true);
+    coop_init_tables(ws);
+    coop_load_points(ws, pts[0], &lines[line_a], pts[1], &lines[line_b], true);
+    if ((threadIdx.x & (COOP_LANES - 1)) == 0) ws.use[1 - g] = 0;  // machine g owns pairing g
+    coop_sync();
+    coop_prepare_all_lines(ws, &lines[line_a], &lines[line_b]);
+    coop_miller_loop(ws);
+    __syncthreads();
+    if (g != 0) return;
+    // machine 0: F = F_0 * F_1, final exponentiation
+    const int lane = threadIdx.x;
+    if (lane < 12) ws.reg[6][lane] = sm.ws[1].reg[0][lane];
+    coop_sync();
+    coop_mul(ws, 0, 0, 6);
+    coop_final_exp_is_one(ws);
     if (threadIdx.x == 0) *ok = ws.result;
 }
 
 // > 48 KB of dynamic shared memory needs the per-function opt-in, once per device context
 static int pairing_smem_opt_in() {
     KZG_CUDA_TRY(cudaFuncSetAttribute(monomial_form_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairingSmem)));
-    KZG_CUDA_TRY(cudaFuncSetAttribute(pairing_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairingSmem)));
+    KZG_CUDA_TRY(cudaFuncSetAttribute(pairing_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairingSmem2)));
     return RET_OK;
 }
 
@@ -118,7 +141,7 @@ int setup_is_monomial_form(cudaStream_t stream, Launch& L, Ctx* c, const uint8_t
 }
 
 int launch_pairing_check(Launch& L, int* d_ok, const G1* A, const G1* B, const G1* B_extra, int line_a, int line_b) {
-    pairing_check_kernel<<<1, COOP_LANES, sizeof(PairingSmem), L.stream>>>(d_ok, A, B, B_extra, (const G2Lines*)L.ctx->g2_lines, line_a, line_b);
+    pairing_check_kernel<<<1, 2 * COOP_LANES, sizeof(PairingSmem2), L.stream>>>(d_ok, A, B, B_extra, (const G2Lines*)L.ctx->g2_lines, line_a, line_b);
     KZG_CUDA_TRY(cudaGetLastError());
     L.count(1, "pairing_check");
     return RET_OK;

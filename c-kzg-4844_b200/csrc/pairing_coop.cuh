@@ -26,12 +26,16 @@ constexpr int COOP_LANES = 64;
 constexpr int COOP_NREG = 8;
 
 #if KZG_DEVICE_PATH
+// A cooperative machine is a GROUP of 64 consecutive threads (two warps) of the CTA, meeting at its own named barrier
+// (id 1 + group): a 64-thread CTA is one machine, a 128-thread CTA runs two independent ones side by side (the two
+// Miller loops of a pairing check, pairing.cu).
+__device__ __forceinline__ void coop_sync() { asm volatile("bar.sync %0, 64;" ::"r"(1 + (int)(threadIdx.x >> 6)) : "memory"); }
 #define COOP_BEGIN \
     {              \
-        const int lane = threadIdx.x;
-#define COOP_END      \
-    }                 \
-    __syncthreads();
+        const int lane = threadIdx.x & (COOP_LANES - 1);
+#define COOP_END \
+    }            \
+    coop_sync();
 #else
 #define COOP_BEGIN for (int lane = 0; lane < COOP_LANES; lane++) {
 #define COOP_END }
@@ -325,17 +329,13 @@ KZG_HD_NOINLINE void coop_pow_x(CoopWS& ws, int d, int s) {
     coop_conj(ws, d, d);
 }
 
-// ws.result = [ e(+-P1, Q1) * e(P2, Q2) == 1 ]
-KZG_HD void coop_pairing_product_is_one(CoopWS& ws, const G1& P1, const G2Lines* L1, const G1& P2, const G2Lines* L2, bool negate_first) {
-    enum { F = 0, E = 1, T0 = 2, T1 = 3, T2 = 4, T3 = 5, X = 6, Y = 7 };
-    coop_init_tables(ws);
-    coop_load_points(ws, P1, L1, P2, L2, negate_first);
+// reg[F] = conj(Miller loop) over the pairs whose ws.use[] flag is set (lines already evaluated: coop_prepare_all_lines)
+KZG_HD void coop_miller_loop(CoopWS& ws) {
+    enum { F = 0 };
     const bool use0 = ws.use[0] != 0, use1 = ws.use[1] != 0;
-    // ---- Miller loop ----
     coop_set_one(ws, F);
     const uint64_t z = BLS_X_ABS;
     int k = 0;
-    coop_prepare_all_lines(ws, L1, L2);
     for (int b = 62; b >= 0; b--) {
         if (b != 62) coop_sqr(ws, F, F);
         if (use0) coop_line(ws, F, F, 0, k);
@@ -348,6 +348,21 @@ KZG_HD void coop_pairing_product_is_one(CoopWS& ws, const G1& P1, const G2Lines*
         }
     }
     coop_conj(ws, F, F);
+}
+KZG_HD void coop_final_exp_is_one(CoopWS& ws);
+
+// ws.result = [ e(+-P1, Q1) * e(P2, Q2) == 1 ]
+KZG_HD void coop_pairing_product_is_one(CoopWS& ws, const G1& P1, const G2Lines* L1, const G1& P2, const G2Lines* L2, bool negate_first) {
+    coop_init_tables(ws);
+    coop_load_points(ws, P1, L1, P2, L2, negate_first);
+    coop_prepare_all_lines(ws, L1, L2);
+    coop_miller_loop(ws);
+    coop_final_exp_is_one(ws);
+}
+
+// ws.result = [ reg[F]^((p^12 - 1) / r) == 1 ]
+KZG_HD void coop_final_exp_is_one(CoopWS& ws) {
+    enum { F = 0, E = 1, T0 = 2, T1 = 3, T2 = 4, T3 = 5, X = 6, Y = 7 };
     // ---- final exponentiation, easy part: E = F^((p^6-1)(p^2+1)) ----
     coop_inv(ws, X, F);
     coop_conj(ws, Y, F);

@@ -215,6 +215,10 @@ int ckzg_b200_selftest_mulbench(int ilp, int iters, int blocks, int threads, flo
  * of uint32, [0] = record count (set to 0), [1] = capacity, records follow:
  * kernel id << 28 | warp in block << 24 | %smid << 8 | %warpid.  Test/measurement hook. */
 int ckzg_b200_debug_placement(uint32_t *dev_buf);
+/* Measurement hook: best-of-`reps` wall time (ms) of uploading `bytes` from HOST memory the way every HOST-mode call does
+ * (pageable sources: pinned staging ring filled by the context's host threads, CKZG_B200_HOST_THREADS /
+ * CKZG_B200_STAGE_SLOT_MB; pinned sources: one DMA).  mode 1: cudaHostRegister + direct DMA + cudaHostUnregister. */
+int ckzg_b200_debug_upload(ckzg_b200_ctx *ctx, const uint8_t *host, uint64_t bytes, int reps, int mode, double *ms_best);
 /* op 0: [k]P (+Q), op 1: validate (subgroup), op 2: uncompress only; compressed points, HOST memory.
  * ok_out[i] = 1 if the input decoded/validated.  k = 8 limbs per scalar. */
 int ckzg_b200_selftest_g1(int op, uint8_t *out48, int *ok_out, const uint8_t *p48, const uint32_t *k, const uint8_t *q48, uint64_t n);

@@ -162,7 +162,21 @@ int hc_coop_pairing_product_is_one(const uint8_t* p1, const uint8_t* q1, const u
     }
     static CoopWS ws;
     coop_pairing_product_is_one(ws, A, &L1, Bp, &L2, negate_first != 0);
-    return ws.result;
+    const int single = ws.result;
+    // the two-machine form of pairing_check_kernel (pairing.cu): one Miller loop per machine, product, final exponentiation
+    static CoopWS w2[2];
+    for (int g = 0; g < 2; g++) {
+        coop_init_tables(w2[g]);
+        coop_load_points(w2[g], A, &L1, Bp, &L2, negate_first != 0);
+        w2[g].use[1 - g] = 0;
+        coop_prepare_all_lines(w2[g], &L1, &L2);
+        coop_miller_loop(w2[g]);
+    }
+    for (int lane = 0; lane < 12; lane++) w2[0].reg[6][lane] = w2[1].reg[0][lane];
+    coop_mul(w2[0], 0, 0, 6);
+    coop_final_exp_is_one(w2[0]);
+    if (w2[0].result != single) return -2;
+    return single;
 }
 #endif
 }
