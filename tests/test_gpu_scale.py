@@ -269,3 +269,37 @@ def test_fk20_affine_batch_matches_single_blob_path(env):
             assert b"".join(p) == got_p[6144 * i : 6144 * (i + 1)], i
     finally:
         mod.coalesce_enable(ts, True)
+
+
+def test_device_mode_ordering_against_the_callers_streams(env):
+    """DEVICE-mode contract (include/ckzg_b200.h): engine calls run on blocking streams, so writes enqueued on the legacy
+    default stream are seen without a synchronize; a producer on a non-blocking side stream is named with
+    ckzg_b200_set_caller_stream.  Here the CORRECT proofs are written into a buffer of wrong ones behind ~20 ms of
+    queued work, and the call must see them."""
+    import torch
+
+    mod, ts, n, host, dev, cms, prs = env
+    m = 256
+    wrong = prs[: 48 * m].roll(48)  # every proof belongs to the neighbouring blob
+    filler = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
+    # (1) legacy default stream, no synchronize
+    buf = wrong.clone()
+    for _ in range(8):
+        filler.fill_(3)
+    buf.copy_(prs[: 48 * m])
+    assert mod.verify_blob_kzg_proof_batch_device(dev.data_ptr(), cms.data_ptr(), buf.data_ptr(), m, ts) is True
+    # (2) a non-blocking side stream, named for this thread
+    side = torch.cuda.Stream()
+    buf2 = wrong.clone()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        for _ in range(8):
+            filler.fill_(5)
+        buf2.copy_(prs[: 48 * m])
+    mod.set_caller_stream(side.cuda_stream)
+    try:
+        assert mod.verify_blob_kzg_proof_batch_device(dev.data_ptr(), cms.data_ptr(), buf2.data_ptr(), m, ts) is True
+    finally:
+        mod.set_caller_stream(0)
+    torch.cuda.synchronize()
+    assert mod.verify_blob_kzg_proof_batch_device(dev.data_ptr(), cms.data_ptr(), wrong.data_ptr(), m, ts) is False
