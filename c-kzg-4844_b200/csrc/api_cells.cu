@@ -58,7 +58,9 @@ int ckzg_b200_compute_cells_and_kzg_proofs_batch(ckzg_b200_ctx* ctx, uint8_t* ce
     Call call(reinterpret_cast<Ctx*>(ctx));
     if (!call.ok) return RET_ERROR;
     Launch L = call.launch();
-    const uint64_t CHUNK = 512;  // bounds the per-blob scratch (0.6 MiB with proofs)
+    // bounds the per-blob scratch (0.6 MiB with proofs); big batches take 2048 at a time so that the one-thread-per-
+    // butterfly G1 FFT stages (fk20_fft.cu, >= 1024 vectors) have 131 k chains to spread over the sub-partitions
+    const uint64_t CHUNK = (proofs && n >= 2048) ? 2048 : 512;
     const uint64_t chunk = n < CHUNK ? n : CHUNK;
     const uint8_t* d_blobs;
     TRY(call.stage_in(&d_blobs, blobs, n * BLOB_BYTES, mem));
@@ -143,7 +145,7 @@ int ckzg_b200_recover_cells_and_kzg_proofs_batch(ckzg_b200_ctx* ctx, uint8_t* re
     if (!call.ok) return RET_ERROR;
     Launch L = call.launch();
     const bool dev = mem == CKZG_B200_DEVICE;
-    const uint64_t CHUNK = 256;
+    const uint64_t CHUNK = (recovered_proofs && n >= 2048) ? 2048 : 256;
     const uint64_t chunk = n < CHUNK ? n : CHUNK;
     const uint8_t *d_cells_in, *d_slot, *d_present;
     TRY(call.stage_in(&d_cells_in, cells, n * num_cells * CELL_BYTES, mem));

@@ -298,9 +298,17 @@ int launch_fk20_msm(Launch& L, G1* u_brp, const uint32_t* S, uint64_t n) {
     }
     static const int affine_min = getenv("CKZG_B200_FK_AFFINE_MIN") ? atoi(getenv("CKZG_B200_FK_AFFINE_MIN")) : 8;  // 0 = never
     if (affine_min > 0 && n >= (uint64_t)affine_min) {
+        // 13 MB of level scratch per blob: slices of 512 blobs (6.6 GB) fill the GPU many times over, larger batches
+        // (the FFTs behind take up to 2048 at once) reuse the same scratch slice by slice
+        const uint64_t SL = 512;
+        const uint64_t slice = n < SL ? n : SL;
         void* ws = nullptr;
-        KZG_CUDA_TRY(cudaMallocAsync(&ws, fk20_msm_affine_workspace_bytes(n, L.ctx->fk_c), L.stream));
-        int rc = launch_fk20_msm_affine(L, u_brp, S, n, ws);
+        KZG_CUDA_TRY(cudaMallocAsync(&ws, fk20_msm_affine_workspace_bytes(slice, L.ctx->fk_c), L.stream));
+        int rc = RET_OK;
+        for (uint64_t off = 0; off < n && rc == RET_OK; off += slice) {
+            const uint64_t m = (n - off < slice) ? n - off : slice;
+            rc = launch_fk20_msm_affine(L, u_brp + off * 128, S + off * 128 * 64 * 8, m, ws);
+        }
         cudaFreeAsync(ws, L.stream);
         return rc;
     }

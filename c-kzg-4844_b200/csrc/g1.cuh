@@ -296,6 +296,18 @@ KZG_HD bool g1a_validate(G1Affine& out, const uint8_t* in) {
 // j = 9..17: 2^(8(j-9)) Q.
 constexpr int G1_LEVELS = 18;
 
+KZG_HD G1 g1_load(const G1* src) {
+#if KZG_DEVICE_PATH
+    G1 a;
+    const uint4* q = reinterpret_cast<const uint4*>(src);
+    uint4* d = reinterpret_cast<uint4*>(&a);
+#pragma unroll
+    for (int i = 0; i < 12; i++) d[i] = q[i];
+    return a;
+#else
+    return *src;
+#endif
+}
 KZG_HD void g1_store(G1* dst, const G1& a) {
 #if KZG_DEVICE_PATH
     uint4* q = reinterpret_cast<uint4*>(dst);

@@ -344,3 +344,24 @@ def test_load_trusted_setup_error_branches_on_device(ref):
         accepted = name in ("valid", "lagrange_in_both_slots", "g2_0_other_point", "g2_64_other_point")
         assert want == (0 if accepted else 1), (name, want)
     assert load(libs["gpu"], mono, lag, g2, 16) == load(libs["ref"], mono, lag, g2, 16) == 1
+
+
+def test_g1_fft_one_thread_per_butterfly_matches_quad_form_and_reference(env, ref, monkeypatch):
+    """Batches of >= 1024 blobs run the FK20 G1 FFT stages with one thread per butterfly (fk20_fft.cu
+    g1_fft_stage_thread_kernel), smaller ones with four lanes per group operation.  Forced on for the 256-blob batch of
+    this module (8 structured blobs included): identical bytes to the quad form, which the tests above pin against the
+    reference -- and six blobs are compared with the reference directly."""
+    import torch
+
+    mod, ts, n = env["mod"], env["ts"], env["n"]
+    monkeypatch.setenv("CKZG_B200_FFT_THREAD_MIN", "1")
+    cells = torch.empty_like(env["cells"])
+    cprf = torch.empty_like(env["cprf"])
+    mod.compute_cells_and_kzg_proofs_device(cells.data_ptr(), cprf.data_ptr(), env["dev"].data_ptr(), n, ts)
+    monkeypatch.delenv("CKZG_B200_FFT_THREAD_MIN")
+    assert torch.equal(cells, env["cells"])
+    assert torch.equal(cprf, env["cprf"])
+    hp = cprf.cpu().numpy().tobytes()
+    for i in SAMPLE[::3] + [255]:
+        _, want_p = ref.compute_cells_and_kzg_proofs(env["hb"][BLOB * i : BLOB * (i + 1)], want_cells=False)
+        assert hp[6144 * i : 6144 * (i + 1)] == want_p, i
