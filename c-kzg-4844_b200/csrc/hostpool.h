@@ -126,7 +126,10 @@ class HostPool {
     bool stop_ = false;
 };
 
-// CKZG_B200_HOST_THREADS (default: min(8, hardware threads / visible devices), at least 2)
+// CKZG_B200_HOST_THREADS (default: min(16, hardware threads / visible devices), at least 2).  Measured on a 16-core
+// B200 host (tools/upload_probe.py, profiles/R2_summary.md): staging 512 MiB of pageable memory runs at 23.7 / 35.9 /
+// 42.1 GB/s with 2 / 8 / 16 threads and 8 MiB slots, against 55.6 GB/s for pinned memory and 18.4 GB/s for
+// cudaHostRegister + direct DMA + unregister.
 inline int host_threads_default() {
     if (const char* env = getenv("CKZG_B200_HOST_THREADS")) {
         const int v = atoi(env);
@@ -137,7 +140,7 @@ inline int host_threads_default() {
     int hw = (int)std::thread::hardware_concurrency();
     if (hw <= 0) hw = 4;
     int t = hw / ndev;
-    return t > 8 ? 8 : (t < 2 ? 2 : t);
+    return t > 16 ? 16 : (t < 2 ? 2 : t);
 }
 
 // true if `p` is ordinary pageable host memory (not cudaHostAlloc / cudaHostRegister memory)

@@ -42,6 +42,15 @@ def test_concurrent_callers_are_merged(lib):
     assert batches < req / 3 and largest >= 8 and peak <= 2
 
 
+def test_gather_window_fills_batches_under_many_callers(lib):
+    """Round 2: 64 callers, two batches in flight: a leader holds its batch open for the callers that usually arrive
+    together (bounded by 1/16 of the last batch's duration), so batches average well above the 9 of pure group commit --
+    and a lone caller (first test) still never waits."""
+    rc, (req, batches, largest, peak) = run(lib, 64, 20, 64, 2, 3000)
+    assert rc == 0 and req == 1280 and peak <= 2
+    assert req / batches >= 16, (req, batches, largest)
+
+
 def test_batch_cap_and_inflight_limit(lib):
     rc, (req, batches, largest, peak) = run(lib, 48, 10, 5, 1, 500)
     assert rc == 0 and req == 480 and largest <= 5 and peak == 1
