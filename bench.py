@@ -260,7 +260,7 @@ def run_b200(args):
     os.environ["CKZG_B200_DEVICE"] = str(local_rank)
     ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 8)
     # host threads per rank (staging memcpy, verify_cell sub-batch hashes): the ranks share the box's cores
-    os.environ.setdefault("CKZG_B200_HOST_THREADS", str(max(2, min(16, ncpu // world))))
+    os.environ.setdefault("CKZG_B200_HOST_THREADS", str(max(2, min(8, ncpu // world))))
     mod = entry.load_package()
     par = __import__("importlib").import_module("ckzg_b200.parallel")
     ts = mod.load_trusted_setup()
@@ -607,7 +607,7 @@ def run_b200(args):
         if rank == 0:
             try:
                 os.environ["CKZG_B200_DEVICES"] = ",".join(str(i) for i in range(world))
-                os.environ["CKZG_B200_HOST_THREADS"] = str(max(2, min(16, ncpu // world)))
+                os.environ["CKZG_B200_HOST_THREADS"] = str(max(2, min(8, ncpu // world)))
                 ts_all = mod.load_trusted_setup()
                 del os.environ["CKZG_B200_DEVICES"]
                 reps = world

@@ -126,10 +126,11 @@ class HostPool {
     bool stop_ = false;
 };
 
-// CKZG_B200_HOST_THREADS (default: min(16, hardware threads / visible devices), at least 2).  Measured on a 16-core
-// B200 host (tools/upload_probe.py, profiles/R2_summary.md): staging 512 MiB of pageable memory runs at 23.7 / 35.9 /
-// 42.1 GB/s with 2 / 8 / 16 threads and 8 MiB slots, against 55.6 GB/s for pinned memory and 18.4 GB/s for
-// cudaHostRegister + direct DMA + unregister.
+// CKZG_B200_HOST_THREADS (default: min(8, hardware threads / visible devices), at least 2).  Measured on a 16-core
+// B200 host (tools/upload_probe.py, profiles/R2_summary.md): staging 512 MiB of pageable memory ALONE runs at 23.7 /
+// 35.9 / 42.1 GB/s with 2 / 8 / 16 threads and 8 MiB slots, against 55.6 GB/s for pinned memory and 18.4 GB/s for
+// cudaHostRegister + direct DMA + unregister.  Inside a real call 16 threads on 16 cores lose to 8 (e2e_pageable 27 ms
+// against 19-22 ms at 4096 blobs: the caller's launch thread and the driver's own threads need cores too), so 8 it is.
 inline int host_threads_default() {
     if (const char* env = getenv("CKZG_B200_HOST_THREADS")) {
         const int v = atoi(env);
@@ -140,7 +141,7 @@ inline int host_threads_default() {
     int hw = (int)std::thread::hardware_concurrency();
     if (hw <= 0) hw = 4;
     int t = hw / ndev;
-    return t > 16 ? 16 : (t < 2 ? 2 : t);
+    return t > 8 ? 8 : (t < 2 ? 2 : t);
 }
 
 // true if `p` is ordinary pageable host memory (not cudaHostAlloc / cudaHostRegister memory)
