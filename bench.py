@@ -352,8 +352,14 @@ def run_b200(args):
     value = world * n / (ms_per_step / 1000.0)
 
     # ---- e2e: the same step through HOST pointers (pinned), and through pageable memory ----
+    mod.profile_enable(ts, 1)
     e_ms, e_wall, _ = timed(step_of(verify_host), args.steps, max(3, args.warmup - 1))
+    prof_e = mod.profile_dump(ts)
+    mod.profile_enable(ts, 0)
     e2e_value = world * n / (e_ms / 1000.0)
+    # where the end-to-end call's time goes: completion times of its stages relative to the call's first event
+    e2e_stages = {k: round(v[0] / max(1, v[1]), 3) for k, v in prof_e.get("kernels", {}).items() if k.startswith("stage:")}
+    e2e_stages["engine_ms_per_call"] = round(prof_e["call_ms"] / max(1, prof_e["calls"]), 3)
     pg_blobs = np.array(host_blobs.numpy(), copy=True)  # ordinary pageable memory: what a Go slice or Python bytes is
     pg_cms, pg_prs = np.array(host_cms.numpy(), copy=True), np.array(host_prs.numpy(), copy=True)
 
@@ -703,7 +709,7 @@ def run_b200(args):
             "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
             "config": workload_config(n, world, args.sharded and world > 1),
             "timing": "CUDA events on the legacy default stream around the K steps (engine call + all-reduce(MIN) + host read of the verdict each step), max over ranks",
-            "e2e": {"value": e2e_value, "unit": "blobs/s", "h2d_bytes_per_step": n * (BLOB + 96), "d2h_bytes_per_step": 8 + 64 * n, "ms_per_step": e_ms, "memory": "pinned host"},
+            "e2e": {"value": e2e_value, "unit": "blobs/s", "h2d_bytes_per_step": n * (BLOB + 96), "d2h_bytes_per_step": 8 + 64 * n, "ms_per_step": e_ms, "memory": "pinned host", "stages_ms": e2e_stages},
             "e2e_pageable": e2e_pageable, "h2d": h2d,
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "commitment": commitment, "configs": configs, "multi_gpu": multi,
             # stage boundaries inside the TIMED calls (events on the call's stream, stages overlapping as in production)

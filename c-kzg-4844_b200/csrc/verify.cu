@@ -149,9 +149,14 @@ __device__ __forceinline__ uint32_t fma_add(uint32_t x, uint32_t one, uint32_t y
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(one), "r"(y));
     return r;
 }
+//
+// Block range [k0, k1) with the SHA state carried in `states` (8 words per blob): a blob that arrives over PCIe in
+// column pieces is hashed piece by piece, each launch continuing where the last one stopped (api_verify.cu: the last
+// chunk of a host-pointer batch), so that only the final piece's 256 blocks remain when its last byte lands.
 template <bool FMA_ADDS>
 __device__ __forceinline__ void challenge_warp_pair(uint32_t (*kw)[64][32], Fr* __restrict__ z_out, uint8_t* __restrict__ zy, const uint8_t* __restrict__ blobs,
-                                                    const uint8_t* __restrict__ commitments, uint64_t n, int lanes) {
+                                                    const uint8_t* __restrict__ commitments, uint64_t n, int lanes, int k0 = 0, int k1 = CH_BLOCKS,
+                                                    uint32_t* __restrict__ states = nullptr) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane >= lanes) return;
     const uint64_t i = (uint64_t)blockIdx.x * lanes + lane;
@@ -161,14 +166,18 @@ __device__ __forceinline__ void challenge_warp_pair(uint32_t (*kw)[64][32], Fr* 
     const uint8_t* cm = commitments + ii * 48;
     Sha256 st;
     sha256_init(st);
+    if (k0 > 0 && warp == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) st.h[j] = states[ii * 8 + j];
+    }
     uint4 nx0, nx1, nx2, nx3;  // schedule warp: the NEXT block's 64 message bytes, in flight during this block's expansion
     nx0 = nx1 = nx2 = nx3 = make_uint4(0, 0, 0, 0);
 #pragma unroll 1
-    for (int k = 0; k <= CH_BLOCKS; k++) {
+    for (int k = k0; k <= k1; k++) {
         if (warp == 1) {
-            if (k < CH_BLOCKS) {
+            if (k < k1) {
                 uint32_t w[16];
-                if (k >= 1 && k < 2048) {
+                if (k > k0 && k >= 1 && k < 2048) {
                     w[0] = bswap32(nx0.x); w[1] = bswap32(nx0.y); w[2] = bswap32(nx0.z); w[3] = bswap32(nx0.w);
                     w[4] = bswap32(nx1.x); w[5] = bswap32(nx1.y); w[6] = bswap32(nx1.z); w[7] = bswap32(nx1.w);
                     w[8] = bswap32(nx2.x); w[9] = bswap32(nx2.y); w[10] = bswap32(nx2.z); w[11] = bswap32(nx2.w);
@@ -176,7 +185,7 @@ __device__ __forceinline__ void challenge_warp_pair(uint32_t (*kw)[64][32], Fr* 
                 } else {
                     challenge_message_block(w, k, blob, cm);
                 }
-                if (k + 1 < 2048) {  // a global load costs about as much as half an expansion: issue it a block ahead
+                if (k + 1 < 2048 && k + 1 < k1) {  // a global load costs about as much as half an expansion: issue it a block ahead
                     const uint4* p = blob + (4 * (k + 1) - 2);
                     nx0 = __ldg(p); nx1 = __ldg(p + 1); nx2 = __ldg(p + 2); nx3 = __ldg(p + 3);
                 }
@@ -198,7 +207,7 @@ __device__ __forceinline__ void challenge_warp_pair(uint32_t (*kw)[64][32], Fr* 
                     }
                 }
             }
-        } else if (k > 0) {
+        } else if (k > k0) {
             const uint32_t(*src)[32] = kw[(k - 1) & 1];
             uint32_t a = st.h[0], b = st.h[1], c = st.h[2], d = st.h[3], e = st.h[4], f = st.h[5], g = st.h[6], h = st.h[7];
             uint32_t one = 1u;
@@ -250,18 +259,23 @@ __device__ __forceinline__ void challenge_warp_pair(uint32_t (*kw)[64][32], Fr* 
         pair_barrier();
     }
     if (warp == 0 && live) {
-        Fr z = fr_from_digest(st.h);
-        z_out[i] = z;
-        store_fr_be(zy + i * 64, z);
+        if (k1 < CH_BLOCKS) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) states[i * 8 + j] = st.h[j];
+        } else {
+            Fr z = fr_from_digest(st.h);
+            z_out[i] = z;
+            store_fr_be(zy + i * 64, z);
+        }
     }
 }
 
 template <bool FMA_ADDS>
 __global__ void __launch_bounds__(64) blob_challenge_kernel(Fr* __restrict__ z_out, uint8_t* __restrict__ zy, const uint8_t* __restrict__ blobs,
-                                                          const uint8_t* __restrict__ commitments, uint64_t n, int lanes) {
+                                                          const uint8_t* __restrict__ commitments, uint64_t n, int lanes, int k0, int k1, uint32_t* __restrict__ states) {
     __shared__ uint32_t kw[2][64][32];  // [buffer][round][lane] = K[t] + W[t]
     place_record(1);
-    challenge_warp_pair<FMA_ADDS>(kw, z_out, zy, blobs, commitments, n, lanes);
+    challenge_warp_pair<FMA_ADDS>(kw, z_out, zy, blobs, commitments, n, lanes, k0, k1, states);
 }
 
 __global__ void z_from_bytes_kernel(Fr* z_out, uint8_t* zy, const uint8_t* z_bytes, uint64_t n, int* bad) {
@@ -750,12 +764,19 @@ static int hash_lanes(uint64_t n) {
 }
 
 int launch_blob_challenges(Launch& L, Fr* z, uint8_t* zy, const uint8_t* blobs, const uint8_t* commitments48, uint64_t n) {
+    return launch_blob_challenges_range(L, z, zy, blobs, commitments48, n, 0, CH_BLOCKS, nullptr);
+}
+int blob_challenge_blocks() { return CH_BLOCKS; }
+// SHA-256 blocks [k0, k1) of every blob's challenge hash; states (8 words per blob) carries the chaining value between
+// launches (read if k0 > 0, written if k1 < blob_challenge_blocks(); z / zy are written by the launch that ends the hash)
+int launch_blob_challenges_range(Launch& L, Fr* z, uint8_t* zy, const uint8_t* blobs, const uint8_t* commitments48, uint64_t n, int k0, int k1, uint32_t* states) {
     if (!n) return RET_OK;
+    if (k0 < 0 || k1 > CH_BLOCKS || k0 >= k1 || ((k0 > 0 || k1 < CH_BLOCKS) && !states)) return RET_ERROR;
     const int lanes = hash_lanes(n);
     if (sha_fma_adds())
-        blob_challenge_kernel<true><<<blocks_for(n, lanes), 64, 0, L.stream>>>(z, zy, blobs, commitments48, n, lanes);
+        blob_challenge_kernel<true><<<blocks_for(n, lanes), 64, 0, L.stream>>>(z, zy, blobs, commitments48, n, lanes, k0, k1, states);
     else
-        blob_challenge_kernel<false><<<blocks_for(n, lanes), 64, 0, L.stream>>>(z, zy, blobs, commitments48, n, lanes);
+        blob_challenge_kernel<false><<<blocks_for(n, lanes), 64, 0, L.stream>>>(z, zy, blobs, commitments48, n, lanes, k0, k1, states);
     KZG_CUDA_TRY(cudaGetLastError());
     L.count(1, "blob_challenge");
     return RET_OK;

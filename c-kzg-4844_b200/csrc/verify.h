@@ -21,6 +21,10 @@ int launch_pairing_check(Launch& L, int* d_ok, const G1* A, const G1* B, const G
 // z[i] = hash_to_bls_field(SHA256("FSBLOBVERIFY_V1_" || 0 || 4096 || blob_i || commitment_i))
 // (compute_challenge, src/eip4844/eip4844.c:147).  zy[i*64 .. +32) receives canonical z bytes.
 int launch_blob_challenges(Launch& L, Fr* z, uint8_t* zy, const uint8_t* blobs, const uint8_t* commitments48, uint64_t n);
+// the same hash in pieces: SHA-256 blocks [k0, k1) of blob_challenge_blocks() = 2050 (block k >= 1 covers blob bytes
+// [64k - 32, 64k + 32)), chaining values carried in states (8 words per blob)
+int blob_challenge_blocks();
+int launch_blob_challenges_range(Launch& L, Fr* z, uint8_t* zy, const uint8_t* blobs, const uint8_t* commitments48, uint64_t n, int k0, int k1, uint32_t* states);
 // z[i] from canonical bytes (compute_kzg_proof path); bad[i] = 1 if >= r
 int launch_z_from_bytes(Launch& L, Fr* z, uint8_t* zy, const uint8_t* z_bytes, uint64_t n, int* bad);
 // y[i] = p_i(z[i]) (evaluate_polynomial_in_evaluation_form, eip4844.c:192), canonical y bytes into

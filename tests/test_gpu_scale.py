@@ -303,3 +303,24 @@ def test_device_mode_ordering_against_the_callers_streams(env):
         mod.set_caller_stream(0)
     torch.cuda.synchronize()
     assert mod.verify_blob_kzg_proof_batch_device(dev.data_ptr(), cms.data_ptr(), wrong.data_ptr(), m, ts) is False
+
+
+def test_pinned_host_batch_tail_chunk_hashed_in_column_pieces(env):
+    """Host-pointer batches from PINNED memory send their last chunk in eight column pieces and hash it piece by piece
+    with the SHA state carried between launches (api_verify.cu, verify.cu launch_blob_challenges_range).  A wrong state
+    hand-over would change z and with it the verdict: the valid batch must verify, one flipped byte in the LAST piece
+    of a blob of the last chunk must not, and the pageable route (no pieces) must agree."""
+    import torch
+
+    mod, ts, n, host, dev, cms, prs = env
+    hc, hp = cms.cpu().pin_memory(), prs.cpu().pin_memory()
+    for m in (1024, 700):  # last chunk: 512 blobs / 188 blobs (>= 16 MB: piecewise)
+        pin = host[: 131072 * m].clone().pin_memory()
+        assert mod.verify_blob_kzg_proof_batch_host(pin.data_ptr(), hc.data_ptr(), hp.data_ptr(), m, ts) is True
+        pin[131072 * (m - 3) + 131071] ^= 1  # low byte of the last field element: still canonical
+        assert mod.verify_blob_kzg_proof_batch_host(pin.data_ptr(), hc.data_ptr(), hp.data_ptr(), m, ts) is False
+        pin[131072 * (m - 3) + 131071] ^= 1
+        pin[131072 * (m - 100) + 16384 * 3 + 31] ^= 1  # a byte in the fourth piece
+        assert mod.verify_blob_kzg_proof_batch_host(pin.data_ptr(), hc.data_ptr(), hp.data_ptr(), m, ts) is False
+    pageable = host[: 131072 * 700].numpy().copy()
+    assert mod.verify_blob_kzg_proof_batch_host(pageable.ctypes.data, hc.data_ptr(), hp.data_ptr(), 700, ts) is True
