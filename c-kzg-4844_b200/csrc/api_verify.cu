@@ -88,7 +88,7 @@ struct Stage1 {
     // chunk's z||y is copied to h_zy on a side stream as soon as it exists; zy_done[k] fires when chunk k (blobs
     // [k * zy_chunk, ...)) has landed, so the host hashes the batch transcript BEHIND the GPU instead of after it.
     uint8_t* h_zy = nullptr;
-    uint64_t zy_chunk = 0;
+    std::vector<std::pair<uint64_t, uint64_t>> zy_range;  // (first blob, count) of zy_done[k]
     std::vector<cudaEvent_t> zy_done;
     ~Stage1() {
         for (cudaEvent_t e : zy_done)
@@ -116,6 +116,7 @@ static int stage1_stream_zy(Call& call, Stage1& s, cudaStream_t cpz, uint64_t of
     KZG_CUDA_TRY(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
     cudaEventRecord(done, cpz);
     s.zy_done.push_back(done);
+    s.zy_range.push_back({off, m});
     return RET_OK;
 }
 
@@ -157,9 +158,9 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
         call.mark_on(call.stream, "stage:t_hash_done");
         int rc = RET_OK;
         if (stream_zy) {
-            s.zy_chunk = (n + 3) / 4;  // four chunks: the host hashes chunk k while the GPU evaluates chunk k + 1
-            for (uint64_t off = 0; off < n && rc == RET_OK; off += s.zy_chunk) {
-                const uint64_t m = (n - off < s.zy_chunk) ? n - off : s.zy_chunk;
+            const uint64_t zy_chunk = (n + 3) / 4;  // four chunks: the host hashes chunk k while the GPU evaluates chunk k + 1
+            for (uint64_t off = 0; off < n && rc == RET_OK; off += zy_chunk) {
+                const uint64_t m = (n - off < zy_chunk) ? n - off : zy_chunk;
                 rc = launch_evaluate(L, s.y + off, s.zy + off * 64, nullptr, nullptr, d_blobs + off * BLOB_BYTES, s.z + off, m, s.bad, 0);
                 if (rc == RET_OK) rc = stage1_stream_zy(call, s, cpz, off, m);
             }
@@ -175,8 +176,32 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
     // throughput kernels get in each other's way); ONLY the latency-bound hashes on side streams, the
     // validations and then the evaluations on the main stream: 14.3 ms.  That is the arrangement here.
     const uint64_t CH = host ? 512 : n;
-    const int nchunks = (int)((n + CH - 1) / CH);
-    const int nside = std::min(8, nchunks);
+    // Segments of the batch.  Ordinary segments are chunks of CH blobs: one copy, one hash launch when it has landed.
+    // The TAIL of a pinned host batch -- the last ~1024 blobs, whose bytes take as long to arrive (2.4 ms at 55 GB/s)
+    // as one blob takes to hash (2.1 ms: 2050 dependent SHA-256 blocks) -- travels in column pieces instead: piece p =
+    // bytes [16 KiB p, 16 KiB (p + 1)) of EVERY blob of the tail (one strided copy), hashed piece by piece behind the
+    // copies with the SHA state carried between the launches (verify.cu launch_blob_challenges_range).  When the last
+    // byte of the batch lands, 258 of the 2050 blocks of each tail blob are left to hash (0.3 ms) instead of a whole
+    // chain; earlier chunks finish their hashes under the copies that follow them anyway.  Measured (tools/e2e_probe.py,
+    // R2k, n = 4096): hashes done 2.38 ms after the upload without pieces, 1.43 ms with a 512-blob tail (its bytes
+    // arrive faster than they can be hashed), [R2l] with the 1024-blob tail.  CKZG_B200_TAIL_PIECES=0 switches it off.
+    struct Seg {
+        uint64_t off, m;
+        bool pieces;
+    };
+    std::vector<Seg> segs;
+    static const int tail_pieces = getenv("CKZG_B200_TAIL_PIECES") ? atoi(getenv("CKZG_B200_TAIL_PIECES")) : 8;
+    static const uint64_t tail_blobs = getenv("CKZG_B200_TAIL_BLOBS") ? (uint64_t)atoll(getenv("CKZG_B200_TAIL_BLOBS")) : 1024;
+    uint64_t tail_start = n;
+    if (host && tail_pieces >= 2 && tail_pieces <= 64 && (N_BLOB * 32 / 64) % tail_pieces == 0 && tail_blobs >= 128) {
+        const uint64_t want = n < tail_blobs ? n : tail_blobs;
+        const uint64_t start = ((n - want) / CH) * CH;  // on a chunk boundary
+        if ((n - start) * BLOB_BYTES >= (16u << 20) && !host_ptr_is_pageable(blobs + start * BLOB_BYTES)) tail_start = start;
+    }
+    for (uint64_t off = 0; off < tail_start; off += CH) segs.push_back({off, (tail_start - off < CH) ? tail_start - off : CH, false});
+    if (tail_start < n) segs.push_back({tail_start, n - tail_start, true});
+    const int nsegs = (int)segs.size();
+    const int nside = std::min(8, nsegs);
     // side streams are forked from (ordered after) the call stream and joined / destroyed by the Call on
     // every exit path, so no early return below can leave a kernel reading released scratch
     cudaStream_t side[8], copy = nullptr;
@@ -184,26 +209,16 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
     for (int i = 0; i < nside; i++)
         if (!(side[i] = call.fork())) return RET_ERROR;
     if (host && !(copy = call.fork())) return RET_ERROR;
-    std::vector<cudaEvent_t> hashed(nchunks, nullptr);
-    // The LAST chunk of a pinned host batch travels in column pieces: piece p = bytes [16 KiB p, 16 KiB (p + 1)) of
-    // every blob of the chunk (one strided copy), and its hash runs piece by piece behind the copies with the SHA state
-    // carried between the launches -- when the chunk's last byte lands only 258 of the 2050 blocks of each blob are
-    // left to hash (0.26 ms) instead of the whole 2.1 ms chain.  (Earlier chunks finish their hashes under the
-    // copies that follow them anyway.)  CKZG_B200_TAIL_PIECES=0 switches it off.
-    static const int tail_pieces = getenv("CKZG_B200_TAIL_PIECES") ? atoi(getenv("CKZG_B200_TAIL_PIECES")) : 8;
-    const uint64_t last_off = (uint64_t)(nchunks - 1) * CH, last_m = n - last_off;
-    const bool piecewise = host && tail_pieces >= 2 && tail_pieces <= 64 && (N_BLOB * 32 / 64) % tail_pieces == 0 && last_m * BLOB_BYTES >= (16u << 20) &&
-                           !host_ptr_is_pageable(blobs + last_off * BLOB_BYTES);
+    std::vector<cudaEvent_t> hashed(nsegs, nullptr);
     uint32_t* d_states = nullptr;
-    if (piecewise) TRY(call.alloc(&d_states, last_m * 8));
-    int c = 0;
-    for (uint64_t off = 0; off < n && rc == RET_OK; off += CH, c++) {
-        const uint64_t m = (n - off < CH) ? n - off : CH;
+    if (tail_start < n) TRY(call.alloc(&d_states, (n - tail_start) * 8));
+    for (int c = 0; c < nsegs && rc == RET_OK; c++) {
+        const uint64_t off = segs[c].off, m = segs[c].m;
         cudaStream_t st = side[c % nside];
         Launch Ls = call.launch_on(st);
-        if (piecewise && off == last_off) {
+        if (segs[c].pieces) {
             const int P = tail_pieces;
-            const size_t piece_bytes = BLOB_BYTES / P;        // 16 KiB at P = 8
+            const size_t piece_bytes = BLOB_BYTES / P;  // 16 KiB at P = 8
             const int blocks_per_piece = (int)(piece_bytes / 64);
             for (int p = 0; p < P && rc == RET_OK; p++) {
                 cudaEvent_t landed;
@@ -241,24 +256,22 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
             break;
         }
         cudaEventRecord(hashed[c], st);
-        if (off + CH >= n) call.mark_on(st, "stage:t_hash_done");
+        if (c == 0) call.mark_on(st, "stage:t_first_chunk_hashed");
+        if (c == nsegs - 1) call.mark_on(st, "stage:t_hash_done");
     }
-    // main stream: point validation (independent of the blobs), then each chunk's evaluation as soon as
+    if (copy) call.mark_on(copy, "stage:t_upload_done");
+    // main stream: point validation (independent of the blobs), then each segment's evaluation as soon as
     // its challenges exist
     if (rc == RET_OK)
         rc = s.want_shift ? launch_g1_validate2_levels(L, s.cm, d_cm, s.pf, d_pf, n, s.bad, s.table) : launch_g1_validate2(L, s.cm, d_cm, s.pf, d_pf, n, s.bad);
     call.mark_on(call.stream, "stage:t_validate_done");
-    c = 0;
-    for (uint64_t off = 0; off < n; off += CH, c++) {
-        const uint64_t m = (n - off < CH) ? n - off : CH;
+    for (int c = 0; c < nsegs; c++) {
+        const uint64_t off = segs[c].off, m = segs[c].m;
         if (!hashed[c]) continue;
         cudaStreamWaitEvent(call.stream, hashed[c], 0);
         cudaEventDestroy(hashed[c]);
         if (rc == RET_OK) rc = launch_evaluate(L, s.y + off, s.zy + off * 64, nullptr, nullptr, d_blobs + off * BLOB_BYTES, s.z + off, m, s.bad, 0);
-        if (rc == RET_OK && stream_zy) {
-            s.zy_chunk = CH;
-            rc = stage1_stream_zy(call, s, cpz, off, m);
-        }
+        if (rc == RET_OK && stream_zy) rc = stage1_stream_zy(call, s, cpz, off, m);
     }
     return rc;
 }
@@ -522,8 +535,7 @@ int ckzg_b200_verify_blob_kzg_proof_batch(ckzg_b200_ctx* ctx, int* ok, const uin
         th.begin(n);
         for (size_t k = 0; k < s.zy_done.size() && se == cudaSuccess; k++) {
             se = cudaEventSynchronize(s.zy_done[k]);
-            const uint64_t off = k * s.zy_chunk;
-            if (se == cudaSuccess) th.feed(hc, h_zy, hp, off, (n - off < s.zy_chunk) ? n - off : s.zy_chunk);
+            if (se == cudaSuccess) th.feed(hc, h_zy, hp, s.zy_range[k].first, s.zy_range[k].second);
         }
         th.finish(digest);
     }
