@@ -201,20 +201,26 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
     for (uint64_t off = 0; off < tail_start; off += CH) segs.push_back({off, (tail_start - off < CH) ? tail_start - off : CH, false});
     if (tail_start < n) segs.push_back({tail_start, n - tail_start, true});
     const int nsegs = (int)segs.size();
-    const int nside = std::min(8, nsegs);
+    // Streams: call stream + copy + z||y copy-back + FOUR hash streams + one for the tail = 8, the number of hardware
+    // work queues a process gets by default (CUDA_DEVICE_MAX_CONNECTIONS).  With more streams than queues two streams
+    // share a queue and a kernel can sit behind another stream's wait for a copy that is still seconds of queue away:
+    // measured (R2l) with 11 streams, the first chunk's hash finished at 15.9 ms instead of 3.9 ms.  Four hash streams are
+    // enough: a chunk lands every 1.2 ms and hashes for ~2.4 ms, so chunk c + 4 never waits for chunk c.
+    const int nside = std::min(4, nsegs);
     // side streams are forked from (ordered after) the call stream and joined / destroyed by the Call on
     // every exit path, so no early return below can leave a kernel reading released scratch
-    cudaStream_t side[8], copy = nullptr;
+    cudaStream_t side[4], copy = nullptr, tail_stream = nullptr;
     int rc = RET_OK;
     for (int i = 0; i < nside; i++)
         if (!(side[i] = call.fork())) return RET_ERROR;
     if (host && !(copy = call.fork())) return RET_ERROR;
+    if (tail_start < n && nsegs > 1 && !(tail_stream = call.fork())) return RET_ERROR;
     std::vector<cudaEvent_t> hashed(nsegs, nullptr);
     uint32_t* d_states = nullptr;
     if (tail_start < n) TRY(call.alloc(&d_states, (n - tail_start) * 8));
     for (int c = 0; c < nsegs && rc == RET_OK; c++) {
         const uint64_t off = segs[c].off, m = segs[c].m;
-        cudaStream_t st = side[c % nside];
+        cudaStream_t st = (segs[c].pieces && tail_stream) ? tail_stream : side[c % nside];
         Launch Ls = call.launch_on(st);
         if (segs[c].pieces) {
             const int P = tail_pieces;
