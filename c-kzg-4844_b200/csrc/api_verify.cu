@@ -177,21 +177,24 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
     // validations and then the evaluations on the main stream: 14.3 ms.  That is the arrangement here.
     const uint64_t CH = host ? 512 : n;
     // Segments of the batch.  Ordinary segments are chunks of CH blobs: one copy, one hash launch when it has landed.
-    // The TAIL of a pinned host batch -- the last ~1024 blobs, whose bytes take as long to arrive (2.4 ms at 55 GB/s)
-    // as one blob takes to hash (2.1 ms: 2050 dependent SHA-256 blocks) -- travels in column pieces instead: piece p =
-    // bytes [16 KiB p, 16 KiB (p + 1)) of EVERY blob of the tail (one strided copy), hashed piece by piece behind the
-    // copies with the SHA state carried between the launches (verify.cu launch_blob_challenges_range).  When the last
-    // byte of the batch lands, 258 of the 2050 blocks of each tail blob are left to hash (0.3 ms) instead of a whole
-    // chain; earlier chunks finish their hashes under the copies that follow them anyway.  Measured (tools/e2e_probe.py,
-    // R2k, n = 4096): hashes done 2.38 ms after the upload without pieces, 1.43 ms with a 512-blob tail (its bytes
-    // arrive faster than they can be hashed), [R2l] with the 1024-blob tail.  CKZG_B200_TAIL_PIECES=0 switches it off.
+    // The TAIL of a pinned host batch (the last chunk) travels in column pieces instead: piece p = bytes
+    // [16 KiB p, 16 KiB (p + 1)) of EVERY blob of the tail (one strided copy), hashed piece by piece behind the copies
+    // with the SHA state carried between the launches (verify.cu launch_blob_challenges_range), so that part of the
+    // tail's 2.1 ms hash chain (2050 dependent SHA-256 blocks per blob) is done before its last byte lands; earlier
+    // chunks finish their hashes under the copies that follow them anyway.  Measured (tools/e2e_probe.py, n = 4096,
+    // profiles/e2e_probe_R2k.log, _R2n.log): hashes done 2.38 ms after the upload without pieces, 1.29-1.43 ms with the
+    // 512-blob tail (16.4 -> 15.4 ms per call).  A 1024-blob tail -- whose bytes arrive over 2.4 ms, slower than they
+    // hash -- does finish 0.28 ms after the upload, but in that arrangement, and whenever two chunks share a hash
+    // stream, the EARLIER chunks' hash kernels complete ~12 ms late (eligible at 1.7 ms, done at 15.9 ms: R2l, R2n)
+    // for a reason the event trace does not show; the arrangement kept is the one measured fast three times.
+    // CKZG_B200_TAIL_PIECES=0 switches the pieces off, CKZG_B200_TAIL_BLOBS / CKZG_B200_HASH_STREAMS vary the rest.
     struct Seg {
         uint64_t off, m;
         bool pieces;
     };
     std::vector<Seg> segs;
     static const int tail_pieces = getenv("CKZG_B200_TAIL_PIECES") ? atoi(getenv("CKZG_B200_TAIL_PIECES")) : 8;
-    static const uint64_t tail_blobs = getenv("CKZG_B200_TAIL_BLOBS") ? (uint64_t)atoll(getenv("CKZG_B200_TAIL_BLOBS")) : 1024;
+    static const uint64_t tail_blobs = getenv("CKZG_B200_TAIL_BLOBS") ? (uint64_t)atoll(getenv("CKZG_B200_TAIL_BLOBS")) : 512;
     uint64_t tail_start = n;
     if (host && tail_pieces >= 2 && tail_pieces <= 64 && (N_BLOB * 32 / 64) % tail_pieces == 0 && tail_blobs >= 128) {
         const uint64_t want = n < tail_blobs ? n : tail_blobs;
@@ -201,15 +204,11 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
     for (uint64_t off = 0; off < tail_start; off += CH) segs.push_back({off, (tail_start - off < CH) ? tail_start - off : CH, false});
     if (tail_start < n) segs.push_back({tail_start, n - tail_start, true});
     const int nsegs = (int)segs.size();
-    // Streams: call stream + copy + z||y copy-back + FOUR hash streams + one for the tail = 8, the number of hardware
-    // work queues a process gets by default (CUDA_DEVICE_MAX_CONNECTIONS).  With more streams than queues two streams
-    // share a queue and a kernel can sit behind another stream's wait for a copy that is still seconds of queue away:
-    // measured (R2l) with 11 streams, the first chunk's hash finished at 15.9 ms instead of 3.9 ms.  Four hash streams are
-    // enough: a chunk lands every 1.2 ms and hashes for ~2.4 ms, so chunk c + 4 never waits for chunk c.
-    const int nside = std::min(4, nsegs);
+    static const int max_side = (getenv("CKZG_B200_HASH_STREAMS") && atoi(getenv("CKZG_B200_HASH_STREAMS")) >= 1 && atoi(getenv("CKZG_B200_HASH_STREAMS")) <= 8) ? atoi(getenv("CKZG_B200_HASH_STREAMS")) : 8;
+    const int nside = std::min(max_side, nsegs);
     // side streams are forked from (ordered after) the call stream and joined / destroyed by the Call on
     // every exit path, so no early return below can leave a kernel reading released scratch
-    cudaStream_t side[4], copy = nullptr, tail_stream = nullptr;
+    cudaStream_t side[8], copy = nullptr, tail_stream = nullptr;
     int rc = RET_OK;
     for (int i = 0; i < nside; i++)
         if (!(side[i] = call.fork())) return RET_ERROR;
@@ -253,6 +252,9 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
                 cudaEventRecord(landed, copy);
                 cudaStreamWaitEvent(st, landed, 0);
                 cudaEventDestroy(landed);
+                if (c == 0) call.mark_on(copy, "stage:t_copy0_done");
+                if (c == 0) call.mark_on(st, "stage:t_hash0_start");
+                if (c == 1) call.mark_on(st, "stage:t_hash1_start");
             }
             rc = launch_blob_challenges(Ls, s.z + off, s.zy + off * 64, d_blobs + off * BLOB_BYTES, d_cm + off * 48, m);
         }
