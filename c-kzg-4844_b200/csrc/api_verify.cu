@@ -6,6 +6,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <functional>
 #include <condition_variable>
 #include <memory>
 #include <thread>
@@ -90,6 +91,7 @@ struct Stage1 {
     uint8_t* h_zy = nullptr;
     std::vector<std::pair<uint64_t, uint64_t>> zy_range;  // (first blob, count) of zy_done[k]
     std::vector<cudaEvent_t> zy_done;
+    std::function<void()> on_progress;  // called by the host-driven segment loop between launches (transcript feeding)
     ~Stage1() {
         for (cudaEvent_t e : zy_done)
             if (e) cudaEventDestroy(e);
@@ -268,18 +270,24 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
         if (c == nsegs - 1) call.mark_on(st, "stage:t_hash_done");
     }
     if (copy) call.mark_on(copy, "stage:t_upload_done");
-    // main stream: point validation (independent of the blobs), then each segment's evaluation as soon as
-    // its challenges exist
+    // main stream: point validation (independent of the blobs), then each segment's evaluation as soon as its
+    // challenges exist.  The HOST waits for a segment's hash (cudaEventSynchronize) and only then enqueues its evaluation:
+    // a cudaStreamWaitEvent on the call stream for an event that has not fired yet parks that stream's hardware queue,
+    // and with this many active queues it was not picked up again for ~12 ms (device-side timeline, profiles/
+    // e2e_probe_R2o.log: hashes done at 4.5 ms, first evaluation at 15.6 ms whenever the validation finished before
+    // the first hash).  The calling thread has nothing else to do here, and it uses the gaps to hash the transcript
+    // chunks that have already come back (feed).
     if (rc == RET_OK)
         rc = s.want_shift ? launch_g1_validate2_levels(L, s.cm, d_cm, s.pf, d_pf, n, s.bad, s.table) : launch_g1_validate2(L, s.cm, d_cm, s.pf, d_pf, n, s.bad);
     call.mark_on(call.stream, "stage:t_validate_done");
     for (int c = 0; c < nsegs; c++) {
         const uint64_t off = segs[c].off, m = segs[c].m;
         if (!hashed[c]) continue;
-        cudaStreamWaitEvent(call.stream, hashed[c], 0);
+        if (rc == RET_OK && cudaEventSynchronize(hashed[c]) != cudaSuccess) rc = RET_ERROR;
         cudaEventDestroy(hashed[c]);
         if (rc == RET_OK) rc = launch_evaluate(L, s.y + off, s.zy + off * 64, nullptr, nullptr, d_blobs + off * BLOB_BYTES, s.z + off, m, s.bad, 0);
         if (rc == RET_OK && stream_zy) rc = stage1_stream_zy(call, s, cpz, off, m);
+        if (rc == RET_OK && s.on_progress) s.on_progress();
     }
     return rc;
 }
@@ -515,6 +523,18 @@ int ckzg_b200_verify_blob_kzg_proof_batch(ckzg_b200_ctx* ctx, int* ok, const uin
         cudaEventRecord(fetched, cp);
     }
     if (use_r) s.h_zy = h_zy;  // stream z||y to the host chunk by chunk (n >= 1024), hashed behind the evaluations
+    const uint8_t* hc = (mem == CKZG_B200_DEVICE) ? h_c : commitments;
+    const uint8_t* hp = (mem == CKZG_B200_DEVICE) ? h_p : proofs;
+    TranscriptHasher th;
+    th.begin(n);
+    size_t fed = 0;
+    if (mem == CKZG_B200_HOST)  // host batches: chunks that have come back are hashed while stage 1 is still being driven
+        s.on_progress = [&] {
+            while (fed < s.zy_done.size() && cudaEventQuery(s.zy_done[fed]) == cudaSuccess) {
+                th.feed(hc, h_zy, hp, s.zy_range[fed].first, s.zy_range[fed].second);
+                fed++;
+            }
+        };
     int rc1 = verify_stage1(call, s, blobs, d_cm, d_pf, n, mem);
     if (rc1) {
         if (fetched) {
@@ -529,8 +549,6 @@ int ckzg_b200_verify_blob_kzg_proof_batch(ckzg_b200_ctx* ctx, int* ok, const uin
     const bool streamed = !s.zy_done.empty();
     if (use_r && !streamed) cudaMemcpyAsync(h_zy, s.zy, n * 64, cudaMemcpyDeviceToHost, call.stream);
     cudaMemcpyAsync(h_bad, s.bad, sizeof(int), cudaMemcpyDeviceToHost, call.stream);
-    const uint8_t* hc = (mem == CKZG_B200_DEVICE) ? h_c : commitments;
-    const uint8_t* hp = (mem == CKZG_B200_DEVICE) ? h_p : proofs;
     uint8_t digest[32] = {0};
     cudaError_t se = cudaSuccess;
     if (fetched) {
@@ -538,12 +556,10 @@ int ckzg_b200_verify_blob_kzg_proof_batch(ckzg_b200_ctx* ctx, int* ok, const uin
         cudaEventDestroy(fetched);
     }
     if (streamed && se == cudaSuccess) {
-        // the batch transcript (eip4844.c:612-668), hashed chunk by chunk as the chunks' z||y land
-        TranscriptHasher th;
-        th.begin(n);
-        for (size_t k = 0; k < s.zy_done.size() && se == cudaSuccess; k++) {
-            se = cudaEventSynchronize(s.zy_done[k]);
-            if (se == cudaSuccess) th.feed(hc, h_zy, hp, s.zy_range[k].first, s.zy_range[k].second);
+        // the rest of the batch transcript (eip4844.c:612-668): chunks not yet fed while stage 1 was being driven
+        for (; fed < s.zy_done.size() && se == cudaSuccess; fed++) {
+            se = cudaEventSynchronize(s.zy_done[fed]);
+            if (se == cudaSuccess) th.feed(hc, h_zy, hp, s.zy_range[fed].first, s.zy_range[fed].second);
         }
         th.finish(digest);
     }

@@ -91,6 +91,21 @@ __device__ __forceinline__ void place_record(uint32_t kernel_id) {
     const uint32_t k = atomicAdd(buf, 1u);
     if (k < buf[1]) buf[2 + k] = (kernel_id << 28) | ((threadIdx.x >> 5) << 24) | (smid << 8) | (warpid & 0xffu);
 }
+// Device-side timeline probe (tools/e2e_probe.py --timers): when armed, thread 0 of CTA 0 of the stage-1 kernels
+// stores (id, low 32 bits of %globaltimer) at kernel start (id) and end (id | 0x80) -- when did a kernel really run,
+// as opposed to when the events around it fired.
+__device__ uint32_t* g_time_buf = nullptr;  // [0] = count, [1] = capacity, then (id, ns) pairs
+__device__ __forceinline__ void time_record(uint32_t id) {
+    uint32_t* buf = g_time_buf;
+    if (buf == nullptr || threadIdx.x != 0 || blockIdx.x != 0) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const uint32_t k = atomicAdd(buf, 1u);
+    if (k < buf[1]) {
+        buf[2 + 2 * k] = id;
+        buf[3 + 2 * k] = (uint32_t)t;
+    }
+}
 // CKZG_B200_SHA_ADDS=fma selects the variant with every addition of a round on the FMA pipe (A/B measurements).
 // Measured on B200 (profiles/R2_summary.md, R2e): hash+validate 2.28 ms with ptxas' own split (13 ALU + 2 IMAD.IADD
 // per round) against 2.50 ms with 10 ALU + 8 IMAD -- integer multiply-adds issue at a quarter warp per clock here
@@ -275,7 +290,9 @@ __global__ void __launch_bounds__(64) blob_challenge_kernel(Fr* __restrict__ z_o
                                                           const uint8_t* __restrict__ commitments, uint64_t n, int lanes, int k0, int k1, uint32_t* __restrict__ states) {
     __shared__ uint32_t kw[2][64][32];  // [buffer][round][lane] = K[t] + W[t]
     place_record(1);
+    time_record(1u | ((uint32_t)k0 << 8));
     challenge_warp_pair<FMA_ADDS>(kw, z_out, zy, blobs, commitments, n, lanes, k0, k1, states);
+    time_record(0x81u | ((uint32_t)k0 << 8));
 }
 
 __global__ void z_from_bytes_kernel(Fr* z_out, uint8_t* zy, const uint8_t* z_bytes, uint64_t n, int* bad) {
@@ -491,6 +508,7 @@ __global__ void __launch_bounds__(EV_THREADS) evaluate_tree_kernel(Fr* __restric
                                                                   const Fr* __restrict__ roots_brp, int* __restrict__ bad, int bad_stride) {
     __shared__ Fr sh[EV_THREADS];
     const int blob = blockIdx.x, t = threadIdx.x;
+    time_record(3u);
     const uint8_t* src = blobs + (size_t)blob * BLOB_BYTES;
     const Fr* zp = zpow + (size_t)blob * 12;
     Fr Z[4];
@@ -933,6 +951,7 @@ __global__ void g1_validate2_levels_kernel(G1Affine* __restrict__ out_cm, const 
                                            uint64_t n, int* __restrict__ bad, G1* __restrict__ table) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 2 * n) return;
+    time_record(2u);
     const bool is_cm = i >= n;
     const uint64_t k = is_cm ? i - n : i;
     const uint8_t* src = (is_cm ? in_cm : in_pf) + k * 48;
@@ -950,6 +969,10 @@ int launch_g1_validate2_levels(Launch& L, G1Affine* out_cm, const uint8_t* in_cm
     g1_validate2_levels_kernel<<<blocks_for(2 * n, 32), 32, 0, L.stream>>>(out_cm, in_cm, out_pf, in_pf, n, bad, table);
     KZG_CUDA_TRY(cudaGetLastError());
     L.count(1, "g1_validate");
+    return RET_OK;
+}
+int debug_set_timer_buffer(uint32_t* dev_buf) {
+    KZG_CUDA_TRY(cudaMemcpyToSymbol(g_time_buf, &dev_buf, sizeof(dev_buf)));
     return RET_OK;
 }
 int debug_set_placement_buffer(uint32_t* dev_buf) {

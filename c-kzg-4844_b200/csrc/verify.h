@@ -48,6 +48,7 @@ int launch_g1_validate2_levels(Launch& L, G1Affine* out_cm, const uint8_t* in_cm
 int launch_g1_validate_levels_ab(Launch& L, G1Affine* out_a, const uint8_t* in_a, uint64_t na, uint64_t col_a, G1Affine* out_b, const uint8_t* in_b, uint64_t nb, uint64_t col_b,
                                  G1* table, uint64_t npts, int* bad);
 int debug_set_placement_buffer(uint32_t* dev_buf);
+int debug_set_timer_buffer(uint32_t* dev_buf);
 int launch_g1_validate_ab(Launch& L, G1Affine* out_a, const uint8_t* in_a, uint64_t n, G1Affine* out_b, const uint8_t* in_b, uint64_t nb, int* bad);
 // r = hash_to_bls_field(digest): the batch transcript itself (eip4844.c:597-680) is hashed on the host
 int launch_r_from_digest(Launch& L, Fr* r, const uint8_t* digest32);

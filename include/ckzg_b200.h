@@ -215,6 +215,10 @@ int ckzg_b200_selftest_mulbench(int ilp, int iters, int blocks, int threads, flo
  * of uint32, [0] = record count (set to 0), [1] = capacity, records follow:
  * kernel id << 28 | warp in block << 24 | %smid << 8 | %warpid.  Test/measurement hook. */
 int ckzg_b200_debug_placement(uint32_t *dev_buf);
+/* Arms (or, with NULL, disarms) the device-side timeline probe of the stage-1 kernels: dev_buf[0] = record count (set to 0),
+ * [1] = capacity, then (kernel id, low 32 bits of %globaltimer in ns) pairs written by CTA 0 at kernel start and end
+ * (end: id | 0x80; hash kernels carry their first SHA block in bits 8+).  Measurement hook (tools/e2e_probe.py). */
+int ckzg_b200_debug_timers(uint32_t *dev_buf);
 /* Measurement hook: best-of-`reps` wall time (ms) of uploading `bytes` from HOST memory the way every HOST-mode call does
  * (pageable sources: pinned staging ring filled by the context's host threads, CKZG_B200_HOST_THREADS /
  * CKZG_B200_STAGE_SLOT_MB; pinned sources: one DMA).  mode 1: cudaHostRegister + direct DMA + cudaHostUnregister. */
