@@ -91,7 +91,6 @@ struct Stage1 {
     uint8_t* h_zy = nullptr;
     std::vector<std::pair<uint64_t, uint64_t>> zy_range;  // (first blob, count) of zy_done[k]
     std::vector<cudaEvent_t> zy_done;
-    std::function<void()> on_progress;  // called by the host-driven segment loop between launches (transcript feeding)
     ~Stage1() {
         for (cudaEvent_t e : zy_done)
             if (e) cudaEventDestroy(e);
@@ -187,8 +186,11 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
     // profiles/e2e_probe_R2k.log, _R2n.log): hashes done 2.38 ms after the upload without pieces, 1.29-1.43 ms with the
     // 512-blob tail (16.4 -> 15.4 ms per call).  A 1024-blob tail -- whose bytes arrive over 2.4 ms, slower than they
     // hash -- does finish 0.28 ms after the upload, but in that arrangement, and whenever two chunks share a hash
-    // stream, the EARLIER chunks' hash kernels complete ~12 ms late (eligible at 1.7 ms, done at 15.9 ms: R2l, R2n)
-    // for a reason the event trace does not show; the arrangement kept is the one measured fast three times.
+    // stream, the EVENTS recorded behind the earlier chunks' hash kernels fire ~11 ms after those kernels end (device
+    // timers, profiles/e2e_probe_R2o.log / _R2p.log: hashes end at 4.5 ... 9.4 ms, first evaluation at 15.6 ms --
+    // also when the host waits for the event itself and launches the evaluation afterwards).  In the arrangement
+    // kept here the validation kernel starts together with the first hash and the events fire on time; it is the one
+    // measured fast in every run (R2k, R2l, R2n, R2o, R2p), the cause of the late events is not understood.
     // CKZG_B200_TAIL_PIECES=0 switches the pieces off, CKZG_B200_TAIL_BLOBS / CKZG_B200_HASH_STREAMS vary the rest.
     struct Seg {
         uint64_t off, m;
@@ -270,24 +272,18 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
         if (c == nsegs - 1) call.mark_on(st, "stage:t_hash_done");
     }
     if (copy) call.mark_on(copy, "stage:t_upload_done");
-    // main stream: point validation (independent of the blobs), then each segment's evaluation as soon as its
-    // challenges exist.  The HOST waits for a segment's hash (cudaEventSynchronize) and only then enqueues its evaluation:
-    // a cudaStreamWaitEvent on the call stream for an event that has not fired yet parks that stream's hardware queue,
-    // and with this many active queues it was not picked up again for ~12 ms (device-side timeline, profiles/
-    // e2e_probe_R2o.log: hashes done at 4.5 ms, first evaluation at 15.6 ms whenever the validation finished before
-    // the first hash).  The calling thread has nothing else to do here, and it uses the gaps to hash the transcript
-    // chunks that have already come back (feed).
+    // main stream: point validation (independent of the blobs), then each segment's evaluation as soon as
+    // its challenges exist
     if (rc == RET_OK)
         rc = s.want_shift ? launch_g1_validate2_levels(L, s.cm, d_cm, s.pf, d_pf, n, s.bad, s.table) : launch_g1_validate2(L, s.cm, d_cm, s.pf, d_pf, n, s.bad);
     call.mark_on(call.stream, "stage:t_validate_done");
     for (int c = 0; c < nsegs; c++) {
         const uint64_t off = segs[c].off, m = segs[c].m;
         if (!hashed[c]) continue;
-        if (rc == RET_OK && cudaEventSynchronize(hashed[c]) != cudaSuccess) rc = RET_ERROR;
+        cudaStreamWaitEvent(call.stream, hashed[c], 0);
         cudaEventDestroy(hashed[c]);
         if (rc == RET_OK) rc = launch_evaluate(L, s.y + off, s.zy + off * 64, nullptr, nullptr, d_blobs + off * BLOB_BYTES, s.z + off, m, s.bad, 0);
         if (rc == RET_OK && stream_zy) rc = stage1_stream_zy(call, s, cpz, off, m);
-        if (rc == RET_OK && s.on_progress) s.on_progress();
     }
     return rc;
 }
@@ -528,13 +524,6 @@ int ckzg_b200_verify_blob_kzg_proof_batch(ckzg_b200_ctx* ctx, int* ok, const uin
     TranscriptHasher th;
     th.begin(n);
     size_t fed = 0;
-    if (mem == CKZG_B200_HOST)  // host batches: chunks that have come back are hashed while stage 1 is still being driven
-        s.on_progress = [&] {
-            while (fed < s.zy_done.size() && cudaEventQuery(s.zy_done[fed]) == cudaSuccess) {
-                th.feed(hc, h_zy, hp, s.zy_range[fed].first, s.zy_range[fed].second);
-                fed++;
-            }
-        };
     int rc1 = verify_stage1(call, s, blobs, d_cm, d_pf, n, mem);
     if (rc1) {
         if (fetched) {

@@ -93,7 +93,10 @@ __global__ void __launch_bounds__(2 * COOP_LANES) pairing_check_kernel(int* ok, 
     if (g != 0) return;
     // machine 0: F = F_0 * F_1, final exponentiation
     const int lane = threadIdx.x;
-    if (lane < 12) ws.reg[6][lane] = sm.ws[1].reg[0][lane];
+    if (lane < 12) {
+        ws.reg[6][lane] = sm.ws[1].reg[0][lane];
+        ws.nreg[6][lane] = sm.ws[1].nreg[0][lane];
+    }
     coop_sync();
     coop_mul(ws, 0, 0, 6);
     coop_final_exp_is_one(ws);

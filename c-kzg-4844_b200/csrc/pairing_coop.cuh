@@ -50,8 +50,9 @@ __device__ __forceinline__ void coop_sync() { asm volatile("bar.sync %0, 64;" ::
 // reduction is the one the Montgomery multiplier performs anyway (its result is < p whatever the
 // size of the operands, as long as x*y < p * 2^448).  Bounds, in multiples of p (checked against the
 // term counts by tools/gen_pairing_tables.py):
-//   products < 1;  partial output sums < 8 + 16;  stored coefficients < 5 * 24 = 120 (256 after a
-//   conjugation);  input sums < 8 * 256 + 2048 = 4096 < 2^12, so x*y / 2^448 < 2^(2*393-448) << p.
+//   products and their stored negatives p - v <= 1;  output sums (<= 36 terms) <= 36, stored with their negative
+//   64 p - v <= 64 (a conjugation swaps the two copies);  input sums (<= 8 terms) <= 512 < 2^10, so
+//   x*y / 2^448 < 2^(2*391-448) << p.
 // The previous version reduced after every addition: ~2600 instructions per tower operation, two
 // thirds of them in the sums; this one needs ~1200 (14-limb product included).
 // Values cross to the 12-limb canonical form (pairing.cuh tower code: Frobenius, the one inversion,
@@ -85,6 +86,46 @@ KZG_HD Fp w_to_fp(const FpW& v) {
 }
 KZG_HD void w_acc(FpW& acc, const FpW& v) { limbs_add<14>(acc.l, acc.l, v.l); }
 
+// Shared-memory form of a wide value: 14 limbs padded to 64 bytes, so that a value is FOUR 128-bit words (4 LDS.128
+// instead of 14 LDS.32 per term of a sum -- the sums around the products cost more instructions than the products,
+// profiles/R2_summary.md).
+struct alignas(16) FpS {
+    uint32_t l[16];
+};
+KZG_HD FpW s_load(const FpS* p) {
+    FpW r;
+#if KZG_DEVICE_PATH
+    const uint4* q = reinterpret_cast<const uint4*>(p->l);
+    const uint4 a = q[0], b = q[1], c = q[2], d = q[3];
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    r.l[8] = c.x; r.l[9] = c.y; r.l[10] = c.z; r.l[11] = c.w;
+    r.l[12] = d.x; r.l[13] = d.y;
+#else
+    for (int i = 0; i < 14; i++) r.l[i] = p->l[i];
+#endif
+    return r;
+}
+KZG_HD void s_store(FpS* p, const FpW& v) {
+#if KZG_DEVICE_PATH
+    uint4* q = reinterpret_cast<uint4*>(p->l);
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+    q[2] = make_uint4(v.l[8], v.l[9], v.l[10], v.l[11]);
+    q[3] = make_uint4(v.l[12], v.l[13], 0u, 0u);
+#else
+    for (int i = 0; i < 14; i++) p->l[i] = v.l[i];
+    p->l[14] = p->l[15] = 0;
+#endif
+}
+// the stored negative of a coefficient: 64 p - v (v < 64 p).  Every coefficient and every product is kept in BOTH
+// signs, so a signed sum is a plain sum of selected copies: no per-limb sign mask, no offset to start from.
+KZG_HD FpW w_neg64(const FpW& v) {
+    FpW t;
+    limbs_sub<14>(t.l, FPW_OFF64, v.l);
+    return t;
+}
+
 // lane schedules copied into shared memory at kernel start (a few KB; constant-bank reads through
 // generic pointers were the slow part of the first version)
 struct CoopTables {
@@ -94,24 +135,38 @@ struct CoopTables {
 
 struct CoopWS {
     CoopTables tb;
-    FpW prod[54];
-    FpW part[12][5];  // partial output sums (5 lanes per output coefficient)
-    FpW reg[COOP_NREG][12];
-    FpW lv[2][MILLER_LINES][5];  // every line of both pairs evaluated at the (scaled) point: A.c0*s, A.c1*s, B.c0*xs, B.c1*xs, ys
+    FpS prod[54], nprod[54];  // the products of the running operation and their negatives (p - v)
+    FpS part[12][5];          // partial output sums (5 lanes per output coefficient)
+    FpS reg[COOP_NREG][12], nreg[COOP_NREG][12];  // registers and their negatives (64 p - v)
+    FpS lv[2][MILLER_LINES][5];  // every line of both pairs evaluated at the (scaled) point: A.c0*s, A.c1*s, B.c0*xs, B.c1*xs, ys
     FpW pt[2][3];    // per pair: s = ZZ*ZZZ and xs = X*ZZZ (times 2^512: see coop_load_points), ys = Y*ZZ (wide)
-    FpW onew;        // the constant one, second operand of the cyclotomic square's pass-through products
-    FpW zerow;       // padding operand of the sum loops
+    FpS onew;        // the constant one, second operand of the cyclotomic square's pass-through products
+    FpS zerow;       // padding operand of the sum loops
     Fp canon[12];    // scratch for the excursions into the 12-limb tower code
     int use[2];
     int result;
 };
+// coefficient `lane` of register d := v (both signs)
+KZG_HD void coop_put(CoopWS& ws, int d, int lane, const FpW& v) {
+    s_store(&ws.reg[d][lane], v);
+    s_store(&ws.nreg[d][lane], w_neg64(v));
+}
 
-// One step of a signed sum: code 0 = padding (adds the zero operand), else +-(index + 1) into `a`
-// (index < 12) or `b`.  No branch: every lane of the warp runs the same carry chain.
-KZG_HD void coop_acc_term(FpW& acc, int code, const FpW* a, const FpW* b, const FpW* zero) {
+// One step of a signed sum: code 0 = padding (adds the zero operand), else +-(index + 1): index < 12 selects `a`
+// (or, for a negative code, its stored negative `na`), larger indices `b` (never negative: tools/gen_pairing_tables.py
+// asserts it).  No branch: every lane of the warp runs the same four loads and the same carry chain.
+KZG_HD void coop_acc_term(FpW& acc, int code, const FpS* a, const FpS* na, const FpS* b, const FpS* zero) {
     const int idx = (code < 0 ? -code : code) - 1;
-    const FpW* src = (code == 0) ? zero : (idx < 12 ? a + idx : b + (idx - 12));
-    limbs_addsub<14>(acc.l, src->l, code < 0 ? 0xffffffffu : 0u);
+    const FpS* src = (code == 0) ? zero : (idx < 12 ? ((code < 0 ? na : a) + idx) : (b + (idx - 12)));
+    const FpW v = s_load(src);
+    limbs_add<14>(acc.l, acc.l, v.l);
+}
+// output sums: the operands are the products (or their negatives)
+KZG_HD void coop_acc_prod(FpW& acc, int code, const FpS* prod, const FpS* nprod, const FpS* zero) {
+    const int idx = (code < 0 ? -code : code) - 1;
+    const FpS* src = (code == 0) ? zero : ((code < 0 ? nprod : prod) + idx);
+    const FpW v = s_load(src);
+    limbs_add<14>(acc.l, acc.l, v.l);
 }
 
 struct CoopOp {
@@ -139,8 +194,8 @@ KZG_HD void coop_init_tables(CoopWS& ws) {
     coop_copy_table(ws.tb, COOP_OP_SQR, lane, COOP_SQR_NPROD, COOP_SQR_XOFF, COOP_SQR_YOFF, COOP_SQR_OOFF, COOP_SQR_XT, COOP_SQR_YT, COOP_SQR_OT);
     coop_copy_table(ws.tb, COOP_OP_LINE, lane, COOP_LINE_NPROD, COOP_LINE_XOFF, COOP_LINE_YOFF, COOP_LINE_OOFF, COOP_LINE_XT, COOP_LINE_YT, COOP_LINE_OT);
     coop_copy_table(ws.tb, COOP_OP_CYC, lane, COOP_CYC_NPROD, COOP_CYC_XOFF, COOP_CYC_YOFF, COOP_CYC_OOFF, COOP_CYC_XT, COOP_CYC_YT, COOP_CYC_OT);
-    if (lane == 0) ws.onew = FpW::one();
-    if (lane == 1) ws.zerow = FpW::zero();
+    if (lane == 0) s_store(&ws.onew, FpW::one());
+    if (lane == 1) s_store(&ws.zerow, FpW::zero());
     COOP_END
 }
 KZG_HD CoopOp coop_table(const CoopWS& ws, int op) {
@@ -148,21 +203,25 @@ KZG_HD CoopOp coop_table(const CoopWS& ws, int op) {
     return CoopOp{np[op], ws.tb.off[op][0], ws.tb.off[op][1], ws.tb.off[op][2], ws.tb.xt[op], ws.tb.yt[op], ws.tb.ot[op]};
 }
 
-// dst = op(a, b); dst may alias a or b (the outputs read only the products).
-// Sums start from a multiple of p that exceeds their negative part (2048 p for the inputs, 16 p for the
-// outputs) and run modulo 2^448, so one accumulator serves additions and subtractions alike.
-KZG_HD_NOINLINE void coop_run(CoopWS& ws, int op, FpW* dst, const FpW* a, const FpW* b) {
+// reg[d] = op(reg[a], b); d may equal a (the outputs read only the products).  `b`: twelve coefficients of another
+// register, the five values of a line, or the constant one.  All sums are plain sums of stored copies (see FpS).
+KZG_HD_NOINLINE void coop_run(CoopWS& ws, int op, int d, int ra, const FpS* b) {
     const CoopOp T = coop_table(ws, op);
+    const FpS *a = ws.reg[ra], *na = ws.nreg[ra];
     COOP_BEGIN
     for (int L = lane; L < T.nprod; L += COOP_LANES) {
         const int bx = T.xo[L], nx = T.xo[L + 1] - bx, by = T.yo[L], ny = T.yo[L + 1] - by;
         const int n = nx > ny ? nx : ny;
-        FpW x = FpW::from_limbs(FPW_OFF2048), y = FpW::from_limbs(FPW_OFF2048);
+        FpW x = FpW::zero(), y = FpW::zero();
         for (int t = 0; t < n; t++) {  // the two chains are independent: they overlap in the pipeline
-            coop_acc_term(x, t < nx ? T.xt[bx + t] : 0, a, b, &ws.zerow);
-            coop_acc_term(y, t < ny ? T.yt[by + t] : 0, a, b, &ws.zerow);
+            coop_acc_term(x, t < nx ? T.xt[bx + t] : 0, a, na, b, &ws.zerow);
+            coop_acc_term(y, t < ny ? T.yt[by + t] : 0, a, na, b, &ws.zerow);
         }
-        ws.prod[L] = mul(x, y);  // < p
+        const FpW pr = mul(x, y);  // < p
+        s_store(&ws.prod[L], pr);
+        FpW npr;
+        limbs_sub<14>(npr.l, FPW_MOD, pr.l);  // p - v in (0, p]
+        s_store(&ws.nprod[L], npr);
     }
     COOP_END
     // output sums: up to 36 signed products per coefficient -> 5 lanes per coefficient (<= 8 terms each)
@@ -170,56 +229,56 @@ KZG_HD_NOINLINE void coop_run(CoopWS& ws, int op, FpW* dst, const FpW* a, const 
     if (lane < 60) {
         const int k = lane / 5, sub = lane % 5;
         // two accumulators (alternate terms): two independent carry chains in flight instead of one
-        FpW acc = FpW::from_limbs(FPW_OFF16), acc2 = FpW::zero();
+        FpW acc = FpW::zero(), acc2 = FpW::zero();
         const int end = T.oo[k + 1];
         for (int t = T.oo[k] + sub; t < end; t += 10) {
-            coop_acc_term(acc, T.ot[t], ws.prod, ws.prod + 12, &ws.zerow);
-            coop_acc_term(acc2, t + 5 < end ? T.ot[t + 5] : 0, ws.prod, ws.prod + 12, &ws.zerow);
+            coop_acc_prod(acc, T.ot[t], ws.prod, ws.nprod, &ws.zerow);
+            coop_acc_prod(acc2, t + 5 < end ? T.ot[t + 5] : 0, ws.prod, ws.nprod, &ws.zerow);
         }
-        w_acc(acc, acc2);       // modulo 2^448: acc2 alone may be "negative"
-        ws.part[k][sub] = acc;  // < 24 p
+        w_acc(acc, acc2);
+        s_store(&ws.part[k][sub], acc);  // <= 8 p
     }
     COOP_END
     COOP_BEGIN
     if (lane < 12) {
-        FpW u = ws.part[lane][0], v = ws.part[lane][2];
-        w_acc(u, ws.part[lane][1]);
-        w_acc(v, ws.part[lane][3]);
-        w_acc(u, ws.part[lane][4]);
+        FpW u = s_load(&ws.part[lane][0]), v = s_load(&ws.part[lane][2]);
+        w_acc(u, s_load(&ws.part[lane][1]));
+        w_acc(v, s_load(&ws.part[lane][3]));
+        w_acc(u, s_load(&ws.part[lane][4]));
         w_acc(u, v);
-        dst[lane] = u;  // < 120 p
+        coop_put(ws, d, lane, u);  // <= 36 p, and 64 p - u
     }
     COOP_END
 }
 
-KZG_HD void coop_mul(CoopWS& ws, int d, int a, int b) { coop_run(ws, COOP_OP_MUL, ws.reg[d], ws.reg[a], ws.reg[b]); }
-KZG_HD void coop_sqr(CoopWS& ws, int d, int a) { coop_run(ws, COOP_OP_SQR, ws.reg[d], ws.reg[a], ws.reg[a]); }
-KZG_HD void coop_cyc(CoopWS& ws, int d, int a) { coop_run(ws, COOP_OP_CYC, ws.reg[d], ws.reg[a], &ws.onew); }
-KZG_HD void coop_line(CoopWS& ws, int d, int a, int pair, int k) { coop_run(ws, COOP_OP_LINE, ws.reg[d], ws.reg[a], ws.lv[pair][k]); }
+KZG_HD void coop_mul(CoopWS& ws, int d, int a, int b) { coop_run(ws, COOP_OP_MUL, d, a, ws.reg[b]); }
+KZG_HD void coop_sqr(CoopWS& ws, int d, int a) { coop_run(ws, COOP_OP_SQR, d, a, ws.reg[a]); }
+KZG_HD void coop_cyc(CoopWS& ws, int d, int a) { coop_run(ws, COOP_OP_CYC, d, a, &ws.onew); }
+KZG_HD void coop_line(CoopWS& ws, int d, int a, int pair, int k) { coop_run(ws, COOP_OP_LINE, d, a, ws.lv[pair][k]); }
 
-// conjugation over Fp6: negate the coefficients of the odd powers of w (256 p - v; v < 256 p)
+// conjugation over Fp6: negate the coefficients of the odd powers of w = swap their two stored copies
 KZG_HD_NOINLINE void coop_conj(CoopWS& ws, int d, int a) {
     COOP_BEGIN
     if (lane < 12) {
-        int k = lane >> 1;
-        FpW v = ws.reg[a][lane];
-        if (k & 1) {
-            FpW t;
-            limbs_sub<14>(t.l, FPW_OFF256, v.l);
-            v = t;
-        }
-        ws.reg[d][lane] = v;
+        const int k = lane >> 1;
+        const FpW v = s_load(&ws.reg[a][lane]), nv = s_load(&ws.nreg[a][lane]);
+        s_store(&ws.reg[d][lane], (k & 1) ? nv : v);
+        s_store(&ws.nreg[d][lane], (k & 1) ? v : nv);
     }
     COOP_END
 }
 KZG_HD_NOINLINE void coop_copy(CoopWS& ws, int d, int a) {
     COOP_BEGIN
-    if (lane < 12) ws.reg[d][lane] = ws.reg[a][lane];
+    if (lane < 12) {
+        const FpW v = s_load(&ws.reg[a][lane]), nv = s_load(&ws.nreg[a][lane]);
+        s_store(&ws.reg[d][lane], v);
+        s_store(&ws.nreg[d][lane], nv);
+    }
     COOP_END
 }
 KZG_HD void coop_set_one(CoopWS& ws, int d) {
     COOP_BEGIN
-    if (lane < 12) ws.reg[d][lane] = (lane == 0) ? FpW::one() : FpW::zero();
+    if (lane < 12) coop_put(ws, d, lane, (lane == 0) ? FpW::one() : FpW::zero());
     COOP_END
 }
 // a^(p^power), power = 1 or 2; d != a.  Lane k < 6 owns the Fp2 coefficient of w^k (12-limb tower code).
@@ -227,16 +286,16 @@ KZG_HD_NOINLINE void coop_frobenius(CoopWS& ws, int d, int a, int power) {
     COOP_BEGIN
     if (lane < 6) {
         Fp2 c;
-        c.c0 = w_to_fp(ws.reg[a][2 * lane]);
-        c.c1 = w_to_fp(ws.reg[a][2 * lane + 1]);
+        c.c0 = w_to_fp(s_load(&ws.reg[a][2 * lane]));
+        c.c1 = w_to_fp(s_load(&ws.reg[a][2 * lane + 1]));
         if (power == 1) {
             c = f2_conj(c);
             if (lane != 0) c = f2_mul(c, frob_gamma1(lane));
         } else if (lane != 0) {
             c = f2_mul_fp(c, Fp::from_limbs(FROB_GAMMA2[lane]));
         }
-        ws.reg[d][2 * lane] = w_from_fp(c.c0);
-        ws.reg[d][2 * lane + 1] = w_from_fp(c.c1);
+        coop_put(ws, d, 2 * lane, w_from_fp(c.c0));
+        coop_put(ws, d, 2 * lane + 1, w_from_fp(c.c1));
     }
     COOP_END
 }
@@ -263,7 +322,7 @@ KZG_HD void coop_from_tower(Fp* c, const Fp12& r) {
 // the one inversion of the final exponentiation: serial on lane 0, in the 12-limb tower code
 KZG_HD_NOINLINE void coop_inv(CoopWS& ws, int d, int a) {
     COOP_BEGIN
-    if (lane < 12) ws.canon[lane] = w_to_fp(ws.reg[a][lane]);
+    if (lane < 12) ws.canon[lane] = w_to_fp(s_load(&ws.reg[a][lane]));
     COOP_END
     COOP_BEGIN
     if (lane == 0) {
@@ -272,7 +331,7 @@ KZG_HD_NOINLINE void coop_inv(CoopWS& ws, int d, int a) {
     }
     COOP_END
     COOP_BEGIN
-    if (lane < 12) ws.reg[d][lane] = w_from_fp(ws.canon[lane]);
+    if (lane < 12) coop_put(ws, d, lane, w_from_fp(ws.canon[lane]));
     COOP_END
 }
 
@@ -313,7 +372,7 @@ KZG_HD_NOINLINE void coop_prepare_all_lines(CoopWS& ws, const G2Lines* L1, const
         else if (j == 2) v = mul(w_ext(l.B.c0), ws.pt[pair][1]);
         else if (j == 3) v = mul(w_ext(l.B.c1), ws.pt[pair][1]);
         else v = ws.pt[pair][2];
-        ws.lv[pair][k][j] = v;
+        s_store(&ws.lv[pair][k][j], v);
     }
     COOP_END
 }
@@ -389,7 +448,7 @@ KZG_HD void coop_final_exp_is_one(CoopWS& ws) {
     coop_mul(ws, X, X, E);            // E^3
     coop_mul(ws, T3, T3, X);
     COOP_BEGIN
-    if (lane < 12) ws.canon[lane] = w_to_fp(ws.reg[T3][lane]);
+    if (lane < 12) ws.canon[lane] = w_to_fp(s_load(&ws.reg[T3][lane]));
     COOP_END
     COOP_BEGIN
     if (lane == 0) {

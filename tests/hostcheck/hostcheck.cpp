@@ -172,7 +172,10 @@ int hc_coop_pairing_product_is_one(const uint8_t* p1, const uint8_t* q1, const u
         coop_prepare_all_lines(w2[g], &L1, &L2);
         coop_miller_loop(w2[g]);
     }
-    for (int lane = 0; lane < 12; lane++) w2[0].reg[6][lane] = w2[1].reg[0][lane];
+    for (int lane = 0; lane < 12; lane++) {
+        w2[0].reg[6][lane] = w2[1].reg[0][lane];
+        w2[0].nreg[6][lane] = w2[1].nreg[0][lane];
+    }
     coop_mul(w2[0], 0, 0, 6);
     coop_final_exp_is_one(w2[0]);
     if (w2[0].result != single) return -2;

@@ -320,6 +320,9 @@ def emit():
             os_ += expand(o, "p")
             oo.append(len(os_))
         assert max(abs(t) for t in xs + ys) < 64 and max(abs(t) for t in os_) <= 64  # outputs: products only
+        # pairing_coop.cuh keeps a negated copy of every `a` coefficient and of every product, never of a `b` operand
+        # (line values, the constant one): a subtracted input must be one of the twelve `a` coefficients
+        assert all(t > 0 or -t <= 12 for t in xs + ys), op
         # bounds the unreduced sums of pairing_coop.cuh rely on
         assert max(b - a for a, b in zip(xo, xo[1:])) <= 8 and max(b - a for a, b in zip(yo, yo[1:])) <= 8
         assert max(b - a for a, b in zip(oo, oo[1:])) <= 40 and len(products) <= 64
@@ -342,7 +345,7 @@ def emit():
         return ", ".join("0x%08xu" % ((v >> (32 * i)) & 0xFFFFFFFF) for i in range(14))
     out.append("// ---- wide domain: 14 limbs, R_w = 2^448; sums are never reduced, only the multiplier reduces ----\n")
     for name, v in (("FPW_MOD", P), ("FPW_ONE", (1 << 448) % P), ("FPW_R2", (1 << 896) % P), ("FPW_C512", (1 << 512) % P),
-                    ("FPW_C576", (1 << 576) % P), ("FPW_OFF16", 16 * P), ("FPW_OFF256", 256 * P), ("FPW_OFF2048", 2048 * P)):
+                    ("FPW_C576", (1 << 576) % P), ("FPW_OFF16", 16 * P), ("FPW_OFF64", 64 * P), ("FPW_OFF256", 256 * P), ("FPW_OFF2048", 2048 * P)):
         out.append("KZG_CONST uint32_t %s[14] = {%s};\n" % (name, limbs14(v)))
     path = os.path.join(ROOT, "c-kzg-4844_b200", "csrc", "pairing_tables.cuh")
     with open(path, "w") as f:
