@@ -3,7 +3,7 @@ sys.path.insert(0, os.getcwd())
 import torch, numpy as np
 import __graft_entry__ as entry, bench
 mod = entry.load_package(); ts = mod.load_trusted_setup()
-n = 4096
+n = int(os.environ.get("PROBE_N", "4096"))
 host = torch.from_numpy(bench.synth_blobs(n, 1)).pin_memory(); dev = host.cuda()
 cms = torch.empty(48*n, dtype=torch.uint8, device='cuda'); prs = torch.empty(48*n, dtype=torch.uint8, device='cuda')
 mod.blob_to_kzg_commitment_device(cms.data_ptr(), dev.data_ptr(), n, ts); mod.compute_blob_kzg_proof_device(prs.data_ptr(), dev.data_ptr(), cms.data_ptr(), n, ts)
