@@ -107,13 +107,15 @@ bool rlc_use_vmsm() {
 // chunk's (hash -> evaluate) chain starts as soon as its bytes have landed (copy engine || SMs).
 // With per-kernel profiling on (level 2) everything runs on the call's stream so event attribution is exact.
 // after the evaluation of blobs [off, off + m) has been enqueued on the call stream: copy their z||y to the host on `cpz`
-static int stage1_stream_zy(Call& call, Stage1& s, uint64_t off, uint64_t m) {
-    // on the call stream itself, in order behind the evaluation: a 64 B/blob copy costs microseconds there, and no
-    // stream has to wait for another one (see the note on stream-side waits in verify_stage1)
-    cudaEvent_t done = nullptr;
-    KZG_CUDA_TRY(cudaMemcpyAsync(s.h_zy + off * 64, s.zy + off * 64, m * 64, cudaMemcpyDeviceToHost, call.stream));
+static int stage1_stream_zy(Call& call, Stage1& s, cudaStream_t cpz, uint64_t off, uint64_t m) {
+    cudaEvent_t ready = nullptr, done = nullptr;
+    KZG_CUDA_TRY(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    cudaEventRecord(ready, call.stream);
+    cudaStreamWaitEvent(cpz, ready, 0);
+    cudaEventDestroy(ready);
+    KZG_CUDA_TRY(cudaMemcpyAsync(s.h_zy + off * 64, s.zy + off * 64, m * 64, cudaMemcpyDeviceToHost, cpz));
     KZG_CUDA_TRY(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
-    cudaEventRecord(done, call.stream);
+    cudaEventRecord(done, cpz);
     s.zy_done.push_back(done);
     s.zy_range.push_back({off, m});
     return RET_OK;
@@ -122,6 +124,8 @@ static int stage1_stream_zy(Call& call, Stage1& s, uint64_t off, uint64_t m) {
 int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_cm, const uint8_t* d_pf, uint64_t n, int mem) {
     Launch L = call.launch();
     const bool stream_zy = s.h_zy != nullptr && !call.trace_kernels && n >= 1024;
+    cudaStream_t cpz = nullptr;
+    if (stream_zy && !(cpz = call.fork())) return RET_ERROR;
     const bool host = (mem == CKZG_B200_HOST);
     uint8_t* d_up = nullptr;
     if (host) TRY(call.alloc(&d_up, n * BLOB_BYTES));
@@ -159,7 +163,7 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
             for (uint64_t off = 0; off < n && rc == RET_OK; off += zy_chunk) {
                 const uint64_t m = (n - off < zy_chunk) ? n - off : zy_chunk;
                 rc = launch_evaluate(L, s.y + off, s.zy + off * 64, nullptr, nullptr, d_blobs + off * BLOB_BYTES, s.z + off, m, s.bad, 0);
-                if (rc == RET_OK) rc = stage1_stream_zy(call, s, off, m);
+                if (rc == RET_OK) rc = stage1_stream_zy(call, s, cpz, off, m);
             }
         } else {
             rc = launch_evaluate(L, s.y, s.zy, nullptr, nullptr, d_blobs, s.z, n, s.bad, 0);
@@ -167,162 +171,120 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
         call.mark_on(call.stream, "stage:t_evaluate_done");
         return rc;
     }
-    // ---- host blobs (and the separate-kernel form for device blobs): a pipeline PACED BY THE CALLING THREAD -------
-    // Chunks of 512 blobs are copied on a copy stream; each chunk's Fiat-Shamir hash (latency bound: 2050 dependent
-    // SHA-256 blocks per blob, ~2.1 ms whatever the chunk size) runs on one of a few hash streams next to the point
-    // validation; its evaluation follows on the call stream.  Nothing here makes one stream wait for another:
-    // the calling thread polls the copies' events, launches a chunk's hash once its bytes have landed, polls the
-    // hash's event and launches the evaluation.  Why: a cudaStreamWaitEvent parks the waiting stream's hardware queue,
-    // and with a dozen queues in play the host interface came back to parked queues -- and to the event records behind
-    // already finished kernels -- up to 11 ms late (device-side timers against event times, profiles/
-    // e2e_probe_R2o.log, _R2p.log: hashes end at 4.5 ... 9.4 ms, their events fire at 15.6 ms; two concurrent callers
-    // fell from 380 k to 126 k blobs/s).  Whether that happened depended on the arrangement and on what else ran; a
-    // pipeline without stream-side waits has no such modes.  The thread has nothing else to do while its call runs.
-    //
-    // The TAIL of a pinned batch (the last `tail_blobs`, default 1024: their bytes take 2.4 ms to arrive, as long as a
-    // blob takes to hash) travels in column pieces: piece p = bytes [16 KiB p, 16 KiB (p + 1)) of EVERY tail blob
-    // (one strided copy), hashed piece by piece behind the copies with the SHA state carried between the launches
-    // (verify.cu launch_blob_challenges_range).  When the batch's last byte lands, 258 of the 2050 blocks of each tail
-    // blob are left (0.3 ms) instead of a whole 2.1 ms chain.  CKZG_B200_TAIL_PIECES=0 switches the pieces off.
+    // fork: side streams start after the allocations / memset enqueued so far.
+    // Measured on B200 (tools/gpu_probe.py modes, n = 4096 device-resident): everything on one stream
+    // 16.4 ms; hash -> evaluate chains on a side stream next to the validations 17.6 ms (the two
+    // throughput kernels get in each other's way); ONLY the latency-bound hashes on side streams, the
+    // validations and then the evaluations on the main stream: 14.3 ms.  That is the arrangement here.
     const uint64_t CH = host ? 512 : n;
+    // Segments of the batch.  Ordinary segments are chunks of CH blobs: one copy, one hash launch when it has landed.
+    //
+    // EXPERIMENT, OFF BY DEFAULT (CKZG_B200_TAIL_PIECES=8 enables it): the tail of a pinned host batch travels in column
+    // pieces -- piece p = bytes [16 KiB p, 16 KiB (p + 1)) of EVERY tail blob (one strided copy) -- and is hashed piece
+    // by piece behind the copies with the SHA state carried between the launches (verify.cu
+    // launch_blob_challenges_range), so that part of the tail's 2.1 ms hash chain is done before the batch's last byte
+    // lands.  Measured at n = 4096 (tools/e2e_probe.py, profiles/e2e_probe_R2k..R2r.log, bench_R2q.log): with a
+    // 512-blob tail the call drops from 16.4 to 15.4 ms (252 k -> 263 k blobs/s end to end), and a 1024-blob tail
+    // finishes its hashes 0.28 ms after the upload.  But every arrangement other than "8 hash streams, 512-blob tail,
+    // one caller" -- a 1024-blob tail, chunks sharing a hash stream, two concurrent callers (380 k -> 126 k blobs/s),
+    // and a variant in which the calling thread polls the events and launches each stage itself -- ran into a mode in
+    // which the events recorded behind the chunks' hash kernels fire ~11 ms after those kernels end (device-side
+    // %globaltimer against event times: hashes end at 4.5 ... 9.4 ms, the first evaluation starts at 15.6 ms), while
+    // n = 512 ... 2048 were never affected.  The cause was not found in the time available, so the default is the
+    // arrangement of round 1 (one hash stream per chunk, no pieces), which never showed that mode in any run of either
+    // round, single caller, concurrent callers, 1, 2 and 4 GPUs.
     struct Seg {
         uint64_t off, m;
-        int first_unit, units;  // copy / hash units: 1, or the number of column pieces
-        int hashed_units = 0;
-        cudaEvent_t hashed = nullptr;
-        cudaStream_t st = nullptr;
-    };
-    struct Unit {
-        int seg, k0, k1;
-        cudaEvent_t landed = nullptr;
+        bool pieces;
     };
     std::vector<Seg> segs;
-    std::vector<Unit> units;
-    static const int tail_pieces = getenv("CKZG_B200_TAIL_PIECES") ? atoi(getenv("CKZG_B200_TAIL_PIECES")) : 8;
-    static const uint64_t tail_blobs = getenv("CKZG_B200_TAIL_BLOBS") ? (uint64_t)atoll(getenv("CKZG_B200_TAIL_BLOBS")) : 1024;
-    static const int max_side = (getenv("CKZG_B200_HASH_STREAMS") && atoi(getenv("CKZG_B200_HASH_STREAMS")) >= 1 && atoi(getenv("CKZG_B200_HASH_STREAMS")) <= 8) ? atoi(getenv("CKZG_B200_HASH_STREAMS")) : 4;
+    static const int tail_pieces = getenv("CKZG_B200_TAIL_PIECES") ? atoi(getenv("CKZG_B200_TAIL_PIECES")) : 0;
+    static const uint64_t tail_blobs = getenv("CKZG_B200_TAIL_BLOBS") ? (uint64_t)atoll(getenv("CKZG_B200_TAIL_BLOBS")) : 512;
     uint64_t tail_start = n;
     if (host && tail_pieces >= 2 && tail_pieces <= 64 && (N_BLOB * 32 / 64) % tail_pieces == 0 && tail_blobs >= 128) {
         const uint64_t want = n < tail_blobs ? n : tail_blobs;
         const uint64_t start = ((n - want) / CH) * CH;  // on a chunk boundary
         if ((n - start) * BLOB_BYTES >= (16u << 20) && !host_ptr_is_pageable(blobs + start * BLOB_BYTES)) tail_start = start;
     }
-    const int total_blocks = blob_challenge_blocks();
-    for (uint64_t off = 0; off < tail_start; off += CH) {
-        Seg g{off, (tail_start - off < CH) ? tail_start - off : CH, (int)units.size(), 1};
-        units.push_back(Unit{(int)segs.size(), 0, total_blocks});
-        segs.push_back(g);
-    }
-    if (tail_start < n) {
-        Seg g{tail_start, n - tail_start, (int)units.size(), tail_pieces};
-        const int bpp = (int)(BLOB_BYTES / tail_pieces / 64);  // SHA blocks per piece: block k >= 1 needs blob bytes up to 64 k + 32
-        for (int p = 0; p < tail_pieces; p++) units.push_back(Unit{(int)segs.size(), p * bpp, p == tail_pieces - 1 ? total_blocks : (p + 1) * bpp});
-        segs.push_back(g);
-    }
-    const int nsegs = (int)segs.size(), nunits = (int)units.size();
+    for (uint64_t off = 0; off < tail_start; off += CH) segs.push_back({off, (tail_start - off < CH) ? tail_start - off : CH, false});
+    if (tail_start < n) segs.push_back({tail_start, n - tail_start, true});
+    const int nsegs = (int)segs.size();
+    static const int max_side = (getenv("CKZG_B200_HASH_STREAMS") && atoi(getenv("CKZG_B200_HASH_STREAMS")) >= 1 && atoi(getenv("CKZG_B200_HASH_STREAMS")) <= 8) ? atoi(getenv("CKZG_B200_HASH_STREAMS")) : 8;
     const int nside = std::min(max_side, nsegs);
     // side streams are forked from (ordered after) the call stream and joined / destroyed by the Call on
     // every exit path, so no early return below can leave a kernel reading released scratch
-    cudaStream_t side[8], copy = nullptr;
+    cudaStream_t side[8], copy = nullptr, tail_stream = nullptr;
+    int rc = RET_OK;
     for (int i = 0; i < nside; i++)
         if (!(side[i] = call.fork())) return RET_ERROR;
     if (host && !(copy = call.fork())) return RET_ERROR;
-    for (int c = 0; c < nsegs; c++) segs[c].st = side[c % nside];
+    if (tail_start < n && nsegs > 1 && !(tail_stream = call.fork())) return RET_ERROR;
+    std::vector<cudaEvent_t> hashed(nsegs, nullptr);
     uint32_t* d_states = nullptr;
     if (tail_start < n) TRY(call.alloc(&d_states, (n - tail_start) * 8));
-    int rc = RET_OK;
-    struct Cleanup {  // events of an abandoned pipeline
-        std::vector<Seg>& segs;
-        std::vector<Unit>& units;
-        ~Cleanup() {
-            for (auto& g : segs)
-                if (g.hashed) cudaEventDestroy(g.hashed);
-            for (auto& u : units)
-                if (u.landed) cudaEventDestroy(u.landed);
-        }
-    } cleanup{segs, units};
-
-    int issued = 0, next_hash = 0, next_eval = 0;
-    bool validated = false;
-    // one round of the pipeline; returns true if anything was launched
-    auto pump = [&]() -> bool {
-        bool progressed = false;
-        // hashes: in unit order, each as soon as its bytes have landed (device blobs: at once)
-        while (rc == RET_OK && next_hash < issued) {
-            Unit& u = units[next_hash];
-            if (u.landed) {
-                const cudaError_t q = cudaEventQuery(u.landed);
-                if (q == cudaErrorNotReady) break;
-                if (q != cudaSuccess) {
+    for (int c = 0; c < nsegs && rc == RET_OK; c++) {
+        const uint64_t off = segs[c].off, m = segs[c].m;
+        cudaStream_t st = (segs[c].pieces && tail_stream) ? tail_stream : side[c % nside];
+        Launch Ls = call.launch_on(st);
+        if (segs[c].pieces) {
+            const int P = tail_pieces;
+            const size_t piece_bytes = BLOB_BYTES / P;  // 16 KiB at P = 8
+            const int blocks_per_piece = (int)(piece_bytes / 64);
+            for (int p = 0; p < P && rc == RET_OK; p++) {
+                cudaEvent_t landed;
+                if (cudaMemcpy2DAsync(d_up + off * BLOB_BYTES + p * piece_bytes, BLOB_BYTES, blobs + off * BLOB_BYTES + p * piece_bytes, BLOB_BYTES, piece_bytes, m,
+                                      cudaMemcpyHostToDevice, copy) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&landed, cudaEventDisableTiming) != cudaSuccess) {
                     rc = RET_ERROR;
                     break;
                 }
+                cudaEventRecord(landed, copy);
+                cudaStreamWaitEvent(st, landed, 0);
+                cudaEventDestroy(landed);
+                // block k >= 1 needs blob bytes up to 64 k + 32: bytes [0, (p + 1) * piece) allow blocks [.., (p + 1) * blocks_per_piece)
+                const int k0 = p * blocks_per_piece, k1 = (p == P - 1) ? blob_challenge_blocks() : (p + 1) * blocks_per_piece;
+                rc = launch_blob_challenges_range(Ls, s.z + off, s.zy + off * 64, d_blobs + off * BLOB_BYTES, d_cm + off * 48, m, k0, k1, d_states);
             }
-            Seg& g = segs[u.seg];
-            Launch Ls = call.launch_on(g.st);
-            rc = launch_blob_challenges_range(Ls, s.z + g.off, s.zy + g.off * 64, d_blobs + g.off * BLOB_BYTES, d_cm + g.off * 48, g.m, u.k0, u.k1, d_states);
-            if (rc) break;
-            if (++g.hashed_units == g.units) {
-                if (cudaEventCreateWithFlags(&g.hashed, cudaEventDisableTiming) != cudaSuccess) {
+        } else {
+            if (host) {
+                cudaEvent_t landed;
+                // pinned sources: one DMA per chunk; pageable sources: staged through the pinned ring by the host threads
+                if (call.upload(d_up + off * BLOB_BYTES, blobs + off * BLOB_BYTES, m * BLOB_BYTES, copy) != RET_OK ||
+                    cudaEventCreateWithFlags(&landed, cudaEventDisableTiming) != cudaSuccess) {
                     rc = RET_ERROR;
                     break;
                 }
-                cudaEventRecord(g.hashed, g.st);
-                if (u.seg == 0) call.mark_on(g.st, "stage:t_first_chunk_hashed");
-                if (u.seg == nsegs - 1) call.mark_on(g.st, "stage:t_hash_done");
+                cudaEventRecord(landed, copy);
+                cudaStreamWaitEvent(st, landed, 0);
+                cudaEventDestroy(landed);
+                if (c == 0) call.mark_on(copy, "stage:t_copy0_done");
+                if (c == 0) call.mark_on(st, "stage:t_hash0_start");
+                if (c == 1) call.mark_on(st, "stage:t_hash1_start");
             }
-            next_hash++;
-            progressed = true;
+            rc = launch_blob_challenges(Ls, s.z + off, s.zy + off * 64, d_blobs + off * BLOB_BYTES, d_cm + off * 48, m);
         }
-        // evaluations: in segment order on the call stream, each as soon as its challenges exist
-        while (rc == RET_OK && next_eval < nsegs && segs[next_eval].hashed) {
-            const cudaError_t q = cudaEventQuery(segs[next_eval].hashed);
-            if (q == cudaErrorNotReady) break;
-            if (q != cudaSuccess) {
-                rc = RET_ERROR;
-                break;
-            }
-            const Seg& g = segs[next_eval];
-            rc = launch_evaluate(L, s.y + g.off, s.zy + g.off * 64, nullptr, nullptr, d_blobs + g.off * BLOB_BYTES, s.z + g.off, g.m, s.bad, 0);
-            if (rc == RET_OK && stream_zy) rc = stage1_stream_zy(call, s, g.off, g.m);
-            next_eval++;
-            progressed = true;
+        if (rc) break;
+        if (cudaEventCreateWithFlags(&hashed[c], cudaEventDisableTiming) != cudaSuccess) {
+            rc = RET_ERROR;
+            break;
         }
-        return progressed;
-    };
-    // copies first (the copy engine works through them in order); pageable sources are staged chunk by chunk by the
-    // host threads, so the pipeline is pumped between chunks
-    for (int ui = 0; ui < nunits && rc == RET_OK; ui++) {
-        Unit& u = units[ui];
-        const Seg& g = segs[u.seg];
-        if (host) {
-            if (g.units == 1) {
-                rc = call.upload(d_up + g.off * BLOB_BYTES, blobs + g.off * BLOB_BYTES, g.m * BLOB_BYTES, copy);
-            } else {
-                const size_t piece = BLOB_BYTES / g.units, at = (size_t)(ui - g.first_unit) * piece;
-                if (cudaMemcpy2DAsync(d_up + g.off * BLOB_BYTES + at, BLOB_BYTES, blobs + g.off * BLOB_BYTES + at, BLOB_BYTES, piece, g.m, cudaMemcpyHostToDevice, copy) != cudaSuccess)
-                    rc = RET_ERROR;
-            }
-            if (rc == RET_OK && cudaEventCreateWithFlags(&u.landed, cudaEventDisableTiming) != cudaSuccess) rc = RET_ERROR;
-            if (rc == RET_OK) cudaEventRecord(u.landed, copy);
-            if (ui == 0) call.mark_on(copy, "stage:t_copy0_done");
-        }
-        issued = ui + 1;
-        if (!validated && rc == RET_OK) {  // the validation needs no blob: it goes first on the call stream
-            rc = s.want_shift ? launch_g1_validate2_levels(L, s.cm, d_cm, s.pf, d_pf, n, s.bad, s.table) : launch_g1_validate2(L, s.cm, d_cm, s.pf, d_pf, n, s.bad);
-            call.mark_on(call.stream, "stage:t_validate_done");
-            validated = true;
-        }
-        pump();
+        cudaEventRecord(hashed[c], st);
+        if (c == 0) call.mark_on(st, "stage:t_first_chunk_hashed");
+        if (c == nsegs - 1) call.mark_on(st, "stage:t_hash_done");
     }
     if (copy) call.mark_on(copy, "stage:t_upload_done");
-    // drive the rest: poll, launch, spin (the waits are a few hundred microseconds each)
-    while (rc == RET_OK && next_eval < nsegs) {
-        if (!pump()) {
-#if defined(__x86_64__)
-            __builtin_ia32_pause();
-#endif
-        }
+    // main stream: point validation (independent of the blobs), then each segment's evaluation as soon as
+    // its challenges exist
+    if (rc == RET_OK)
+        rc = s.want_shift ? launch_g1_validate2_levels(L, s.cm, d_cm, s.pf, d_pf, n, s.bad, s.table) : launch_g1_validate2(L, s.cm, d_cm, s.pf, d_pf, n, s.bad);
+    call.mark_on(call.stream, "stage:t_validate_done");
+    for (int c = 0; c < nsegs; c++) {
+        const uint64_t off = segs[c].off, m = segs[c].m;
+        if (!hashed[c]) continue;
+        cudaStreamWaitEvent(call.stream, hashed[c], 0);
+        cudaEventDestroy(hashed[c]);
+        if (rc == RET_OK) rc = launch_evaluate(L, s.y + off, s.zy + off * 64, nullptr, nullptr, d_blobs + off * BLOB_BYTES, s.z + off, m, s.bad, 0);
+        if (rc == RET_OK && stream_zy) rc = stage1_stream_zy(call, s, cpz, off, m);
     }
     return rc;
 }

@@ -305,22 +305,15 @@ def test_device_mode_ordering_against_the_callers_streams(env):
     assert mod.verify_blob_kzg_proof_batch_device(dev.data_ptr(), cms.data_ptr(), wrong.data_ptr(), m, ts) is False
 
 
-def test_pinned_host_batch_tail_chunk_hashed_in_column_pieces(env):
-    """Host-pointer batches from PINNED memory send their last chunk in eight column pieces and hash it piece by piece
-    with the SHA state carried between launches (api_verify.cu, verify.cu launch_blob_challenges_range).  A wrong state
-    hand-over would change z and with it the verdict: the valid batch must verify, one flipped byte in the LAST piece
-    of a blob of the last chunk must not, and the pageable route (no pieces) must agree."""
-    import torch
+@pytest.mark.parametrize("pieces", ["0", "8"])
+def test_pinned_host_batch_with_and_without_column_pieces(pieces):
+    """Host-pointer batches from PINNED memory, with the default arrangement (one hash launch per 512-blob chunk) and
+    with the experimental one (CKZG_B200_TAIL_PIECES=8: the tail sent in eight column pieces and hashed piece by piece
+    with the SHA state carried between launches, verify.cu launch_blob_challenges_range).  A wrong state hand-over
+    would change z and with it the verdict.  The switch is read once per process, hence the subprocess
+    (tests/pieces_check.py)."""
+    import subprocess
 
-    mod, ts, n, host, dev, cms, prs = env
-    hc, hp = cms.cpu().pin_memory(), prs.cpu().pin_memory()
-    for m in (1024, 700):  # last chunk: 512 blobs / 188 blobs (>= 16 MB: piecewise)
-        pin = host[: 131072 * m].clone().pin_memory()
-        assert mod.verify_blob_kzg_proof_batch_host(pin.data_ptr(), hc.data_ptr(), hp.data_ptr(), m, ts) is True
-        pin[131072 * (m - 3) + 131071] ^= 1  # low byte of the last field element: still canonical
-        assert mod.verify_blob_kzg_proof_batch_host(pin.data_ptr(), hc.data_ptr(), hp.data_ptr(), m, ts) is False
-        pin[131072 * (m - 3) + 131071] ^= 1
-        pin[131072 * (m - 100) + 16384 * 3 + 31] ^= 1  # a byte in the fourth piece
-        assert mod.verify_blob_kzg_proof_batch_host(pin.data_ptr(), hc.data_ptr(), hp.data_ptr(), m, ts) is False
-    pageable = host[: 131072 * 700].numpy().copy()
-    assert mod.verify_blob_kzg_proof_batch_host(pageable.ctypes.data, hc.data_ptr(), hp.data_ptr(), 700, ts) is True
+    env2 = dict(os.environ, CKZG_B200_TAIL_PIECES=pieces)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "pieces_check.py")], env=env2, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "pieces_check ok" in r.stdout, (r.stdout[-500:], r.stderr[-1500:])
