@@ -234,6 +234,22 @@ int ckzg_b200_ctx_create(ckzg_b200_ctx** out, const uint8_t* g1_monomial_bytes, 
 
 void ckzg_b200_ctx_destroy(ckzg_b200_ctx* ctx) { ctx_free(reinterpret_cast<Ctx*>(ctx)); }
 int ckzg_b200_ctx_device(const ckzg_b200_ctx* ctx) { return reinterpret_cast<const Ctx*>(ctx)->device; }
+// what the two lazily built fixed-base tables occupy right now (0 = not built yet / bucket form) and what the next build would choose
+int ckzg_b200_ctx_table_info(const ckzg_b200_ctx* ctx, uint64_t out[6]) {
+    if (!ctx || !out) return RET_BADARGS;
+    const Ctx* c = reinterpret_cast<const Ctx*>(ctx);
+    out[0] = c->commit_table ? (uint64_t)fk_geom(c->commit_c).points_for(N_BLOB) * sizeof(G1Affine) : 0;
+    out[1] = (uint64_t)(c->commit_table ? c->commit_c : 0);
+    out[2] = c->fk_ready.load() ? (uint64_t)fk_geom(c->fk_c).table_points() * sizeof(G1Affine) : 0;
+    out[3] = (uint64_t)(c->fk_ready.load() ? c->fk_c : 0);
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(c->device);
+    out[4] = (uint64_t)plan_commit_window();
+    out[5] = (uint64_t)plan_fk_window();
+    if (prev >= 0) cudaSetDevice(prev);
+    return RET_OK;
+}
 int ckzg_b200_ctx_device_count(const ckzg_b200_ctx* ctx) {
     const Ctx* c = reinterpret_cast<const Ctx*>(ctx);
     return c->peers.empty() ? 1 : (int)c->peers.size();

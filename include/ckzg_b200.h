@@ -70,6 +70,17 @@ int ckzg_b200_ctx_device(const ckzg_b200_ctx *ctx);
  * frozen API unchanged drives all listed GPUs.  DEVICE-memory inputs always run on the device that owns them.
  */
 int ckzg_b200_ctx_device_count(const ckzg_b200_ctx *ctx);
+/*
+ * Device memory.  A context holds ~40 MB of setup data.  Two fixed-base tables are built on FIRST USE of the APIs that
+ * need them and sized from the HBM that is free on the device at that moment (verification-only users build neither):
+ *   commitments / proofs (blob_to_kzg_commitment, compute_*_proof): window 14 -> 61 GB | 13 -> 32 GB | 12 -> 18 GB |
+ *       none (a 9 MB table + bucket MSM) when less than 60 GB are free;   CKZG_B200_COMMIT_WINDOW = 0 | 10..14 pins it;
+ *   FK20 cell proofs (compute_cells_and_kzg_proofs, recover_*):          window 12 -> 35 GB | 10 -> 10.5 GB | 8 -> 3.2 GB;
+ *                                                                        CKZG_B200_FK_WINDOW = 8 | 10 | 12 pins it.
+ * Results are identical for every choice.  out = { commitment table bytes (0 = not built / bucket form), its window,
+ * FK20 table bytes (0 = not built), its window, the window a commitment-table build would choose NOW, same for FK20 }.
+ */
+int ckzg_b200_ctx_table_info(const ckzg_b200_ctx *ctx, uint64_t out[6]);
 
 /*
  * Batched blob_to_kzg_commitment (src/eip4844/eip4844.c:264 applied to n blobs).

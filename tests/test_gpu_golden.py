@@ -114,6 +114,22 @@ def test_table_plans_agree(gpu, ref, monkeypatch):
             small.close() if hasattr(small, "close") else None
 
 
+def test_table_info_reports_the_lazily_built_tables(gpu):
+    """ckzg_b200_ctx_table_info: the memory the two fixed-base tables take is visible through the API (they are
+    built on first use: this module's earlier tests have used commitments and cell proofs)."""
+    import ctypes as C
+
+    out = (C.c_uint64 * 6)()
+    gpu.blob_to_kzg_commitment(synth_blob(1))
+    gpu.compute_cells_and_kzg_proofs(synth_blob(1))
+    assert gpu.lib.ckzg_b200_ctx_table_info(_engine(gpu), out) == 0
+    commit_bytes, commit_c, fk_bytes, fk_c, plan_commit, plan_fk = list(out)
+    assert fk_c in (8, 10, 12) and fk_bytes == 8192 * ((256 + fk_c - 1) // fk_c) * (1 << (fk_c - 1)) * 96
+    assert (commit_c == 0 and commit_bytes == 0) or (10 <= commit_c <= 14 and commit_bytes == 4096 * ((256 + commit_c - 1) // commit_c) * (1 << (commit_c - 1)) * 96)
+    assert plan_commit in (0, 12, 13, 14) or 10 <= plan_commit <= 14
+    assert plan_fk in (8, 10, 12)
+
+
 def _engine(gpu):
     import ctypes as C
 
