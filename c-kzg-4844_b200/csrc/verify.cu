@@ -504,24 +504,29 @@ __device__ __forceinline__ Fr evt_subtree(const uint8_t* __restrict__ src, int l
     }
 }
 
-__global__ void __launch_bounds__(EV_THREADS) evaluate_tree_kernel(Fr* __restrict__ y_out, uint8_t* __restrict__ zy, const uint8_t* __restrict__ blobs, const Fr* __restrict__ zpow,
-                                                                  const Fr* __restrict__ roots_brp, int* __restrict__ bad, int bad_stride) {
-    __shared__ Fr sh[EV_THREADS];
+// TREE_LOG leaves-per-thread exponent: 2^TREE_LOG consecutive leaves and the TREE_LOG levels above them stay in one
+// thread's registers, the remaining 12 - TREE_LOG levels go through shared memory with half the threads dropping out
+// per level.  4 (256 threads) and 5 (128 threads) are both built; CKZG_B200_EVAL_LEAVES selects (A/B, profiles/).
+template <int TREE_LOG>
+__global__ void __launch_bounds__(N_BLOB >> TREE_LOG) evaluate_tree_kernel(Fr* __restrict__ y_out, uint8_t* __restrict__ zy, const uint8_t* __restrict__ blobs,
+                                                                          const Fr* __restrict__ zpow, const Fr* __restrict__ roots_brp, int* __restrict__ bad, int bad_stride) {
+    constexpr int THREADS = N_BLOB >> TREE_LOG;
+    __shared__ Fr sh[THREADS];
     const int blob = blockIdx.x, t = threadIdx.x;
     time_record(3u);
     const uint8_t* src = blobs + (size_t)blob * BLOB_BYTES;
     const Fr* zp = zpow + (size_t)blob * 12;
-    Fr Z[4];
+    Fr Z[TREE_LOG];
 #pragma unroll
-    for (int k = 0; k < 4; k++) Z[k] = load_fr(zp + k);
+    for (int k = 0; k < TREE_LOG; k++) Z[k] = load_fr(zp + k);
     bool isbad = false;
-    Fr v = evt_subtree<4>(src, EV_PER * t, Z, roots_brp, isbad);
+    Fr v = evt_subtree<TREE_LOG>(src, (1 << TREE_LOG) * t, Z, roots_brp, isbad);
     if (isbad && bad) bad[(size_t)blob * bad_stride] = 1;
     sh[t] = v;
     __syncthreads();
 #pragma unroll 1
-    for (int k = 4; k < 12; k++) {
-        const int active = EV_THREADS >> (k - 3);
+    for (int k = TREE_LOG; k < 12; k++) {
+        const int active = THREADS >> (k - TREE_LOG + 1);
         Fr nv;
         if (t < active) {
             Fr l = sh[2 * t], r = sh[2 * t + 1];
@@ -821,7 +826,11 @@ int launch_evaluate(Launch& L, Fr* y, uint8_t* zy, Fr* inv_or_null, int* m_or_nu
         KZG_CUDA_TRY(cudaMallocAsync((void**)&zpow, n * 12 * sizeof(Fr), L.stream));
         evaluate_zpow_kernel<<<blocks_for(n, 32), 32, 0, L.stream>>>(zpow, z, n);
         KZG_CUDA_TRY(cudaGetLastError());
-        evaluate_tree_kernel<<<(unsigned)n, EV_THREADS, 0, L.stream>>>(y, zy, blobs, zpow, L.ctx->roots_brp, bad, bad_stride);
+        static const int leaves_log = (getenv("CKZG_B200_EVAL_LEAVES") && atoi(getenv("CKZG_B200_EVAL_LEAVES")) == 32) ? 5 : 4;
+        if (leaves_log == 5)
+            evaluate_tree_kernel<5><<<(unsigned)n, N_BLOB >> 5, 0, L.stream>>>(y, zy, blobs, zpow, L.ctx->roots_brp, bad, bad_stride);
+        else
+            evaluate_tree_kernel<4><<<(unsigned)n, N_BLOB >> 4, 0, L.stream>>>(y, zy, blobs, zpow, L.ctx->roots_brp, bad, bad_stride);
         KZG_CUDA_TRY(cudaGetLastError());
         KZG_CUDA_TRY(cudaFreeAsync(zpow, L.stream));
         L.count(2, "evaluate");
