@@ -19,9 +19,9 @@ echo "== ncu launch list (short bench under ncu; numbers printed there are NOT b
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 1 --no-extra --no-cpu-baseline > $OUT/ncu_bench_$TAG.log 2>&1
 tail -1 $OUT/ncu_bench_$TAG.log | cut -c1-200
-echo "== ncu --set full: pairing (with source), one FFT stage with one thread per butterfly (1024 blobs)"
+echo "== ncu --set full: pairing (with source), one FFT stage with one thread per butterfly (2048 blobs)"
 bash tools/prof_pairing_source.sh $TAG
-timeout 900 ncu --set full --clock-control none -k regex:g1_fft_stage_thread_kernel -s 9 -c 1 -f -o /tmp/prof_${TAG}_fftthread python tools/prof_cells.py 1024 > $OUT/ncu_${TAG}_fftthread.log 2>&1
+timeout 900 ncu --set full --clock-control none -k regex:g1_fft_stage_thread_kernel -s 9 -c 1 -f -o /tmp/prof_${TAG}_fftthread python tools/prof_cells.py 2048 > $OUT/ncu_${TAG}_fftthread.log 2>&1
 ncu -i /tmp/prof_${TAG}_fftthread.ncu-rep --page raw --csv > $OUT/raw_${TAG}_fftthread.csv 2>/dev/null
 python tools/ncu_summary.py $OUT/raw_${TAG}_fftthread.csv > $OUT/ncu_${TAG}_fftthread_summary.txt 2>&1
 head -20 $OUT/ncu_${TAG}_fftthread_summary.txt
