@@ -27,6 +27,10 @@ global batch (`sharded_single_challenge`) and the in-library multi-device contex
 all N GPUs through the frozen-API entry point) are measured beside it at N > 1.
 Inputs are larger than L2 (512 MiB of blobs per step vs 126 MB), so no explicit flush is needed.
 """
+import os as _os
+
+# four hardware work queues per device (must be set before CUDA is initialised; see c-kzg-4844_b200/csrc/api.cu)
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "4")
 import argparse
 import ctypes
 import json

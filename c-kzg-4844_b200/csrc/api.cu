@@ -17,6 +17,17 @@
 
 namespace kzg {
 
+// Hardware work queues.  A process gets CUDA_DEVICE_MAX_CONNECTIONS (default 8) hardware queues per device and its
+// streams are spread over them.  A host-pointer verification uses a dozen streams (copies, four to eight hash streams,
+// copy-back, the call stream), and with eight or more queues active the host interface came back to queues late:
+// events recorded behind finished kernels fired up to 11 ms after the kernels had ended, erratically -- one arrangement
+// fast, its neighbour 30 % slower, two concurrent callers anywhere between 95 k and 395 k blobs/s (profiles/
+// e2e_probe_R2k ... R2y.log).  With FOUR queues every arrangement measured was fast and stable (R2y: 14.9 ms per 4096-blob
+// call, two callers 364 k blobs/s), with 32 every one was slow.  The variable only counts if it is set before the CUDA
+// context exists, so the library sets it (without overriding the user's value) when it is loaded; a host process that
+// initialises CUDA before loading the library (PyTorch) sets it itself (bench.py, tests/conftest.py).
+__attribute__((constructor)) static void ckzg_b200_default_connections() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "4", 0); }
+
 cudaStream_t& caller_stream_tls() {
     static thread_local cudaStream_t s = nullptr;
     return s;

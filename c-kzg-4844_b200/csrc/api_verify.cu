@@ -178,28 +178,26 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
     // validations and then the evaluations on the main stream: 14.3 ms.  That is the arrangement here.
     const uint64_t CH = host ? 512 : n;
     // Segments of the batch.  Ordinary segments are chunks of CH blobs: one copy, one hash launch when it has landed.
-    //
-    // EXPERIMENT, OFF BY DEFAULT (CKZG_B200_TAIL_PIECES=8 enables it): the tail of a pinned host batch travels in column
-    // pieces -- piece p = bytes [16 KiB p, 16 KiB (p + 1)) of EVERY tail blob (one strided copy) -- and is hashed piece
-    // by piece behind the copies with the SHA state carried between the launches (verify.cu
-    // launch_blob_challenges_range), so that part of the tail's 2.1 ms hash chain is done before the batch's last byte
-    // lands.  Measured at n = 4096 (tools/e2e_probe.py, profiles/e2e_probe_R2k..R2r.log, bench_R2q.log): with a
-    // 512-blob tail the call drops from 16.4 to 15.4 ms (252 k -> 263 k blobs/s end to end), and a 1024-blob tail
-    // finishes its hashes 0.28 ms after the upload.  But every arrangement other than "8 hash streams, 512-blob tail,
-    // one caller" -- a 1024-blob tail, chunks sharing a hash stream, two concurrent callers (380 k -> 126 k blobs/s),
-    // and a variant in which the calling thread polls the events and launches each stage itself -- ran into a mode in
-    // which the events recorded behind the chunks' hash kernels fire ~11 ms after those kernels end (device-side
-    // %globaltimer against event times: hashes end at 4.5 ... 9.4 ms, the first evaluation starts at 15.6 ms), while
-    // n = 512 ... 2048 were never affected.  The cause was not found in the time available, so the default is the
-    // arrangement of round 1 (one hash stream per chunk, no pieces), which never showed that mode in any run of either
-    // round, single caller, concurrent callers, 1, 2 and 4 GPUs.
+    // The TAIL of a pinned host batch -- the last 1024 blobs, whose bytes take 2.4 ms to arrive, as long as one blob
+    // takes to hash (2050 dependent SHA-256 blocks) -- travels in column pieces instead: piece p = bytes
+    // [16 KiB p, 16 KiB (p + 1)) of EVERY tail blob (one strided copy), hashed piece by piece behind the copies with the
+    // SHA state carried between the launches (verify.cu launch_blob_challenges_range).  When the batch's last byte
+    // lands, 258 of the 2050 blocks of each tail blob are left to hash (0.3 ms) instead of a whole 2.1 ms chain; earlier
+    // chunks finish their hashes under the copies that follow them anyway.  16.4 -> 14.9 ms per 4096-blob call
+    // (tools/e2e_probe.py, profiles/e2e_probe_R2y.log).
+    // This arrangement (tail pieces, four hash streams) is used when the process runs with at most four hardware work
+    // queues (CUDA_DEVICE_MAX_CONNECTIONS <= 4: the library's default when it is loaded before CUDA is initialised,
+    // api.cu); with more queues it -- like any arrangement but the one of round 1 -- ran into events firing ~11 ms late
+    // (profiles/e2e_probe_R2k ... R2x.log), so there the round-1 arrangement stays: one hash stream per chunk, no pieces.
+    // CKZG_B200_TAIL_PIECES / CKZG_B200_TAIL_BLOBS / CKZG_B200_HASH_STREAMS override.
     struct Seg {
         uint64_t off, m;
         bool pieces;
     };
     std::vector<Seg> segs;
-    static const int tail_pieces = getenv("CKZG_B200_TAIL_PIECES") ? atoi(getenv("CKZG_B200_TAIL_PIECES")) : 0;
-    static const uint64_t tail_blobs = getenv("CKZG_B200_TAIL_BLOBS") ? (uint64_t)atoll(getenv("CKZG_B200_TAIL_BLOBS")) : 512;
+    static const int hw_queues = (getenv("CUDA_DEVICE_MAX_CONNECTIONS") && atoi(getenv("CUDA_DEVICE_MAX_CONNECTIONS")) >= 1) ? atoi(getenv("CUDA_DEVICE_MAX_CONNECTIONS")) : 8;
+    static const int tail_pieces = getenv("CKZG_B200_TAIL_PIECES") ? atoi(getenv("CKZG_B200_TAIL_PIECES")) : (hw_queues <= 4 ? 8 : 0);
+    static const uint64_t tail_blobs = getenv("CKZG_B200_TAIL_BLOBS") ? (uint64_t)atoll(getenv("CKZG_B200_TAIL_BLOBS")) : 1024;
     uint64_t tail_start = n;
     if (host && tail_pieces >= 2 && tail_pieces <= 64 && (N_BLOB * 32 / 64) % tail_pieces == 0 && tail_blobs >= 128) {
         const uint64_t want = n < tail_blobs ? n : tail_blobs;
@@ -209,7 +207,7 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
     for (uint64_t off = 0; off < tail_start; off += CH) segs.push_back({off, (tail_start - off < CH) ? tail_start - off : CH, false});
     if (tail_start < n) segs.push_back({tail_start, n - tail_start, true});
     const int nsegs = (int)segs.size();
-    static const int max_side = (getenv("CKZG_B200_HASH_STREAMS") && atoi(getenv("CKZG_B200_HASH_STREAMS")) >= 1 && atoi(getenv("CKZG_B200_HASH_STREAMS")) <= 8) ? atoi(getenv("CKZG_B200_HASH_STREAMS")) : 8;
+    static const int max_side = (getenv("CKZG_B200_HASH_STREAMS") && atoi(getenv("CKZG_B200_HASH_STREAMS")) >= 1 && atoi(getenv("CKZG_B200_HASH_STREAMS")) <= 8) ? atoi(getenv("CKZG_B200_HASH_STREAMS")) : (hw_queues <= 4 ? 4 : 8);
     const int nside = std::min(max_side, nsegs);
     // side streams are forked from (ordered after) the call stream and joined / destroyed by the Call on
     // every exit path, so no early return below can leave a kernel reading released scratch

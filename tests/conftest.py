@@ -1,3 +1,7 @@
+import os as _os
+
+# four hardware work queues per device (must be set before CUDA is initialised; see c-kzg-4844_b200/csrc/api.cu)
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "4")
 import os, sys
 
 import pytest

@@ -31,3 +31,17 @@ if os.environ.get("PROBE_TIMERS"):
     names = {1: "hash", 2: "validate", 3: "evaluate"}
     out = sorted(((t - t0) & 0xffffffff, i) for i, t in recs)
     print("device timeline (us since the first record; hash:<first block>):", ", ".join("%s%s%s@%d" % (names.get(i & 0x7f, "?"), ":%d" % (i >> 8) if (i & 0x7f) == 1 else "", " end" if i & 0x80 else "", dt // 1000) for dt, i in out))
+if os.environ.get("PROBE_CALLERS"):
+    import threading
+    k = int(os.environ["PROBE_CALLERS"])
+    def worker():
+        for _ in range(6):
+            mod.verify_blob_kzg_proof_batch_host(host.data_ptr(), hc.data_ptr(), hp.data_ptr(), n, ts)
+    th = [threading.Thread(target=worker) for _ in range(k)]
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    print("%d concurrent callers: %.0f blobs/s end to end" % (k, k * 6 * n / (time.perf_counter() - t0)))
