@@ -21,7 +21,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libckzg_b200.so")
+LIB_PATH = os.environ.get("CKZG_B200_LIB") or os.path.join(_HERE, "libckzg_b200.so")  # the override: A/B builds of the same library
 SETUP_TXT = os.path.join(_HERE, "data", "trusted_setup.txt")
 
 BYTES_PER_BLOB = 131072

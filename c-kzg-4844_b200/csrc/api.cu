@@ -120,6 +120,7 @@ static void ctx_free(Ctx* c) {
     cudaFree(c->roots);
     cudaFree(c->roots_brp);
     cudaFree(c->g2_lines);
+    cudaFree(c->pairing_tables);
     cudaFree(c->g2_points);
     cudaFree(c->fk_table);
     cudaFree(c->commit_table);
@@ -406,6 +407,10 @@ int ckzg_b200_debug_upload(ckzg_b200_ctx* ctx, const uint8_t* host, uint64_t byt
 
 int ckzg_b200_debug_placement(uint32_t* dev_buf) { return debug_set_placement_buffer(dev_buf); }
 int ckzg_b200_debug_timers(uint32_t* dev_buf) { return debug_set_timer_buffer(dev_buf); }
+int ckzg_b200_debug_pairing_probe(ckzg_b200_ctx* ctx, long long* ticks64, int* ok, const uint8_t* two_g1_48, int reps) {
+    if (!ctx || !ticks64 || !ok || !two_g1_48 || reps < 1) return RET_BADARGS;
+    return debug_pairing_probe(reinterpret_cast<Ctx*>(ctx), ticks64, ok, two_g1_48, reps);
+}
 int ckzg_b200_selftest_mulbench(int ilp, int iters, int blocks, int threads, float* ms_out) { return selftest_mulbench(ilp, iters, blocks, threads, ms_out); }
 int ckzg_b200_selftest_field(int op, uint32_t* out, const uint32_t* a, const uint32_t* b, uint64_t n) { return selftest_field(op, out, a, b, n); }
 int ckzg_b200_selftest_g1(int op, uint8_t* out48, int* ok_out, const uint8_t* p48, const uint32_t* k, const uint8_t* q48, uint64_t n) {

@@ -220,6 +220,19 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
     std::vector<cudaEvent_t> hashed(nsegs, nullptr);
     uint32_t* d_states = nullptr;
     if (tail_start < n) TRY(call.alloc(&d_states, (n - tail_start) * 8));
+    // EXPERIMENT, OFF (CKZG_B200_VALIDATE_FIRST=1 enables it): the point validation enqueued on the main stream BEFORE the
+    // segments.  Enqueued after them (the default, below) it starts 5.2 ms into the call: streams share hardware work
+    // queues, a queue hands out its entries in order, and the validation sits behind another stream's wait for a chunk
+    // that has not landed yet (device timeline, profiles/e2e_probe_R3a.log); the evaluations of the first four chunks
+    // then run in one burst beside the last chunks' hashes.  Moving it to the front did start it at once -- and the
+    // hash of chunk 4 then started 15.5 ms into the call instead of 6.4 (profiles/e2e_probe_R3b.log): 22.1 ms per call
+    // against 14.4.  Which stream lands behind which in a queue is not under the library's control; the order below is
+    // the one whose measured timeline is good.
+    static const bool validate_first = getenv("CKZG_B200_VALIDATE_FIRST") && atoi(getenv("CKZG_B200_VALIDATE_FIRST")) == 1;
+    if (validate_first) {
+        TRY(s.want_shift ? launch_g1_validate2_levels(L, s.cm, d_cm, s.pf, d_pf, n, s.bad, s.table) : launch_g1_validate2(L, s.cm, d_cm, s.pf, d_pf, n, s.bad));
+        call.mark_on(call.stream, "stage:t_validate_done");
+    }
     for (int c = 0; c < nsegs && rc == RET_OK; c++) {
         const uint64_t off = segs[c].off, m = segs[c].m;
         cudaStream_t st = (segs[c].pieces && tail_stream) ? tail_stream : side[c % nside];
@@ -273,15 +286,20 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
     if (copy) call.mark_on(copy, "stage:t_upload_done");
     // main stream: point validation (independent of the blobs), then each segment's evaluation as soon as
     // its challenges exist
-    if (rc == RET_OK)
+    if (rc == RET_OK && !validate_first) {
         rc = s.want_shift ? launch_g1_validate2_levels(L, s.cm, d_cm, s.pf, d_pf, n, s.bad, s.table) : launch_g1_validate2(L, s.cm, d_cm, s.pf, d_pf, n, s.bad);
-    call.mark_on(call.stream, "stage:t_validate_done");
+        call.mark_on(call.stream, "stage:t_validate_done");
+    }
+    call.host_mark("host:t_stage1_enqueued");
     for (int c = 0; c < nsegs; c++) {
         const uint64_t off = segs[c].off, m = segs[c].m;
         if (!hashed[c]) continue;
+        if (c == nsegs - 1) call.mark_on(call.stream, "stage:t_earlier_evaluations_done");
         cudaStreamWaitEvent(call.stream, hashed[c], 0);
         cudaEventDestroy(hashed[c]);
+        if (c == nsegs - 1) call.mark_on(call.stream, "stage:t_last_evaluation_start");
         if (rc == RET_OK) rc = launch_evaluate(L, s.y + off, s.zy + off * 64, nullptr, nullptr, d_blobs + off * BLOB_BYTES, s.z + off, m, s.bad, 0);
+        if (c == nsegs - 1) call.mark_on(call.stream, "stage:t_last_evaluation_done");
         if (rc == RET_OK && stream_zy) rc = stage1_stream_zy(call, s, cpz, off, m);
     }
     return rc;
@@ -553,6 +571,7 @@ int ckzg_b200_verify_blob_kzg_proof_batch(ckzg_b200_ctx* ctx, int* ok, const uin
     }
     if (se == cudaSuccess) se = cudaStreamSynchronize(call.stream);
     KZG_CUDA_TRY(se);
+    call.host_mark("host:t_stage1_synced");
     if (*h_bad) return RET_BADARGS;
 
     Fr* d_r;
@@ -583,7 +602,9 @@ int ckzg_b200_verify_blob_kzg_proof_batch(ckzg_b200_ctx* ctx, int* ok, const uin
     // e(A, [tau]G2) == e(B, G2)   (eip4844.c:751)
     TRY(launch_pairing_check(L, d_ok, d_AB + 0, d_AB + 1, nullptr, LINE_G2_TAU, LINE_G2_GEN));
     if (stage_marks) call.mark("stage:pairing");
+    call.host_mark("host:t_stage2_enqueued");
     TRY(read_flag(call, d_ok, ok));
+    call.host_mark("host:t_verdict_read");
     return RET_OK;
 }
 

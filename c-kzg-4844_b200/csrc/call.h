@@ -1,5 +1,6 @@
 // Per-call plumbing shared by the api*.cu files.
 #pragma once
+#include <chrono>
 #include <functional>
 #include <vector>
 
@@ -42,6 +43,15 @@ struct Call {
     ProfTrace timeline;           // level 1: completion times of side-stream work, relative to "begin"
     uint8_t* ring = nullptr;      // pinned staging ring of upload() (from the context's pool)
     cudaEvent_t ring_ev[4];
+    std::chrono::steady_clock::time_point t_entry = std::chrono::steady_clock::now();
+    // level-1 profiling only: HOST time since the call object was created (where the wall time outside the device
+    // events goes: stream creation, enqueueing, the waits, teardown), reported as "host:..." entries of the dump
+    void host_mark(const char* name) {
+        if (!profiling || trace_kernels) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_entry).count();
+        std::lock_guard<std::mutex> g(ctx->prof.mu);
+        ctx->prof.add(name, ms);
+    }
 
     explicit Call(Ctx* c) : ctx(c) {
         if (cudaGetDevice(&prev_device) != cudaSuccess) return;
@@ -58,13 +68,16 @@ struct Call {
         profiling = c->prof.level >= 1;
         trace_kernels = c->prof.level >= 2;
         if (profiling) mark("begin");
+        host_mark("host:t_call_created");
     }
     ~Call() {
         if (stream) {
             join_sides();
             for (void* p : allocs) cudaFreeAsync(p, stream);
             if (profiling) mark("end");
+            host_mark("host:t_teardown_enqueued");
             cudaStreamSynchronize(stream);
+            host_mark("host:t_final_sync");
             if (profiling && trace.ev.size() >= 2) {
                 std::lock_guard<std::mutex> g(ctx->prof.mu);
                 float ms = 0;
@@ -86,6 +99,7 @@ struct Call {
             for (auto& e : timeline.ev) cudaEventDestroy(e.first);
             for (cudaStream_t sd : sides) cudaStreamDestroy(sd);
             cudaStreamDestroy(stream);
+            host_mark("host:t_exit");
         }
         if (prev_device >= 0) cudaSetDevice(prev_device);
     }

@@ -71,6 +71,7 @@ struct Ctx {
     Fr* roots_brp = nullptr;              // [8192] brp(roots_of_unity[0..8191]) (first 4096 = blob domain)
     Fr* roots = nullptr;                  // [8193] w^i
     void* g2_lines = nullptr;             // precomputed Miller-loop lines for G2 gen, [tau]G2, [tau^64]G2
+    void* pairing_tables = nullptr;       // lane schedules of the cooperative pairing arithmetic (pairing.cu pairing_tables_kernel)
     void* g2_points = nullptr;            // [65] affine G2 (Fp2 coordinates)
     void* rec_shiftA = nullptr;           // 7^k / 8192   (recover.cu)
     void* rec_shiftB = nullptr;           // 7^-k / 8192
@@ -224,6 +225,8 @@ int launch_msm_affine(Launch& L, G1* result, const uint8_t* scalars, bool big_en
 // points -> canonical 48-byte compression (one thread per point)
 int launch_g1_compress(Launch& L, uint8_t* out48, const G1* pts, uint64_t n);
 
+// ---- pairing.cu: measurement hook ----
+int debug_pairing_probe(Ctx* c, long long* ticks_host, int* ok_host, const uint8_t* two48_host, int reps);
 // ---- selftest.cu ---------------------------------------------------------------------------------
 int selftest_field(int op, uint32_t* out, const uint32_t* a, const uint32_t* b, uint64_t n);
 int selftest_mulbench(int ilp, int iters, int blocks, int threads, float* ms_out);

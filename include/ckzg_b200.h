@@ -230,6 +230,12 @@ int ckzg_b200_debug_placement(uint32_t *dev_buf);
  * [1] = capacity, then (kernel id, low 32 bits of %globaltimer in ns) pairs written by CTA 0 at kernel start and end
  * (end: id | 0x80; hash kernels carry their first SHA block in bits 8+).  Measurement hook (tools/e2e_probe.py). */
 int ckzg_b200_debug_timers(uint32_t *dev_buf);
+/* Measurement hook (tools/pairing_probe.py): one pairing check e(-P0, G2[0]) e(P1, G2[1]) on the two compressed G1 points
+ * given (HOST memory) with clock64() marks -- ticks64[0..9] = start, inputs ready, Miller loops done, product of the two
+ * Miller values, before / after the Fp12 inversion, easy part done, first exponentiation by the curve parameter done, hard
+ * part done, verdict -- followed by `reps` repetitions of each cooperative tower operation: ticks64[16 + 2k], [17 + 2k] =
+ * start / end for k = cyclotomic square, product, square, line product, conjugation, copy, Frobenius, inversion (2 runs). */
+int ckzg_b200_debug_pairing_probe(ckzg_b200_ctx *ctx, long long *ticks64, int *ok, const uint8_t *two_g1_48, int reps);
 /* Measurement hook: best-of-`reps` wall time (ms) of uploading `bytes` from HOST memory the way every HOST-mode call does
  * (pageable sources: pinned staging ring filled by the context's host threads, CKZG_B200_HOST_THREADS /
  * CKZG_B200_STAGE_SLOT_MB; pinned sources: one DMA).  mode 1: cudaHostRegister + direct DMA + cudaHostUnregister. */

@@ -161,12 +161,17 @@ int hc_coop_pairing_product_is_one(const uint8_t* p1, const uint8_t* q1, const u
         if (!g1_is_inf(Bp)) { G1 d = g1_dbl(Bp); g1_madd(d, P2, true); Bp = d; }
     }
     static CoopWS ws;
-    coop_pairing_product_is_one(ws, A, &L1, Bp, &L2, negate_first != 0);
+    static CoopLines ln1;
+    coop_pairing_product_is_one(ws, &ln1, A, &L1, Bp, &L2, negate_first != 0);
     const int single = ws.result;
     // the two-machine form of pairing_check_kernel (pairing.cu): one Miller loop per machine, product, final exponentiation
     static CoopWS w2[2];
+    static CoopLines ln2;  // one store for both machines: each fills its own pair
     for (int g = 0; g < 2; g++) {
         coop_init_tables(w2[g]);
+        coop_attach_lines(w2[g], &ln2);
+        w2[g].run2 = 0;  // the general schedule (coop_run) on this path, its packed / tree form (coop_run2) on the others
+        w2[g].cyc2 = 0;
         coop_load_points(w2[g], A, &L1, Bp, &L2, negate_first != 0);
         w2[g].use[1 - g] = 0;
         coop_prepare_all_lines(w2[g], &L1, &L2);
@@ -177,8 +182,36 @@ int hc_coop_pairing_product_is_one(const uint8_t* p1, const uint8_t* q1, const u
         w2[0].nreg[6][lane] = w2[1].nreg[0][lane];
     }
     coop_mul(w2[0], 0, 0, 6);
+    // the product kernel's final exponentiation: machine 0 squares, machine 1 multiplies (roles run in turn on the host),
+    // cooperative inversion; compared with the one-machine form on a copy of the same Miller value
+    static CoopWS w3[2];
+    w3[0] = w2[0];
+    w3[1] = w2[1];
+    w3[0].run2 = w3[1].run2 = 1;
+    w3[0].cyc2 = w3[1].cyc2 = 1;
     coop_final_exp_is_one(w2[0]);
     if (w2[0].result != single) return -2;
+    coop_final_exp_is_one_duo(w3[0], w3[1], 0);
+    if (w3[0].result != single) return -3;
+    // the four-machine Miller loop of the product kernel (roles in turn on the host) + the two-machine final exponentiation
+    static CoopWS w4[4];
+    static CoopLines ln4;
+    for (int g = 0; g < 4; g++) {
+        coop_init_tables(w4[g]);
+        coop_attach_lines(w4[g], &ln4);
+        coop_load_points(w4[g], A, &L1, Bp, &L2, negate_first != 0);
+    }
+    for (int g = 0; g < 4; g++) coop_prepare_all_lines(w4[g], &L1, &L2, g, 4);
+    coop_miller_quad(w4, 0);
+    coop_final_exp_is_one_duo(w4[0], w4[1], 0);
+    if (w4[0].result != single) return -5;
+    // the cooperative inversion alone: reg[1] * inv(reg[1]) == 1 on the value the easy part left in register 1
+    coop_inv_norm(w2[0], 6, 1, 7, 5);
+    coop_mul(w2[0], 4, 6, 1);
+    for (int i = 0; i < 12; i++) {
+        const Fp c = w_to_fp(s_load(&w2[0].reg[4][i]));
+        if (i == 0 ? !eq(c, Fp::one()) : !is_zero(c)) return -4;
+    }
     return single;
 }
 #endif

@@ -14,7 +14,7 @@ t0 = time.perf_counter()
 for _ in range(10): mod.verify_blob_kzg_proof_batch_host(host.data_ptr(), hc.data_ptr(), hp.data_ptr(), n, ts)
 dt = (time.perf_counter() - t0) / 10
 p = mod.profile_dump(ts); mod.profile_enable(ts, 0)
-print(os.environ.get('CKZG_B200_TAIL_PIECES'), 'wall ms', round(dt*1e3, 3), {k: round(v[0]/max(1,v[1]), 3) for k, v in p['kernels'].items() if k.startswith('stage')}, 'engine', round(p['call_ms']/p['calls'], 3))
+print(os.environ.get('CKZG_B200_TAIL_PIECES'), 'wall ms', round(dt*1e3, 3), {k: round(v[0]/max(1,v[1]), 3) for k, v in p['kernels'].items() if k.startswith('stage') or k.startswith('host')}, 'engine', round(p['call_ms']/p['calls'], 3))
 if os.environ.get("PROBE_TIMERS"):
     import ctypes as C
     buf = torch.zeros(2 + 2 * 4096, dtype=torch.int32, device="cuda")

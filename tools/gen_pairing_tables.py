@@ -339,13 +339,37 @@ def emit():
         out.append(arr("int8_t", "COOP_%s_OT" % U, os_))
         out.append("\n")
         print("%-5s terms: X %d  Y %d  O %d  (max out form %d)" % (op, len(xs), len(ys), len(os_), max(b - a for a, b in zip(oo, oo[1:]))), file=sys.stderr)
+    # ---- cyclotomic square, second form (coop_cyc2): every product carries ONE weight (2, 3 or 6: the Granger-Scott
+    # outputs are 3 t +- 2 z), applied by the lane that owns the product, so the output forms are plain signed sums
+    # of at most 7 scaled products -- one pass of 12 lanes instead of 60 partial sums and a second gathering pass ----
+    products, outputs = build("cyc")
+    weight = {}
+    for o in outputs:
+        for (k, idx), c in o.t.items():
+            assert k == "p"
+            assert weight.setdefault(idx, abs(c)) == abs(c), "a product with two weights"
+    W = [weight[i] for i in range(len(products))]
+    assert all(w in (2, 3, 6) for w in W)
+    o2, oo2, worst = [], [0], 0
+    for o in outputs:
+        terms = sorted(o.t.items(), key=lambda kv: kv[0][1])
+        o2 += [(idx + 1) if c > 0 else -(idx + 1) for (k, idx), c in terms]
+        oo2.append(len(o2))
+        # bound in multiples of p: a scaled product is < w p, its stored negative 8 p - v <= 8 p
+        worst = max(worst, sum(W[idx] if c > 0 else 8 for (k, idx), c in terms))
+    assert max(b - a for a, b in zip(oo2, oo2[1:])) <= 8 and worst <= 64, worst
+    out.append("// ---- cyc, second form: weights per product, unit output terms (at most 8 per coefficient, sum <= %d p) ----\n" % worst)
+    out.append("KZG_CONST int8_t COOP_CYC2_W[%d] = {%s};\n" % (len(W), ", ".join(map(str, W))))
+    out.append("KZG_CONST int16_t COOP_CYC2_OOFF[13] = {%s};\n" % ", ".join(map(str, oo2)))
+    out.append("KZG_CONST int8_t COOP_CYC2_OT[%d] = {%s};\n\n" % (len(o2), ", ".join(map(str, o2))))
+    print("cyc2  weights %s  O %d (max out form %d, bound %d p)" % (sorted(set(W)), len(o2), max(b - a for a, b in zip(oo2, oo2[1:])), worst), file=sys.stderr)
     # ---- constants of the 14-limb "wide" Montgomery domain (R_w = 2^448) ----
     def limbs14(v):
         assert 0 <= v < 1 << 448
         return ", ".join("0x%08xu" % ((v >> (32 * i)) & 0xFFFFFFFF) for i in range(14))
     out.append("// ---- wide domain: 14 limbs, R_w = 2^448; sums are never reduced, only the multiplier reduces ----\n")
     for name, v in (("FPW_MOD", P), ("FPW_ONE", (1 << 448) % P), ("FPW_R2", (1 << 896) % P), ("FPW_C512", (1 << 512) % P),
-                    ("FPW_C576", (1 << 576) % P), ("FPW_OFF16", 16 * P), ("FPW_OFF64", 64 * P), ("FPW_OFF256", 256 * P), ("FPW_OFF2048", 2048 * P)):
+                    ("FPW_C576", (1 << 576) % P), ("FPW_OFF8", 8 * P), ("FPW_OFF16", 16 * P), ("FPW_OFF64", 64 * P), ("FPW_OFF256", 256 * P), ("FPW_OFF2048", 2048 * P)):
         out.append("KZG_CONST uint32_t %s[14] = {%s};\n" % (name, limbs14(v)))
     path = os.path.join(ROOT, "c-kzg-4844_b200", "csrc", "pairing_tables.cuh")
     with open(path, "w") as f:
