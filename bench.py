@@ -365,7 +365,7 @@ def run_b200(args):
         verify_host()
     prof_e = mod.profile_dump(ts)
     mod.profile_enable(ts, 0)
-    e2e_stages = {k: round(v[0] / max(1, v[1]), 3) for k, v in prof_e.get("kernels", {}).items() if k.startswith("stage:")}
+    e2e_stages = {k: round(v[0] / max(1, v[1]), 3) for k, v in prof_e.get("kernels", {}).items() if k.startswith("stage:") or k.startswith("host:")}
     e2e_stages["engine_ms_per_call"] = round(prof_e["call_ms"] / max(1, prof_e["calls"]), 3)
     pg_blobs = np.array(host_blobs.numpy(), copy=True)  # ordinary pageable memory: what a Go slice or Python bytes is
     pg_cms, pg_prs = np.array(host_cms.numpy(), copy=True), np.array(host_prs.numpy(), copy=True)

@@ -114,6 +114,7 @@ static void ctx_free(Ctx* c) {
     int prev = -1;
     cudaGetDevice(&prev);
     cudaSetDevice(c->device);
+    c->stream_pool_destroy();
     cudaFree(c->g1_monomial);
     cudaFree(c->g1_lagrange_brp);
     cudaFree(c->msm_table);

@@ -37,6 +37,7 @@ struct Call {
     std::vector<std::pair<void*, size_t>> pinned;  // returned to the context's pool after the final sync
     int prev_device = -1;
     bool ok = false;
+    bool pooled = true;           // streams come from / go back to the context's pool (not under profiling)
     bool profiling = false;       // whole-call begin/end events
     bool trace_kernels = false;   // per-kernel events (level 2)
     ProfTrace trace;
@@ -56,7 +57,11 @@ struct Call {
     explicit Call(Ctx* c) : ctx(c) {
         if (cudaGetDevice(&prev_device) != cudaSuccess) return;
         if (cudaSetDevice(c->device) != cudaSuccess) return;
-        if (cudaStreamCreateWithFlags(&stream, cudaStreamDefault) != cudaSuccess) return;
+        // level-1 profiling records timing events on every side stream; with pooled streams that run fell into the
+        // late-event mode (18.6 ms per host batch against 13.5 unprofiled, profiles/e2e_pool_R3e.log), with streams of
+        // its own it does not: profiled calls take fresh streams
+        pooled = c->prof.level == 0;
+        if (!(stream = c->stream_acquire(0, pooled))) return;
         if (cudaStream_t cs = caller_stream_tls()) {
             cudaEvent_t e = nullptr;
             if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return;
@@ -97,8 +102,10 @@ struct Call {
             for (auto& b : pinned) ctx->pin_release(b.first, b.second);
             for (auto& e : trace.ev) cudaEventDestroy(e.first);
             for (auto& e : timeline.ev) cudaEventDestroy(e.first);
-            for (cudaStream_t sd : sides) cudaStreamDestroy(sd);
-            cudaStreamDestroy(stream);
+            // last forked, first returned: the pool hands streams out from its end, so the next call's k-th fork gets
+            // the stream this call's k-th fork had (the same hardware queue for the same role, call after call)
+            for (size_t i = sides.size(); i-- > 0;) ctx->stream_release(1, sides[i], pooled);
+            ctx->stream_release(0, stream, pooled);
             host_mark("host:t_exit");
         }
         if (prev_device >= 0) cudaSetDevice(prev_device);
@@ -108,9 +115,9 @@ struct Call {
     cudaStream_t fork() {
         cudaStream_t sd = nullptr;
         cudaEvent_t e = nullptr;
-        if (cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (!(sd = ctx->stream_acquire(1, pooled))) return nullptr;
         if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
-            cudaStreamDestroy(sd);
+            ctx->stream_release(1, sd, pooled);
             return nullptr;
         }
         cudaEventRecord(e, stream);

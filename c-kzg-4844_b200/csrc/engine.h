@@ -103,6 +103,47 @@ struct Ctx {
     // Small pool of pinned host buffers for the device->host hops inside a call (a pageable destination
     // makes cudaMemcpyAsync stage through the driver and block).  Buffers are reused across calls and
     // released with the context.
+    // Streams of finished calls, kept for the next one.  A host-pointer batch verification uses nine streams; creating
+    // them delayed the first copy by 0.3 ms and destroying them kept the caller 0.5 ms after the verdict had arrived
+    // (host marks, profiles/e2e_probe_R3c.log: 14.47 ms per call of which 13.88 between the device events).  A call's
+    // streams are idle when it returns them (its destructor synchronises), so reuse needs no further ordering.
+    // kind 0: blocking (call streams), 1: non-blocking (side streams).  CKZG_B200_STREAM_POOL=0: create / destroy per call.
+    std::mutex stream_mu;
+    std::vector<cudaStream_t> stream_free[2];
+    static bool stream_pool_on() {
+        static const bool on = !(getenv("CKZG_B200_STREAM_POOL") && atoi(getenv("CKZG_B200_STREAM_POOL")) == 0);
+        return on;
+    }
+    cudaStream_t stream_acquire(int kind, bool pooled = true) {
+        if (pooled && stream_pool_on()) {
+            std::lock_guard<std::mutex> g(stream_mu);
+            if (!stream_free[kind].empty()) {
+                cudaStream_t s = stream_free[kind].back();
+                stream_free[kind].pop_back();
+                return s;
+            }
+        }
+        cudaStream_t s = nullptr;
+        if (cudaStreamCreateWithFlags(&s, kind ? cudaStreamNonBlocking : cudaStreamDefault) != cudaSuccess) return nullptr;
+        return s;
+    }
+    void stream_release(int kind, cudaStream_t s, bool pooled = true) {
+        if (pooled && stream_pool_on()) {
+            std::lock_guard<std::mutex> g(stream_mu);
+            if (stream_free[kind].size() < 64) {
+                stream_free[kind].push_back(s);
+                return;
+            }
+        }
+        cudaStreamDestroy(s);
+    }
+    void stream_pool_destroy() {
+        std::lock_guard<std::mutex> g(stream_mu);
+        for (int k = 0; k < 2; k++) {
+            for (cudaStream_t s : stream_free[k]) cudaStreamDestroy(s);
+            stream_free[k].clear();
+        }
+    }
     std::mutex pin_mu;
     std::vector<std::pair<void*, size_t>> pin_free;
     void* pin_acquire(size_t bytes, size_t* got) {

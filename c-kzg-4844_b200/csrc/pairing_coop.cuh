@@ -68,6 +68,86 @@ struct FpWTag {
 };
 using FpW = Fe<FpWTag>;
 
+// ------------------------------------------------------------------------------------------------
+// The wide product in radix 2^29 (compile with -DCOOP_W29=1; MEASURED SLOWER, off).  The 32-bit-limb Montgomery product
+// of field.cuh is a sequence of carry chains -- every multiply-add waits for the carry of the one before, PTX has a
+// single carry flag, and one warp alone on its scheduler reaches 65 % of the multiplier's rate (1.25 us per 14-limb
+// product, half of a cyclotomic square).  With 29-bit limbs a column of 14 products (< 2^58 each) and the 14 reduction
+// terms under it fit a 64-bit accumulator, so the 392 multiply-adds are INDEPENDENT IMAD.WIDE instructions with 64-bit
+// accumulation, no carry flag anywhere; the carries are resolved once at the end (split every column in three 29-bit
+// pieces, one short 32-bit carry chain, repack to 32-bit words).  R_w = 2^(29 * 14) = 2^406: for operands < 2^391 the
+// result is < p + 2^376 -- NOT reduced below p; the stored negative of a product is then 2 p - v
+// (tools/gen_pairing_tables.py checks the totals).  Plain C++: the same code runs in tests/hostcheck.
+// Measured on B200 (profiles/pairing_probe_R3e.log): cyclotomic square 2.63 us against 2.36 us, product 3.81 against
+// 3.47, whole check 1.41 ms against 1.26 ms.  The 392 wide multiply-adds alone are 1570 cycles of the quarter-rate
+// multiplier, and splitting / recombining the limbs adds ~370 instructions per product (1488 against 1112 per
+// cyclotomic square): what the carry chains lose in latency the conversions lose in issue slots.  Kept, off, with its
+// host test, as the record of the experiment.
+// ------------------------------------------------------------------------------------------------
+#ifndef COOP_W29
+#define COOP_W29 0
+#endif
+constexpr uint32_t W29_MASK = (1u << 29) - 1;
+// 14 radix-2^32 words (value < 2^406) -> 14 radix-2^29 limbs
+KZG_HD void w_split29(uint32_t* o, const uint32_t* l) {
+#pragma unroll
+    for (int k = 0; k < 14; k++) {
+        const int bit = 29 * k, w = bit >> 5, sh = bit & 31;
+        uint32_t v = l[w] >> sh;
+        if (sh > 3 && w + 1 < 14) v |= l[w + 1] << (32 - sh);
+        o[k] = v & W29_MASK;
+    }
+}
+KZG_HD void w_mul29(uint32_t* out, const uint32_t* x, const uint32_t* y) {
+    uint32_t a[14], b[14];
+    w_split29(a, x);
+    w_split29(b, y);
+    uint64_t t[28];
+#pragma unroll
+    for (int k = 0; k < 28; k++) t[k] = 0;
+#pragma unroll
+    for (int i = 0; i < 14; i++)
+#pragma unroll
+        for (int j = 0; j < 14; j++) t[i + j] += (uint64_t)a[i] * b[j];
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 14; i++) {
+        const uint64_t s = t[i] + c;
+        const uint32_t m = ((uint32_t)s * FPW_INV29) & W29_MASK;
+        c = (s + (uint64_t)m * FPW_P29[0]) >> 29;  // the low 29 bits cancel
+#pragma unroll
+        for (int j = 1; j < 14; j++) t[i + j] += (uint64_t)m * FPW_P29[j];
+    }
+    t[14] += c;
+    // columns 14..27 (< 2^63 each) -> lazy 29-bit limbs (three pieces per column) -> exact limbs (one carry chain)
+    uint32_t q[17];
+#pragma unroll
+    for (int k = 0; k < 17; k++) q[k] = 0;
+#pragma unroll
+    for (int k = 0; k < 14; k++) {
+        const uint64_t v = t[14 + k];
+        q[k] += (uint32_t)v & W29_MASK;
+        q[k + 1] += (uint32_t)(v >> 29) & W29_MASK;
+        q[k + 2] += (uint32_t)(v >> 58);
+    }
+    uint32_t r[17], cc = 0;
+#pragma unroll
+    for (int k = 0; k < 17; k++) {
+        const uint32_t sum = q[k] + cc;
+        r[k] = sum & W29_MASK;
+        cc = sum >> 29;
+    }
+    // 29-bit limbs -> 32-bit words (the value is < 2 p < 2^382: twelve words, the top two are zero)
+#pragma unroll
+    for (int w = 0; w < 14; w++) {
+        const int bit = 32 * w, k = bit / 29, off = bit - 29 * k;
+        uint64_t v = (uint64_t)r[k] >> off;
+        if (k + 1 < 17) v |= (uint64_t)r[k + 1] << (29 - off);
+        if (k + 2 < 17) v |= (uint64_t)r[k + 2] << (58 - off);
+        out[w] = (uint32_t)v;
+    }
+}
+
 KZG_HD FpW w_ext(const Fp& a) {  // the same integer on 14 limbs
     FpW r;
 #pragma unroll
@@ -75,11 +155,37 @@ KZG_HD FpW w_ext(const Fp& a) {  // the same integer on 14 limbs
     r.l[12] = r.l[13] = 0;
     return r;
 }
-// 12-limb Montgomery form (v * 2^384) -> wide form (v * 2^448): times 2^512 / 2^448
-KZG_HD FpW w_from_fp(const Fp& a) { return mul(w_ext(a), FpW::from_limbs(FPW_C512)); }
-// wide (any size within the bounds above) -> canonical 12-limb Montgomery form: times 2^384 / 2^448
+// the wide product: x * y / R_w mod p for operands within the bounds above
+KZG_HD FpW w_mul(const FpW& x, const FpW& y) {
+#if COOP_W29
+    FpW r;
+    w_mul29(r.l, x.l, y.l);  // < p + 2^376
+    return r;
+#else
+    return mul(x, y);  // < p
+#endif
+}
+#if COOP_W29
+#define FPW_CONST_ONE FPW29_ONE
+#define FPW_CONST_CIN FPW29_CIN
+#define FPW_CONST_CPT FPW29_CPT
+#define FPW_CONST_PNEG FPW_2P /* stored negative of a product: 2 p - v */
+#else
+#define FPW_CONST_ONE FPW_ONE
+#define FPW_CONST_CIN FPW_C512
+#define FPW_CONST_CPT FPW_C576
+#define FPW_CONST_PNEG FPW_MOD /* products are < p: p - v */
+#endif
+KZG_HD FpW w_one() { return FpW::from_limbs(FPW_CONST_ONE); }
+// 12-limb Montgomery form (v * 2^384) -> wide form (v * R_w): one wide product with 2^(2 RW - 384)
+KZG_HD FpW w_from_fp(const Fp& a) { return w_mul(w_ext(a), FpW::from_limbs(FPW_CONST_CIN)); }
+// wide (any size within the bounds above) -> canonical 12-limb Montgomery form: times 2^384 / R_w
 KZG_HD Fp w_to_fp(const FpW& v) {
-    FpW t = mul(v, w_ext(Fp::one()));
+    FpW t = w_mul(v, w_ext(Fp::one()));
+#if COOP_W29
+    FpW u;
+    if (limbs_sub<14>(u.l, t.l, FPW_MOD) == 0) t = u;  // < 2 p -> < p
+#endif
     Fp r;
 #pragma unroll
     for (int i = 0; i < 12; i++) r.l[i] = t.l[i];
@@ -258,7 +364,7 @@ KZG_HD void coop_init_tables(CoopWS& ws) {
     coop_copy_table(ws.tb, COOP_OP_SQR, lane, COOP_SQR_NPROD, COOP_SQR_XOFF, COOP_SQR_YOFF, COOP_SQR_OOFF, COOP_SQR_XT, COOP_SQR_YT, COOP_SQR_OT);
     coop_copy_table(ws.tb, COOP_OP_LINE, lane, COOP_LINE_NPROD, COOP_LINE_XOFF, COOP_LINE_YOFF, COOP_LINE_OOFF, COOP_LINE_XT, COOP_LINE_YT, COOP_LINE_OT);
     coop_copy_table(ws.tb, COOP_OP_CYC, lane, COOP_CYC_NPROD, COOP_CYC_XOFF, COOP_CYC_YOFF, COOP_CYC_OOFF, COOP_CYC_XT, COOP_CYC_YT, COOP_CYC_OT);
-    if (lane == 0) s_store(&ws.onew, FpW::one());
+    if (lane == 0) s_store(&ws.onew, w_one());
     if (lane == 1) s_store(&ws.zerow, FpW::zero());
     if (lane == 2) ws.ticks = nullptr;
     if (lane == 3) ws.cyc2 = 1;
@@ -290,7 +396,7 @@ __device__ __forceinline__ void coop_init_from(CoopWS& ws, const CoopTables* bui
     const uint4* src = reinterpret_cast<const uint4*>(built);
     uint4* dst = reinterpret_cast<uint4*>(&ws.tb);
     for (int i = lane; i < (int)(sizeof(CoopTables) / 16); i += COOP_LANES) dst[i] = src[i];
-    if (lane == 0) s_store(&ws.onew, FpW::one());
+    if (lane == 0) s_store(&ws.onew, w_one());
     if (lane == 1) s_store(&ws.zerow, FpW::zero());
     if (lane == 2) ws.ticks = nullptr;
     if (lane == 3) ws.cyc2 = 1;
@@ -317,10 +423,10 @@ KZG_HD_NOINLINE void coop_run(CoopWS& ws, int op, int d, int ra, const FpS* b) {
             coop_acc_term(x, t < nx ? T.xt[bx + t] : 0, a, na, b, &ws.zerow);
             coop_acc_term(y, t < ny ? T.yt[by + t] : 0, a, na, b, &ws.zerow);
         }
-        const FpW pr = mul(x, y);  // < p
+        const FpW pr = w_mul(x, y);  // < p (+ 2^376)
         s_store(&ws.prod[L], pr);
         FpW npr;
-        limbs_sub<14>(npr.l, FPW_MOD, pr.l);  // p - v in (0, p]
+        limbs_sub<14>(npr.l, FPW_CONST_PNEG, pr.l);  // p - v in (0, p], or 2 p - v
         s_store(&ws.nprod[L], npr);
     }
     COOP_END
@@ -397,7 +503,7 @@ KZG_HD_NOINLINE void coop_cyc2(CoopWS& ws, int d, int ra) {
         w_acc(y2, y3);
         w_acc(x, x2);
         w_acc(y, y2);
-        const FpW pr = w_small_mul(mul(x, y), (uint32_t)ws.tb.w2[lane]);  // < 6 p
+        const FpW pr = w_small_mul(w_mul(x, y), (uint32_t)ws.tb.w2[lane]);  // < 6.3 p
         s_store(&ws.prod[lane], pr);
         FpW npr;
         limbs_sub<14>(npr.l, FPW_OFF8, pr.l);  // 8 p - v in (2 p, 8 p]
@@ -451,10 +557,10 @@ KZG_HD_NOINLINE void coop_run2(CoopWS& ws, int op, int d, int ra, const FpS* b) 
     if (lane < nprod) {
         const FpW x = coop_sum8_in(ws.tb.px[op][lane], a, na, b, zero);
         const FpW y = coop_sum8_in(ws.tb.py[op][lane], a, na, b, zero);
-        const FpW pr = mul(x, y);  // < p
+        const FpW pr = w_mul(x, y);  // < p (+ 2^376)
         s_store(&ws.prod[lane], pr);
         FpW npr;
-        limbs_sub<14>(npr.l, FPW_MOD, pr.l);  // p - v in (0, p]
+        limbs_sub<14>(npr.l, FPW_CONST_PNEG, pr.l);  // p - v in (0, p], or 2 p - v
         s_store(&ws.nprod[lane], npr);
     }
     COOP_END
@@ -524,7 +630,7 @@ KZG_HD_NOINLINE void coop_copy(CoopWS& ws, int d, int a) {
 }
 KZG_HD void coop_set_one(CoopWS& ws, int d) {
     COOP_BEGIN
-    if (lane < 12) coop_put(ws, d, lane, (lane == 0) ? FpW::one() : FpW::zero());
+    if (lane < 12) coop_put(ws, d, lane, (lane == 0) ? w_one() : FpW::zero());
     COOP_END
 }
 // a^(p^power), power = 1 or 2; d != a.  Lane k < 6 owns the Fp2 coefficient of w^k (12-limb tower code).
@@ -642,7 +748,7 @@ KZG_HD void coop_load_points(CoopWS& ws, const G1& P1, const G2Lines* L1, const 
         }
         // s and xs meet a 12-limb line coefficient (c * 2^384) in one WIDE product that must come out as
         // c*s * 2^448: carry them as s * 2^512, i.e. times 2^576 / 2^448.  ys enters the line as it is.
-        ws.pt[pair][j] = (j == 2) ? w_from_fp(v) : mul(w_ext(v), FpW::from_limbs(FPW_C576));
+        ws.pt[pair][j] = (j == 2) ? w_from_fp(v) : w_mul(w_ext(v), FpW::from_limbs(FPW_CONST_CPT));
     }
     if (lane == 6) ws.use[0] = (!g1_is_inf(P1) && !L1->is_inf) ? 1 : 0;
     if (lane == 7) ws.use[1] = (!g1_is_inf(P2) && !L2->is_inf) ? 1 : 0;
@@ -661,10 +767,10 @@ KZG_HD_NOINLINE void coop_prepare_all_lines(CoopWS& ws, const G2Lines* L1, const
         if (!ws.use[pair]) continue;
         const LineCoeff& l = (pair ? L2 : L1)->line[k];
         FpW v;
-        if (j == 0) v = mul(w_ext(l.A.c0), ws.pt[pair][0]);
-        else if (j == 1) v = mul(w_ext(l.A.c1), ws.pt[pair][0]);
-        else if (j == 2) v = mul(w_ext(l.B.c0), ws.pt[pair][1]);
-        else if (j == 3) v = mul(w_ext(l.B.c1), ws.pt[pair][1]);
+        if (j == 0) v = w_mul(w_ext(l.A.c0), ws.pt[pair][0]);
+        else if (j == 1) v = w_mul(w_ext(l.A.c1), ws.pt[pair][0]);
+        else if (j == 2) v = w_mul(w_ext(l.B.c0), ws.pt[pair][1]);
+        else if (j == 3) v = w_mul(w_ext(l.B.c1), ws.pt[pair][1]);
         else v = ws.pt[pair][2];
         s_store(&ws.ln->lv[pair][k][j], v);
     }

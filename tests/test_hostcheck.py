@@ -290,3 +290,19 @@ def test_cooperative_pairing_schedule_host(hc):
         assert hc.hc_coop_pairing_product_is_one(c(wrong), g2_compress(G2), c(aG1), g2_compress(bG2), 1, scale) == 0
         assert hc.hc_coop_pairing_product_is_one(inf, g2_compress(G2), inf, g2_compress(bG2), 1, scale) == 1
         assert hc.hc_coop_pairing_product_is_one(inf, g2_compress(G2), c(aG1), g2_compress(bG2), 1, scale) == 0
+
+
+def test_cooperative_pairing_with_the_radix_29_wide_product():
+    """The alternative wide product of pairing_coop.cuh (29-bit limbs, 64-bit column accumulators, R_w = 2^406; off in
+    the product build because it measured slower) through the same cooperative pairing check."""
+    hc29 = C.CDLL(build(defines=("COOP_W29=1",), tag="_w29"))
+    rnd = random.Random(29)
+    G1, G2 = B.G1_GEN_J, B.G2_GEN_J
+    c = lambda p: B.g1_compress(p)
+    for scale in (0, 1):
+        a, b = rnd.randrange(1, R), rnd.randrange(1, R)
+        aG1, bG2, abG1 = B.g1_mul(G1, a), B.g2_mul(G2, b), B.g1_mul(G1, a * b % R)
+        assert hc29.hc_coop_pairing_product_is_one(c(abG1), g2_compress(G2), c(aG1), g2_compress(bG2), 1, scale) == 1
+        assert hc29.hc_coop_pairing_product_is_one(c(abG1), g2_compress(G2), c(aG1), g2_compress(bG2), 0, scale) == 0
+    inf = c(B.G1_INF)
+    assert hc29.hc_coop_pairing_product_is_one(inf, g2_compress(G2), inf, g2_compress(bG2), 1, 0) == 1

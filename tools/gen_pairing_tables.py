@@ -371,6 +371,23 @@ def emit():
     for name, v in (("FPW_MOD", P), ("FPW_ONE", (1 << 448) % P), ("FPW_R2", (1 << 896) % P), ("FPW_C512", (1 << 512) % P),
                     ("FPW_C576", (1 << 576) % P), ("FPW_OFF8", 8 * P), ("FPW_OFF16", 16 * P), ("FPW_OFF64", 64 * P), ("FPW_OFF256", 256 * P), ("FPW_OFF2048", 2048 * P)):
         out.append("KZG_CONST uint32_t %s[14] = {%s};\n" % (name, limbs14(v)))
+    # ---- the radix-2^29 multiplier of the wide domain (w_mul29): R_w = 2^406 = 2^(29 * 14) ----
+    # conversions between the 12-limb Montgomery form (v 2^384) and the wide form (v 2^RW) go through one wide product
+    # with 2^(2 RW - 384); the scaled point coordinates meet a 12-limb line coefficient in one wide product and are
+    # carried as s 2^(2 RW - 384), i.e. one product of the 12-limb form with 2^(3 RW - 768)
+    RW = 406
+    out.append("// ---- radix-2^29 multiplier: R_w = 2^406; products come out < p + 2^376 (not reduced below p) ----\n")
+    for name, v in (("FPW29_ONE", (1 << RW) % P), ("FPW29_CIN", (1 << (2 * RW - 384)) % P), ("FPW29_CPT", (1 << (3 * RW - 768)) % P), ("FPW_2P", 2 * P),
+                    ("FPW_OFF128", 128 * P)):
+        out.append("KZG_CONST uint32_t %s[14] = {%s};\n" % (name, limbs14(v)))
+    out.append("KZG_CONST uint32_t FPW_P29[14] = {%s};\n" % ", ".join("0x%08xu" % ((P >> (29 * i)) & ((1 << 29) - 1)) for i in range(14)))
+    out.append("#define FPW_INV29 0x%08xu  // -1 / p mod 2^29\n" % ((-pow(P, -1, 1 << 29)) % (1 << 29)))
+    # worst-case output sums when a product is < 1.05 p and its stored negative 2 p - v <= 2 p (in p / 100)
+    for op in ("mul", "sqr", "line"):
+        products, outputs = build(op)
+        worst = max(sum(105 * c if c > 0 else 200 * (-c) for c in o.t.values()) for o in outputs)
+        print("%-5s worst output sum with unreduced products: %.1f p" % (op, worst / 100), file=sys.stderr)
+        assert worst <= 128 * 100
     path = os.path.join(ROOT, "c-kzg-4844_b200", "csrc", "pairing_tables.cuh")
     with open(path, "w") as f:
         f.write("".join(out))
