@@ -228,10 +228,21 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
     // hash of chunk 4 then started 15.5 ms into the call instead of 6.4 (profiles/e2e_probe_R3b.log): 22.1 ms per call
     // against 14.4.  Which stream lands behind which in a queue is not under the library's control; the order below is
     // the one whose measured timeline is good.
-    static const bool validate_first = getenv("CKZG_B200_VALIDATE_FIRST") && atoi(getenv("CKZG_B200_VALIDATE_FIRST")) == 1;
-    if (validate_first) {
+    // (2 = a third arrangement: the validation on a side stream of its own, forked here, joined before the first evaluation)
+    static const int validate_mode = getenv("CKZG_B200_VALIDATE_FIRST") ? atoi(getenv("CKZG_B200_VALIDATE_FIRST")) : 0;
+    const bool validate_first = validate_mode == 1 || validate_mode == 2;
+    cudaEvent_t validated = nullptr;
+    if (validate_mode == 1) {
         TRY(s.want_shift ? launch_g1_validate2_levels(L, s.cm, d_cm, s.pf, d_pf, n, s.bad, s.table) : launch_g1_validate2(L, s.cm, d_cm, s.pf, d_pf, n, s.bad));
         call.mark_on(call.stream, "stage:t_validate_done");
+    } else if (validate_mode == 2) {
+        cudaStream_t vs = call.fork();
+        if (!vs) return RET_ERROR;
+        Launch Lv = call.launch_on(vs);
+        TRY(s.want_shift ? launch_g1_validate2_levels(Lv, s.cm, d_cm, s.pf, d_pf, n, s.bad, s.table) : launch_g1_validate2(Lv, s.cm, d_cm, s.pf, d_pf, n, s.bad));
+        KZG_CUDA_TRY(cudaEventCreateWithFlags(&validated, cudaEventDisableTiming));
+        cudaEventRecord(validated, vs);
+        call.mark_on(vs, "stage:t_validate_done");
     }
     for (int c = 0; c < nsegs && rc == RET_OK; c++) {
         const uint64_t off = segs[c].off, m = segs[c].m;
@@ -289,6 +300,10 @@ int verify_stage1(Call& call, Stage1& s, const uint8_t* blobs, const uint8_t* d_
     if (rc == RET_OK && !validate_first) {
         rc = s.want_shift ? launch_g1_validate2_levels(L, s.cm, d_cm, s.pf, d_pf, n, s.bad, s.table) : launch_g1_validate2(L, s.cm, d_cm, s.pf, d_pf, n, s.bad);
         call.mark_on(call.stream, "stage:t_validate_done");
+    }
+    if (validated) {
+        cudaStreamWaitEvent(call.stream, validated, 0);
+        cudaEventDestroy(validated);
     }
     call.host_mark("host:t_stage1_enqueued");
     for (int c = 0; c < nsegs; c++) {
