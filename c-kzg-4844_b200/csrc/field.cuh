@@ -440,7 +440,31 @@ KZG_HD void limbs_shl1(uint32_t* a) {
     for (int i = N - 1; i > 0; i--) a[i] = (a[i] << 1) | (a[i - 1] >> 31);
     a[0] <<= 1;
 }
+// shifts by t bits, 1 <= t <= 31 (funnel shifts: the same instruction count as a shift by one)
+template <int N>
+KZG_HD void limbs_shr(uint32_t* a, int t) {
+#pragma unroll
+    for (int i = 0; i < N - 1; i++) a[i] = (a[i] >> t) | (a[i + 1] << (32 - t));
+    a[N - 1] >>= t;
+}
+template <int N>
+KZG_HD void limbs_shl(uint32_t* a, int t) {
+#pragma unroll
+    for (int i = N - 1; i > 0; i--) a[i] = (a[i] << t) | (a[i - 1] >> (32 - t));
+    a[0] <<= t;
+}
+// trailing zero bits of a nonzero word
+KZG_HD int word_ctz(uint32_t w) {
+#if KZG_DEVICE_PATH
+    return __ffs((int)w) - 1;
+#else
+    return __builtin_ctz(w);
+#endif
+}
 
+// Steps of Kaliski's phase 1 that only shift are merged: after a subtraction of two odd numbers the difference has
+// two trailing zero bits on average, and "v >>= 1, r <<= 1, k++" repeated t times is "v >>= t, r <<= t, k += t" -- the
+// same sequence of values, ~0.7 n iterations instead of ~1.4 n (the subtraction step brings its own first halving).
 template <class F>
 KZG_HD_NOINLINE Fe<F> inv_binary(const Fe<F>& a) {
     constexpr int N = F::N;
@@ -457,27 +481,35 @@ KZG_HD_NOINLINE Fe<F> inv_binary(const Fe<F>& a) {
     // invariants: u, v > 0 until the end; gcd(u, v) = 1; r, s < 2p (fits: 2p < 2^(32N))
     while (!limbs_is_zero<N>(v)) {
         if (!(v[0] & 1u)) {
-            limbs_shr1<N>(v);
-            limbs_shl1<N>(r);
+            const int t = v[0] ? word_ctz(v[0]) : 31;  // a zero low word: 31 now, the rest in the next rounds
+            limbs_shr<N>(v, t);
+            limbs_shl<N>(r, t);
+            k += t;
         } else if (!(u[0] & 1u)) {
-            limbs_shr1<N>(u);
-            limbs_shl1<N>(s);
+            const int t = u[0] ? word_ctz(u[0]) : 31;
+            limbs_shr<N>(u, t);
+            limbs_shl<N>(s, t);
+            k += t;
         } else {
-            uint32_t t[N];
-            if (limbs_sub<N>(t, v, u) == 0) {  // v >= u
+            uint32_t d[N];
+            if (limbs_sub<N>(d, v, u) == 0) {  // v >= u
+                // v - u is even; if it is zero the loop ends after this one halving (u = v = gcd = 1)
+                const int t = limbs_is_zero<N>(d) ? 1 : (d[0] ? word_ctz(d[0]) : 31);
 #pragma unroll
-                for (int i = 0; i < N; i++) v[i] = t[i];
-                limbs_shr1<N>(v);
+                for (int i = 0; i < N; i++) v[i] = d[i];
+                limbs_shr<N>(v, t);
                 limbs_add<N>(s, s, r);
-                limbs_shl1<N>(r);
+                limbs_shl<N>(r, t);
+                k += t;
             } else {
-                limbs_sub<N>(u, u, v);
-                limbs_shr1<N>(u);
+                limbs_sub<N>(u, u, v);  // u > v: the difference is even and not zero
+                const int t = u[0] ? word_ctz(u[0]) : 31;
+                limbs_shr<N>(u, t);
                 limbs_add<N>(r, r, s);
-                limbs_shl1<N>(s);
+                limbs_shl<N>(s, t);
+                k += t;
             }
         }
-        k++;
     }
     if (limbs_geq<N>(r, F::mod())) limbs_sub<N>(r, r, F::mod());
     Fe<F> x;  // x = p - r = (integer a)^-1 * 2^k  (mod p), as a plain integer
