@@ -306,3 +306,57 @@ def test_cooperative_pairing_with_the_radix_29_wide_product():
         assert hc29.hc_coop_pairing_product_is_one(c(abG1), g2_compress(G2), c(aG1), g2_compress(bG2), 0, scale) == 0
     inf = c(B.G1_INF)
     assert hc29.hc_coop_pairing_product_is_one(inf, g2_compress(G2), inf, g2_compress(bG2), 1, 0) == 1
+
+
+def _sim_branches(a, mod):
+    """Which rare branches of inv_binary (field.cuh: merged shift steps) the input reaches: a low word of zeros in
+    the 'v even' / 'u even' steps, and in the difference of the two subtraction steps."""
+    u, v, hit = mod, a, set()
+    while v:
+        if v % 2 == 0:
+            if v % (1 << 32) == 0:
+                hit.add("v_even_zero_word")
+            t = min(31, (v & -v).bit_length() - 1)
+            v >>= t
+        elif u % 2 == 0:
+            if u % (1 << 32) == 0:
+                hit.add("u_even_zero_word")
+            t = min(31, (u & -u).bit_length() - 1)
+            u >>= t
+        elif v >= u:
+            d = v - u
+            if d and d % (1 << 32) == 0:
+                hit.add("v_minus_u_zero_word")
+            v = d >> (1 if d == 0 else min(31, (d & -d).bit_length() - 1))
+        else:
+            d = u - v
+            if d % (1 << 32) == 0:
+                hit.add("u_minus_v_zero_word")
+            u = d >> min(31, (d & -d).bit_length() - 1)
+    return hit
+
+
+def test_inversion_differences_with_a_zero_low_word(hc):
+    """Inputs built so that a difference of the binary-Euclid loop has 32 or more trailing zero bits (probability 2^-32
+    for random inputs): the merged shift then goes 31 bits at a time and continues in the even steps."""
+    for mod, n, fn in ((P, 12, hc.hc_fp_inv), (R, 8, hc.hc_fr_inv)):
+        out = (C.c_uint32 * n)()
+        cases, seen = [], set()
+        for e in (32, 33, 40, 63, 64, 65, 96, 200):
+            for m in (1, 3, 5, 0x1234567):
+                a = mod - (m << e)  # first step: u - v = m 2^e
+                if 0 < a < mod:
+                    cases.append(a)
+        # second step v - u' with u' = (mod - a) / 2: 3 a = mod (mod 2^k)
+        for k in (33, 40, 64, 70):
+            a0 = mod * pow(3, -1, 1 << k) % (1 << k)
+            for j in range((mod // 2) >> k, ((mod // 2) >> k) + 200):
+                a = a0 + (j << k)
+                if mod // 3 < a < mod and (mod - a) % 4 == 2:
+                    cases.append(a)
+                    break
+        for a in cases:
+            seen |= _sim_branches(a, mod)
+            fn(out, limbs(a, n))
+            assert val(out) == pow(a, mod - 2, mod), hex(a)
+        assert {"u_minus_v_zero_word", "v_minus_u_zero_word", "u_even_zero_word"} <= seen, seen
